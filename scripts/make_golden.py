@@ -1,0 +1,124 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in-process.
+
+Build-container only (needs /root/reference).  For every case it runs the reference twice
+(O1 = stock, O2 = `utils.svdecon` swapped for an exact float64 SVD), checks the
+oracle restatement (`oracle/facemap_oracle.py`) against it, and stores a reduced set of outputs:
+geometry, avgframe/avgmotion, motion, singular values, the leading KEEP mask components and the
+leading KEEP projected traces on a window of frames.
+
+    python scripts/make_golden.py            # writes tests/golden/<case>.npz
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from facemap_b200.synth import SynthVideo  # noqa: E402
+from oracle import facemap_oracle as orc  # noqa: E402
+from oracle.ref_harness import run_reference  # noqa: E402
+
+KEEP = 16
+
+
+def motion_roi(ivid, y0, y1, x0, x1):
+    return {"rind": 1, "rtype": "motion SVD", "iROI": 0, "ivid": ivid, "color": (0, 0, 0),
+            "yrange": np.arange(y0, y1), "xrange": np.arange(x0, x1), "saturation": 0}
+
+
+CASES = {
+    # name: (views [(H, W, seed)], N, sbin, motSVD, movSVD, rois)
+    "single_s2": ([(64, 96, 0)], 2300, 2, True, True, None),
+    "multi_roi_s4": ([(96, 128, 0), (80, 112, 1)], 2200, 4, True, True,
+                     [motion_roi(0, 10, 70, 17, 90), motion_roi(1, 8, 60, 20, 100)]),
+    "onechunk_s1": ([(24, 32, 2)], 1300, 1, True, False, None),
+    "crop_s3": ([(50, 70, 3)], 2100, 3, True, False, None),
+    "short_s2": ([(40, 56, 4)], 700, 2, True, True, None),
+}
+
+
+def case_videos(name):
+    views, N, *_ = CASES[name]
+    return [SynthVideo(H, W, N, seed=seed).all_frames() for (H, W, seed) in views]
+
+
+def frame_window(N):
+    """Frames kept for the trace fixtures: start (Q1/Q2 + first seam) and the tail."""
+    idx = np.concatenate((np.arange(0, min(N, 520)), np.arange(max(0, N - 60), N)))
+    return np.unique(idx)
+
+
+def reduce_proc(p, N, prefix, out):
+    w = frame_window(N)
+    out[prefix + "frame_window"] = w
+    for key in ("Lybin", "Lxbin", "sybin", "sxbin"):
+        out[prefix + key] = np.asarray(p[key])
+    out[prefix + "LYbin"] = np.int64(p["LYbin"])
+    out[prefix + "LXbin"] = np.int64(p["LXbin"])
+    for key in ("avgframe", "avgmotion"):
+        for i, a in enumerate(p[key]):
+            out[f"{prefix}{key}_{i}"] = np.asarray(a)
+    out[prefix + "avgframe_reshape"] = p["avgframe_reshape"]
+    out[prefix + "avgmotion_reshape"] = p["avgmotion_reshape"]
+    for i, a in enumerate(p["motion"]):
+        out[f"{prefix}motion_{i}"] = a
+    out[prefix + "motSv"] = np.asarray(p["motSv"])
+    out[prefix + "movSv"] = np.asarray(p["movSv"])
+    for mk, vk in (("motMask", "motSVD"), ("movMask", "movSVD")):
+        out[f"{prefix}{mk}_n"] = np.int64(len(p[mk]))
+        for i, a in enumerate(p[mk]):
+            out[f"{prefix}{mk}_{i}_shape"] = np.array(a.shape)
+            out[f"{prefix}{mk}_{i}"] = a[:, :KEEP].copy()
+        for i, a in enumerate(p[vk]):
+            out[f"{prefix}{vk}_{i}_shape"] = np.array(a.shape)
+            out[f"{prefix}{vk}_{i}"] = a[w][:, :KEEP].copy() if a.shape[0] == N else a
+    if p["rois"] is not None:
+        for i, r in enumerate(p["rois"]):
+            if r["rind"] == 1:
+                out[f"{prefix}roi{i}_yrange_bin"] = r["yrange_bin"]
+                out[f"{prefix}roi{i}_xrange_bin"] = r["xrange_bin"]
+
+
+def same(a, b):
+    if isinstance(a, list):
+        return len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and np.array_equal(a, b)
+
+
+def main():
+    outdir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(outdir, exist_ok=True)
+    only = sys.argv[1:]
+    for name, (views, N, sbin, mot, mov, rois) in CASES.items():
+        if only and name not in only:
+            continue
+        vids = case_videos(name)
+        out = {"case": np.array(name), "N": np.int64(N), "sbin": np.int64(sbin),
+               "motSVD": np.bool_(mot), "movSVD": np.bool_(mov), "keep": np.int64(KEEP),
+               "views": np.array(views)}
+        for mode, exact in (("stock", False), ("exact", True)):
+            t = time.time()
+            p = run_reference([vids], sbin=sbin, motSVD=mot, movSVD=mov, rois=rois, exact=exact)
+            tr = time.time() - t
+            t = time.time()
+            o = orc.run_oracle(vids, sbin=sbin, motSVD=mot, movSVD=mov, rois=rois, svd=mode)
+            to = time.time() - t
+            bad = [k for k in ("Lybin", "Lxbin", "sybin", "sxbin", "avgframe", "avgmotion",
+                               "avgframe_reshape", "avgmotion_reshape", "motion", "motSv", "movSv",
+                               "motMask", "movMask", "motMask_reshape", "movMask_reshape",
+                               "motSVD", "movSVD") if not same(p[k], o[k])]
+            print(f"{name:14s} {mode:5s} reference {tr:6.1f}s oracle {to:6.1f}s  "
+                  f"oracle==reference bit-for-bit: {'YES' if not bad else 'NO ' + str(bad)}")
+            reduce_proc(p, N, mode + "/", out)
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), **out)
+        print("  wrote", name + ".npz", os.path.getsize(os.path.join(outdir, name + ".npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
