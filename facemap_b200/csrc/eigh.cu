@@ -1,0 +1,146 @@
+// Symmetric eigensolve through cuSOLVER (syevd) — the single library call on the path.
+// It stands in for the LAPACK work inside the reference's svdecon (facemap/utils.py:751-776:
+// sklearn randomized_svd -> scipy lu/qr/gesdd; matlab/utils/svdecon.m:24 `eig`).  Its time is
+// reported separately by the host and never claimed as a kernel of this library.
+#include <cusolverDn.h>
+#include "common.cuh"
+
+struct fm_solver {
+  cusolverDnHandle_t handle = nullptr;
+  cusolverDnParams_t params = nullptr;
+  void* d_work = nullptr;
+  size_t d_work_bytes = 0;
+  void* h_work = nullptr;
+  size_t h_work_bytes = 0;
+  int* d_info = nullptr;
+  float* d_f32 = nullptr;      // staging for the float32 solve
+  size_t d_f32_elems = 0;
+};
+
+namespace fm {
+
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)in[i];
+}
+
+#define FM_SOLVER_TRY(expr)                                                          \
+  do {                                                                               \
+    cusolverStatus_t _s = (expr);                                                    \
+    if (_s != CUSOLVER_STATUS_SUCCESS) {                                             \
+      fm::set_error("%s failed with cusolverStatus %d (%s:%d)", #expr, (int)_s, __FILE__, __LINE__); \
+      return FM_ERR_SOLVER;                                                          \
+    }                                                                                \
+  } while (0)
+
+static int ensure_workspace(fm_solver* s, size_t dbytes, size_t hbytes) {
+  if (dbytes > s->d_work_bytes) {
+    if (s->d_work) cudaFree(s->d_work);
+    s->d_work = nullptr;
+    s->d_work_bytes = 0;
+    FM_CUDA_TRY(cudaMalloc(&s->d_work, dbytes));
+    s->d_work_bytes = dbytes;
+  }
+  if (hbytes > s->h_work_bytes) {
+    free(s->h_work);
+    s->h_work = malloc(hbytes);
+    FM_REQUIRE(s->h_work != nullptr, "fm_syevd: host workspace allocation of %zu bytes failed", hbytes);
+    s->h_work_bytes = hbytes;
+  }
+  return FM_OK;
+}
+
+}  // namespace fm
+
+extern "C" int fm_solver_create(fm_solver** out) {
+  using namespace fm;
+  FM_REQUIRE(out != nullptr, "fm_solver_create: null output");
+  fm_solver* s = new fm_solver();
+  cusolverStatus_t st = cusolverDnCreate(&s->handle);
+  if (st != CUSOLVER_STATUS_SUCCESS) {
+    set_error("cusolverDnCreate failed with status %d", (int)st);
+    delete s;
+    return FM_ERR_SOLVER;
+  }
+  st = cusolverDnCreateParams(&s->params);
+  if (st != CUSOLVER_STATUS_SUCCESS) {
+    set_error("cusolverDnCreateParams failed with status %d", (int)st);
+    cusolverDnDestroy(s->handle);
+    delete s;
+    return FM_ERR_SOLVER;
+  }
+  if (cudaMalloc(&s->d_info, sizeof(int)) != cudaSuccess) {
+    set_error("fm_solver_create: cudaMalloc(devInfo) failed");
+    cusolverDnDestroyParams(s->params);
+    cusolverDnDestroy(s->handle);
+    delete s;
+    return FM_ERR_CUDA;
+  }
+  *out = s;
+  return FM_OK;
+}
+
+extern "C" int fm_solver_destroy(fm_solver* s) {
+  if (!s) return FM_OK;
+  if (s->d_work) cudaFree(s->d_work);
+  if (s->d_f32) cudaFree(s->d_f32);
+  if (s->d_info) cudaFree(s->d_info);
+  free(s->h_work);
+  if (s->params) cusolverDnDestroyParams(s->params);
+  if (s->handle) cusolverDnDestroy(s->handle);
+  delete s;
+  return FM_OK;
+}
+
+extern "C" int fm_syevd(fm_solver* s, double* G, int n, double* lam, int use_fp32, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(s && G && lam && n >= 1, "fm_syevd: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FM_SOLVER_TRY(cusolverDnSetStream(s->handle, st));
+  const size_t nn = (size_t)n * n;
+  void* A = G;
+  void* W = lam;
+  cudaDataType dt = CUDA_R_64F;
+  if (use_fp32) {
+    const size_t need = nn + (size_t)n;
+    if (need > s->d_f32_elems) {
+      if (s->d_f32) cudaFree(s->d_f32);
+      s->d_f32 = nullptr;
+      s->d_f32_elems = 0;
+      FM_CUDA_TRY(cudaMalloc(&s->d_f32, need * sizeof(float)));
+      s->d_f32_elems = need;
+    }
+    f64_to_f32_kernel<<<(unsigned)cdiv((int64_t)nn, 256), 256, 0, st>>>(G, s->d_f32, nn);
+    FM_LAUNCH_CHECK();
+    A = s->d_f32;
+    W = s->d_f32 + nn;
+    dt = CUDA_R_32F;
+  }
+  size_t dbytes = 0, hbytes = 0;
+  // G is symmetric and fully populated, so row-major == column-major; eigenvector j comes back as
+  // column j of the column-major result, i.e. ROW j of the row-major array.
+  FM_SOLVER_TRY(cusolverDnXsyevd_bufferSize(s->handle, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER,
+                                            n, dt, A, n, dt, W, dt, &dbytes, &hbytes));
+  int rc = ensure_workspace(s, dbytes, hbytes);
+  if (rc != FM_OK) return rc;
+  FM_SOLVER_TRY(cusolverDnXsyevd(s->handle, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dt, A, n,
+                                 dt, W, dt, s->d_work, dbytes, s->h_work, hbytes, s->d_info));
+  if (use_fp32) {
+    f32_to_f64_kernel<<<(unsigned)cdiv((int64_t)nn, 256), 256, 0, st>>>(s->d_f32, G, nn);
+    FM_LAUNCH_CHECK();
+    f32_to_f64_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(s->d_f32 + nn, lam, (size_t)n);
+    FM_LAUNCH_CHECK();
+  }
+  int info = 0;
+  FM_CUDA_TRY(cudaMemcpyAsync(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FM_CUDA_TRY(cudaStreamSynchronize(st));
+  if (info != 0) {
+    set_error("cusolverDnXsyevd: devInfo = %d (n = %d)", info, n);
+    return FM_ERR_SOLVER;
+  }
+  return FM_OK;
+}

@@ -1,0 +1,200 @@
+// Small kernels around the GEMMs: PCA centring terms, split-K reduction into the float64 Gram,
+// top-k extraction with the reference's sign rule, transpose, ROI gather.
+// Reference seams: facemap/utils.py:751-776 (svdecon) -> sklearn/decomposition/_pca.py:733-758,
+// sklearn/utils/extmath.py:924-982 (svd_flip); facemap/process.py:218-222, 479-483 (ROI slices).
+#include "common.cuh"
+
+namespace fm {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// mean[r] = sum_c X[r,c] / ncols, float64 accumulation, one block per row.
+__global__ void __launch_bounds__(256) row_means_kernel(const float* __restrict__ X, int64_t ldx, int64_t ncols,
+                                                        double* __restrict__ mean) {
+  __shared__ double sh[8];
+  const float* row = X + (size_t)blockIdx.x * ldx;
+  double acc = 0.0;
+  const bool v4 = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  if (v4) {
+    const int64_t n4 = ncols / 4;
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    for (int64_t i = threadIdx.x; i < n4; i += 256) {
+      const float4 v = r4[i];
+      acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+    }
+    for (int64_t i = n4 * 4 + threadIdx.x; i < ncols; i += 256) acc += (double)row[i];
+  } else {
+    for (int64_t i = threadIdx.x; i < ncols; i += 256) acc += (double)row[i];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? sh[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) mean[blockIdx.x] = v / (double)ncols;
+  }
+}
+
+// G[i,j] = sum_s part[s,i,j] - ncols*mean[i]*mean[j]; with upper_only the (i>j) entries are read
+// from (j,i).
+__global__ void gram_assemble_kernel(const float* __restrict__ part, int ksplit, int n, int64_t ldw,
+                                     const double* __restrict__ mean, double ncols, int upper_only,
+                                     double* __restrict__ G) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n || j >= n) return;
+  int si = i, sj = j;
+  if (upper_only && i > j) { si = j; sj = i; }
+  double acc = 0.0;
+  const size_t plane = (size_t)n * ldw;
+  for (int s = 0; s < ksplit; ++s) acc += (double)part[(size_t)s * plane + (size_t)si * ldw + sj];
+  if (mean) acc -= ncols * mean[i] * mean[j];
+  G[(size_t)i * n + j] = acc;
+}
+
+// one block per component c
+__global__ void __launch_bounds__(256) topk_kernel(const double* __restrict__ evec, const double* __restrict__ lam,
+                                                   int n, int k, const double* __restrict__ mean,
+                                                   float* __restrict__ Wt, int64_t ldwt, float* __restrict__ sval,
+                                                   float* __restrict__ rbias, float* __restrict__ rscale) {
+  __shared__ double s_abs[256];
+  __shared__ int s_idx[256];
+  __shared__ double s_dot[8];
+  __shared__ double s_sign;
+  const int c = blockIdx.x;
+  const double* v = evec + (size_t)(n - 1 - c) * n;
+  // argmax |v| with the smallest index on ties (np.argmax)
+  double best = -1.0;
+  int bidx = 0;
+  for (int j = threadIdx.x; j < n; j += 256) {
+    const double a = fabs(v[j]);
+    if (a > best) { best = a; bidx = j; }
+  }
+  s_abs[threadIdx.x] = best;
+  s_idx[threadIdx.x] = bidx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double a = s_abs[threadIdx.x + o];
+      const int ia = s_idx[threadIdx.x + o];
+      if (a > s_abs[threadIdx.x] || (a == s_abs[threadIdx.x] && ia < s_idx[threadIdx.x])) {
+        s_abs[threadIdx.x] = a;
+        s_idx[threadIdx.x] = ia;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s_sign = (v[s_idx[0]] < 0.0) ? -1.0 : 1.0;
+  __syncthreads();
+  const double sg = s_sign;
+  double dot = 0.0;
+  for (int j = threadIdx.x; j < n; j += 256) {
+    const float w = (float)(sg * v[j]);
+    Wt[(size_t)c * ldwt + j] = w;
+    if (mean) dot += (double)w * mean[j];
+  }
+  for (int64_t j = n + threadIdx.x; j < ldwt; j += 256) Wt[(size_t)c * ldwt + j] = 0.f;  // pad
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) s_dot[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d = 0.0;
+    for (int w = 0; w < 8; ++w) d += s_dot[w];
+    const double l = lam[n - 1 - c];
+    const float s = (float)sqrt(l > 0.0 ? l : 0.0);
+    const float inv = s > 0.f ? 1.0f / s : 0.f;
+    if (sval) sval[c] = s;
+    if (rscale) rscale[c] = inv;
+    // epilogue form rscale*acc + rbias: with a scale the bias is pre-multiplied
+    if (rbias) rbias[c] = rscale ? (float)(-d * (double)inv) : (float)(-d);
+  }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, int64_t ldin, int rows, int cols,
+                                 float* __restrict__ out, int64_t ldout) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * ldin + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(size_t)c * ldout + r] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void gather_roi_kernel(const float* __restrict__ X, int64_t ldx, int rows, int64_t col0, int Lxb,
+                                  int y0, int x0, int ny, int nx, float* __restrict__ out, int64_t ldout) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (q >= ny * nx) return;
+  const int y = q / nx, x = q - y * nx;
+  out[(size_t)r * ldout + q] = X[(size_t)r * ldx + col0 + (size_t)(y0 + y) * Lxb + (x0 + x)];
+}
+
+}  // namespace fm
+
+extern "C" int fm_row_means(const float* X, int64_t ldx, int rows, int64_t ncols, double* mean, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(X && mean && rows >= 0 && ncols >= 1 && ldx >= ncols, "fm_row_means: bad args");
+  if (rows == 0) return FM_OK;
+  row_means_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, ldx, ncols, mean);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+extern "C" int fm_gram_assemble(const float* part, int ksplit, int n, int64_t ldw, const double* mean,
+                                int64_t ncols, int upper_only, double* G, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(part && G && ksplit >= 1 && n >= 1 && ldw >= n, "fm_gram_assemble: bad args");
+  dim3 block(32, 8), grid((unsigned)cdiv(n, 32), (unsigned)cdiv(n, 8));
+  gram_assemble_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      part, ksplit, n, ldw, mean, (double)ncols, upper_only, G);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+extern "C" int fm_topk_components(const double* evec, const double* lam, int n, int k, const double* mean,
+                                  float* Wt, int64_t ldwt, float* sval, float* rbias, float* rscale,
+                                  void* stream) {
+  using namespace fm;
+  FM_REQUIRE(evec && lam && Wt && n >= 1 && k >= 1 && k <= n && ldwt >= n, "fm_topk_components: bad args");
+  topk_kernel<<<k, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(evec, lam, n, k, mean, Wt, ldwt, sval,
+                                                                    rbias, rscale);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+extern "C" int fm_transpose(const float* in, int64_t ldin, int rows, int cols, float* out, int64_t ldout,
+                            void* stream) {
+  using namespace fm;
+  FM_REQUIRE(in && out && rows >= 0 && cols >= 0 && ldin >= cols && ldout >= rows, "fm_transpose: bad args");
+  if (rows == 0 || cols == 0) return FM_OK;
+  dim3 block(32, 8), grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32));
+  FM_REQUIRE(grid.y <= 65535, "fm_transpose: too many rows (%d)", rows);
+  transpose_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, ldin, rows, cols, out, ldout);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+extern "C" int fm_gather_roi(const float* X, int64_t ldx, int rows, int64_t col0, int Lxb, int y0, int y1,
+                             int x0, int x1, float* out, int64_t ldout, void* stream) {
+  using namespace fm;
+  const int ny = y1 - y0, nx = x1 - x0;
+  FM_REQUIRE(X && out && rows >= 0 && ny >= 1 && nx >= 1 && x1 <= Lxb && ldout >= (int64_t)ny * nx,
+             "fm_gather_roi: bad args");
+  if (rows == 0) return FM_OK;
+  FM_REQUIRE(rows <= 65535, "fm_gather_roi: too many rows per call (%d)", rows);
+  dim3 grid((unsigned)cdiv((int64_t)ny * nx, 256), (unsigned)rows);
+  gather_roi_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, ldx, rows, col0, Lxb, y0, x0, ny,
+                                                                             nx, out, ldout);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}

@@ -1,0 +1,208 @@
+"""Thin Python wrappers over the C-ABI (include/facemap_b200.h): torch tensors in, raw pointers and
+the current CUDA stream out.  torch is used for device memory and streams only.
+
+Reference seams (facemap = /root/reference/facemap):
+  bin_motion      spatial_bin + |diff| + avg subtract + energy    process.py:34-43, 201-212, 448-463
+  gemm_tn         `X @ U` and the products inside utils.svdecon     process.py:485-510, utils.py:751-776
+  Solver.syevd    the LAPACK work inside svdecon                     utils.py:773-775
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import FacemapB200Error, Rois, check, ptr
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need(t, dtype, name, dims=None):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise FacemapB200Error(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise FacemapB200Error(f"{name}: expected {dtype}, got {t.dtype}")
+    if dims is not None and t.dim() != dims:
+        raise FacemapB200Error(f"{name}: expected {dims} dims, got {t.dim()}")
+
+
+def round_up(x: int, m: int) -> int:
+    return (int(x) + m - 1) // m * m
+
+
+def alloc_matrix(rows: int, cols: int, device, zero: bool = False) -> torch.Tensor:
+    """float32 [rows, cols] view whose row pitch is a multiple of 32 elements (128 B): a legal TMA
+    operand for fm_gemm_tn whatever `cols` is."""
+    ld = max(32, round_up(cols, 32))
+    buf = (torch.zeros if zero else torch.empty)((max(rows, 1), ld), dtype=torch.float32, device=device)
+    return buf[:rows, :cols]
+
+
+def launch_count() -> int:
+    return int(_lib.load().fm_launch_count())
+
+
+def bin_motion(frames, sbin, *, prev_sum=None, avgmotion=None, avgframe=None, x_mot=None, x_mov=None,
+               col0=0, energy=None, rois=None, roi_energy=None, last_sum=None, tsum_bin=None,
+               tsum_adiff=None):
+    """K1 on one view.  frames: uint8 [T,H,W] contiguous.  See fm_bin_motion in the header."""
+    _need(frames, torch.uint8, "frames", 3)
+    if not frames.is_contiguous():
+        raise FacemapB200Error("frames must be contiguous [T, H, W]")
+    T, H, W = frames.shape
+    _need(prev_sum, torch.int32, "prev_sum")
+    _need(avgmotion, torch.float32, "avgmotion")
+    _need(avgframe, torch.float32, "avgframe")
+    _need(x_mot, torch.float32, "x_mot", 2)
+    _need(x_mov, torch.float32, "x_mov", 2)
+    _need(energy, torch.int64, "energy")
+    _need(roi_energy, torch.int64, "roi_energy")
+    _need(last_sum, torch.int32, "last_sum")
+    _need(tsum_bin, torch.int64, "tsum_bin")
+    _need(tsum_adiff, torch.int64, "tsum_adiff")
+    npix = (H // sbin) * (W // sbin)
+    rows = T if prev_sum is not None else T - 1
+    ldx = 0
+    for x in (x_mot, x_mov):
+        if x is not None:
+            if x.stride(1) != 1 or x.shape[0] < rows or col0 + npix > x.shape[1]:
+                raise FacemapB200Error(f"x operand too small or not row-major: {tuple(x.shape)}, rows {rows}")
+            if ldx and x.stride(0) != ldx:
+                raise FacemapB200Error("x_mot and x_mov must share a row pitch")
+            ldx = x.stride(0)
+    for v, n, name in ((avgmotion, npix, "avgmotion"), (avgframe, npix, "avgframe"), (prev_sum, npix, "prev_sum"),
+                       (last_sum, npix, "last_sum"), (tsum_bin, npix, "tsum_bin"), (tsum_adiff, npix, "tsum_adiff"),
+                       (energy, rows, "energy")):
+        if v is not None and (v.numel() < n or not v.is_contiguous()):
+            raise FacemapB200Error(f"{name}: needs {n} contiguous elements, has {v.numel()}")
+    r = None
+    if roi_energy is not None:
+        r = rois if isinstance(rois, Rois) else Rois.from_rects(rois or [])
+        if roi_energy.numel() < r.n * rows:
+            raise FacemapB200Error("roi_energy too small")
+    lib = _lib.load()
+    check(lib.fm_bin_motion(ptr(frames), T, H, W, int(sbin), ptr(prev_sum), ptr(avgmotion), ptr(avgframe),
+                            ptr(x_mot), ptr(x_mov), ldx, int(col0), ptr(energy),
+                            C.byref(r) if r is not None else None, ptr(roi_energy), ptr(last_sum),
+                            ptr(tsum_bin), ptr(tsum_adiff), _stream()), "fm_bin_motion")
+    return rows
+
+
+def mean_update(acc, tsum, sbin, count, finalize_div=0):
+    _need(acc, torch.float32, "acc")
+    _need(tsum, torch.int64, "tsum")
+    check(_lib.load().fm_mean_update(ptr(acc), ptr(tsum), acc.numel(), int(sbin), int(count), int(finalize_div),
+                                     _stream()), "fm_mean_update")
+
+
+def gemm_tn(A, B, C_out=None, *, rscale=None, rbias=None, ksplit=1, workspace=None, upper_only=False, impl=0):
+    """C[M,N] = rscale[m] * (A[M,K] @ B[N,K]^T) + rbias[m]; both operands K-contiguous float32.
+    With ksplit > 1 the raw partial products go to `workspace` [ksplit, M, ldw] instead."""
+    _need(A, torch.float32, "A", 2)
+    _need(B, torch.float32, "B", 2)
+    M, K = A.shape
+    N, K2 = B.shape
+    if K != K2 or A.stride(1) != 1 or B.stride(1) != 1:
+        raise FacemapB200Error(f"gemm_tn: operands must be [M,K] and [N,K] row-major, got {tuple(A.shape)} {tuple(B.shape)}")
+    ldc = ldw = 0
+    if ksplit > 1:
+        _need(workspace, torch.float32, "workspace", 3)
+        if workspace.shape[0] < ksplit or workspace.shape[1] != M or workspace.shape[2] < N or workspace.stride(2) != 1 \
+                or workspace.stride(0) != M * workspace.stride(1):
+            raise FacemapB200Error(f"gemm_tn: workspace must be [ksplit, M, >=N] packed, got {tuple(workspace.shape)}")
+        ldw = workspace.stride(1)
+    else:
+        _need(C_out, torch.float32, "C", 2)
+        if C_out.shape[0] < M or C_out.shape[1] < N or C_out.stride(1) != 1:
+            raise FacemapB200Error(f"gemm_tn: C must be row-major [>=M, >=N], got {tuple(C_out.shape)}")
+        ldc = C_out.stride(0)
+    _need(rscale, torch.float32, "rscale")
+    _need(rbias, torch.float32, "rbias")
+    check(_lib.load().fm_gemm_tn(ptr(A), A.stride(0), ptr(B), B.stride(0), M, N, K, ptr(C_out), ldc, ptr(rscale),
+                                 ptr(rbias), int(ksplit), ptr(workspace), ldw, int(bool(upper_only)), int(impl),
+                                 _stream()), "fm_gemm_tn")
+
+
+def row_means(X, out=None):
+    _need(X, torch.float32, "X", 2)
+    rows, cols = X.shape
+    if out is None:
+        out = torch.empty(rows, dtype=torch.float64, device=X.device)
+    check(_lib.load().fm_row_means(ptr(X), X.stride(0), rows, cols, ptr(out), _stream()), "fm_row_means")
+    return out
+
+
+def gram_assemble(workspace, ksplit, n, mean, ncols, upper_only, out=None):
+    if out is None:
+        out = torch.empty((n, n), dtype=torch.float64, device=workspace.device)
+    check(_lib.load().fm_gram_assemble(ptr(workspace), int(ksplit), int(n), workspace.stride(-2), ptr(mean), int(ncols),
+                                       int(bool(upper_only)), ptr(out), _stream()), "fm_gram_assemble")
+    return out
+
+
+class Solver:
+    """cuSOLVER handle + workspaces (fm_solver)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(_lib.load().fm_solver_create(C.byref(self._h)), "fm_solver_create")
+
+    def syevd(self, G, use_fp32=False):
+        """G: float64 [n,n] symmetric, overwritten by eigenvectors (row j <-> j-th smallest eigenvalue).
+        Returns lam (float64 [n], ascending).  Synchronises the stream."""
+        _need(G, torch.float64, "G", 2)
+        n = G.shape[0]
+        if G.shape[1] != n or not G.is_contiguous():
+            raise FacemapB200Error("syevd: G must be a contiguous square matrix")
+        lam = torch.empty(n, dtype=torch.float64, device=G.device)
+        check(_lib.load().fm_syevd(self._h, ptr(G), n, ptr(lam), int(bool(use_fp32)), _stream()), "fm_syevd")
+        return lam
+
+    def close(self):
+        if self._h:
+            _lib.load().fm_solver_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def topk_components(evec, lam, k, mean, Wt, want_scale=False):
+    """Top-k eigenpairs -> Wt[k, n] (sign-fixed, float32), sval[k], rbias[k], rscale[k] (if wanted).
+    With want_scale the bias is pre-multiplied by rscale so that a GEMM epilogue
+    `rscale*acc + rbias` yields (acc - w.mean)/sval."""
+    n = evec.shape[0]
+    dev = evec.device
+    sval = torch.empty(k, dtype=torch.float32, device=dev)
+    rbias = torch.empty(k, dtype=torch.float32, device=dev)
+    rscale = torch.empty(k, dtype=torch.float32, device=dev) if want_scale else None
+    if Wt.shape[0] < k or Wt.shape[1] < n:
+        raise FacemapB200Error("topk_components: Wt too small")
+    check(_lib.load().fm_topk_components(ptr(evec), ptr(lam), n, int(k), ptr(mean), ptr(Wt), Wt.stride(0), ptr(sval),
+                                         ptr(rbias), ptr(rscale), _stream()), "fm_topk_components")
+    return sval, rbias, rscale
+
+
+def transpose(src, dst):
+    """dst[c, r] = src[r, c]."""
+    _need(src, torch.float32, "src", 2)
+    _need(dst, torch.float32, "dst", 2)
+    rows, cols = src.shape
+    if dst.shape[0] < cols or dst.shape[1] < rows or src.stride(1) != 1 or dst.stride(1) != 1:
+        raise FacemapB200Error("transpose: shape mismatch")
+    check(_lib.load().fm_transpose(ptr(src), src.stride(0), rows, cols, ptr(dst), dst.stride(0), _stream()),
+          "fm_transpose")
+
+
+def gather_roi(X, rows, col0, Lxb, rect, out):
+    y0, y1, x0, x1 = rect
+    check(_lib.load().fm_gather_roi(ptr(X), X.stride(0), int(rows), int(col0), int(Lxb), int(y0), int(y1), int(x0),
+                                    int(x1), ptr(out), out.stride(0), _stream()), "fm_gather_roi")

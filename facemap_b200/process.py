@@ -1,0 +1,269 @@
+"""Drop-in for `facemap.process.run` (reference: /root/reference/facemap/process.py:638-903) on the
+B200 kernels.  Same signature, same config precedence (parent > proc > kwargs, :676-708), same
+`*_proc.npy` dict (keys/dtypes/shapes of :859-892) and the same quirks, written by
+`save` (:605-635).  Only the SVD/motion outputs are produced; pupil / blink / running ROIs are
+outside this library's scope and come back empty.
+
+Beyond the reference signature, `filenames` may also be a FrameSource or a list of uint8
+[T,H,W] arrays/tensors (one per simultaneous view), and `process_source` returns the dict without
+writing it.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, svd
+from .frames import FrameSource, as_source
+from .utils import binned_inds, multivideo_reshape, roi_bin_ranges, video_placement
+
+
+def save(proc, savepath=None):
+    """Write the proc dict next to the first video (or into `savepath`) as `<name>_proc.npy`, plus
+    a flattened `.mat` when proc["save_mat"] (reference process.py:605-635)."""
+    first = proc["filenames"][0][0]
+    folder, name = os.path.split(first)
+    stem = os.path.splitext(name)[0]
+    if savepath is not None:
+        folder = savepath
+    savename = os.path.join(folder, f"{stem}_proc.npy")
+    np.save(savename, proc)
+    if proc["save_mat"]:
+        from scipy import io
+
+        if "save_path" in proc and proc["save_path"] is None:
+            proc["save_path"] = folder
+        if proc["rois"] is None:
+            proc["rois"] = 0
+        flat = {}
+        for key, val in proc.items():
+            if isinstance(val, list) and len(val) > 0 and isinstance(val[0], np.ndarray):
+                for i, a in enumerate(val):
+                    flat[f"{key}_{i}"] = a
+            else:
+                flat[key] = val
+        io.savemat(os.path.join(folder, f"{stem}_proc.mat"), flat)
+    return savename
+
+
+def _motion_from_energy(E_views, sbin, N):
+    """Reference float semantics of `M[.] += imbin_mot.sum(-1)` per view (process.py:460) applied
+    to exact integer energies, then the chunk-0 layout (quirk Q1): entries [0, nt1-1) hold the
+    diffs of frames 1..nt1-1, entry nt1-1 stays 0."""
+    s2 = float(sbin * sbin)
+    acc = np.zeros(N, np.float32)
+    for e in E_views:
+        if sbin == 1:
+            acc = acc + e.astype(np.float32)                    # float32 sums in the reference
+        else:
+            acc = (acc.astype(np.float64) + e.astype(np.float64) / s2).astype(np.float32)
+    nt1 = min(500, N)
+    out = np.zeros(N, np.float32)
+    out[:nt1 - 1] = acc[1:nt1]
+    out[nt1:] = acc[nt1:]
+    return out
+
+
+def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD=True, device=None,
+                   eig_fp32=False, gemm_impl=0, timing=None, dist=None, keep_on_device=False):
+    """Run the three stages on a FrameSource and return the proc-dict entries this path owns.
+
+    timing: optional dict that receives per-stage device times (ms) and wall times.
+    dist:   optional facemap_b200.parallel.Shard (frame-range sharding across ranks)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    _lib.require_device(dev.index or 0)
+    torch.cuda.set_device(dev)
+    source = as_source(source)
+    N = source.nframes
+    Ly, Lx = list(source.Ly), list(source.Lx)
+    Lybin, Lxbin, iinds = binned_inds(Ly, Lx, sbin)
+    LYbin, LXbin, sybin, sxbin = video_placement(Lybin, Lxbin)
+    nroi = 0
+    if rois is not None:
+        for r in rois:
+            if r["rind"] == 1:
+                r["yrange_bin"], r["xrange_bin"] = roi_bin_ranges(r, sbin)   # mutated in place, like the reference
+                nroi += 1
+    geo = svd.Geometry(Ly, Lx, sbin, rois)
+    mods = [m for m, on in (("mot", motSVD), ("mov", movSVD)) if on]
+    timer = svd.StageTimer(enabled=timing is not None)
+    wall0 = time.perf_counter()
+    ws = svd.SvdWorkspace(dev, eig_fp32=eig_fp32, gemm_impl=gemm_impl)
+
+    # ---- stage 1 ----
+    if dist is None or dist.world == 1:
+        avgframe, avgmotion = svd.stage1_means(source, geo, dev, timer)
+    else:
+        avgframe, avgmotion = dist.stage1(source, geo, dev, timer)
+
+    # ---- stage 2 ----
+    masks = {}
+    if (fullSVD or nroi > 0) and mods:
+        if dist is None or dist.world == 1:
+            Yt, ks, nsegs = svd.stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, dev, timer)
+        else:
+            Yt, ks, nsegs = dist.stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, dev, timer)
+        masks = svd.stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer)
+        del Yt
+    nsegs_plan = svd.stage2_plan(N)[1]
+    nc_plan = svd.stage2_plan(N)[2]
+
+    # ---- stage 3 ----
+    V, E, E_roi = {}, None, None
+    if mods and masks:
+        if dist is None or dist.world == 1:
+            V, E, E_roi = svd.stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, dev, timer)
+        else:
+            V, E, E_roi = dist.stage3(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, dev, timer)
+
+    # ---- assemble (device -> host) ----
+    t_asm = time.perf_counter()
+    with timer("assemble.d2h"):
+        avgframe_h = avgframe.cpu().numpy()
+        avgmotion_h = avgmotion.cpu().numpy()
+        E_h = E.cpu().numpy() if E is not None else None
+        E_roi_h = E_roi.cpu().numpy() if E_roi is not None else None
+    avgframe_l = [avgframe_h[ir].copy() for ir in iinds]
+    avgmotion_l = [avgmotion_h[ir].copy() for ir in iinds]
+    proc = {
+        "Ly": Ly, "Lx": Lx, "sbin": sbin, "fullSVD": fullSVD,
+        "Lybin": Lybin, "Lxbin": Lxbin, "sybin": sybin, "sxbin": sxbin, "LYbin": LYbin, "LXbin": LXbin,
+        "avgframe": avgframe_l, "avgmotion": avgmotion_l,
+        "avgframe_reshape": np.squeeze(multivideo_reshape(avgframe_h[:, None], LYbin, LXbin, sybin, sxbin,
+                                                          Lybin, Lxbin, iinds)),
+        "avgmotion_reshape": np.squeeze(multivideo_reshape(avgmotion_h[:, None], LYbin, LXbin, sybin, sxbin,
+                                                           Lybin, Lxbin, iinds)),
+        "rois": rois,
+    }
+
+    def host(t):
+        return t if keep_on_device else t.cpu().numpy()
+
+    U_out = {"mot": [], "mov": []}
+    U_resh = {"mot": [], "mov": []}
+    S_out = {"mot": [], "mov": []}
+    V_out = {"mot": [], "mov": []}
+    if fullSVD or nroi > 0:
+        S_out = {"mot": np.zeros(500, np.float32), "mov": np.zeros(500, np.float32)}
+        for m in ("mot", "mov"):
+            if m in masks:
+                _, Us, sv = masks[m]
+                with timer("assemble.d2h"):
+                    U_out[m] = [host(u) for u in Us]
+                    S_out[m] = host(sv)
+            elif m not in mods:
+                # quirk Q7: ROI placeholders exist for a modality that is switched off
+                for (_, y0, y1, x0, x1) in geo.mot_rois:
+                    n = (y1 - y0) * (x1 - x0)
+                    U_out[m].append(np.zeros((n, nsegs_plan * min(nc_plan, n)), np.float32))
+        for m in ("mot", "mov"):
+            U_resh[m] = list(U_out[m])
+            if m in mods and not keep_on_device:
+                if fullSVD:
+                    U_resh[m][0] = multivideo_reshape(U_out[m][0], LYbin, LXbin, sybin, sxbin, Lybin, Lxbin, iinds)
+                for j, (_, y0, y1, x0, x1) in enumerate(geo.mot_rois):
+                    U_resh[m][1 + j] = U_out[m][1 + j].copy().reshape(y1 - y0, x1 - x0, -1)
+    # projections and motion energy
+    M = []
+    if mods and masks:
+        for m in mods:
+            for idx, v in enumerate(V[m]):
+                if v is None:
+                    V_out[m].append(np.zeros((0, 1), np.float32))
+                    continue
+                if N > 1:
+                    v[0].copy_(v[1])                    # quirk Q2: first projected row duplicated
+                with timer("assemble.d2h"):
+                    V_out[m].append(host(v))
+        if fullSVD:
+            M.append(_motion_from_energy([E_h[v] for v in range(len(Ly))], sbin, N) if motSVD
+                     else np.zeros(N, np.float32))
+        else:
+            M.append(np.zeros((0,), np.float32))
+        for j in range(nroi):
+            M.append(_motion_from_energy([E_roi_h[j]], sbin, N) if motSVD else np.zeros(N, np.float32))
+        # quirk Q4: the avg arrays of a view carrying a motion ROI are saved 2-D
+        for v in range(len(Ly)):
+            if geo.rois_on_view[v]:
+                if motSVD:
+                    avgmotion_l[v] = avgmotion_l[v].reshape(Lybin[v], Lxbin[v])
+                if movSVD:
+                    avgframe_l[v] = avgframe_l[v].reshape(Lybin[v], Lxbin[v])
+    proc.update({
+        "motion": M, "motSv": S_out["mot"], "movSv": S_out["mov"],
+        "motMask": U_out["mot"], "movMask": U_out["mov"],
+        "motMask_reshape": U_resh["mot"], "movMask_reshape": U_resh["mov"],
+        "motSVD": V_out["mot"], "movSVD": V_out["mov"],
+    })
+    if timing is not None:
+        timing["device_ms"] = timer.report()
+        timing["wall_s"] = time.perf_counter() - wall0
+        timing["assemble_wall_s"] = time.perf_counter() - t_asm
+    ws.solver.close()
+    return proc
+
+
+def run(filenames, sbin=1, motSVD=True, movSVD=False, GUIobject=None, parent=None, proc=None, savepath=None):
+    """Process video files: SVD of the motion and/or raw movie, projections of every frame, motion
+    energy.  Arguments, precedence and return value as facemap.process.run (process.py:638-708):
+
+    filenames : 2-D list, one inner list of simultaneously recorded views per sequential block
+    sbin      : spatial bin factor;  motSVD / movSVD : which decompositions to compute
+    parent    : GUI main window (settings are read from its widgets);  GUIobject : Qt module
+    proc      : settings dict (sbin, fullSVD, save_mat, rois, sy, sx, savepath) overriding kwargs
+    savepath  : output folder (default: folder of the first video)
+    Returns the path of the written `_proc.npy`."""
+    start = time.time()
+    rois = None
+    sy, sx = 0, 0
+    if parent is not None:
+        from facemap import utils as ref_utils  # only reachable from the reference GUI
+
+        filenames = parent.filenames
+        sbin = parent.sbin
+        rois = ref_utils.roi_to_dict(parent.ROIs, parent.rROI)
+        fullSVD = parent.multivideo_svd_checkbox.isChecked()
+        save_mat = parent.save_mat.isChecked()
+        sy, sx = parent.sy, parent.sx
+        motSVD, movSVD = parent.motSVD_checkbox.isChecked(), parent.movSVD_checkbox.isChecked()
+    elif proc is None:
+        fullSVD, save_mat = True, False
+    else:
+        sbin, fullSVD, save_mat, rois = proc["sbin"], proc["fullSVD"], proc["save_mat"], proc["rois"]
+        sy, sx = proc["sy"], proc["sx"]
+        savepath = proc["savepath"] if savepath is None else savepath
+
+    source = as_source(filenames)
+    names = filenames if not isinstance(filenames, FrameSource) and isinstance(filenames[0], (list, tuple)) \
+        else [["array_input.avi"]]
+    try:
+        out = process_source(source, sbin=sbin, motSVD=motSVD, movSVD=movSVD, rois=rois, fullSVD=fullSVD)
+    finally:
+        source.close()
+    if parent is not None:
+        parent.update_status_bar("Computed projection")
+    if GUIobject is not None:
+        GUIobject.QApplication.processEvents()
+    full = {
+        "filenames": names, "save_path": savepath, "Ly": out["Ly"], "Lx": out["Lx"], "sbin": sbin,
+        "fullSVD": fullSVD, "save_mat": save_mat,
+        "Lybin": out["Lybin"], "Lxbin": out["Lxbin"], "sybin": out["sybin"], "sxbin": out["sxbin"],
+        "LYbin": out["LYbin"], "LXbin": out["LXbin"],
+        "avgframe": out["avgframe"], "avgmotion": out["avgmotion"],
+        "avgframe_reshape": out["avgframe_reshape"], "avgmotion_reshape": out["avgmotion_reshape"],
+        "motion": out["motion"], "motSv": out["motSv"], "movSv": out["movSv"],
+        "motMask": out["motMask"], "movMask": out["movMask"],
+        "motMask_reshape": out["motMask_reshape"], "movMask_reshape": out["movMask_reshape"],
+        "motSVD": out["motSVD"], "movSVD": out["movSVD"],
+        "pupil": [], "running": [], "blink": [], "rois": rois, "sy": sy, "sx": sx,
+    }
+    savename = save(full, savepath)
+    if parent is not None:
+        parent.update_status_bar("Output saved in " + str(savepath))
+    if GUIobject is not None:
+        GUIobject.QApplication.processEvents()
+    print("run time %0.2fs" % (time.time() - start))
+    return savename

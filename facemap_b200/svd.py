@@ -1,0 +1,428 @@
+"""Device pipeline of the motion/movie-SVD path: the three stages of facemap.process.run rebuilt on
+the C-ABI kernels.  Python here only sequences kernel launches and owns buffers (torch = memory,
+streams, collectives); every array operation on frames or matrices is a kernel of this library
+(or the one cuSOLVER call).
+
+Reference map (facemap = /root/reference/facemap):
+  stage1_means      subsampled_mean           process.py:53-102
+  stage2_masks      compute_SVD               process.py:105-299  (svdecon: utils.py:751-776)
+  stage3_project    process_ROIs (SVD parts)  process.py:302-530
+
+svdecon is evaluated in its Gram form (matlab/utils/svdecon.m:16-43; the dead block at
+utils.py:753-772) with the PCA centring of the live code (sklearn _pca.py:733-736) folded in as a
+rank-1 correction:  G = X X^T - p m m^T,  G = W L W^T,  U S = X^T W - 1 (m^T W).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from ._lib import FacemapB200Error, Rois
+from .utils import binned_inds
+
+NCOMPS = 500        # process.py:764
+CHUNK_SVD = 1000    # process.py:134
+BUDGET_SVD = 15000  # process.py:135
+NC_CHUNK = 250      # process.py:136
+NUM_SMS = 148
+
+
+class StageTimer:
+    """CUDA-event stopwatch: `with timer("name"):` accumulates device time per label; nothing is
+    synchronised until report()."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+        self.spans = []
+
+    class _Span:
+        def __init__(self, owner, name):
+            self.owner, self.name = owner, name
+
+        def __enter__(self):
+            if self.owner.enabled:
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.b = torch.cuda.Event(enable_timing=True)
+                self.a.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.owner.enabled:
+                self.b.record()
+                self.owner.spans.append((self.name, self.a, self.b))
+            return False
+
+    def __call__(self, name):
+        return StageTimer._Span(self, name)
+
+    def report(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.spans:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+def _gram_ksplit(n, kdim):
+    """split-K factor for an n x n upper-triangular Gram over `kdim`: enough CTAs for ~2 waves,
+    at least 512 K elements per split."""
+    mt, nt = math.ceil(n / 128), math.ceil(n / 256)
+    tiles = sum(1 for i in range(mt) for j in range(nt) if (j + 1) * 256 - 1 >= i * 128)
+    want = math.ceil(2 * NUM_SMS / max(tiles, 1))
+    return int(max(1, min(want, kdim // 512 if kdim >= 1024 else 1, 64)))
+
+
+class SvdWorkspace:
+    """Reusable device buffers for the Gram -> eigensolve -> left-vector sequence."""
+
+    def __init__(self, device, eig_fp32=False, gemm_impl=0):
+        self.device = device
+        self.solver = K.Solver()
+        self.eig_fp32 = eig_fp32
+        self.gemm_impl = gemm_impl
+        self._ws = None
+        self._bufs = {}
+
+    def workspace(self, ksplit, n):
+        ld = max(32, K.round_up(n, 32))
+        need = ksplit * n * ld
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.float32, device=self.device)
+        return self._ws[:need].view(ksplit, n, ld)
+
+    def matrix(self, tag, rows, cols):
+        ld = max(32, K.round_up(cols, 32))
+        need = max(rows, 1) * ld
+        buf = self._bufs.get(tag)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(need, dtype=torch.float32, device=self.device)
+            self._bufs[tag] = buf
+        return buf[:need].view(max(rows, 1), ld)[:rows, :cols]
+
+
+def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
+    """Centred Gram of the rows of X [n, p], eigensolve, top-k.  Returns (Wt [k, n], sval, rbias,
+    rscale): the right singular vectors of X^T (sign-fixed), singular values, and the epilogue
+    terms for the left-vector GEMM."""
+    n, p = X.shape
+    with timer(label + ".colmean"):
+        mean = K.row_means(X)
+    ksplit = _gram_ksplit(n, p)
+    part = ws.workspace(ksplit, n)
+    with timer(label + ".gram"):
+        if ksplit > 1:
+            K.gemm_tn(X, X, ksplit=ksplit, workspace=part, upper_only=True, impl=ws.gemm_impl)
+        else:
+            K.gemm_tn(X, X, part[0], upper_only=True, impl=ws.gemm_impl)
+        G = K.gram_assemble(part, ksplit, n, mean, p, True)
+    with timer(label + ".syevd"):
+        lam = ws.solver.syevd(G, use_fp32=ws.eig_fp32)
+    with timer(label + ".topk"):
+        Wt = ws.matrix(label + ".Wt", k, n)
+        sval, rbias, rscale = K.topk_components(G, lam, k, mean, Wt, want_scale=want_scale)
+    return Wt, sval, rbias, rscale
+
+
+def chunk_components(ws, X, k, out_Yt, timer, label="chunk"):
+    """svdecon(X^T, k) of one chunk: writes (U S)^T = W^T X - (W^T m) 1^T into out_Yt [k, p]
+    (facemap/process.py:246-251; ROI variant :213-242)."""
+    n, p = X.shape
+    Wt, _, rbias, _ = gram_eig(ws, X, k, timer, False, label)
+    with timer(label + ".left"):
+        Xt = ws.matrix(label + ".Xt", p, n)
+        K.transpose(X, Xt)
+        K.gemm_tn(Wt, Xt, out_Yt, rbias=rbias, impl=ws.gemm_impl)
+
+
+def merge_components(ws, Yt, k, timer, label="merge"):
+    """svdecon(Y, k) for Y = [U_1 S_1 ... ] given as Yt [c, p] (facemap/process.py:264-295).
+    Returns (Ut [k, p], U [p, k], sval [k])."""
+    c, p = Yt.shape
+    Wt, sval, rbias, rscale = gram_eig(ws, Yt, k, timer, True, label)
+    with timer(label + ".left"):
+        Y = ws.matrix(label + ".Y", p, c)
+        K.transpose(Yt, Y)
+        Ut = K.alloc_matrix(k, p, Yt.device)
+        K.gemm_tn(Wt, Y, Ut, rscale=rscale, rbias=rbias, impl=ws.gemm_impl)
+        U = torch.empty((p, k), dtype=torch.float32, device=Yt.device)
+        K.transpose(Ut, U)
+    return Ut, U, sval
+
+
+class Geometry:
+    def __init__(self, Ly, Lx, sbin, rois):
+        self.Ly, self.Lx, self.sbin = list(Ly), list(Lx), int(sbin)
+        self.Lyb, self.Lxb, self.ir = binned_inds(Ly, Lx, sbin)
+        self.npix_v = [int(a) * int(b) for a, b in zip(self.Lyb, self.Lxb)]
+        self.col0 = [0] + list(np.cumsum(self.npix_v)[:-1].astype(int))
+        self.p = int(sum(self.npix_v))
+        # motion ROIs (rind == 1), in list order: (view, y0, y1, x0, x1) in binned coordinates
+        self.mot_rois = []
+        for r in (rois or []):
+            if r["rind"] == 1:
+                yb, xb = r["yrange_bin"], r["xrange_bin"]
+                if yb.size == 0 or xb.size == 0:
+                    raise FacemapB200Error("motion ROI is empty after binning")
+                self.mot_rois.append((int(r["ivid"]), int(yb[0]), int(yb[-1]) + 1, int(xb[0]), int(xb[-1]) + 1))
+        self.roi_npix = [(y1 - y0) * (x1 - x0) for (_, y0, y1, x0, x1) in self.mot_rois]
+        self.rois_on_view = [[j for j, r in enumerate(self.mot_rois) if r[0] == v] for v in range(len(Ly))]
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 1
+# ---------------------------------------------------------------------------------------------
+def stage1_plan(N, block_frames):
+    """facemap/process.py:61-67."""
+    nf = min(1000, N)
+    nt0 = int(min(100, min(block_frames)))
+    nsegs = int(np.floor(nf / nt0))
+    tf = np.floor(np.linspace(0, N - nt0, nsegs)).astype(int)
+    return nt0, tf
+
+
+def stage1_means(source, geo: Geometry, device, timer, segments=None):
+    """avgframe, avgmotion (float32 [p] device tensors).  `segments` restricts the work to a
+    subset of segment indices and returns the raw per-segment integer sums instead (multi-GPU)."""
+    N = source.nframes
+    nt0, tf = stage1_plan(N, source.block_frames)
+    p = geo.p
+    avgframe = torch.zeros(p, dtype=torch.float32, device=device)
+    avgmotion = torch.zeros(p, dtype=torch.float32, device=device)
+    nseg = len(tf)
+    todo = range(nseg) if segments is None else segments
+    sums = {}
+    for i in todo:
+        t = int(tf[i])
+        with timer("stage1.fetch"):
+            frames = source.fetch(t, t + nt0, device)
+        tsb = torch.zeros(p, dtype=torch.int64, device=device)
+        tsa = torch.zeros(p, dtype=torch.int64, device=device)
+        with timer("stage1.bin"):
+            for v, fr in enumerate(frames):
+                c0, n = geo.col0[v], geo.npix_v[v]
+                K.bin_motion(fr, geo.sbin, tsum_bin=tsb[c0:c0 + n], tsum_adiff=tsa[c0:c0 + n])
+        sums[i] = (tsb, tsa, int(frames[0].shape[0]))
+    if segments is not None:
+        return sums, nseg
+    with timer("stage1.mean"):
+        for i in range(nseg):                       # float32 accumulation in segment order
+            tsb, tsa, T = sums[i]
+            K.mean_update(avgframe, tsb, geo.sbin, T)
+            K.mean_update(avgmotion, tsa, geo.sbin, max(T - 1, 1))
+        K.mean_update(avgframe, None, geo.sbin, 1, finalize_div=nseg)
+        K.mean_update(avgmotion, None, geo.sbin, 1, finalize_div=nseg)
+    return avgframe, avgmotion
+
+
+def stage1_finish(all_sums, nseg, geo, device):
+    """Reduce per-segment integer sums (any order of arrival) in the reference's segment order."""
+    avgframe = torch.zeros(geo.p, dtype=torch.float32, device=device)
+    avgmotion = torch.zeros(geo.p, dtype=torch.float32, device=device)
+    for i in range(nseg):
+        tsb, tsa, T = all_sums[i]
+        K.mean_update(avgframe, tsb, geo.sbin, T)
+        K.mean_update(avgmotion, tsa, geo.sbin, max(T - 1, 1))
+    K.mean_update(avgframe, None, geo.sbin, 1, finalize_div=nseg)
+    K.mean_update(avgmotion, None, geo.sbin, 1, finalize_div=nseg)
+    return avgframe, avgmotion
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 2
+# ---------------------------------------------------------------------------------------------
+def stage2_plan(N, ncomps=NCOMPS):
+    """facemap/process.py:134-141."""
+    nt0 = min(CHUNK_SVD, N)
+    nsegs = int(min(np.floor(BUDGET_SVD / nt0), np.floor(N / nt0)))
+    nc = min(NC_CHUNK, nt0 - 1)
+    if nsegs == 1:
+        nc = min(ncomps, nt0 - 1)
+    tf = np.floor(np.linspace(0, N - nt0 - 1, nsegs)).astype(int)
+    return nt0, nsegs, nc, tf
+
+
+def _bin_chunk(frames, geo, avgframe, avgmotion, mods, X, prev=None, last=None, energy=None, roi_energy=None):
+    """K1 over every view of one fetched chunk into the modality matrices X[m] ([rows, p])."""
+    rows = None
+    for v, fr in enumerate(frames):
+        c0, n = geo.col0[v], geo.npix_v[v]
+        rects = [geo.mot_rois[j][1:] for j in geo.rois_on_view[v]]
+        rows = K.bin_motion(
+            fr, geo.sbin,
+            prev_sum=None if prev is None else prev[v],
+            avgmotion=avgmotion[c0:c0 + n] if "mot" in mods else None,
+            avgframe=avgframe[c0:c0 + n] if "mov" in mods else None,
+            x_mot=X.get("mot"), x_mov=X.get("mov"), col0=c0,
+            energy=None if energy is None else energy[v],
+            rois=Rois.from_rects(rects) if (roi_energy is not None and rects) else None,
+            roi_energy=None if (roi_energy is None or not rects) else roi_energy[v],
+            last_sum=None if last is None else last[v])
+    return rows
+
+
+def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer, chunks=None):
+    """Per-chunk components.  Returns Yt[m][idx] = list over chunks of [k, p_idx] blocks
+    (idx 0 = full frame, 1+j = motion ROI j), for the chunk indices in `chunks` (default all)."""
+    N = source.nframes
+    nt0, nsegs, nc, tf = stage2_plan(N)
+    nroi = len(geo.mot_rois)
+    todo = list(range(nsegs)) if chunks is None else list(chunks)
+    sizes = [geo.p] + geo.roi_npix
+    # one stacked buffer per (modality, target): rows = chunk-major blocks of k components
+    ks = [min(nc, s) for s in sizes]
+    Yt = {m: [K.alloc_matrix(len(todo) * ks[i], sizes[i], device) if (i > 0 or fullSVD) else None
+              for i in range(1 + nroi)] for m in mods}
+    X = {m: ws.matrix("X." + m, nt0 - 1, geo.p) for m in mods}
+    for slot, ci in enumerate(todo):
+        t = int(tf[ci])
+        with timer("stage2.fetch"):
+            frames = source.fetch(t, t + nt0, device)
+        with timer("stage2.bin"):
+            rows = _bin_chunk(frames, geo, avgframe, avgmotion, mods, X)
+        for m in mods:
+            Xm = X[m][:rows]
+            for j, (v, y0, y1, x0, x1) in enumerate(geo.mot_rois):       # process.py:213-242
+                pr = sizes[1 + j]
+                Xr = ws.matrix("Xroi", rows, pr)
+                with timer("stage2.roi_gather"):
+                    K.gather_roi(Xm, rows, geo.col0[v], int(geo.Lxb[v]), (y0, y1, x0, x1), Xr)
+                kk = ks[1 + j]
+                chunk_components(ws, Xr, kk, Yt[m][1 + j][slot * kk:(slot + 1) * kk], timer, "stage2.roi")
+            if fullSVD:                                                    # process.py:246-259
+                kk = ks[0]
+                chunk_components(ws, Xm, kk, Yt[m][0][slot * kk:(slot + 1) * kk], timer, "stage2.chunk")
+    return Yt, ks, nsegs
+
+
+def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS):
+    """Second-level SVD (process.py:264-295).  Returns per modality lists Ut, U, and Sv (the
+    singular values of the LAST target processed, quirk Q3)."""
+    out = {}
+    for m in mods:
+        Uts, Us = [], []
+        sv = torch.zeros(500, dtype=torch.float32, device=ws.device)
+        for idx, Y in enumerate(Yt[m]):
+            if Y is None:                       # fullSVD off: placeholder like process.py:153-160
+                Uts.append(None)
+                Us.append(torch.zeros((0, 1), dtype=torch.float32, device=ws.device))
+                continue
+            p_idx = Y.shape[1]
+            if nsegs > 1:
+                k = min(ncomps, p_idx - 1)
+                Ut, U, s = merge_components(ws, Y, k, timer, "stage2.merge" if idx == 0 else "stage2.roi_merge")
+                sv = s
+            else:                               # quirk Q6: single chunk -> U S as is, Sv stays zero
+                Ut = Y
+                U = torch.empty((p_idx, Y.shape[0]), dtype=torch.float32, device=ws.device)
+                K.transpose(Y, U)
+            Uts.append(Ut)
+            Us.append(U)
+        out[m] = (Uts, Us, sv)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 3
+# ---------------------------------------------------------------------------------------------
+def projection_rows_per_batch(p, k, budget_bytes=6 << 30):
+    """Rows per projection GEMM: whole waves of 128-row tiles over the 148 SMs, bounded by the
+    X-buffer budget."""
+    ntn = max(1, math.ceil(k / 256))
+    rows_wave = max(1, NUM_SMS // ntn) * 128
+    rows = 2 * rows_wave
+    cap = max(128, (budget_bytes // (4 * max(p, 1))) // 128 * 128)
+    return int(min(rows, cap))
+
+
+def stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, device, timer,
+                   frame_range=None, fetch_frames=2368):
+    """Projection of every frame in [f0, f1) onto the masks (process.py:394-515).
+
+    Returns V[m] = list of [f1-f0, k] device tensors (index 0 full frame, 1+j ROI j), and the
+    integer energies E [nviews, f1-f0], E_roi [nroi, f1-f0] with row i <-> frame f0+i holding
+    sum |S_t - S_{t-1}| (row for frame 0 is zero).  Reference row conventions (Q1/Q2) are applied
+    by the caller, which sees the whole video."""
+    N = source.nframes
+    f0, f1 = (0, N) if frame_range is None else frame_range
+    nroi = len(geo.mot_rois)
+    nv = len(geo.Ly)
+    n_out = f1 - f0
+    V = {}
+    for m in mods:
+        Uts = masks[m][0]
+        V[m] = [None if Ut is None else torch.zeros((n_out, Ut.shape[0]), dtype=torch.float32, device=device)
+                for Ut in Uts]
+    E = torch.zeros((nv, n_out), dtype=torch.int64, device=device)
+    E_roi = torch.zeros((max(nroi, 1), n_out), dtype=torch.int64, device=device)
+    kmax = max([Ut.shape[0] for m in mods for Ut in masks[m][0] if Ut is not None] + [1])
+    rows_batch = projection_rows_per_batch(geo.p, kmax)
+    X = {m: ws.matrix("X3." + m, rows_batch, geo.p) for m in mods}
+    carry = [[torch.zeros(n, dtype=torch.int32, device=device) for n in geo.npix_v] for _ in range(2)]
+    have_carry = False
+    flip = 0
+    # the frame before f0 seeds the carry so that a shard starting mid-video is seamless (1-frame halo)
+    if f0 > 0:
+        with timer("stage3.fetch"):
+            halo = source.fetch(f0 - 1, f0, device)
+        for v, fr in enumerate(halo):
+            K.bin_motion(fr, geo.sbin, last_sum=carry[flip][v])
+        have_carry = True
+
+    t = f0
+    while t < f1:
+        # fill one GEMM batch with several fetches
+        filled = 0
+        row_frame0 = None
+        while t < f1 and filled < rows_batch:
+            nfetch = min(fetch_frames, f1 - t, rows_batch - filled + (0 if have_carry else 1))
+            with timer("stage3.fetch"):
+                frames = source.fetch(t, t + nfetch, device)
+            T = int(frames[0].shape[0])
+            rows = T if have_carry else T - 1
+            first_frame = t if have_carry else t + 1
+            if row_frame0 is None:
+                row_frame0 = first_frame
+            with timer("stage3.bin"):
+                Xv = {m: X[m][filled:filled + rows] for m in mods} if rows > 0 else {m: None for m in mods}
+                o = first_frame - f0
+                energy = [E[v, o:o + rows] for v in range(nv)]
+                roi_e = []
+                for v in range(nv):
+                    js = geo.rois_on_view[v]
+                    roi_e.append(None)
+                    if js:
+                        # ROI energies of one view must be contiguous [n_on_view, rows]
+                        roi_e[v] = torch.zeros((len(js), max(rows, 1)), dtype=torch.int64, device=device)
+                _bin_chunk(frames, geo, avgframe, avgmotion, mods if rows > 0 else [], Xv,
+                           prev=carry[flip] if have_carry else None, last=carry[1 - flip],
+                           energy=energy if rows > 0 else None,
+                           roi_energy=roi_e if (nroi and rows > 0) else None)
+                if nroi and rows > 0:
+                    for v in range(nv):
+                        for q, j in enumerate(geo.rois_on_view[v]):
+                            E_roi[j, o:o + rows] = roi_e[v][q, :rows]
+            flip = 1 - flip
+            have_carry = True
+            filled += rows
+            t += T
+        if filled == 0:
+            continue
+        o = row_frame0 - f0
+        for m in mods:
+            Uts = masks[m][0]
+            Xm = X[m][:filled]
+            if fullSVD and Uts[0] is not None:
+                with timer("stage3.project"):
+                    K.gemm_tn(Xm, Uts[0], V[m][0][o:o + filled], impl=ws.gemm_impl)
+            for j, (v, y0, y1, x0, x1) in enumerate(geo.mot_rois):
+                for r0 in range(0, filled, 32768):
+                    r1 = min(filled, r0 + 32768)
+                    Xr = ws.matrix("X3roi", r1 - r0, geo.roi_npix[j])
+                    with timer("stage3.roi"):
+                        K.gather_roi(Xm[r0:r1], r1 - r0, geo.col0[v], int(geo.Lxb[v]), (y0, y1, x0, x1), Xr)
+                        K.gemm_tn(Xr, Uts[1 + j], V[m][1 + j][o + r0:o + r1], impl=ws.gemm_impl)
+    return V, E, E_roi

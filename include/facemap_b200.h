@@ -1,0 +1,154 @@
+/*
+ * facemap_b200 — C-ABI of the B200-native motion/movie-SVD hot path.
+ *
+ * The reference (MouseLand/facemap) has no FFI: its seams are NumPy expressions inside
+ * facemap/process.py and facemap/utils.py.  Each entry point below replaces one such seam; the
+ * reference lines it stands in for are cited on every declaration (paths relative to the
+ * reference checkout).  The Python host (facemap_b200/process.py) binds these with ctypes — see
+ * INTEGRATION.md for the stub a facemap maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all launches go to
+ *     that stream, nothing synchronises unless stated;
+ *   - matrices are row-major float32 with an explicit leading dimension `ld*` counted in
+ *     elements; GEMM operands need ld % 4 == 0 and 16-byte aligned bases (TMA requirement);
+ *   - return value: 0 on success, non-zero on error; fm_last_error() gives the text of the
+ *     last error raised on the calling thread;
+ *   - there is no CPU fallback: without a Blackwell (sm_100) device every compute entry point
+ *     fails with FM_ERR_NO_DEVICE.
+ */
+#ifndef FACEMAP_B200_H
+#define FACEMAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FM_OK 0
+#define FM_ERR_INVALID 1
+#define FM_ERR_CUDA 2
+#define FM_ERR_NO_DEVICE 3
+#define FM_ERR_SOLVER 4
+
+#define FM_MAX_ROIS 8
+
+/* library / device ----------------------------------------------------------------------- */
+int fm_version(void);
+const char* fm_last_error(void);
+/* 0 if device `dev` is an sm_100 part this library was built for. */
+int fm_check_device(int dev);
+/* number of kernels this library launched on the calling process since load (all threads). */
+uint64_t fm_launch_count(void);
+
+/* ROI rectangles in BINNED coordinates of one view, half-open [y0,y1) x [x0,x1).
+ * facemap/process.py:716-723 (yrange_bin / xrange_bin), :464-500 (use in the projection loop) */
+typedef struct fm_rois {
+  int32_t n;
+  int32_t y0[FM_MAX_ROIS], y1[FM_MAX_ROIS], x0[FM_MAX_ROIS], x1[FM_MAX_ROIS];
+} fm_rois;
+
+/*
+ * K1 — fused spatial_bin + frame diff + |.| + average subtract (+ motion energy, + running sums).
+ * Replaces, for one view: spatial_bin (facemap/process.py:34-43), np.abs(np.diff(.)) and the
+ * avg subtraction (:201-212 stage 2, :448-463 stage 3), imbin_mot.sum(-1) (:460, :480) and the
+ * per-segment sums of subsampled_mean (:77-87).
+ *
+ *   frames      uint8 [T, H, W] contiguous
+ *   prev_sum    int32 [Lyb*Lxb] integer block sums of the frame preceding frames[0] (the carried
+ *               `imend`, process.py:449-453) or NULL.  With prev_sum: rows = T, row r <-> frame r.
+ *               Without: rows = T-1, row r <-> frame r+1 (first chunk, process.py:455-457).
+ *   avgmotion / avgframe   float32 [Lyb*Lxb] or NULL (NULL = subtract nothing)
+ *   x_mot       float32 [rows, ldx]; written at columns [col0, col0 + Lyb*Lxb):
+ *               f32( |b_t - b_{t-1}| - avgmotion ), b = blocksum / sbin^2 evaluated in float64
+ *   x_mov       float32 [rows, ldx]: f32( b_t - avgframe )                     (either may be NULL)
+ *   energy      uint64 [rows]: += sum over the view of |S_t - S_{t-1}| (integer block sums S);
+ *               caller zeroes.  motion = energy / sbin^2.
+ *   roi_energy  uint64 [rois->n, rows]: the same restricted to each ROI rectangle (or NULL)
+ *   last_sum    int32 [Lyb*Lxb]: block sums of frames[T-1] (next call's prev_sum) or NULL
+ *   tsum_bin    int64 [Lyb*Lxb]: += sum_t S_t over ALL T frames          (stage 1) or NULL
+ *   tsum_adiff  int64 [Lyb*Lxb]: += sum over rows of |S_t - S_{t-1}|     (stage 1) or NULL
+ */
+int fm_bin_motion(const uint8_t* frames, int T, int H, int W, int sbin,
+                  const int32_t* prev_sum, const float* avgmotion, const float* avgframe,
+                  float* x_mot, float* x_mov, int64_t ldx, int64_t col0,
+                  unsigned long long* energy, const fm_rois* rois, unsigned long long* roi_energy,
+                  int32_t* last_sum, long long* tsum_bin, long long* tsum_adiff, void* stream);
+
+/*
+ * Stage-1 accumulator update, bit-compatible with subsampled_mean (facemap/process.py:82-86,
+ * 95-96): acc32 = f32( f64(acc32) + (f64(tsum) / sbin^2) / count ) for n pixels.
+ * `finalize_div` > 0 additionally divides by that segment count in float32 (process.py:95-96).
+ */
+int fm_mean_update(float* acc, const long long* tsum, int64_t n, int sbin, int count,
+                   int finalize_div, void* stream);
+
+/*
+ * K2/K3/K4 — C[M,N] = rscale[m] * (A[M,K] . B[N,K]^T) + rbias[m]      (3xTF32 on tcgen05/TMEM)
+ * A and B are both K-contiguous (row-major [rows, K]).  Replaces the dense contractions of the
+ * path: X @ U (facemap/process.py:485,495,503,510), and the GEMMs inside utils.svdecon
+ * (facemap/utils.py:751-776 -> sklearn randomized_svd; here Gram + eigensolve, the formulation
+ * of matlab/utils/svdecon.m:16-43).
+ *   rscale, rbias   float32 [M] or NULL
+ *   ksplit >= 1: if > 1, `C` is ignored and raw partial products are written to
+ *                workspace[ksplit, M, ldw] (no scale/bias); reduce with fm_gram_assemble.
+ *   upper_only != 0: tiles entirely below the diagonal are skipped (symmetric Gram).
+ *   impl: 0 = tcgen05 3xTF32 (product path), 1 = plain FP32 FFMA reference kernel (validation).
+ */
+int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int K,
+               float* C, int64_t ldc, const float* rscale, const float* rbias,
+               int ksplit, float* workspace, int64_t ldw, int upper_only, int impl, void* stream);
+
+/* bytes of workspace fm_gemm_tn needs for (M, ldw, ksplit). */
+int64_t fm_gemm_workspace_bytes(int M, int64_t ldw, int ksplit);
+
+/*
+ * PCA centring pieces (sklearn/decomposition/_pca.py:733-736 called from facemap/utils.py:773):
+ *   fm_row_means : mean[r] = (1/ncols) sum_c X[r, c]   (float64)
+ *   fm_gram_assemble : G[i,j] (float64, n x n) = sum_s part[s,i,j] - ncols * mean[i] * mean[j]
+ *                      taking part from the upper triangle when upper_only and mirroring.
+ */
+int fm_row_means(const float* X, int64_t ldx, int rows, int64_t ncols, double* mean, void* stream);
+int fm_gram_assemble(const float* part, int ksplit, int n, int64_t ldw, const double* mean,
+                     int64_t ncols, int upper_only, double* G, void* stream);
+
+/*
+ * Symmetric eigensolve (cuSOLVER syevd — the one library call on the path; timed separately,
+ * not claimed as a kernel).  G is float64 n x n, overwritten with eigenvectors (row j =
+ * eigenvector of the j-th smallest eigenvalue); lam[n] ascending.  `use_fp32` solves in float32
+ * (G is converted in place to/from).  Synchronises the stream (reads devInfo).
+ */
+typedef struct fm_solver fm_solver;
+int fm_solver_create(fm_solver** out);
+int fm_solver_destroy(fm_solver* s);
+int fm_syevd(fm_solver* s, double* G, int n, double* lam, int use_fp32, void* stream);
+
+/*
+ * Top-k extraction with the reference's sign rule (sklearn/utils/extmath.py:924-982,
+ * u_based_decision=False: the largest-|.| entry of each right singular vector is positive):
+ *   Wt[c, j]  = sgn_c * evec[n-1-c][j]                    float32 [k, ldwt]  (c = 0..k-1)
+ *   sval[c]   = sqrt(max(lam[n-1-c], 0))                  float32 [k]
+ *   rscale[c] = 1 / sval[c] (0 if sval == 0)              float32 [k]   (may be NULL)
+ *   rbias[c]  = - sum_j Wt[c, j] * mean[j]                float32 [k]   (centring of X^T W; may
+ *               be NULL); when rscale is requested the bias is pre-multiplied by rscale[c] so
+ *               that fm_gemm_tn's epilogue rscale*acc + rbias gives (acc - w.mean) / sval.
+ */
+int fm_topk_components(const double* evec, const double* lam, int n, int k, const double* mean,
+                       float* Wt, int64_t ldwt, float* sval, float* rbias, float* rscale,
+                       void* stream);
+
+/* out[c, r] = in[r, c]  (rows x cols float32 -> cols x rows). */
+int fm_transpose(const float* in, int64_t ldin, int rows, int cols, float* out, int64_t ldout,
+                 void* stream);
+
+/* ROI column gather (facemap/process.py:218-222, 479-483): out[r, (y-y0)*(x1-x0) + (x-x0)] =
+ * X[r, col0 + y*Lxb + x] for the binned rectangle. */
+int fm_gather_roi(const float* X, int64_t ldx, int rows, int64_t col0, int Lxb,
+                  int y0, int y1, int x0, int x1, float* out, int64_t ldout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACEMAP_B200_H */

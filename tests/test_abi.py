@@ -1,0 +1,70 @@
+"""The C-ABI library builds, loads and exports every symbol include/facemap_b200.h declares; the
+ctypes table covers them all.  No compute call is made (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "facemap_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = _declared_symbols()
+    for must in ("fm_bin_motion", "fm_gemm_tn", "fm_syevd", "fm_row_means", "fm_gram_assemble",
+                 "fm_topk_components", "fm_transpose", "fm_gather_roi", "fm_mean_update"):
+        assert must in syms
+
+
+def test_library_builds_and_exports_every_symbol():
+    from facemap_b200 import _lib, build
+
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    for s in _declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert set(_lib.SIGNATURES) == set(_declared_symbols())
+    assert _lib.load().fm_version() >= 100
+
+
+def test_library_carries_blackwell_tensor_code():
+    """SASS of the GEMM must contain tcgen05 MMA (UTC*MMA), TMEM loads (LDTM) and TMA (UTMALDG)."""
+    import shutil
+    import subprocess
+
+    from facemap_b200 import build
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", build.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert re.search(r"UTC\w*MMA", sass), "no tcgen05.mma in SASS"
+    assert "LDTM" in sass and "UTMALDG" in sass
+
+
+def test_no_device_fails_loudly():
+    import torch
+
+    from facemap_b200 import _lib
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.FacemapB200Error):
+        _lib.require_device(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "facemap_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

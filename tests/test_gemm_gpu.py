@@ -1,0 +1,83 @@
+"""3xTF32 tcgen05 GEMM (fm_gemm_tn) against a float64 torch matmul and against the library's own
+plain-FP32 reference kernel.  Tolerance: 3xTF32 keeps ~22 mantissa bits per product, so the result
+must sit within 2e-6 * sum|a||b| of the exact value (fp32 accumulation included)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(rows, cols, dev, seed, ld_pad=0):
+    from facemap_b200 import kernels as K
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    m = K.alloc_matrix(rows, cols, dev)
+    m.copy_(torch.randn((rows, cols), generator=g) * (1 + torch.rand((rows, 1), generator=g) * 5))
+    return m
+
+
+SHAPES = [
+    # M, N, K
+    (128, 128, 32), (128, 256, 64), (100, 90, 50), (250, 700, 999), (999, 999, 1280), (300, 500, 4100),
+    (64, 24, 8), (513, 129, 333), (129, 3750, 257),
+]
+
+
+@pytest.mark.parametrize("impl", [0, 2, 3, 4])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_matches_fp64(cuda_device, M, N, K, impl):
+    from facemap_b200 import kernels as Kn
+
+    dev = cuda_device
+    A, B = _rand(M, K, dev, 1), _rand(N, K, dev, 2)
+    C = Kn.alloc_matrix(M, N, dev, zero=True)
+    Kn.gemm_tn(A, B, C, impl=impl)
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().T
+    bound = (A.double().abs() @ B.double().abs().T) * 2e-6 + 1e-30
+    err = (C.double() - ref).abs()
+    assert bool((err <= bound).all()), f"max err/bound {float((err / bound).max()):.3g}"
+    # and against the FP32 FFMA reference kernel of the library
+    C2 = Kn.alloc_matrix(M, N, dev, zero=True)
+    Kn.gemm_tn(A, B, C2, impl=1)
+    torch.cuda.synchronize()
+    assert bool(((C2.double() - ref).abs() <= bound * 4).all())
+
+
+def test_gemm_scale_bias_epilogue(cuda_device):
+    from facemap_b200 import kernels as Kn
+
+    dev = cuda_device
+    M, N, K = 250, 1280, 999
+    A, B = _rand(M, K, dev, 3), _rand(N, K, dev, 4)
+    rs = torch.rand(M, device=dev) + 0.5
+    rb = torch.randn(M, device=dev)
+    C = Kn.alloc_matrix(M, N, dev)
+    Kn.gemm_tn(A, B, C, rscale=rs, rbias=rb)
+    torch.cuda.synchronize()
+    ref = (A.double() @ B.double().T) * rs.double()[:, None] + rb.double()[:, None]
+    assert float((C.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("n,K,ksplit", [(999, 4096, 7), (300, 2000, 3), (1000, 640, 20), (3750, 1100, 2)])
+def test_gram_splitk_upper_assemble(cuda_device, n, K, ksplit):
+    """split-K partials + fm_gram_assemble == centred Gram in float64 (the svdecon core)."""
+    from facemap_b200 import kernels as Kn
+
+    dev = cuda_device
+    X = _rand(n, K, dev, 5)
+    ld = Kn.round_up(n, 32)
+    ws = torch.full((ksplit, n, ld), float("nan"), dtype=torch.float32, device=dev)
+    Kn.gemm_tn(X, X, ksplit=ksplit, workspace=ws, upper_only=True)
+    mean = Kn.row_means(X)
+    G = Kn.gram_assemble(ws, min(ksplit, (K + 31) // 32), n, mean, K, True)
+    torch.cuda.synchronize()
+    Xd = X.double()
+    md = Xd.mean(dim=1)
+    assert float((mean - md).abs().max()) < 1e-12 * float(Xd.abs().max()) * K
+    ref = Xd @ Xd.T - K * torch.outer(md, md)
+    scale = float(torch.diagonal(Xd @ Xd.T).max())
+    assert bool(torch.isfinite(G).all())
+    assert float((G - ref).abs().max()) / scale < 2e-6
+    assert torch.equal(G, G.T)

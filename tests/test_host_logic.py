@@ -1,0 +1,94 @@
+"""Host-side logic of the product (geometry, plans, frame sources, output conventions) against
+the oracle restatement and hand-computed cases.  CPU only."""
+import numpy as np
+import pytest
+
+from facemap_b200 import utils
+from oracle import facemap_oracle as orc
+from tests.helpers import motion_roi
+
+
+def test_binned_inds_and_placement_match_oracle():
+    rng = np.random.RandomState(0)
+    for trial in range(200):
+        nv = rng.randint(1, 7)
+        Ly = list(rng.randint(8, 200, nv))
+        Lx = list(rng.randint(8, 200, nv))
+        sbin = int(rng.randint(1, 8))
+        a = utils.binned_inds(Ly, Lx, sbin)
+        b = orc.binned_geometry(Ly, Lx, sbin)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert all(np.array_equal(x, y) for x, y in zip(a[2], b[2]))
+        LY, LX, sy, sx = utils.video_placement(a[0], a[1])
+        LY2, LX2, sy2, sx2 = orc.canvas_layout(a[0], a[1])
+        assert (LY, LX) == (LY2, LX2) and np.array_equal(sy, sy2) and np.array_equal(sx, sx2)
+        X = rng.rand(int((a[0] * a[1]).sum()), 3).astype(np.float32)
+        assert np.array_equal(utils.multivideo_reshape(X, LY, LX, sy, sx, a[0], a[1], a[2]),
+                              orc.scatter_canvas(X, LY, LX, sy, sx, a[0], a[1], a[2]))
+
+
+def test_roi_bin_ranges_keep_reference_quirk_q5():
+    r = motion_roi(0, 10, 70, 17, 90)
+    yb, xb = utils.roi_bin_ranges(r, 4)
+    yo, xo = orc.roi_bin_ranges(r, 4)
+    assert np.array_equal(yb, yo) and np.array_equal(xb, xo)
+    assert xb.size == 19 and yb.size == 15        # x stop 89/4 = 22.25 rounds up (Q5)
+
+
+@pytest.mark.parametrize("N", [3, 99, 100, 700, 1000, 1001, 1999, 2000, 2300, 14999, 15000, 16001, 100000])
+def test_stage_plans_match_oracle(N):
+    from facemap_b200 import svd
+
+    if N >= 100:
+        nt0, tf = svd.stage1_plan(N, [N])
+        nt0o, tfo = orc.stage1_sample_times(N, [N])
+        assert nt0 == nt0o and np.array_equal(tf, tfo)
+    a, b = svd.stage2_plan(N), orc.stage2_plan(N)
+    assert a[:3] == b[:3] and np.array_equal(a[3], b[3])
+
+
+def test_motion_layout_quirk_q1():
+    from facemap_b200.process import _motion_from_energy
+
+    for N in (1300, 300):
+        e = np.arange(N, dtype=np.int64) * 16          # energy of frame t = 16 t  (row 0 unused)
+        m = _motion_from_energy([e], 4, N)
+        nt1 = min(500, N)
+        assert np.array_equal(m[:nt1 - 1], np.arange(1, nt1, dtype=np.float32))
+        assert m[nt1 - 1] == 0
+        assert np.array_equal(m[nt1:], np.arange(nt1, N, dtype=np.float32))
+    # two views accumulate in float32 like `M[0][t:] += imbin_mot.sum(-1)` (process.py:460)
+    e0 = np.full(600, 2 ** 25 + 3, np.int64)
+    e1 = np.full(600, 5, np.int64)
+    m = _motion_from_energy([e0, e1], 1, 600)
+    assert m[10] == np.float32(np.float32(2 ** 25 + 3) + np.float32(5))
+
+
+def test_frame_sources_clamp_like_get_frames():
+    import torch
+
+    from facemap_b200.frames import HostArraySource, as_source
+
+    v = np.arange(10 * 2 * 3, dtype=np.uint8).reshape(10, 2, 3)
+    src = as_source([v])
+    assert isinstance(src, HostArraySource)
+    assert src.clamp(8, 508) == (8, 10) and src.clamp(-5, 3) == (0, 3) and src.clamp(0, 10) == (0, 10)
+    assert src.nframes == 10 and src.Ly == [2] and src.Lx == [3] and src.block_frames == [10]
+    assert src.h2d_bytes(4) == 24
+    with pytest.raises(ValueError):
+        HostArraySource([v, v[:5]])
+    with pytest.raises(TypeError):
+        as_source(42)
+    with pytest.raises(ValueError):
+        HostArraySource([torch.zeros(3, 4, 4)])
+
+
+def test_gram_ksplit_and_batch_sizes():
+    from facemap_b200 import svd
+
+    assert svd._gram_ksplit(999, 19200) >= 8
+    assert svd._gram_ksplit(3750, 19200) >= 1
+    assert svd._gram_ksplit(999, 300) == 1
+    r = svd.projection_rows_per_batch(19200, 500)
+    assert r % 128 == 0 and r * 19200 * 4 <= 6 << 30
+    assert svd.projection_rows_per_batch(1310720, 500) % 128 == 0

@@ -1,0 +1,152 @@
+"""K1 (fused bin + diff + |.| + avg subtract + energy + running sums) against the oracle.
+Integer outputs must be bit-exact; float outputs bit-exact for power-of-two sbin and within
+1 ulp otherwise (north_star tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import facemap_oracle as orc
+from tests.helpers import ulp_distance
+
+pytestmark = pytest.mark.gpu
+
+
+def _video(T, H, W, seed):
+    rng = np.random.RandomState(seed)
+    base = rng.randint(0, 256, size=(1, H, W))
+    drift = rng.randint(-40, 41, size=(T, H, W))
+    return np.clip(base + np.cumsum(drift, axis=0) // 4 + rng.randint(0, 30, size=(T, H, W)), 0, 255).astype(np.uint8)
+
+
+def _oracle(frames, sbin, avgmot, avgfrm):
+    T, H, W = frames.shape
+    Lyb, Lxb = H // sbin, W // sbin
+    S = orc.bin_sums_int(frames, sbin, Lyb, Lxb)                       # int64 [T, p]
+    b = orc.bin_frames(frames, sbin, Lyb, Lxb)                          # reference float binning
+    d = np.abs(np.diff(b, axis=0))
+    xm = (d - avgmot).astype(np.float32)
+    xf = (b[1:] - avgfrm).astype(np.float32)
+    dS = np.abs(np.diff(S, axis=0))
+    return S, xm, xf, dS
+
+
+CASES = [
+    # T, H, W, sbin   (vector path needs W % min(16, 4*sbin) == 0)
+    (40, 64, 96, 4), (37, 60, 100, 4), (33, 48, 64, 2), (20, 24, 32, 1), (25, 64, 128, 8),
+    (19, 64, 64, 16), (21, 50, 70, 3), (18, 61, 67, 4), (16, 30, 50, 5), (140, 32, 48, 4),
+]
+
+
+@pytest.mark.parametrize("T,H,W,sbin", CASES)
+def test_k1_matches_oracle(cuda_device, T, H, W, sbin):
+    from facemap_b200 import kernels as K
+
+    frames = _video(T, H, W, seed=T + H + sbin)
+    Lyb, Lxb = H // sbin, W // sbin
+    p = Lyb * Lxb
+    rng = np.random.RandomState(1)
+    avgmot = (rng.rand(p) * 3).astype(np.float32)
+    avgfrm = (rng.rand(p) * 200).astype(np.float32)
+    S, xm, xf, dS = _oracle(frames, sbin, avgmot, avgfrm)
+
+    dev = cuda_device
+    fr = torch.from_numpy(frames).to(dev)
+    pad = 5
+    Xm = K.alloc_matrix(T - 1, p + pad, dev, zero=True)
+    Xf = K.alloc_matrix(T - 1, p + pad, dev, zero=True)
+    energy = torch.zeros(T - 1, dtype=torch.int64, device=dev)
+    last = torch.zeros(p, dtype=torch.int32, device=dev)
+    tsb = torch.zeros(p, dtype=torch.int64, device=dev)
+    tsa = torch.zeros(p, dtype=torch.int64, device=dev)
+    rows = K.bin_motion(fr, sbin, avgmotion=torch.from_numpy(avgmot).to(dev), avgframe=torch.from_numpy(avgfrm).to(dev),
+                        x_mot=Xm, x_mov=Xf, col0=pad, energy=energy, last_sum=last, tsum_bin=tsb, tsum_adiff=tsa)
+    torch.cuda.synchronize()
+    assert rows == T - 1
+    assert np.array_equal(energy.cpu().numpy(), dS.sum(axis=1))
+    assert np.array_equal(last.cpu().numpy(), S[-1])
+    assert np.array_equal(tsb.cpu().numpy(), S.sum(axis=0))
+    assert np.array_equal(tsa.cpu().numpy(), dS.sum(axis=0))
+    gm, gf = Xm.cpu().numpy()[:, pad:], Xf.cpu().numpy()[:, pad:]
+    assert np.all(Xm.cpu().numpy()[:, :pad] == 0), "columns before col0 must be untouched"
+    pow2 = sbin & (sbin - 1) == 0
+    if pow2:
+        assert np.array_equal(gm, xm) and np.array_equal(gf, xf)
+    else:
+        assert ulp_distance(gm, xm) <= 1 and ulp_distance(gf, xf) <= 1
+
+
+@pytest.mark.parametrize("T,H,W,sbin", [(50, 64, 96, 4), (30, 50, 70, 3), (45, 32, 64, 1)])
+def test_k1_carry_is_seamless(cuda_device, T, H, W, sbin):
+    """Processing [0,a) then [a,T) with the carried block sums equals one pass (process.py:449-453)."""
+    from facemap_b200 import kernels as K
+
+    frames = _video(T, H, W, seed=7)
+    Lyb, Lxb = H // sbin, W // sbin
+    p = Lyb * Lxb
+    dev = cuda_device
+    fr = torch.from_numpy(frames).to(dev)
+    whole = K.alloc_matrix(T - 1, p, dev)
+    e_whole = torch.zeros(T - 1, dtype=torch.int64, device=dev)
+    K.bin_motion(fr, sbin, x_mot=whole, energy=e_whole)
+    a = 17
+    part = K.alloc_matrix(T - 1, p, dev)
+    e_part = torch.zeros(T - 1, dtype=torch.int64, device=dev)
+    carry = torch.zeros(p, dtype=torch.int32, device=dev)
+    K.bin_motion(fr[:a].contiguous(), sbin, x_mot=part[:a - 1], energy=e_part[:a - 1], last_sum=carry)
+    rows = K.bin_motion(fr[a:].contiguous(), sbin, prev_sum=carry, x_mot=part[a - 1:], energy=e_part[a - 1:])
+    torch.cuda.synchronize()
+    assert rows == T - a
+    assert torch.equal(whole, part) and torch.equal(e_whole, e_part)
+
+
+def test_k1_roi_energy(cuda_device):
+    from facemap_b200 import kernels as K
+
+    T, H, W, sbin = 30, 64, 96, 4
+    frames = _video(T, H, W, seed=3)
+    Lyb, Lxb = H // sbin, W // sbin
+    S = orc.bin_sums_int(frames, sbin, Lyb, Lxb).reshape(T, Lyb, Lxb)
+    dS = np.abs(np.diff(S, axis=0))
+    rects = [(2, 9, 3, 20), (0, 16, 0, 24), (5, 6, 7, 8)]
+    dev = cuda_device
+    fr = torch.from_numpy(frames).to(dev)
+    energy = torch.zeros(T - 1, dtype=torch.int64, device=dev)
+    roi_e = torch.zeros((len(rects), T - 1), dtype=torch.int64, device=dev)
+    K.bin_motion(fr, sbin, energy=energy, rois=rects, roi_energy=roi_e)
+    torch.cuda.synchronize()
+    got = roi_e.cpu().numpy()
+    for q, (y0, y1, x0, x1) in enumerate(rects):
+        assert np.array_equal(got[q], dS[:, y0:y1, x0:x1].sum(axis=(1, 2)))
+    assert np.array_equal(energy.cpu().numpy(), dS.sum(axis=(1, 2)))
+
+
+def test_stage1_mean_update_bit_exact(cuda_device):
+    """fm_mean_update reproduces subsampled_mean's float32 += float64 accumulation (process.py:82-96)."""
+    from facemap_b200 import kernels as K
+
+    for sbin in (1, 2, 4):
+        H, W, T = 32 * sbin // (2 if sbin > 1 else 1), 48, 100
+        segs = [_video(T, H, W, seed=s) for s in range(3)]
+        Lyb, Lxb = H // sbin, W // sbin
+        p = Lyb * Lxb
+        ref_f = np.zeros(p, np.float32)
+        ref_m = np.zeros(p, np.float32)
+        dev = cuda_device
+        acc_f = torch.zeros(p, dtype=torch.float32, device=dev)
+        acc_m = torch.zeros(p, dtype=torch.float32, device=dev)
+        for fr in segs:
+            b = orc.bin_frames(fr, sbin, Lyb, Lxb)
+            ref_f += b.mean(axis=0)
+            ref_m += np.abs(np.diff(b, axis=0)).mean(axis=0)
+            tsb = torch.zeros(p, dtype=torch.int64, device=dev)
+            tsa = torch.zeros(p, dtype=torch.int64, device=dev)
+            K.bin_motion(torch.from_numpy(fr).to(dev), sbin, tsum_bin=tsb, tsum_adiff=tsa)
+            K.mean_update(acc_f, tsb, sbin, T)
+            K.mean_update(acc_m, tsa, sbin, T - 1)
+        ref_f /= float(len(segs))
+        ref_m /= float(len(segs))
+        K.mean_update(acc_f, None, sbin, 1, finalize_div=len(segs))
+        K.mean_update(acc_m, None, sbin, 1, finalize_div=len(segs))
+        torch.cuda.synchronize()
+        assert np.array_equal(acc_f.cpu().numpy(), ref_f), f"avgframe sbin={sbin}"
+        assert np.array_equal(acc_m.cpu().numpy(), ref_m), f"avgmotion sbin={sbin}"

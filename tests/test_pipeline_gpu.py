@@ -1,0 +1,197 @@
+"""Whole path on the GPU (facemap_b200.process.process_source) against
+  (a) the committed golden fixtures = outputs of the UNMODIFIED reference run in the build
+      container (scripts/make_golden.py; "stock" = O1, "exact" = O2 of SURVEY.md §8c), and
+  (b) the oracle restatement run live on the same bytes.
+
+Gates (north_star): geometry exact; avgframe / avgmotion / motion bit-exact for power-of-two sbin
+(<= 1 ulp otherwise); singular values <= 1e-4 relative; sign-aligned masks with principal-angle
+sine <= 1e-3; projected traces <= 1e-3 relative — the SVD gates on the spectrally resolved
+leading components against O2, and on the components O1 itself resolves against O1 (F3)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import facemap_oracle as orc
+from tests.helpers import (CASES, KEEP, case_rois, case_videos, frame_window, sign_align, subspace_sin,
+                           ulp_distance)
+
+pytestmark = pytest.mark.gpu
+
+S_RTOL = 1e-4
+ANGLE_TOL = 1e-3
+TRACE_RTOL = 1e-3
+
+
+def _run_cuda(name, device, source_kind="device", **kw):
+    from facemap_b200 import process
+    from facemap_b200.frames import DeviceArraySource, HostArraySource
+
+    views, N, sbin, mot, mov, _ = CASES[name]
+    vids = case_videos(name)
+    if source_kind == "device":
+        src = DeviceArraySource([torch.from_numpy(v).to(device) for v in vids])
+    else:
+        src = HostArraySource(vids)
+    return process.process_source(src, sbin=sbin, motSVD=mot, movSVD=mov, rois=case_rois(name), **kw), vids
+
+
+def svd_metrics(S_ref, U_ref, V_ref, S, U, V, kmax):
+    """relative S error, per-prefix subspace sine and sign-aligned trace error for the first kmax
+    components (U: [p, >=kmax] masks, V: [frames, >=kmax] traces)."""
+    kmax = min(kmax, U_ref.shape[1], U.shape[1])
+    out = {"S_rel": None, "angle": [], "trace_rel": [], "sign_agree": 0}
+    if S_ref is not None and len(S_ref) >= kmax and np.any(S_ref):
+        out["S_rel"] = np.abs(S[:kmax].astype(np.float64) - S_ref[:kmax]) / S_ref[:kmax]
+    Ua, sg = sign_align(U[:, :kmax], U_ref[:, :kmax])
+    out["sign_agree"] = int((sg > 0).sum())
+    for k in range(1, kmax + 1):
+        out["angle"].append(subspace_sin(U[:, :k], U_ref[:, :k]))
+    Va = V[:, :kmax] * sg[None, :]
+    num = np.linalg.norm(Va.astype(np.float64) - V_ref[:, :kmax], axis=0)
+    den = np.linalg.norm(V_ref[:, :kmax].astype(np.float64), axis=0) + 1e-30
+    out["trace_rel"] = num / den
+    return out
+
+
+def leading_resolved(S, angle_budget=ANGLE_TOL, eps=2e-7):
+    """How many leading components a float32-grade Gram can pin to `angle_budget`: the subspace of
+    the first k components moves by ~ eps * S0^2 / (S_k^2 - S_{k+1}^2)."""
+    S = np.asarray(S, np.float64)
+    k_ok = 0
+    for k in range(1, len(S)):
+        gap = S[k - 1] ** 2 - S[k] ** 2
+        if gap <= 0 or eps * S[0] ** 2 / gap > angle_budget / 4:
+            break
+        k_ok = k
+    return k_ok
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_integer_stages_match_reference_golden(cuda_device, golden_dir, name):
+    """geometry, avgframe, avgmotion, motion vs the unmodified reference (both oracles agree here)."""
+    proc, _ = _run_cuda(name, cuda_device)
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    sbin = CASES[name][2]
+    pow2 = sbin & (sbin - 1) == 0
+    for key in ("Lybin", "Lxbin", "sybin", "sxbin"):
+        assert np.array_equal(np.asarray(proc[key]), z["stock/" + key]), key
+    assert int(proc["LYbin"]) == int(z["stock/LYbin"]) and int(proc["LXbin"]) == int(z["stock/LXbin"])
+    for key in ("avgframe", "avgmotion"):
+        for i, a in enumerate(proc[key]):
+            ref = z[f"stock/{key}_{i}"]
+            assert a.shape == ref.shape, (key, i, a.shape, ref.shape)      # quirk Q4 included
+            if pow2:
+                assert np.array_equal(a, ref), (key, i)
+            else:
+                assert ulp_distance(a, ref) <= 1, (key, i)
+        ref = z[f"stock/{key}_reshape"]
+        got = proc[f"{key}_reshape"]
+        assert got.shape == ref.shape and (np.array_equal(got, ref) if pow2 else ulp_distance(got, ref) <= 1)
+    for i, m in enumerate(proc["motion"]):
+        ref = z[f"stock/motion_{i}"]
+        assert m.shape == ref.shape
+        if pow2:
+            assert np.array_equal(m, ref), f"motion[{i}]"                   # quirk Q1 included
+        else:
+            assert np.allclose(m, ref, rtol=2e-7, atol=0), f"motion[{i}]"
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_svd_outputs_match_exact_oracle_golden(cuda_device, golden_dir, name):
+    """S, masks and traces vs O2 (reference with an exact float64 svdecon), leading components."""
+    proc, _ = _run_cuda(name, cuda_device)
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    N = CASES[name][1]
+    w = frame_window(N)
+    for mk, vk, sk in (("motMask", "motSVD", "motSv"), ("movMask", "movSVD", "movSv")):
+        n_ref = int(z[f"exact/{mk}_n"])
+        assert len(proc[mk]) == n_ref, mk
+        for i in range(n_ref):
+            shape = tuple(z[f"exact/{mk}_{i}_shape"])
+            assert tuple(proc[mk][i].shape) == shape, (mk, i, proc[mk][i].shape, shape)
+            if shape[0] == 0 or not CASES[name][3 if mk == "motMask" else 4]:
+                continue
+            U_ref, V_ref = z[f"exact/{mk}_{i}"], z[f"exact/{vk}_{i}"]
+            assert tuple(proc[vk][i].shape) == tuple(z[f"exact/{vk}_{i}_shape"])
+            S_ref = z[f"exact/{sk}"] if i == n_ref - 1 else None          # quirk Q3: last target wins
+            S = np.asarray(proc[sk])
+            if S_ref is not None:
+                assert S.shape == S_ref.shape
+            # resolved prefix from the mask's own spectrum when available, else a short prefix
+            kres = min(KEEP, leading_resolved(S_ref) if (S_ref is not None and np.any(S_ref)) else 6)
+            kres = max(kres, 3)
+            met = svd_metrics(S_ref, U_ref, V_ref, S, proc[mk][i], proc[vk][i][w], kres)
+            if met["S_rel"] is not None:
+                assert met["S_rel"].max() <= S_RTOL, (mk, i, met["S_rel"])
+            assert max(met["angle"][:kres]) <= ANGLE_TOL, (mk, i, met["angle"])
+            assert met["trace_rel"].max() <= TRACE_RTOL, (mk, i, met["trace_rel"])
+    # all singular values, not only the leading ones
+    for sk in ("motSv", "movSv"):
+        S_ref, S = z["exact/" + sk].astype(np.float64), np.asarray(proc[sk]).astype(np.float64)
+        if np.any(S_ref):
+            big = S_ref >= 3e-3 * S_ref[0]
+            assert (np.abs(S - S_ref)[big] / S_ref[big]).max() <= S_RTOL, sk
+
+
+def test_against_live_oracle_all_components(cuda_device):
+    """All 500 components vs the oracle run live (exact float64 svdecon): S everywhere above the
+    float32 floor, mask subspace of the resolved prefix, traces; orthonormality of the masks."""
+    from facemap_b200 import process
+    from facemap_b200.frames import DeviceArraySource
+    from facemap_b200.synth import SynthVideo
+
+    H, W, N, sbin = 96, 128, 2600, 2
+    v = SynthVideo(H, W, N, seed=5).all_frames()
+    o = orc.run_oracle([v], sbin=sbin, motSVD=True, movSVD=False, svd="exact")
+    p = process.process_source(DeviceArraySource([torch.from_numpy(v).to(cuda_device)]), sbin=sbin)
+    assert np.array_equal(p["avgmotion"][0], o["avgmotion"][0])
+    assert np.array_equal(p["motion"][0], o["motion"][0])
+    S_ref, S = o["motSv"].astype(np.float64), p["motSv"].astype(np.float64)
+    assert S.shape == S_ref.shape == (500,)
+    big = S_ref >= 3e-3 * S_ref[0]
+    assert (np.abs(S - S_ref)[big] / S_ref[big]).max() <= S_RTOL
+    U, U_ref = p["motMask"][0], o["motMask"][0]
+    assert U.shape == U_ref.shape
+    gram = U.astype(np.float64).T @ U.astype(np.float64)
+    assert np.abs(gram - np.eye(500)).max() < 1e-4
+    kres = max(3, leading_resolved(S_ref))
+    met = svd_metrics(S_ref, U_ref, o["motSVD"][0], S, U, p["motSVD"][0], kres)
+    assert max(met["angle"]) <= ANGLE_TOL, met["angle"]
+    assert met["trace_rel"].max() <= TRACE_RTOL, met["trace_rel"]
+    # the projection is self-consistent for EVERY component: V == X @ U recomputed in float64
+    # on a window of frames (stage 3 does not depend on which basis of a near-degenerate pair won)
+    Lyb, Lxb = H // sbin, W // sbin
+    b = orc.bin_frames(v[999:1031], sbin, Lyb, Lxb)
+    X = (np.abs(np.diff(b, axis=0)) - o["avgmotion"][0]).astype(np.float32).astype(np.float64)
+    Vw = X @ U.astype(np.float64)
+    got = p["motSVD"][0][1000:1031].astype(np.float64)
+    assert np.abs(got - Vw).max() <= 2e-5 * np.abs(Vw).max()
+
+
+def test_host_source_equals_device_source(cuda_device):
+    """Frames streamed from host memory give bit-identical outputs to HBM-resident frames."""
+    a, _ = _run_cuda("short_s2", cuda_device, "device")
+    b, _ = _run_cuda("short_s2", cuda_device, "host")
+    for key in ("avgframe", "avgmotion", "motion", "motMask", "motSVD", "movMask", "movSVD"):
+        for x, y in zip(a[key], b[key]):
+            assert np.array_equal(x, y), key
+    assert np.array_equal(a["motSv"], b["motSv"])
+
+
+def test_run_writes_reference_proc_file(cuda_device, tmp_path):
+    """process.run: same signature / file naming / keys as facemap.process.run (process.py:605-647, 859-892)."""
+    from facemap_b200 import process
+
+    vids = case_videos("short_s2")
+    name = process.run([torch.from_numpy(v) for v in vids], sbin=2, motSVD=True, movSVD=True, savepath=str(tmp_path))
+    assert name == os.path.join(str(tmp_path), "array_input_proc.npy")
+    d = np.load(name, allow_pickle=True).item()
+    expect = {"filenames", "save_path", "Ly", "Lx", "sbin", "fullSVD", "save_mat", "Lybin", "Lxbin", "sybin", "sxbin",
+              "LYbin", "LXbin", "avgframe", "avgmotion", "avgframe_reshape", "avgmotion_reshape", "motion", "motSv",
+              "movSv", "motMask", "movMask", "motMask_reshape", "movMask_reshape", "motSVD", "movSVD", "pupil",
+              "running", "blink", "rois", "sy", "sx"}
+    assert set(d.keys()) == expect
+    assert d["motSVD"][0].dtype == np.float32 and d["motSVD"][0].shape[0] == CASES["short_s2"][1]
+    assert np.array_equal(d["motSVD"][0][0], d["motSVD"][0][1])            # quirk Q2
