@@ -144,3 +144,32 @@ extern "C" int fm_syevd(fm_solver* s, double* G, int n, double* lam, int use_fp3
   }
   return FM_OK;
 }
+
+// Batched variant (cusolverDnXsyevBatched): `batch` symmetric n x n float64 matrices stored back to
+// back; each is overwritten by its eigenvectors (rows), lam is [batch, n].
+extern "C" int fm_syevd_batched(fm_solver* s, double* G, int n, int batch, double* lam, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(s && G && lam && n >= 1 && batch >= 1, "fm_syevd_batched: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FM_SOLVER_TRY(cusolverDnSetStream(s->handle, st));
+  size_t dbytes = 0, hbytes = 0;
+  FM_SOLVER_TRY(cusolverDnXsyevBatched_bufferSize(s->handle, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER,
+                                                  n, CUDA_R_64F, G, n, CUDA_R_64F, lam, CUDA_R_64F, &dbytes, &hbytes,
+                                                  batch));
+  int rc = ensure_workspace(s, dbytes + sizeof(int) * (size_t)batch, hbytes);
+  if (rc != FM_OK) return rc;
+  int* info = reinterpret_cast<int*>(static_cast<char*>(s->d_work) + dbytes);
+  FM_SOLVER_TRY(cusolverDnXsyevBatched(s->handle, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
+                                       CUDA_R_64F, G, n, CUDA_R_64F, lam, CUDA_R_64F, s->d_work, dbytes, s->h_work,
+                                       hbytes, info, batch));
+  int h_info[64];
+  const int ncheck = batch < 64 ? batch : 64;
+  FM_CUDA_TRY(cudaMemcpyAsync(h_info, info, sizeof(int) * ncheck, cudaMemcpyDeviceToHost, st));
+  FM_CUDA_TRY(cudaStreamSynchronize(st));
+  for (int i = 0; i < ncheck; ++i)
+    if (h_info[i] != 0) {
+      set_error("cusolverDnXsyevBatched: devInfo[%d] = %d (n = %d)", i, h_info[i], n);
+      return FM_ERR_SOLVER;
+    }
+  return FM_OK;
+}

@@ -198,3 +198,52 @@ extern "C" int fm_gather_roi(const float* X, int64_t ldx, int rows, int64_t col0
   FM_LAUNCH_CHECK();
   return FM_OK;
 }
+
+// C[m,n] = rscale[m] * sum_s part[s,m,n] + rbias[m]: reduction of split-K partial products in
+// float64 (the tensor cores accumulate with truncation, so short K chains + an exact reduction
+// keep the GEMMs at float32 grade).
+namespace fm {
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int ksplit, int M, int N, int64_t ldw,
+                                     const float* __restrict__ rscale, const float* __restrict__ rbias,
+                                     float* __restrict__ C, int64_t ldc) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int m = blockIdx.y;
+  if (n >= N) return;
+  const size_t plane = (size_t)M * ldw;
+  const float* src = part + (size_t)m * ldw + n;
+  const double sc = rscale ? (double)rscale[m] : 1.0;
+  const double bi = rbias ? (double)rbias[m] : 0.0;
+  if (n + 4 <= N && (ldw % 4 == 0) && (ldc % 4 == 0) &&
+      (((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(C)) & 15) == 0)) {
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int s = 0; s < ksplit; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (size_t)s * plane);
+      a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+    }
+    *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) =
+        make_float4((float)(a0 * sc + bi), (float)(a1 * sc + bi), (float)(a2 * sc + bi), (float)(a3 * sc + bi));
+  } else {
+    for (int j = 0; j < 4 && n + j < N; ++j) {
+      double a = 0;
+      for (int s = 0; s < ksplit; ++s) a += (double)src[(size_t)s * plane + j];
+      C[(size_t)m * ldc + n + j] = (float)(a * sc + bi);
+    }
+  }
+}
+}  // namespace fm
+
+extern "C" int fm_splitk_reduce(const float* part, int ksplit, int M, int N, int64_t ldw, const float* rscale,
+                                const float* rbias, float* C, int64_t ldc, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(part && C && ksplit >= 1 && M >= 1 && N >= 1 && ldw >= N && ldc >= N, "fm_splitk_reduce: bad args");
+  FM_REQUIRE(M <= 65535 * 16, "fm_splitk_reduce: too many rows");
+  dim3 grid((unsigned)cdiv(cdiv(N, 4), 128), (unsigned)M);
+  if (M > 65535) {  // fold rows into z for very tall outputs
+    set_error("fm_splitk_reduce: M > 65535 unsupported");
+    return FM_ERR_INVALID;
+  }
+  splitk_reduce_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part, ksplit, M, N, ldw, rscale,
+                                                                                rbias, C, ldc);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}

@@ -128,6 +128,18 @@ def gemm_tn(A, B, C_out=None, *, rscale=None, rbias=None, ksplit=1, workspace=No
                                  _stream()), "fm_gemm_tn")
 
 
+def splitk_reduce(workspace, ksplit, C_out, *, rscale=None, rbias=None):
+    """C[m,n] = rscale[m] * sum_s workspace[s,m,n] + rbias[m], summed in float64."""
+    _need(workspace, torch.float32, "workspace", 3)
+    _need(C_out, torch.float32, "C", 2)
+    M = workspace.shape[1]
+    N = min(workspace.shape[2], C_out.shape[1])
+    if C_out.shape[0] < M or C_out.stride(1) != 1 or workspace.shape[0] < ksplit:
+        raise FacemapB200Error("splitk_reduce: shape mismatch")
+    check(_lib.load().fm_splitk_reduce(ptr(workspace), int(ksplit), M, N, workspace.stride(1), ptr(rscale), ptr(rbias),
+                                       ptr(C_out), C_out.stride(0), _stream()), "fm_splitk_reduce")
+
+
 def row_means(X, out=None):
     _need(X, torch.float32, "X", 2)
     rows, cols = X.shape
@@ -161,6 +173,16 @@ class Solver:
             raise FacemapB200Error("syevd: G must be a contiguous square matrix")
         lam = torch.empty(n, dtype=torch.float64, device=G.device)
         check(_lib.load().fm_syevd(self._h, ptr(G), n, ptr(lam), int(bool(use_fp32)), _stream()), "fm_syevd")
+        return lam
+
+    def syevd_batched(self, G):
+        """G: float64 [batch, n, n]; overwritten by eigenvectors (rows).  Returns lam [batch, n]."""
+        _need(G, torch.float64, "G", 3)
+        b, n, n2 = G.shape
+        if n != n2 or not G.is_contiguous():
+            raise FacemapB200Error("syevd_batched: G must be contiguous [batch, n, n]")
+        lam = torch.empty((b, n), dtype=torch.float64, device=G.device)
+        check(_lib.load().fm_syevd_batched(self._h, ptr(G), n, b, ptr(lam), _stream()), "fm_syevd_batched")
         return lam
 
     def close(self):

@@ -1,0 +1,122 @@
+"""Frame-range sharding of the path across the GPUs of one box (one process per GPU,
+torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+
+The reference is single-process; this is the one parallelism strategy the path
+admits:
+  stage 1  the 10 mean segments are dealt round-robin; their INTEGER sums are all-reduced (exact,
+           order independent) and the float32 accumulation is replayed in segment order on every
+           rank, so avgframe/avgmotion are bit-identical to the single-GPU result;
+  stage 2  the <= 15 SVD chunks are dealt round-robin; one all-gather collects the per-chunk
+           component blocks (U S)^T; the merge eigensolve is replicated (deterministic);
+  stage 3  contiguous frame ranges aligned to the reference's 500-frame grid, one-frame halo, no
+           communication; the projections / energies are all-gathered at the end.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import svd
+
+
+def assign_round_robin(n_items, world):
+    """item i -> rank i % world."""
+    return [list(range(r, n_items, world)) for r in range(world)]
+
+
+def frame_ranges(N, world, align=500):
+    """`world` contiguous [f0, f1) ranges covering [0, N), boundaries on multiples of `align`
+    (the reference's projection chunk grid, process.py:394), as even as that allows."""
+    nblocks = -(-N // align)
+    cuts = [min(N, align * ((nblocks * r) // world)) for r in range(world)] + [N]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class Shard:
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    # ---- collectives on plain tensors (device agnostic: used by the gloo CPU tests too) ----
+    def allreduce_segment_sums(self, local, nseg, p, device):
+        """local: {segment index: (tsum_bin int64[p], tsum_adiff int64[p], T)} for the segments this
+        rank computed -> the same dict for ALL segments (integer all-reduce, exact)."""
+        pack = torch.zeros((nseg, 2, p), dtype=torch.int64, device=device)
+        counts = torch.zeros(nseg, dtype=torch.int64, device=device)
+        for i, (tsb, tsa, T) in local.items():
+            pack[i, 0] = tsb
+            pack[i, 1] = tsa
+            counts[i] = T
+        dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
+        counts = counts.tolist()
+        return {i: (pack[i, 0], pack[i, 1], int(counts[i])) for i in range(nseg)}
+
+    def gather_chunk_blocks(self, local, k, nsegs):
+        """local: [n_local * k, p] blocks of the chunks assign_round_robin gives this rank (in that
+        order) -> [nsegs * k, p] in chunk order on every rank (one all-gather, padded to equal size)."""
+        p = local.shape[1]
+        per = -(-nsegs // self.world)
+        send = torch.zeros((per * k, p), dtype=local.dtype, device=local.device)
+        send[:local.shape[0]] = local
+        recv = torch.empty((self.world * per * k, p), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        out = torch.empty((nsegs * k, p), dtype=local.dtype, device=local.device)
+        owners = assign_round_robin(nsegs, self.world)
+        for r, items in enumerate(owners):
+            for slot, ci in enumerate(items):
+                src = (r * per + slot) * k
+                out[ci * k:(ci + 1) * k] = recv[src:src + k]
+        return out
+
+    def gather_rows(self, local, ranges):
+        """local rows of this rank's frame range -> all rows [N, ...] on every rank."""
+        longest = max(b - a for a, b in ranges)
+        tail = tuple(local.shape[1:])
+        send = torch.zeros((longest,) + tail, dtype=local.dtype, device=local.device)
+        send[:local.shape[0]] = local
+        recv = torch.empty((self.world * longest,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        return torch.cat([recv[r * longest:r * longest + (b - a)] for r, (a, b) in enumerate(ranges)], dim=0)
+
+    # ---- the three stages ----
+    def stage1(self, source, geo, device, timer):
+        N = source.nframes
+        _, tf = svd.stage1_plan(N, source.block_frames)
+        mine = assign_round_robin(len(tf), self.world)[self.rank]
+        local, nseg = svd.stage1_means(source, geo, device, timer, segments=mine)
+        with timer("stage1.allreduce"):
+            sums = self.allreduce_segment_sums(local, nseg, geo.p, device)
+        return svd.stage1_finish(sums, nseg, geo, device)
+
+    def stage2_chunks(self, source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer):
+        nsegs = svd.stage2_plan(source.nframes)[1]
+        mine = assign_round_robin(nsegs, self.world)[self.rank]
+        Yt, ks, _ = svd.stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer, chunks=mine)
+        full = {}
+        with timer("stage2.allgather"):
+            for m in mods:
+                full[m] = []
+                for idx, blk in enumerate(Yt[m]):
+                    if blk is None:
+                        full[m].append(None)
+                        continue
+                    g = self.gather_chunk_blocks(blk, ks[idx], nsegs)
+                    out = svd.K.alloc_matrix(g.shape[0], g.shape[1], device)
+                    out.copy_(g)
+                    full[m].append(out)
+        return full, ks, nsegs
+
+    def stage3(self, source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, device, timer):
+        ranges = frame_ranges(source.nframes, self.world)
+        f0, f1 = ranges[self.rank]
+        V, E, E_roi = svd.stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, device, timer,
+                                         frame_range=(f0, f1))
+        with timer("stage3.allgather"):
+            Vf = {m: [None if v is None else self.gather_rows(v, ranges) for v in V[m]] for m in mods}
+            Ef = self.gather_rows(E.t().contiguous(), ranges).t().contiguous()
+            Erf = self.gather_rows(E_roi.t().contiguous(), ranges).t().contiguous()
+        return Vf, Ef, Erf

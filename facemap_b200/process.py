@@ -91,7 +91,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     mods = [m for m, on in (("mot", motSVD), ("mov", movSVD)) if on]
     timer = svd.StageTimer(enabled=timing is not None)
     wall0 = time.perf_counter()
-    ws = svd.SvdWorkspace(dev, eig_fp32=eig_fp32, gemm_impl=gemm_impl)
+    ws = svd.SvdWorkspace(dev, eig_fp32=eig_fp32, gemm_impl=gemm_impl, timer=timer)
 
     # ---- stage 1 ----
     if dist is None or dist.world == 1:

@@ -67,25 +67,57 @@ class StageTimer:
         return out
 
 
+# tcgen05 accumulates in float32 with truncation: every MMA into a running sum loses up to one ulp
+# of it, always in the same direction, so the relative bias grows with the length of the K chain.
+# Contractions are therefore cut into short chains (split-K) that are reduced exactly in float64.
+KCHAIN_GRAM = 640     # Gram matrices feed an eigensolve: keep the bias ~1e-5 of an entry
+KCHAIN_GEMM = 2400    # projections / left vectors: ~3e-5, far inside the 1e-3 trace tolerance
+
+
 def _gram_ksplit(n, kdim):
-    """split-K factor for an n x n upper-triangular Gram over `kdim`: enough CTAs for ~2 waves,
-    at least 512 K elements per split."""
+    """split-K factor for an n x n upper-triangular Gram over `kdim`: K chains of <= KCHAIN_GRAM and
+    at least ~2 waves of CTAs."""
     mt, nt = math.ceil(n / 128), math.ceil(n / 256)
     tiles = sum(1 for i in range(mt) for j in range(nt) if (j + 1) * 256 - 1 >= i * 128)
-    want = math.ceil(2 * NUM_SMS / max(tiles, 1))
-    return int(max(1, min(want, kdim // 512 if kdim >= 1024 else 1, 64)))
+    want = max(math.ceil(kdim / KCHAIN_GRAM), math.ceil(2 * NUM_SMS / max(tiles, 1)))
+    return int(max(1, min(want, math.ceil(kdim / 32), 64)))
+
+
+def _gemm_ksplit(kdim):
+    return int(max(1, math.ceil(kdim / KCHAIN_GEMM)))
 
 
 class SvdWorkspace:
     """Reusable device buffers for the Gram -> eigensolve -> left-vector sequence."""
 
-    def __init__(self, device, eig_fp32=False, gemm_impl=0):
+    def __init__(self, device, eig_fp32=False, gemm_impl=0, timer=None):
         self.device = device
+        self.timer = timer if timer is not None else StageTimer(enabled=False)
         self.solver = K.Solver()
         self.eig_fp32 = eig_fp32
         self.gemm_impl = gemm_impl
         self._ws = None
         self._bufs = {}
+
+    def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm"):
+        """C = rscale * (A @ B^T) + rbias with K chains of <= KCHAIN_GEMM reduced in float64."""
+        ksplit = _gemm_ksplit(A.shape[1])
+        if ksplit == 1:
+            with self.timer(label + ".mma"):
+                K.gemm_tn(A, B, C_out, rscale=rscale, rbias=rbias, impl=self.gemm_impl)
+            return
+        M, N = A.shape[0], B.shape[0]
+        ld = max(32, K.round_up(N, 32))
+        need = ksplit * M * ld
+        buf = self._bufs.get("splitk")
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(need, dtype=torch.float32, device=self.device)
+            self._bufs["splitk"] = buf
+        part = buf[:need].view(ksplit, M, ld)
+        with self.timer(label + ".mma"):
+            K.gemm_tn(A, B, ksplit=ksplit, workspace=part, impl=self.gemm_impl)
+        with self.timer(label + ".reduce"):
+            K.splitk_reduce(part, ksplit, C_out, rscale=rscale, rbias=rbias)
 
     def workspace(self, ksplit, n):
         ld = max(32, K.round_up(n, 32))
@@ -113,11 +145,12 @@ def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
         mean = K.row_means(X)
     ksplit = _gram_ksplit(n, p)
     part = ws.workspace(ksplit, n)
-    with timer(label + ".gram"):
+    with timer(label + ".gram.mma"):
         if ksplit > 1:
             K.gemm_tn(X, X, ksplit=ksplit, workspace=part, upper_only=True, impl=ws.gemm_impl)
         else:
             K.gemm_tn(X, X, part[0], upper_only=True, impl=ws.gemm_impl)
+    with timer(label + ".gram.assemble"):
         G = K.gram_assemble(part, ksplit, n, mean, p, True)
     with timer(label + ".syevd"):
         lam = ws.solver.syevd(G, use_fp32=ws.eig_fp32)
@@ -132,10 +165,10 @@ def chunk_components(ws, X, k, out_Yt, timer, label="chunk"):
     (facemap/process.py:246-251; ROI variant :213-242)."""
     n, p = X.shape
     Wt, _, rbias, _ = gram_eig(ws, X, k, timer, False, label)
-    with timer(label + ".left"):
+    with timer(label + ".transpose"):
         Xt = ws.matrix(label + ".Xt", p, n)
         K.transpose(X, Xt)
-        K.gemm_tn(Wt, Xt, out_Yt, rbias=rbias, impl=ws.gemm_impl)
+    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left")
 
 
 def merge_components(ws, Yt, k, timer, label="merge"):
@@ -143,11 +176,12 @@ def merge_components(ws, Yt, k, timer, label="merge"):
     Returns (Ut [k, p], U [p, k], sval [k])."""
     c, p = Yt.shape
     Wt, sval, rbias, rscale = gram_eig(ws, Yt, k, timer, True, label)
-    with timer(label + ".left"):
+    with timer(label + ".transpose"):
         Y = ws.matrix(label + ".Y", p, c)
         K.transpose(Yt, Y)
-        Ut = K.alloc_matrix(k, p, Yt.device)
-        K.gemm_tn(Wt, Y, Ut, rscale=rscale, rbias=rbias, impl=ws.gemm_impl)
+    Ut = K.alloc_matrix(k, p, Yt.device)
+    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left")
+    with timer(label + ".transpose"):
         U = torch.empty((p, k), dtype=torch.float32, device=Yt.device)
         K.transpose(Ut, U)
     return Ut, U, sval
@@ -416,13 +450,12 @@ def stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, d
             Uts = masks[m][0]
             Xm = X[m][:filled]
             if fullSVD and Uts[0] is not None:
-                with timer("stage3.project"):
-                    K.gemm_tn(Xm, Uts[0], V[m][0][o:o + filled], impl=ws.gemm_impl)
+                ws.gemm(Xm, Uts[0], V[m][0][o:o + filled], label="stage3.project")
             for j, (v, y0, y1, x0, x1) in enumerate(geo.mot_rois):
                 for r0 in range(0, filled, 32768):
                     r1 = min(filled, r0 + 32768)
                     Xr = ws.matrix("X3roi", r1 - r0, geo.roi_npix[j])
-                    with timer("stage3.roi"):
+                    with timer("stage3.roi_gather"):
                         K.gather_roi(Xm[r0:r1], r1 - r0, geo.col0[v], int(geo.Lxb[v]), (y0, y1, x0, x1), Xr)
-                        K.gemm_tn(Xr, Uts[1 + j], V[m][1 + j][o + r0:o + r1], impl=ws.gemm_impl)
+                    ws.gemm(Xr, Uts[1 + j], V[m][1 + j][o + r0:o + r1], label="stage3.roi_project")
     return V, E, E_roi

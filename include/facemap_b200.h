@@ -101,6 +101,14 @@ int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, 
                float* C, int64_t ldc, const float* rscale, const float* rbias,
                int ksplit, float* workspace, int64_t ldw, int upper_only, int impl, void* stream);
 
+/*
+ * Reduction of split-K partials: C[m,n] = rscale[m] * sum_s part[s,m,n] + rbias[m], summed in
+ * float64.  tcgen05 accumulates in float32 with truncation, so long contractions are cut into
+ * short K chains (fm_gemm_tn with ksplit > 1) and reduced exactly here.
+ */
+int fm_splitk_reduce(const float* part, int ksplit, int M, int N, int64_t ldw, const float* rscale,
+                     const float* rbias, float* C, int64_t ldc, void* stream);
+
 /* bytes of workspace fm_gemm_tn needs for (M, ldw, ksplit). */
 int64_t fm_gemm_workspace_bytes(int M, int64_t ldw, int ksplit);
 
@@ -124,6 +132,8 @@ typedef struct fm_solver fm_solver;
 int fm_solver_create(fm_solver** out);
 int fm_solver_destroy(fm_solver* s);
 int fm_syevd(fm_solver* s, double* G, int n, double* lam, int use_fp32, void* stream);
+/* `batch` matrices stored back to back (cusolverDnXsyevBatched); lam is [batch, n]. */
+int fm_syevd_batched(fm_solver* s, double* G, int n, int batch, double* lam, void* stream);
 
 /*
  * Top-k extraction with the reference's sign rule (sklearn/utils/extmath.py:924-982,

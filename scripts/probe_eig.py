@@ -1,17 +1,44 @@
-"""GPU probe: cuSOLVER syevd timings (fp64 vs fp32) at the path's sizes."""
-import sys, os, time
+"""GPU probe: cuSOLVER syevd timings at the path's sizes: serial, batched, multi-stream."""
+import sys, os, time, threading
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from facemap_b200 import kernels as K
 dev = torch.device("cuda", 0)
 s = K.Solver()
-for n in (999, 3750):
-    X = torch.randn(n, 4000, device=dev, dtype=torch.float64)
-    G0 = X @ X.T
-    for fp32 in (False, True):
-        for rep in range(3):
-            G = G0.clone(); torch.cuda.synchronize(); t = time.perf_counter()
-            lam = s.syevd(G, use_fp32=fp32); torch.cuda.synchronize(); dt = time.perf_counter() - t
-        ref = torch.linalg.eigvalsh(G0)
-        print(f"syevd n={n} fp32={fp32}: {dt*1e3:.1f} ms, max rel lam err {float(((lam-ref).abs()/ref.abs().max()).max()):.2e}", flush=True)
-        t = time.perf_counter(); torch.linalg.eigh(G0.float() if fp32 else G0); torch.cuda.synchronize(); print("   torch.linalg.eigh:", round((time.perf_counter()-t)*1e3,1), "ms")
+n, B = 999, 15
+X = torch.randn(B, n, 4000, device=dev, dtype=torch.float64)
+G0 = X @ X.transpose(1, 2)
+ref = torch.linalg.eigvalsh(G0[3])
+for rep in range(2):
+    G = G0.clone(); torch.cuda.synchronize(); t = time.perf_counter()
+    lams = [s.syevd(G[i]) for i in range(B)]
+    torch.cuda.synchronize(); print(f"serial {B} x syevd({n}) fp64: {(time.perf_counter()-t)*1e3:.1f} ms", flush=True)
+try:
+    for rep in range(2):
+        G = G0.clone(); torch.cuda.synchronize(); t = time.perf_counter()
+        lam = s.syevd_batched(G)
+        torch.cuda.synchronize(); print(f"batched {B} x syev({n}) fp64: {(time.perf_counter()-t)*1e3:.1f} ms  lam err {float((lam[3]-ref).abs().max()/ref.abs().max()):.2e}", flush=True)
+    # eigenvector check: G0[3] v = lam v for the top one
+    v = G[3][n - 1]; print("  top eigvec residual", float((G0[3] @ v - lam[3][n - 1] * v).norm() / lam[3][n - 1]))
+except Exception as e:
+    print("batched failed:", e)
+# multi-stream / multi-thread: cusolver calls release the GIL (ctypes), one solver + stream per thread
+for nthreads in (2, 4, 8):
+    solvers = [K.Solver() for _ in range(nthreads)]
+    streams = [torch.cuda.Stream() for _ in range(nthreads)]
+    G = G0.clone(); torch.cuda.synchronize()
+    def work(tid):
+        with torch.cuda.stream(streams[tid]):
+            for i in range(tid, B, nthreads):
+                solvers[tid].syevd(G[i])
+    for rep in range(2):
+        G = G0.clone(); torch.cuda.synchronize(); t = time.perf_counter()
+        th = [threading.Thread(target=work, args=(i,)) for i in range(nthreads)]
+        [x.start() for x in th]; [x.join() for x in th]
+        torch.cuda.synchronize(); dt = time.perf_counter() - t
+    print(f"{nthreads} threads/streams {B} x syevd({n}) fp64: {dt*1e3:.1f} ms", flush=True)
+n = 3750
+X = torch.randn(n, 6000, device=dev, dtype=torch.float64); G0 = X @ X.T
+for rep in range(2):
+    G = G0.clone(); torch.cuda.synchronize(); t = time.perf_counter(); s.syevd(G); torch.cuda.synchronize()
+    print(f"syevd({n}) fp64: {(time.perf_counter()-t)*1e3:.1f} ms", flush=True)

@@ -1,0 +1,81 @@
+"""Multi-rank host logic on CPU (gloo, world_size 2 and 3): work assignment, the integer all-reduce
+of stage 1, the chunk-block all-gather of stage 2 and the row gather of stage 3."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from facemap_b200 import parallel
+
+
+def test_assignments_cover_everything_once():
+    for world in (1, 2, 3, 4, 8):
+        for n in (1, 2, 10, 15):
+            got = sorted(i for r in parallel.assign_round_robin(n, world) for i in r)
+            assert got == list(range(n))
+        for N in (1, 499, 500, 501, 2300, 100000, 800000):
+            rg = parallel.frame_ranges(N, world)
+            assert rg[0][0] == 0 and rg[-1][1] == N and len(rg) == world
+            for (a, b), (c, d) in zip(rg[:-1], rg[1:]):
+                assert b == c and a <= b
+                assert b % 500 == 0 or b == N          # boundaries sit on the reference's 500-frame grid
+    assert parallel.frame_ranges(100000, 8) == [(i * 12500, (i + 1) * 12500) for i in range(8)]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = parallel.Shard()
+        p, nseg = 37, 10
+        rng = np.random.RandomState(123)
+        sums_all = rng.randint(0, 10 ** 9, size=(nseg, 2, p)).astype(np.int64)
+        mine = parallel.assign_round_robin(nseg, world)[rank]
+        local = {i: (torch.from_numpy(sums_all[i, 0]), torch.from_numpy(sums_all[i, 1]), 100) for i in mine}
+        full = sh.allreduce_segment_sums(local, nseg, p, torch.device("cpu"))
+        ok1 = all(np.array_equal(full[i][0].numpy(), sums_all[i, 0]) and np.array_equal(full[i][1].numpy(), sums_all[i, 1])
+                  and full[i][2] == 100 for i in range(nseg))
+        # stage-2 block gather: 7 chunks of k=3 rows over `world` ranks
+        nsegs, k, cols = 7, 3, 11
+        blocks = rng.rand(nsegs * k, cols).astype(np.float32)
+        mine = parallel.assign_round_robin(nsegs, world)[rank]
+        loc = torch.from_numpy(np.concatenate([blocks[c * k:(c + 1) * k] for c in mine], axis=0)) if mine \
+            else torch.zeros((0, cols))
+        ok2 = np.array_equal(sh.gather_chunk_blocks(loc, k, nsegs).numpy(), blocks)
+        # stage-3 row gather
+        N = 2300
+        rows = rng.rand(N, 5).astype(np.float32)
+        ranges = parallel.frame_ranges(N, world)
+        a, b = ranges[rank]
+        ok3 = np.array_equal(sh.gather_rows(torch.from_numpy(rows[a:b]), ranges).numpy(), rows)
+        out[rank] = (ok1, ok2, ok3)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shard_collectives_gloo(world):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    out = mgr.dict()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(120)
+        assert pr.exitcode == 0
+    assert len(out) == world and all(all(v) for v in out.values()), dict(out)

@@ -88,7 +88,7 @@ def test_gram_ksplit_and_batch_sizes():
 
     assert svd._gram_ksplit(999, 19200) >= 8
     assert svd._gram_ksplit(3750, 19200) >= 1
-    assert svd._gram_ksplit(999, 300) == 1
+    assert 1 <= svd._gram_ksplit(999, 300) <= 10
     r = svd.projection_rows_per_batch(19200, 500)
     assert r % 128 == 0 and r * 19200 * 4 <= 6 << 30
     assert svd.projection_rows_per_batch(1310720, 500) % 128 == 0
