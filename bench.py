@@ -93,7 +93,7 @@ def make_sources(rank, world, device, want_host):
     asked for (the SVD sample chunks of stage 1/2) on first use — the warm-up steps fill that cache."""
     import torch
 
-    from facemap_b200.frames import FrameSource
+    from facemap_b200.frames import DeviceFrameCache, FrameSource, _H2DPipe
     from facemap_b200.synth import SynthVideo
 
     total = world * FRAMES_PER_GPU
@@ -113,6 +113,8 @@ def make_sources(rank, world, device, want_host):
             self.on_host = on_host
             self.cache = {}
             self.h2d = 0
+            self.pipe = _H2DPipe()
+            self.dcache = DeviceFrameCache()
             self.base = resident
             if on_host:
                 self.base = torch.empty(resident.shape, dtype=torch.uint8).pin_memory()
@@ -129,13 +131,30 @@ def make_sources(rank, world, device, want_host):
                 self.cache[key] = fr.cpu().pin_memory() if self.on_host else fr
             return self.cache[key]
 
+        def plan_access(self, priority, home, dev):
+            if self.on_host:
+                self.dcache.drop()
+                a, b = max(home[0], lo), min(home[1], hi)       # the part of `home` this rank holds in host memory
+                before = self.dcache.bytes
+                self.dcache.start(lambda v, x, y: self.base[x - lo:y - lo], [(H, W)], priority, (a, b), dev)
+                self.h2d += self.dcache.bytes - before
+
+        def prefetch(self, t0, t1, dev):
+            if self.on_host:
+                a, b = self.clamp(t0, t1)
+                if not self.dcache.covers(a, b):
+                    self.pipe.issue((a, b), [self._range(a, b)], dev)
+
         def fetch(self, t0, t1, dev):
             a, b = self.clamp(t0, t1)
-            fr = self._range(a, b)
-            if self.on_host:
-                self.h2d += fr.numel()
-                fr = fr.to(dev, non_blocking=True)
-            return [fr]
+            if not self.on_host:
+                return [self._range(a, b)]
+            if self.dcache.covers(a, b):
+                return self.dcache.get(a, b)
+            if (a, b) not in self.pipe.pending:
+                self.pipe.issue((a, b), [self._range(a, b)], dev)
+            self.h2d += (b - a) * H * W
+            return self.pipe.take((a, b))
 
         def h2d_bytes(self, nframes):
             return int(nframes) * H * W if self.on_host else 0

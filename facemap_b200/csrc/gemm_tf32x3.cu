@@ -135,7 +135,10 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
-template <int BN, int BK>
+// HI_INPLACE: overwrite the raw tile with its TF32-truncated value.  kind::tf32 reads only the top
+// 19 bits of each operand word, so the raw tile already IS the hi operand; the rewrite is kept as
+// a template option (impl 5 in fm_gemm_tn) to let the tests prove the two are bit-identical.
+template <int BN, int BK, bool HI_INPLACE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const GemmParams p) {
@@ -246,7 +249,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
         h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
         l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-        hi[v] = h;
+        if constexpr (HI_INPLACE) hi[v] = h;
         lo[v] = l;
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -394,7 +397,7 @@ static int make_map(CUtensorMap* map, const float* base, int64_t ld, int rows, i
   return FM_OK;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool HI_INPLACE>
 static int launch_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const GemmParams& p, cudaStream_t st) {
   CUtensorMap ta, tb;
   int rc;
@@ -403,12 +406,12 @@ static int launch_tc(const float* A, int64_t lda, const float* B, int64_t ldb, c
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, BK, HI_INPLACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     GemmCfg<BN, BK>::SMEM_BYTES);
   });
   FM_CUDA_TRY(attr_err);
   dim3 grid((unsigned)cdiv(p.N, BN), (unsigned)cdiv(p.M, BM), (unsigned)p.ksplit);
-  gemm_tf32x3_kernel<BN, BK><<<grid, GEMM_THREADS, GemmCfg<BN, BK>::SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_tf32x3_kernel<BN, BK, HI_INPLACE><<<grid, GEMM_THREADS, GemmCfg<BN, BK>::SMEM_BYTES, st>>>(ta, tb, p);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }
@@ -442,16 +445,18 @@ extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
     FM_LAUNCH_CHECK();
     return FM_OK;
   }
-  FM_REQUIRE(impl == 0 || (impl >= 2 && impl <= 4), "fm_gemm_tn: unknown impl %d", impl);
+  FM_REQUIRE(impl == 0 || (impl >= 2 && impl <= 6), "fm_gemm_tn: unknown impl %d", impl);
   FM_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
              "fm_gemm_tn: TMA operands need 16-byte aligned bases and ld %% 4 == 0 (lda=%lld ldb=%lld)",
              (long long)lda, (long long)ldb);
   // impl 0: product configuration; 2..4: tile-shape variants kept for tuning runs
   switch (impl) {
-    case 2: return launch_tc<256, 32>(A, lda, B, ldb, p, st);
-    case 3: return launch_tc<128, 32>(A, lda, B, ldb, p, st);
-    case 4: return launch_tc<128, 16>(A, lda, B, ldb, p, st);
+    case 2: return launch_tc<256, 32, true>(A, lda, B, ldb, p, st);
+    case 3: return launch_tc<128, 32, true>(A, lda, B, ldb, p, st);
+    case 4: return launch_tc<128, 16, true>(A, lda, B, ldb, p, st);
+    case 5: return launch_tc<256, 16, false>(A, lda, B, ldb, p, st);
+    case 6: return launch_tc<128, 32, false>(A, lda, B, ldb, p, st);
     default: break;
   }
-  return (N > 128) ? launch_tc<256, 16>(A, lda, B, ldb, p, st) : launch_tc<128, 32>(A, lda, B, ldb, p, st);
+  return (N > 128) ? launch_tc<256, 16, true>(A, lda, B, ldb, p, st) : launch_tc<128, 32, true>(A, lda, B, ldb, p, st);
 }

@@ -34,6 +34,15 @@ class FrameSource:
         """list (one per view) of contiguous uint8 CUDA tensors [t1'-t0', H, W]."""
         raise NotImplementedError
 
+    def prefetch(self, t0, t1, device):
+        """Hint that [t0, t1) is the next range to be fetched (host sources start the H2D copy on a
+        side stream so it overlaps the kernels of the current range)."""
+
+    def plan_access(self, priority, home, device):
+        """Announce the access pattern of one pass: `priority` = the (t0, t1) ranges stage 1 and 2
+        will read, in order; `home` = the contiguous range stage 3 will sweep.  Host sources use it
+        to upload every frame ONCE, sample ranges first, while the kernels already run."""
+
     def h2d_bytes(self, nframes):
         """bytes that cross PCIe to deliver `nframes` frames (0 for device-resident sources)."""
         return 0
@@ -60,9 +69,108 @@ class DeviceArraySource(FrameSource):
         return [v[a:b] for v in self.views]
 
 
+class _H2DPipe:
+    """Asynchronous host->device copies on a private stream, handed over to the consumer stream
+    with an event (double buffering comes from the caching allocator + record_stream)."""
+
+    def __init__(self):
+        self.stream = None
+        self.pending = {}
+
+    def issue(self, key, host_tensors, device):
+        if key in self.pending:
+            return
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device)
+        with torch.cuda.stream(self.stream):
+            devs = [h.to(device, non_blocking=True) for h in host_tensors]
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.pending[key] = (devs, ev)
+
+    def take(self, key):
+        devs, ev = self.pending.pop(key)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for d in devs:
+            d.record_stream(cur)
+        return devs
+
+
+class DeviceFrameCache:
+    """One-pass upload of a contiguous `home` frame range into HBM in pieces of `piece` frames on
+    a private copy stream: the pieces the SVD sample ranges touch go first, the rest follows in
+    frame order, and readers wait on per-piece events — so the PCIe transfer of the whole video
+    overlaps stages 1-3 and every frame crosses the bus once."""
+
+    def __init__(self, piece=1024, mem_fraction=0.55):
+        self.piece = piece
+        self.mem_fraction = mem_fraction
+        self.stream = None
+        self.home = None
+        self.bufs = None
+        self.events = None
+        self.bytes = 0
+
+    def fits(self, nbytes, device):
+        free, _ = torch.cuda.mem_get_info(device)
+        return nbytes <= self.mem_fraction * free
+
+    def start(self, host_slice, shapes, priority, home, device):
+        """host_slice(view, a, b) -> pinned uint8 [b-a, H, W]; shapes = [(H, W)] per view."""
+        lo, hi = home
+        if hi <= lo:
+            return False
+        nbytes = (hi - lo) * sum(h * w for h, w in shapes)
+        self.bufs = self.events = self.home = None            # drop the previous pass first
+        if not self.fits(nbytes, device):
+            return False
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device)
+        bufs = [torch.empty((hi - lo, h, w), dtype=torch.uint8, device=device) for h, w in shapes]
+        npieces = -(-(hi - lo) // self.piece)
+        order, seen = [], set()
+        for a, b in priority:
+            a, b = max(a, lo), min(b, hi)
+            if a >= b:
+                continue
+            for pc in range((a - lo) // self.piece, (b - 1 - lo) // self.piece + 1):
+                if pc not in seen:
+                    seen.add(pc)
+                    order.append(pc)
+        order += [pc for pc in range(npieces) if pc not in seen]
+        events = [None] * npieces
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            for pc in order:
+                a, b = lo + pc * self.piece, min(hi, lo + (pc + 1) * self.piece)
+                for v in range(len(shapes)):
+                    bufs[v][a - lo:b - lo].copy_(host_slice(v, a, b), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                events[pc] = ev
+        self.bufs, self.events, self.home = bufs, events, (lo, hi)
+        self.bytes += nbytes
+        return True
+
+    def covers(self, a, b):
+        return self.home is not None and a >= self.home[0] and b <= self.home[1]
+
+    def get(self, a, b):
+        lo = self.home[0]
+        cur = torch.cuda.current_stream()
+        for pc in range((a - lo) // self.piece, (b - 1 - lo) // self.piece + 1):
+            cur.wait_event(self.events[pc])
+        return [buf[a - lo:b - lo] for buf in self.bufs]
+
+    def drop(self):
+        self.bufs = self.events = self.home = None
+
+
 class HostArraySource(FrameSource):
-    """Views in host memory.  Each fetch copies through a pinned staging buffer (allocated once
-    per view at the largest request seen) with a non-blocking H2D copy on the current stream."""
+    """Views in host memory.  The arrays are page-locked in place (cudaHostRegister) so that every
+    fetch is a direct DMA from the caller's buffer; if registration is refused the copy goes
+    through a pinned staging buffer.  `prefetch` overlaps the next copy with the current kernels."""
 
     def __init__(self, views, block_frames=None, pin=True):
         self.views = []
@@ -77,30 +185,77 @@ class HostArraySource(FrameSource):
         self.Ly = [int(v.shape[1]) for v in self.views]
         self.Lx = [int(v.shape[2]) for v in self.views]
         self.block_frames = list(block_frames) if block_frames is not None else [self.nframes]
-        self._pinned = all(v.is_pinned() for v in self.views)
-        self._stage = [None] * len(self.views)
+        self._registered = []
+        self._pinned = [v.is_pinned() for v in self.views]
+        self._stage = {}
         self._pin = pin
+        self._pipe = _H2DPipe()
+        self._cache = DeviceFrameCache()
+        self.h2d = 0
+
+    def plan_access(self, priority, home, device):
+        self._ensure_pinned()
+        self._cache.drop()
+        if all(self._pinned):
+            before = self._cache.bytes
+            self._cache.start(lambda v, a, b: self.views[v][a:b], list(zip(self.Ly, self.Lx)), priority, home, device)
+            self.h2d += self._cache.bytes - before
+
+    def _ensure_pinned(self):
+        """page-lock the caller's buffers in place (once, lazily: needs a CUDA context)."""
+        if not self._pin:
+            return
+        for i, v in enumerate(self.views):
+            if self._pinned[i] or v.numel() == 0:
+                continue
+            try:
+                rc = torch.cuda.cudart().cudaHostRegister(v.data_ptr(), v.numel(), 0)
+                ok = int(rc) == 0 if not isinstance(rc, tuple) else int(rc[0]) == 0
+            except Exception:
+                ok = False
+            if ok:
+                self._registered.append(v.data_ptr())
+                self._pinned[i] = True
+        self._pin = False
 
     def h2d_bytes(self, nframes):
         return int(nframes) * sum(h * w for h, w in zip(self.Ly, self.Lx))
 
-    def fetch(self, t0, t1, device):
-        a, b = self.clamp(t0, t1)
+    def _host_slices(self, a, b):
         out = []
         for i, v in enumerate(self.views):
             src = v[a:b]
-            if not self._pinned and self._pin:
-                st = self._stage[i]
-                if st is None or st.shape[0] < b - a:
-                    st = torch.empty((b - a,) + tuple(v.shape[1:]), dtype=torch.uint8).pin_memory()
-                    self._stage[i] = st
-                else:
-                    # the previous copy out of this staging buffer must have drained
-                    torch.cuda.current_stream().synchronize()
-                st[:b - a].copy_(src)
-                src = st[:b - a]
-            out.append(src.to(device, non_blocking=True))
+            if not self._pinned[i]:
+                st = torch.empty(tuple(src.shape), dtype=torch.uint8).pin_memory()   # staging (slow path)
+                st.copy_(src)
+                src = st
+            out.append(src)
         return out
+
+    def prefetch(self, t0, t1, device):
+        self._ensure_pinned()
+        a, b = self.clamp(t0, t1)
+        if not self._cache.covers(a, b):
+            self._pipe.issue((a, b), self._host_slices(a, b), device)
+
+    def fetch(self, t0, t1, device):
+        self._ensure_pinned()
+        a, b = self.clamp(t0, t1)
+        if self._cache.covers(a, b):
+            return self._cache.get(a, b)
+        if (a, b) not in self._pipe.pending:
+            self._pipe.issue((a, b), self._host_slices(a, b), device)
+        self.h2d += self.h2d_bytes(b - a)
+        return self._pipe.take((a, b))
+
+    def close(self):
+        self._cache.drop()
+        for ptr in self._registered:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(ptr)
+            except Exception:
+                pass
+        self._registered = []
 
 
 class VideoFileSource(FrameSource):

@@ -92,6 +92,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     timer = svd.StageTimer(enabled=timing is not None)
     wall0 = time.perf_counter()
     ws = svd.SvdWorkspace(dev, eig_fp32=eig_fp32, gemm_impl=gemm_impl, timer=timer)
+    source.plan_access(*svd.access_plan(source, dist), dev)
 
     # ---- stage 1 ----
     if dist is None or dist.world == 1:

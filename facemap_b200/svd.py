@@ -136,10 +136,8 @@ class SvdWorkspace:
         return buf[:need].view(max(rows, 1), ld)[:rows, :cols]
 
 
-def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
-    """Centred Gram of the rows of X [n, p], eigensolve, top-k.  Returns (Wt [k, n], sval, rbias,
-    rscale): the right singular vectors of X^T (sign-fixed), singular values, and the epilogue
-    terms for the left-vector GEMM."""
+def centred_gram(ws: SvdWorkspace, X, timer, label, out=None):
+    """mean over columns of every row of X [n, p] and the centred Gram  X X^T - p m m^T  (float64)."""
     n, p = X.shape
     with timer(label + ".colmean"):
         mean = K.row_means(X)
@@ -151,7 +149,16 @@ def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
         else:
             K.gemm_tn(X, X, part[0], upper_only=True, impl=ws.gemm_impl)
     with timer(label + ".gram.assemble"):
-        G = K.gram_assemble(part, ksplit, n, mean, p, True)
+        G = K.gram_assemble(part, ksplit, n, mean, p, True, out=out)
+    return mean, G
+
+
+def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
+    """Centred Gram of the rows of X [n, p], eigensolve, top-k.  Returns (Wt [k, n], sval, rbias,
+    rscale): the right singular vectors of X^T (sign-fixed), singular values, and the epilogue
+    terms for the left-vector GEMM."""
+    n, p = X.shape
+    mean, G = centred_gram(ws, X, timer, label)
     with timer(label + ".syevd"):
         lam = ws.solver.syevd(G, use_fp32=ws.eig_fp32)
     with timer(label + ".topk"):
@@ -160,15 +167,25 @@ def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
     return Wt, sval, rbias, rscale
 
 
-def chunk_components(ws, X, k, out_Yt, timer, label="chunk"):
-    """svdecon(X^T, k) of one chunk: writes (U S)^T = W^T X - (W^T m) 1^T into out_Yt [k, p]
-    (facemap/process.py:246-251; ROI variant :213-242)."""
+def left_components(ws, X, evec, lam, mean, k, out_Yt, timer, label):
+    """(U S)^T = W^T X - (W^T m) 1^T for the top-k eigenvectors (rows of `evec`) -> out_Yt [k, p]."""
     n, p = X.shape
-    Wt, _, rbias, _ = gram_eig(ws, X, k, timer, False, label)
+    with timer(label + ".topk"):
+        Wt = ws.matrix(label + ".Wt", k, n)
+        _, rbias, _ = K.topk_components(evec, lam, k, mean, Wt, want_scale=False)
     with timer(label + ".transpose"):
         Xt = ws.matrix(label + ".Xt", p, n)
         K.transpose(X, Xt)
     ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left")
+
+
+def chunk_components(ws, X, k, out_Yt, timer, label="chunk"):
+    """svdecon(X^T, k) of one chunk: writes (U S)^T = W^T X - (W^T m) 1^T into out_Yt [k, p]
+    (facemap/process.py:246-251; ROI variant :213-242)."""
+    mean, G = centred_gram(ws, X, timer, label)
+    with timer(label + ".syevd"):
+        lam = ws.solver.syevd(G, use_fp32=ws.eig_fp32)
+    left_components(ws, X, G, lam, mean, k, out_Yt, timer, label)
 
 
 def merge_components(ws, Yt, k, timer, label="merge"):
@@ -206,6 +223,21 @@ class Geometry:
         self.rois_on_view = [[j for j, r in enumerate(self.mot_rois) if r[0] == v] for v in range(len(Ly))]
 
 
+def access_plan(source, dist=None):
+    """(priority ranges, home range) of one pass for this rank: the stage-1 segments and stage-2
+    chunks it will read, in order, and the frame range it sweeps in stage 3 (with its halo)."""
+    from .parallel import assign_round_robin, frame_ranges
+
+    N = source.nframes
+    rank, world = (0, 1) if dist is None else (dist.rank, dist.world)
+    nt1, tf1 = stage1_plan(N, source.block_frames)
+    nt2, nsegs, _, tf2 = stage2_plan(N)
+    pri = [(int(tf1[i]), int(tf1[i]) + nt1) for i in assign_round_robin(len(tf1), world)[rank]]
+    pri += [(int(tf2[i]), int(tf2[i]) + nt2) for i in assign_round_robin(nsegs, world)[rank]]
+    f0, f1 = frame_ranges(N, world)[rank]
+    return pri, (max(0, f0 - 1), f1)
+
+
 # ---------------------------------------------------------------------------------------------
 # stage 1
 # ---------------------------------------------------------------------------------------------
@@ -229,10 +261,13 @@ def stage1_means(source, geo: Geometry, device, timer, segments=None):
     nseg = len(tf)
     todo = range(nseg) if segments is None else segments
     sums = {}
-    for i in todo:
+    todo = list(todo)
+    for pos, i in enumerate(todo):
         t = int(tf[i])
         with timer("stage1.fetch"):
             frames = source.fetch(t, t + nt0, device)
+            if pos + 1 < len(todo):
+                source.prefetch(int(tf[todo[pos + 1]]), int(tf[todo[pos + 1]]) + nt0, device)
         tsb = torch.zeros(p, dtype=torch.int64, device=device)
         tsa = torch.zeros(p, dtype=torch.int64, device=device)
         with timer("stage1.bin"):
@@ -298,37 +333,62 @@ def _bin_chunk(frames, geo, avgframe, avgmotion, mods, X, prev=None, last=None, 
     return rows
 
 
-def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer, chunks=None):
-    """Per-chunk components.  Returns Yt[m][idx] = list over chunks of [k, p_idx] blocks
-    (idx 0 = full frame, 1+j = motion ROI j), for the chunk indices in `chunks` (default all)."""
+def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer, chunks=None,
+                  x_budget_bytes=24 << 30):
+    """Per-chunk components.  Returns Yt[m][idx] = [n_chunks * k, p_idx] stacked blocks (idx 0 = full
+    frame, 1+j = motion ROI j) for the chunk indices in `chunks` (default all).
+
+    The chunks are processed in groups: K1 + centred Gram for every (chunk, modality, target) of the
+    group, ONE batched eigensolve for all of them (they share n = nt0 - 1), then the left-vector
+    GEMMs.  A group holds as many chunks as fit `x_budget_bytes` of chunk matrices."""
     N = source.nframes
     nt0, nsegs, nc, tf = stage2_plan(N)
     nroi = len(geo.mot_rois)
     todo = list(range(nsegs)) if chunks is None else list(chunks)
     sizes = [geo.p] + geo.roi_npix
-    # one stacked buffer per (modality, target): rows = chunk-major blocks of k components
     ks = [min(nc, s) for s in sizes]
     Yt = {m: [K.alloc_matrix(len(todo) * ks[i], sizes[i], device) if (i > 0 or fullSVD) else None
               for i in range(1 + nroi)] for m in mods}
-    X = {m: ws.matrix("X." + m, nt0 - 1, geo.p) for m in mods}
-    for slot, ci in enumerate(todo):
-        t = int(tf[ci])
-        with timer("stage2.fetch"):
-            frames = source.fetch(t, t + nt0, device)
-        with timer("stage2.bin"):
-            rows = _bin_chunk(frames, geo, avgframe, avgmotion, mods, X)
-        for m in mods:
-            Xm = X[m][:rows]
-            for j, (v, y0, y1, x0, x1) in enumerate(geo.mot_rois):       # process.py:213-242
-                pr = sizes[1 + j]
-                Xr = ws.matrix("Xroi", rows, pr)
-                with timer("stage2.roi_gather"):
-                    K.gather_roi(Xm, rows, geo.col0[v], int(geo.Lxb[v]), (y0, y1, x0, x1), Xr)
-                kk = ks[1 + j]
-                chunk_components(ws, Xr, kk, Yt[m][1 + j][slot * kk:(slot + 1) * kk], timer, "stage2.roi")
-            if fullSVD:                                                    # process.py:246-259
-                kk = ks[0]
-                chunk_components(ws, Xm, kk, Yt[m][0][slot * kk:(slot + 1) * kk], timer, "stage2.chunk")
+    n = nt0 - 1
+    if n < 1 or not todo:
+        return Yt, ks, nsegs
+    targets = ([0] if fullSVD else []) + list(range(1, 1 + nroi))
+    per_chunk = len(mods) * 4 * n * (K.round_up(geo.p, 32) + sum(K.round_up(s, 32) for s in geo.roi_npix))
+    group = int(max(1, min(len(todo), x_budget_bytes // max(per_chunk, 1))))
+    for g0 in range(0, len(todo), group):
+        slots = list(range(g0, min(len(todo), g0 + group)))
+        jobs = []            # (slot, modality, target, X view, mean, label)
+        G = torch.empty((len(slots) * len(mods) * len(targets), n, n), dtype=torch.float64, device=device)
+        for gi, slot in enumerate(slots):
+            t = int(tf[todo[slot]])
+            with timer("stage2.fetch"):
+                frames = source.fetch(t, t + nt0, device)
+                if slot + 1 < len(todo):
+                    source.prefetch(int(tf[todo[slot + 1]]), int(tf[todo[slot + 1]]) + nt0, device)
+            X = {m: ws.matrix(f"X.{m}.{gi}", n, geo.p) for m in mods}
+            with timer("stage2.bin"):
+                rows = _bin_chunk(frames, geo, avgframe, avgmotion, mods, X)
+            assert rows == n
+            for m in mods:
+                for idx in targets:
+                    if idx == 0:
+                        Xt, label = X[m], "stage2.chunk"                       # process.py:246-259
+                    else:                                                      # process.py:213-242
+                        v, y0, y1, x0, x1 = geo.mot_rois[idx - 1]
+                        Xt = ws.matrix(f"Xroi.{m}.{idx}.{gi}", n, sizes[idx])
+                        with timer("stage2.roi_gather"):
+                            K.gather_roi(X[m], n, geo.col0[v], int(geo.Lxb[v]), (y0, y1, x0, x1), Xt)
+                        label = "stage2.roi"
+                    mean, _ = centred_gram(ws, Xt, timer, label, out=G[len(jobs)])
+                    jobs.append((slot, m, idx, Xt, mean, label))
+        with timer("stage2.chunk.syevd"):
+            if ws.eig_fp32 or len(jobs) == 1:
+                lam = torch.stack([ws.solver.syevd(G[i], use_fp32=ws.eig_fp32) for i in range(len(jobs))])
+            else:
+                lam = ws.solver.syevd_batched(G)
+        for i, (slot, m, idx, Xt, mean, label) in enumerate(jobs):
+            kk = ks[idx]
+            left_components(ws, Xt, G[i], lam[i], mean, kk, Yt[m][idx][slot * kk:(slot + 1) * kk], timer, label)
     return Yt, ks, nsegs
 
 
@@ -406,18 +466,30 @@ def stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, d
             K.bin_motion(fr, geo.sbin, last_sum=carry[flip][v])
         have_carry = True
 
-    t = f0
+    # fetch plan: GEMM batches of <= rows_batch rows, each filled by several fetches
+    batches, t, have = [], f0, have_carry
     while t < f1:
-        # fill one GEMM batch with several fetches
+        fetches, filled = [], 0
+        while t < f1 and filled < rows_batch:
+            n = min(fetch_frames, f1 - t, rows_batch - filled + (0 if have else 1))
+            rows = n if have else n - 1
+            fetches.append((t, n, rows, have))
+            filled += rows
+            t += n
+            have = True
+        batches.append(fetches)
+    flat = [f for b in batches for f in b]
+    pos = 0
+    for fetches in batches:
         filled = 0
         row_frame0 = None
-        while t < f1 and filled < rows_batch:
-            nfetch = min(fetch_frames, f1 - t, rows_batch - filled + (0 if have_carry else 1))
+        for (t, n, rows, have) in fetches:
             with timer("stage3.fetch"):
-                frames = source.fetch(t, t + nfetch, device)
-            T = int(frames[0].shape[0])
-            rows = T if have_carry else T - 1
-            first_frame = t if have_carry else t + 1
+                frames = source.fetch(t, t + n, device)
+                if pos + 1 < len(flat):
+                    source.prefetch(flat[pos + 1][0], flat[pos + 1][0] + flat[pos + 1][1], device)
+            pos += 1
+            first_frame = t if have else t + 1
             if row_frame0 is None:
                 row_frame0 = first_frame
             with timer("stage3.bin"):
@@ -432,7 +504,7 @@ def stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, d
                         # ROI energies of one view must be contiguous [n_on_view, rows]
                         roi_e[v] = torch.zeros((len(js), max(rows, 1)), dtype=torch.int64, device=device)
                 _bin_chunk(frames, geo, avgframe, avgmotion, mods if rows > 0 else [], Xv,
-                           prev=carry[flip] if have_carry else None, last=carry[1 - flip],
+                           prev=carry[flip] if have else None, last=carry[1 - flip],
                            energy=energy if rows > 0 else None,
                            roi_energy=roi_e if (nroi and rows > 0) else None)
                 if nroi and rows > 0:
@@ -440,9 +512,7 @@ def stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, d
                         for q, j in enumerate(geo.rois_on_view[v]):
                             E_roi[j, o:o + rows] = roi_e[v][q, :rows]
             flip = 1 - flip
-            have_carry = True
             filled += rows
-            t += T
         if filled == 0:
             continue
         o = row_frame0 - f0

@@ -1,0 +1,41 @@
+"""Multi-GPU check (torchrun, one rank per GPU): the sharded path against the single-GPU path on the
+same video.  Integer-stage outputs must be bit-identical; SVD outputs equal to float32 round-off."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+from facemap_b200 import process
+from facemap_b200.frames import DeviceArraySource
+from facemap_b200.parallel import Shard
+from facemap_b200.synth import SynthVideo
+from tests.helpers import motion_roi, subspace_sin
+
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+sh = Shard()
+ok = True
+for (H, W, N, sbin, mov, rois) in [(96, 128, 5300, 2, False, None), (64, 96, 3100, 4, True, [motion_roi(0, 8, 56, 9, 80)])]:
+    v = torch.from_numpy(SynthVideo(H, W, N, seed=3).all_frames()).to(dev)
+    import copy
+    pd = process.process_source(DeviceArraySource([v]), sbin=sbin, motSVD=True, movSVD=mov, rois=copy.deepcopy(rois), dist=sh)
+    if rank == 0:
+        ps = process.process_source(DeviceArraySource([v]), sbin=sbin, motSVD=True, movSVD=mov, rois=copy.deepcopy(rois))
+        for key in ("avgframe", "avgmotion", "motion"):
+            for a, b in zip(pd[key], ps[key]):
+                same = np.array_equal(a, b); ok &= same
+                print(f"N={N} {key}: bit-identical {same}")
+        for sk, mk, vk in (("motSv", "motMask", "motSVD"), ("movSv", "movMask", "movSVD")):
+            if not len(ps[mk]):
+                continue
+            rel = float(np.abs(pd[sk] - ps[sk]).max() / ps[sk].max())
+            ang = max(subspace_sin(a[:, :10], b[:, :10]) for a, b in zip(pd[mk], ps[mk]))
+            tr = max(float(np.abs(np.abs(a[:, :5]) - np.abs(b[:, :5])).max() / np.abs(b[:, :5]).max()) for a, b in zip(pd[vk], ps[vk]))
+            good = rel < 1e-5 and ang < 1e-4 and tr < 1e-4
+            ok &= good
+            print(f"N={N} {sk}: rel {rel:.2e} angle(10) {ang:.2e} trace {tr:.2e} -> {'ok' if good else 'FAIL'}")
+    dist.barrier()
+if rank == 0:
+    print("DIST CHECK", "PASSED" if ok else "FAILED")
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)

@@ -42,3 +42,11 @@ X = torch.randn(n, 6000, device=dev, dtype=torch.float64); G0 = X @ X.T
 for rep in range(2):
     G = G0.clone(); torch.cuda.synchronize(); t = time.perf_counter(); s.syevd(G); torch.cuda.synchronize()
     print(f"syevd({n}) fp64: {(time.perf_counter()-t)*1e3:.1f} ms", flush=True)
+# batched API on the single merge-sized matrix
+try:
+    for rep in range(2):
+        G = G0.clone().unsqueeze(0).contiguous(); torch.cuda.synchronize(); t = time.perf_counter()
+        lam = s.syevd_batched(G); torch.cuda.synchronize()
+        print(f"XsyevBatched({n}) batch=1 fp64: {(time.perf_counter()-t)*1e3:.1f} ms", flush=True)
+except Exception as e:
+    print("batched 3750 failed:", e)
