@@ -39,3 +39,27 @@ extern "C" int fm_check_device(int dev) {
   }
   return FM_OK;
 }
+
+// Page-lock caller memory in place so H2D copies from it are true DMA.  A refused registration
+// (already registered, not lockable) is not an error of the pipeline: the sticky CUDA error is
+// cleared and the caller falls back to staged copies.
+extern "C" int fm_host_register(void* ptr, size_t bytes) {
+  using namespace fm;
+  FM_REQUIRE(ptr != nullptr && bytes > 0, "fm_host_register: bad args");
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaHostRegister refused: %s", cudaGetErrorString(e));
+    return FM_ERR_CUDA;
+  }
+  return FM_OK;
+}
+
+extern "C" int fm_host_unregister(void* ptr) {
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return FM_ERR_CUDA;
+  }
+  return FM_OK;
+}

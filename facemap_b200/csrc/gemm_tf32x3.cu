@@ -8,7 +8,8 @@
 //
 // One CTA computes a 128 x BN tile over one K range (split-K over blockIdx.z):
 //   warp 0        TMA producer: raw fp32 tiles of A (128x32) and B (BNx32) per stage
-//   warps 2..9    splitter: hi = x & 0xffffe000 (in place), lo = x - hi (second buffer), then
+//   warps 2..9    splitter: lo = x - (x & 0xffffe000) into a second buffer (kind::tf32 reads only the
+//                 top 19 bits of an operand word, so the raw tile itself is the hi operand), then
 //                 fence.proxy.async + arrive; afterwards the same warps run the epilogue
 //   warp 1        TMEM allocation and the single-thread MMA issue: per 8-wide K step
 //                 D += A_lo.B_hi ; D += A_hi.B_lo ; D += A_hi.B_hi   (fp32 accumulate in TMEM)
@@ -451,12 +452,12 @@ extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
              (long long)lda, (long long)ldb);
   // impl 0: product configuration; 2..4: tile-shape variants kept for tuning runs
   switch (impl) {
-    case 2: return launch_tc<256, 32, true>(A, lda, B, ldb, p, st);
-    case 3: return launch_tc<128, 32, true>(A, lda, B, ldb, p, st);
-    case 4: return launch_tc<128, 16, true>(A, lda, B, ldb, p, st);
-    case 5: return launch_tc<256, 16, false>(A, lda, B, ldb, p, st);
-    case 6: return launch_tc<128, 32, false>(A, lda, B, ldb, p, st);
+    case 2: return launch_tc<256, 32, false>(A, lda, B, ldb, p, st);
+    case 3: return launch_tc<128, 32, false>(A, lda, B, ldb, p, st);
+    case 4: return launch_tc<128, 16, false>(A, lda, B, ldb, p, st);
+    case 5: return launch_tc<256, 16, true>(A, lda, B, ldb, p, st);   // explicit hi rewrite (== impl 0 bit for bit)
+    case 6: return launch_tc<128, 32, true>(A, lda, B, ldb, p, st);
     default: break;
   }
-  return (N > 128) ? launch_tc<256, 16, true>(A, lda, B, ldb, p, st) : launch_tc<128, 32, true>(A, lda, B, ldb, p, st);
+  return (N > 128) ? launch_tc<256, 16, false>(A, lda, B, ldb, p, st) : launch_tc<128, 32, false>(A, lda, B, ldb, p, st);
 }

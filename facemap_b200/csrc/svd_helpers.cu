@@ -53,7 +53,7 @@ __global__ void gram_assemble_kernel(const float* __restrict__ part, int ksplit,
   double acc = 0.0;
   const size_t plane = (size_t)n * ldw;
   for (int s = 0; s < ksplit; ++s) acc += (double)part[(size_t)s * plane + (size_t)si * ldw + sj];
-  if (mean) acc -= ncols * mean[i] * mean[j];
+  if (mean) acc -= ncols * (mean[i] * mean[j]);  // commutative product: G stays exactly symmetric
   G[(size_t)i * n + j] = acc;
 }
 

@@ -13,6 +13,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from . import _lib
+
 
 class FrameSource:
     nframes: int
@@ -208,11 +210,7 @@ class HostArraySource(FrameSource):
         for i, v in enumerate(self.views):
             if self._pinned[i] or v.numel() == 0:
                 continue
-            try:
-                rc = torch.cuda.cudart().cudaHostRegister(v.data_ptr(), v.numel(), 0)
-                ok = int(rc) == 0 if not isinstance(rc, tuple) else int(rc[0]) == 0
-            except Exception:
-                ok = False
+            ok = _lib.load().fm_host_register(v.data_ptr(), v.numel()) == 0
             if ok:
                 self._registered.append(v.data_ptr())
                 self._pinned[i] = True
@@ -251,11 +249,16 @@ class HostArraySource(FrameSource):
     def close(self):
         self._cache.drop()
         for ptr in self._registered:
-            try:
-                torch.cuda.cudart().cudaHostUnregister(ptr)
-            except Exception:
-                pass
+            _lib.load().fm_host_unregister(ptr)
         self._registered = []
+        self._pinned = [v.is_pinned() for v in self.views]
+        self._pin = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class VideoFileSource(FrameSource):

@@ -21,6 +21,7 @@
 #ifndef FACEMAP_B200_H
 #define FACEMAP_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -42,6 +43,11 @@ const char* fm_last_error(void);
 int fm_check_device(int dev);
 /* number of kernels this library launched on the calling process since load (all threads). */
 uint64_t fm_launch_count(void);
+
+/* Page-lock / unlock caller-owned host memory in place (HostArraySource: frames stay where the
+ * caller put them and are DMA'd from there).  A refusal returns non-zero and leaves no sticky error. */
+int fm_host_register(void* ptr_host, size_t bytes);
+int fm_host_unregister(void* ptr_host);
 
 /* ROI rectangles in BINNED coordinates of one view, half-open [y0,y1) x [x0,x1).
  * facemap/process.py:716-723 (yrange_bin / xrange_bin), :464-500 (use in the projection loop) */

@@ -26,7 +26,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 2, 3, 4])
+@pytest.mark.parametrize("impl", [0, 2, 3, 4, 5])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm_matches_fp64(cuda_device, M, N, K, impl):
     from facemap_b200 import kernels as Kn
@@ -48,6 +48,21 @@ def test_gemm_matches_fp64(cuda_device, M, N, K, impl):
     assert bool(((C2.double() - ref).abs() <= bound * 4).all())
 
 
+def test_tf32_operand_truncation_makes_hi_rewrite_redundant(cuda_device):
+    """kind::tf32 ignores the low 13 mantissa bits of an operand word: feeding the raw fp32 tile as the
+    hi operand (impl 0) is bit-identical to masking it first (impl 5 / 6)."""
+    from facemap_b200 import kernels as Kn
+
+    dev = cuda_device
+    for (M, N, K, a, b) in [(300, 700, 2049, 0, 5), (200, 100, 777, 0, 6)]:
+        A, B = _rand(M, K, dev, 11), _rand(N, K, dev, 12)
+        C0, C1 = Kn.alloc_matrix(M, N, dev), Kn.alloc_matrix(M, N, dev)
+        Kn.gemm_tn(A, B, C0, impl=a)
+        Kn.gemm_tn(A, B, C1, impl=b)
+        torch.cuda.synchronize()
+        assert torch.equal(C0, C1)
+
+
 def test_gemm_scale_bias_epilogue(cuda_device):
     from facemap_b200 import kernels as Kn
 
@@ -60,7 +75,7 @@ def test_gemm_scale_bias_epilogue(cuda_device):
     Kn.gemm_tn(A, B, C, rscale=rs, rbias=rb)
     torch.cuda.synchronize()
     ref = (A.double() @ B.double().T) * rs.double()[:, None] + rb.double()[:, None]
-    assert float((C.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+    assert float((C.double() - ref).abs().max() / ref.abs().max()) < 2e-5     # one 999-long chain
 
 
 @pytest.mark.parametrize("n,K,ksplit", [(999, 4096, 7), (300, 2000, 3), (1000, 640, 20), (3750, 1100, 2)])
@@ -82,5 +97,6 @@ def test_gram_splitk_upper_assemble(cuda_device, n, K, ksplit):
     ref = Xd @ Xd.T - K * torch.outer(md, md)
     scale = float(torch.diagonal(Xd @ Xd.T).max())
     assert bool(torch.isfinite(G).all())
-    assert float((G - ref).abs().max()) / scale < 2e-6
+    # chains of ~600 K elements: ~220 truncating accumulations x 5.4e-8 = 1.2e-5 of an entry
+    assert float((G - ref).abs().max()) / scale < 3e-5
     assert torch.equal(G, G.T)
