@@ -222,6 +222,7 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("FM_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
 
@@ -276,7 +277,9 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         tm = {}
+        ts = time.perf_counter()
         one_step(dev_src, timing=tm)
+        tm["host_ms"] = 1e3 * (time.perf_counter() - ts)
         timings.append(tm)
     ev1.record()
     barrier()
@@ -352,6 +355,12 @@ def main():
                "sample": f"{nfr} frames of the same 640x480 generator, whole path with the reference's stock randomized "
                          f"svdecon (oracle/facemap_oracle.py), frames in host memory (no decode); {secs:.1f} s"}
 
+    diag = None
+    if os.environ.get("FM_BENCH_DIAG"):
+        tm = {"sync": True}
+        one_step(dev_src, timing=tm)
+        diag = {"rank": rank, "wall_ms": tm.get("wall_ms")}
+        print("DIAG " + json.dumps(diag), file=sys.stderr, flush=True)
     if rank == 0:
         line = {
             "metric": "motion-SVD frames/sec (bin+diff+cov+SVD+proj)", "value": value, "unit": "frames/s",
@@ -364,6 +373,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "stage_ms": {k: round(v, 3) for k, v in sorted(agg.items())},
             "cusolver_ms_per_step": solver_ms,
+            "host_ms_per_step": [round(tm["host_ms"], 1) for tm in timings],
             "kernels_only_frames_per_s": total_frames / ((ms_step - solver_ms) / 1e3) if ms_step > solver_ms else None,
         }
         print(json.dumps(line), flush=True)

@@ -312,6 +312,251 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster on one TPC compute a 256 x 256 tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (128 rows), so per-SM shared-memory
+// traffic for B (TMA fill, lo split, tensor-core operand reads) is halved — shared-memory
+// bandwidth is what caps the single-CTA kernel at ~60 % tensor-pipe utilisation (ncu, round 1).
+// The leader CTA's MMA thread issues tcgen05.mma.cta_group::2; both CTAs' splitter warps arrive on
+// the LEADER's barrier (remote mbarrier arrive); tcgen05.commit multicasts "stage free" and
+// "accumulator ready" to both CTAs.  Every CTA drains its own 128 TMEM lanes.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    const uint64_t now = globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ull) {
+      printf("facemap_b200 gemm(pair): mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int BK>
+struct PairCfg {
+  static constexpr int BN = 256;                           // UMMA N; each CTA stages BN/2 rows of B
+  static constexpr int HI_BYTES = (BM + BN / 2) * BK * 4;  // raw A tile then raw half-B tile
+  static constexpr int STAGE_BYTES = 2 * HI_BYTES;         // + lo tiles
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+};
+
+template <int BK>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const GemmParams p) {
+  using Cfg = PairCfg<BK>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = Cfg::BN;
+  const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the MMAs)
+  const int pair_m0 = (blockIdx.y >> 1) * (2 * BM);
+  const int m0 = pair_m0 + (int)rank * BM;
+  const int n0 = blockIdx.x * BN;
+  if (p.upper_only && n0 + BN - 1 < pair_m0) return;       // whole pair below the diagonal (cluster-uniform)
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // local: TMA landed
+  auto split_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };     // leader's: both CTAs split
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); }; // local: MMAs done with the stage
+  const uint32_t tmem_full_bar = bar_base + 8u * (3 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 1);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int KB = (p.K + BK - 1) / BK;
+  const int kb0 = (int)(((long long)blockIdx.z * KB) / p.ksplit);
+  const int kb1 = (int)(((long long)(blockIdx.z + 1) * KB) / p.ksplit);
+  const int nkb = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(split_bar(s), 2 * NUM_SPLIT_WARPS);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // peer barriers initialised, TMEM allocated
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===== TMA producer (each CTA fills its own stage buffers) =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(full_bar(s), (uint32_t)Cfg::HI_BYTES);
+        tma_load_2d(stage, &tmA, full_bar(s), (kb0 + i) * BK, m0);
+        tma_load_2d(stage + BM * BK * 4, &tmB, full_bar(s), (kb0 + i) * BK, n0 + (int)rank * (BN / 2));
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)((2 * BM) >> 4) << 24);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait_cluster(split_bar(s), ph);
+        tcgen05_fence_after();
+        const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
+        const uint64_t a_hi = make_desc_kmajor<BK>(stage);
+        const uint64_t b_hi = make_desc_kmajor<BK>(stage + BM * BK * 4);
+        const uint64_t a_lo = make_desc_kmajor<BK>(stage + Cfg::HI_BYTES);
+        const uint64_t b_lo = make_desc_kmajor<BK>(stage + Cfg::HI_BYTES + BM * BK * 4);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t adv = (uint64_t)(k * 2);
+          umma_tf32_pair(tmem_acc, a_lo + adv, b_hi + adv, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+          umma_tf32_pair(tmem_acc, a_hi + adv, b_lo + adv, IDESC, 1u);
+          umma_tf32_pair(tmem_acc, a_hi + adv, b_hi + adv, IDESC, 1u);
+        }
+        tcgen05_commit_pair(empty_bar(s));
+      }
+      tcgen05_commit_pair(tmem_full_bar);
+    }
+  } else {
+    // ===== splitter (both CTAs arrive on the leader's barrier), then epilogue =====
+    const int st = threadIdx.x - 64;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      const float4* hi = reinterpret_cast<const float4*>(smem_gen + s * Cfg::STAGE_BYTES);
+      float4* lo = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES + Cfg::HI_BYTES);
+      constexpr int NV = Cfg::HI_BYTES / 16;
+#pragma unroll 4
+      for (int v = st; v < NV; v += 32 * NUM_SPLIT_WARPS) {
+        const float4 x = hi[v];
+        float4 l;
+        l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+        l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+        l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+        l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+        lo[v] = l;
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");   // generic writes -> async proxy, all state spaces
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(split_bar(s), 0);
+    }
+
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < p.M;
+    float scale = 1.f, bias = 0.f;
+    float* dst_row;
+    if (p.ksplit > 1) {
+      dst_row = p.workspace + ((size_t)blockIdx.z * p.M + (size_t)(row_ok ? m : 0)) * p.ldw;
+    } else {
+      dst_row = p.C + (size_t)(row_ok ? m : 0) * p.ldc;
+      if (row_ok && p.rscale) scale = p.rscale[m];
+      if (row_ok && p.rbias) bias = p.rbias[m];
+    }
+    const bool vec_ok = ((p.ksplit > 1 ? p.ldw : p.ldc) % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.ksplit > 1 ? p.workspace : p.C) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 2; c += 32) {
+      const int col = half * (BN / 2) + c;
+      uint32_t r[32];
+      const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
+      TMEM_LD_32x32b_X32(taddr, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int n = n0 + col;
+      if (row_ok && n < p.N) {
+        if (vec_ok && n + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = fmaf(__uint_as_float(r[j + 0]), scale, bias);
+            o.y = fmaf(__uint_as_float(r[j + 1]), scale, bias);
+            o.z = fmaf(__uint_as_float(r[j + 2]), scale, bias);
+            o.w = fmaf(__uint_as_float(r[j + 3]), scale, bias);
+            *reinterpret_cast<float4*>(dst_row + n + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n + j < p.N) dst_row[n + j] = fmaf(__uint_as_float(r[j]), scale, bias);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // the peer's tensor core may still be reading this CTA's shared memory / TMEM
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Plain FP32 FFMA kernel with the same interface: the on-device numerical reference the tests
 // hold the tensor-core kernel against (never used by the pipeline).
 // ---------------------------------------------------------------------------------------------
@@ -417,6 +662,36 @@ static int launch_tc(const float* A, int64_t lda, const float* B, int64_t ldb, c
   return FM_OK;
 }
 
+template <int BK>
+static int launch_pair(const float* A, int64_t lda, const float* B, int64_t ldb, const GemmParams& p, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_map(&ta, A, lda, p.M, p.K, BM, BK)) != FM_OK) return rc;
+  if ((rc = make_map(&tb, B, ldb, p.N, p.K, PairCfg<BK>::BN / 2, BK)) != FM_OK) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    PairCfg<BK>::SMEM_BYTES);
+  });
+  FM_CUDA_TRY(attr_err);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)cdiv(p.N, PairCfg<BK>::BN), (unsigned)(2 * cdiv(p.M, 2 * BM)), (unsigned)p.ksplit);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = PairCfg<BK>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 2;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FM_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<BK>, ta, tb, p));
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
 }  // namespace fm
 
 extern "C" int64_t fm_gemm_workspace_bytes(int M, int64_t ldw, int ksplit) {
@@ -446,7 +721,7 @@ extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
     FM_LAUNCH_CHECK();
     return FM_OK;
   }
-  FM_REQUIRE(impl == 0 || (impl >= 2 && impl <= 6), "fm_gemm_tn: unknown impl %d", impl);
+  FM_REQUIRE(impl == 0 || (impl >= 2 && impl <= 8), "fm_gemm_tn: unknown impl %d", impl);
   FM_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
              "fm_gemm_tn: TMA operands need 16-byte aligned bases and ld %% 4 == 0 (lda=%lld ldb=%lld)",
              (long long)lda, (long long)ldb);
@@ -457,6 +732,8 @@ extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
     case 4: return launch_tc<128, 16, false>(A, lda, B, ldb, p, st);
     case 5: return launch_tc<256, 16, true>(A, lda, B, ldb, p, st);   // explicit hi rewrite (== impl 0 bit for bit)
     case 6: return launch_tc<128, 32, true>(A, lda, B, ldb, p, st);
+    case 7: return launch_pair<16>(A, lda, B, ldb, p, st);            // CTA pair, cta_group::2
+    case 8: return launch_pair<32>(A, lda, B, ldb, p, st);
     default: break;
   }
   return (N > 128) ? launch_tc<256, 16, false>(A, lda, B, ldb, p, st) : launch_tc<128, 32, false>(A, lda, B, ldb, p, st);

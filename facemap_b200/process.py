@@ -91,8 +91,18 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     mods = [m for m, on in (("mot", motSVD), ("mov", movSVD)) if on]
     timer = svd.StageTimer(enabled=timing is not None)
     wall0 = time.perf_counter()
+    marks = []
+
+    def mark(name):
+        """diagnostic wall-clock checkpoints (synchronising) when timing["sync"] is set"""
+        if timing is not None and timing.get("sync"):
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     ws = svd.SvdWorkspace(dev, eig_fp32=eig_fp32, gemm_impl=gemm_impl, timer=timer)
     source.plan_access(*svd.access_plan(source, dist), dev)
+    mark("setup")
 
     # ---- stage 1 ----
     if dist is None or dist.world == 1:
@@ -100,6 +110,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     else:
         avgframe, avgmotion = dist.stage1(source, geo, dev, timer)
 
+    mark("stage1")
     # ---- stage 2 ----
     masks = {}
     if (fullSVD or nroi > 0) and mods:
@@ -107,8 +118,10 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
             Yt, ks, nsegs = svd.stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, dev, timer)
         else:
             Yt, ks, nsegs = dist.stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, dev, timer)
+        mark("stage2.chunks")
         masks = svd.stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer)
         del Yt
+        mark("stage2.merge")
     nsegs_plan = svd.stage2_plan(N)[1]
     nc_plan = svd.stage2_plan(N)[2]
 
@@ -120,6 +133,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         else:
             V, E, E_roi = dist.stage3(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, dev, timer)
 
+    mark("stage3")
     # ---- assemble (device -> host) ----
     t_asm = time.perf_counter()
     with timer("assemble.d2h"):
@@ -199,7 +213,10 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         "motMask_reshape": U_resh["mot"], "movMask_reshape": U_resh["mov"],
         "motSVD": V_out["mot"], "movSVD": V_out["mov"],
     })
+    mark("assemble")
     if timing is not None:
+        if marks:
+            timing["wall_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks[:-1], marks[1:])}
         timing["device_ms"] = timer.report()
         timing["wall_s"] = time.perf_counter() - wall0
         timing["assemble_wall_s"] = time.perf_counter() - t_asm
