@@ -386,16 +386,16 @@ struct PairCfg {
 };
 
 template <int BK>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const GemmParams p) {
   using Cfg = PairCfg<BK>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = Cfg::BN;
   const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the MMAs)
-  const int pair_m0 = (blockIdx.y >> 1) * (2 * BM);
+  const int pair_m0 = (blockIdx.x >> 1) * (2 * BM);          // the pair = 2 consecutive CTAs along x
   const int m0 = pair_m0 + (int)rank * BM;
-  const int n0 = blockIdx.x * BN;
+  const int n0 = blockIdx.y * BN;
   if (p.upper_only && n0 + BN - 1 < pair_m0) return;       // whole pair below the diagonal (cluster-uniform)
 
   extern __shared__ uint8_t smem_raw[];
@@ -675,19 +675,10 @@ static int launch_pair(const float* A, int64_t lda, const float* B, int64_t ldb,
                                     PairCfg<BK>::SMEM_BYTES);
   });
   FM_CUDA_TRY(attr_err);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)cdiv(p.N, PairCfg<BK>::BN), (unsigned)(2 * cdiv(p.M, 2 * BM)), (unsigned)p.ksplit);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = PairCfg<BK>::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 2;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  FM_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel<BK>, ta, tb, p));
+  // cluster shape (2,1,1) is compiled into the kernel (__cluster_dims__); grid.x = 2 CTAs per 256-row pair
+  dim3 grid((unsigned)(2 * cdiv(p.M, 2 * BM)), (unsigned)cdiv(p.N, PairCfg<BK>::BN), (unsigned)p.ksplit);
+  FM_REQUIRE(grid.y <= 65535, "fm_gemm_tn(pair): N too large");
+  gemm_tf32x3_pair_kernel<BK><<<grid, GEMM_THREADS, PairCfg<BK>::SMEM_BYTES, st>>>(ta, tb, p);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }

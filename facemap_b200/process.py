@@ -220,7 +220,6 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         timing["device_ms"] = timer.report()
         timing["wall_s"] = time.perf_counter() - wall0
         timing["assemble_wall_s"] = time.perf_counter() - t_asm
-    ws.solver.close()
     return proc
 
 

@@ -87,13 +87,25 @@ def _gemm_ksplit(kdim):
     return int(max(1, math.ceil(kdim / KCHAIN_GEMM)))
 
 
+_SOLVERS = {}
+
+
+def get_solver(device):
+    """One cuSOLVER handle (+ its device workspace) per device for the life of the process: creating
+    and destroying it per call costs cudaMalloc/cudaFree synchronisations."""
+    key = torch.device(device).index or 0
+    if key not in _SOLVERS:
+        _SOLVERS[key] = K.Solver()
+    return _SOLVERS[key]
+
+
 class SvdWorkspace:
     """Reusable device buffers for the Gram -> eigensolve -> left-vector sequence."""
 
     def __init__(self, device, eig_fp32=False, gemm_impl=0, timer=None):
         self.device = device
         self.timer = timer if timer is not None else StageTimer(enabled=False)
-        self.solver = K.Solver()
+        self.solver = get_solver(device)
         self.eig_fp32 = eig_fp32
         self.gemm_impl = gemm_impl
         self._ws = None
