@@ -49,7 +49,8 @@ SIGNATURES = {
     "fm_host_unregister": (_I, [_P]),
     "fm_bin_motion": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, C.POINTER(Rois), _P, _P, _P, _P, _P]),
     "fm_mean_update": (_I, [_P, _P, _L, _I, _I, _I, _P]),
-    "fm_gemm_tn": (_I, [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _I, _P, _L, _I, _I, _P]),
+    "fm_gemm_tn": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _I, _P, _L, _I, _I, _P]),
+    "fm_split_lo": (_I, [_P, _L, _I, _I, _P, _L, _P]),
     "fm_splitk_reduce": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _L, _P]),
     "fm_gemm_workspace_bytes": (_L, [_I, _L, _I]),
     "fm_row_means": (_I, [_P, _L, _I, _L, _P, _P]),
@@ -58,7 +59,8 @@ SIGNATURES = {
     "fm_solver_destroy": (_I, [_P]),
     "fm_syevd": (_I, [_P, _P, _I, _P, _I, _P]),
     "fm_syevd_batched": (_I, [_P, _P, _I, _I, _P, _P]),
-    "fm_topk_components": (_I, [_P, _P, _I, _I, _P, _P, _L, _P, _P, _P, _P]),
+    "fm_syevdx_top": (_I, [_P, _P, _I, _I, _P, _P]),
+    "fm_topk_components": (_I, [_P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P]),
     "fm_transpose": (_I, [_P, _L, _I, _I, _P, _L, _P]),
     "fm_gather_roi": (_I, [_P, _L, _I, _L, _I, _I, _I, _I, _I, _P, _L, _P]),
 }

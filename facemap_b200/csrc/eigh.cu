@@ -173,3 +173,31 @@ extern "C" int fm_syevd_batched(fm_solver* s, double* G, int n, int batch, doubl
     }
   return FM_OK;
 }
+
+// Top-`k` eigenpairs only (cusolverDnXsyevdx, index range [n-k+1, n]): the first k rows of G
+// receive the eigenvectors of the k largest eigenvalues in ascending order, lam[0..k).
+extern "C" int fm_syevdx_top(fm_solver* s, double* G, int n, int k, double* lam, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(s && G && lam && n >= 1 && k >= 1 && k <= n, "fm_syevdx_top: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FM_SOLVER_TRY(cusolverDnSetStream(s->handle, st));
+  size_t dbytes = 0, hbytes = 0;
+  int64_t meig = 0;
+  double vl = 0.0, vu = 0.0;
+  FM_SOLVER_TRY(cusolverDnXsyevdx_bufferSize(s->handle, s->params, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I,
+                                             CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, G, n, &vl, &vu, n - k + 1, n, &meig,
+                                             CUDA_R_64F, lam, CUDA_R_64F, &dbytes, &hbytes));
+  int rc = ensure_workspace(s, dbytes, hbytes);
+  if (rc != FM_OK) return rc;
+  FM_SOLVER_TRY(cusolverDnXsyevdx(s->handle, s->params, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I,
+                                  CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, G, n, &vl, &vu, n - k + 1, n, &meig, CUDA_R_64F,
+                                  lam, CUDA_R_64F, s->d_work, dbytes, s->h_work, hbytes, s->d_info));
+  int info = 0;
+  FM_CUDA_TRY(cudaMemcpyAsync(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FM_CUDA_TRY(cudaStreamSynchronize(st));
+  if (info != 0 || meig != k) {
+    set_error("cusolverDnXsyevdx: devInfo = %d, found %lld of %d eigenpairs (n = %d)", info, (long long)meig, k, n);
+    return FM_ERR_SOLVER;
+  }
+  return FM_OK;
+}

@@ -139,10 +139,14 @@ struct GemmCfg {
 // HI_INPLACE: overwrite the raw tile with its TF32-truncated value.  kind::tf32 reads only the top
 // 19 bits of each operand word, so the raw tile already IS the hi operand; the rewrite is kept as
 // a template option (impl 5 in fm_gemm_tn) to let the tests prove the two are bit-identical.
-template <int BN, int BK, bool HI_INPLACE>
+// B_PRESPLIT: the lo part of B comes pre-computed from global memory (fm_split_lo; the projection's
+// B operand is the mask matrix, constant over all frames and L2-resident), so TMA fills both B tiles and
+// the splitter warps only touch the A tile — a third of the LDS/STS traffic on the shared-memory pipe
+// that ncu shows to be the limiter of the in-kernel split.
+template <int BN, int BK, bool HI_INPLACE, bool B_PRESPLIT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const GemmParams p) {
+                   const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
   using Cfg = GemmCfg<BN, BK>;
   constexpr int STAGES = Cfg::STAGES;
   const int m0 = blockIdx.y * BM;
@@ -199,9 +203,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), (uint32_t)Cfg::HI_BYTES);
+        mbar_expect_tx(full_bar(s), (uint32_t)(Cfg::HI_BYTES + (B_PRESPLIT ? BN * BK * 4 : 0)));
         tma_load_2d(stage, &tmA, full_bar(s), (kb0 + i) * BK, m0);
         tma_load_2d(stage + BM * BK * 4, &tmB, full_bar(s), (kb0 + i) * BK, n0);
+        if constexpr (B_PRESPLIT)
+          tma_load_2d(stage + Cfg::HI_BYTES + BM * BK * 4, &tmBlo, full_bar(s), (kb0 + i) * BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -240,7 +246,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(full_bar(s), ph);
       float4* hi = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES);
       float4* lo = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES + Cfg::HI_BYTES);
-      constexpr int NV = Cfg::HI_BYTES / 16;
+      constexpr int NV = (B_PRESPLIT ? BM * BK * 4 : Cfg::HI_BYTES) / 16;   // A tile only when B is pre-split
 #pragma unroll 4
       for (int v = st; v < NV; v += 32 * NUM_SPLIT_WARPS) {
         const float4 x = hi[v];
@@ -643,21 +649,27 @@ static int make_map(CUtensorMap* map, const float* base, int64_t ld, int rows, i
   return FM_OK;
 }
 
-template <int BN, int BK, bool HI_INPLACE>
-static int launch_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const GemmParams& p, cudaStream_t st) {
-  CUtensorMap ta, tb;
+template <int BN, int BK, bool HI_INPLACE, bool B_PRESPLIT = false>
+static int launch_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const GemmParams& p, cudaStream_t st,
+                     const float* B_lo = nullptr, int64_t ldb_lo = 0) {
+  CUtensorMap ta, tb, tblo;
   int rc;
   if ((rc = make_map(&ta, A, lda, p.M, p.K, BM, BK)) != FM_OK) return rc;
   if ((rc = make_map(&tb, B, ldb, p.N, p.K, BN, BK)) != FM_OK) return rc;
+  if (B_PRESPLIT) {
+    if ((rc = make_map(&tblo, B_lo, ldb_lo, p.N, p.K, BN, BK)) != FM_OK) return rc;
+  } else {
+    tblo = tb;
+  }
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, BK, HI_INPLACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, BK, HI_INPLACE, B_PRESPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     GemmCfg<BN, BK>::SMEM_BYTES);
   });
   FM_CUDA_TRY(attr_err);
   dim3 grid((unsigned)cdiv(p.N, BN), (unsigned)cdiv(p.M, BM), (unsigned)p.ksplit);
-  gemm_tf32x3_kernel<BN, BK, HI_INPLACE><<<grid, GEMM_THREADS, GemmCfg<BN, BK>::SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_tf32x3_kernel<BN, BK, HI_INPLACE, B_PRESPLIT><<<grid, GEMM_THREADS, GemmCfg<BN, BK>::SMEM_BYTES, st>>>(ta, tb, tblo, p);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }
@@ -689,9 +701,10 @@ extern "C" int64_t fm_gemm_workspace_bytes(int M, int64_t ldw, int ksplit) {
   return (int64_t)ksplit * M * ldw * 4;
 }
 
-extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int K,
-                          float* C, int64_t ldc, const float* rscale, const float* rbias, int ksplit,
-                          float* workspace, int64_t ldw, int upper_only, int impl, void* stream) {
+extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* B_lo,
+                          int64_t ldb_lo, int M, int N, int K, float* C, int64_t ldc, const float* rscale,
+                          const float* rbias, int ksplit, float* workspace, int64_t ldw, int upper_only, int impl,
+                          void* stream) {
   using namespace fm;
   FM_REQUIRE(A && B && M >= 1 && N >= 1 && K >= 1, "fm_gemm_tn: bad shape M=%d N=%d K=%d", M, N, K);
   FM_REQUIRE(lda >= K && ldb >= K, "fm_gemm_tn: leading dimensions smaller than K");
@@ -726,6 +739,12 @@ extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
     case 7: return launch_pair<16>(A, lda, B, ldb, p, st);            // CTA pair, cta_group::2
     case 8: return launch_pair<32>(A, lda, B, ldb, p, st);
     default: break;
+  }
+  if (B_lo != nullptr) {
+    FM_REQUIRE(ldb_lo >= K && ldb_lo % 4 == 0 && (reinterpret_cast<uintptr_t>(B_lo) & 15) == 0,
+               "fm_gemm_tn: B_lo needs a 16-byte aligned base and ldb_lo %% 4 == 0");
+    return (N > 128) ? launch_tc<256, 16, false, true>(A, lda, B, ldb, p, st, B_lo, ldb_lo)
+                     : launch_tc<128, 32, false, true>(A, lda, B, ldb, p, st, B_lo, ldb_lo);
   }
   return (N > 128) ? launch_tc<256, 16, false>(A, lda, B, ldb, p, st) : launch_tc<128, 32, false>(A, lda, B, ldb, p, st);
 }

@@ -59,7 +59,7 @@ __global__ void gram_assemble_kernel(const float* __restrict__ part, int ksplit,
 
 // one block per component c
 __global__ void __launch_bounds__(256) topk_kernel(const double* __restrict__ evec, const double* __restrict__ lam,
-                                                   int n, int k, const double* __restrict__ mean,
+                                                   int n, int nev, int k, const double* __restrict__ mean,
                                                    float* __restrict__ Wt, int64_t ldwt, float* __restrict__ sval,
                                                    float* __restrict__ rbias, float* __restrict__ rscale) {
   __shared__ double s_abs[256];
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) topk_kernel(const double* __restrict__ ev
   __shared__ double s_dot[8];
   __shared__ double s_sign;
   const int c = blockIdx.x;
-  const double* v = evec + (size_t)(n - 1 - c) * n;
+  const double* v = evec + (size_t)(nev - 1 - c) * n;
   // argmax |v| with the smallest index on ties (np.argmax)
   double best = -1.0;
   int bidx = 0;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) topk_kernel(const double* __restrict__ ev
   if (threadIdx.x == 0) {
     double d = 0.0;
     for (int w = 0; w < 8; ++w) d += s_dot[w];
-    const double l = lam[n - 1 - c];
+    const double l = lam[nev - 1 - c];
     const float s = (float)sqrt(l > 0.0 ? l : 0.0);
     const float inv = s > 0.f ? 1.0f / s : 0.f;
     if (sval) sval[c] = s;
@@ -161,12 +161,13 @@ extern "C" int fm_gram_assemble(const float* part, int ksplit, int n, int64_t ld
   return FM_OK;
 }
 
-extern "C" int fm_topk_components(const double* evec, const double* lam, int n, int k, const double* mean,
-                                  float* Wt, int64_t ldwt, float* sval, float* rbias, float* rscale,
-                                  void* stream) {
+extern "C" int fm_topk_components(const double* evec, const double* lam, int n, int nev, int k,
+                                  const double* mean, float* Wt, int64_t ldwt, float* sval, float* rbias,
+                                  float* rscale, void* stream) {
   using namespace fm;
-  FM_REQUIRE(evec && lam && Wt && n >= 1 && k >= 1 && k <= n && ldwt >= n, "fm_topk_components: bad args");
-  topk_kernel<<<k, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(evec, lam, n, k, mean, Wt, ldwt, sval,
+  FM_REQUIRE(evec && lam && Wt && n >= 1 && nev >= 1 && nev <= n && k >= 1 && k <= nev && ldwt >= n,
+             "fm_topk_components: bad args");
+  topk_kernel<<<k, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(evec, lam, n, nev, k, mean, Wt, ldwt, sval,
                                                                     rbias, rscale);
   FM_LAUNCH_CHECK();
   return FM_OK;
@@ -244,6 +245,28 @@ extern "C" int fm_splitk_reduce(const float* part, int ksplit, int M, int N, int
   }
   splitk_reduce_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part, ksplit, M, N, ldw, rscale,
                                                                                 rbias, C, ldc);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+// lo[r,c] = x - tf32_trunc(x): the second operand plane of the 3xTF32 split for a matrix that is
+// reused by many GEMMs (the projection masks).
+namespace fm {
+__global__ void split_lo_kernel(const float* __restrict__ X, int64_t ldx, int rows, int cols, float* __restrict__ lo,
+                                int64_t ldlo) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= cols) return;
+  const float x = X[(size_t)r * ldx + c];
+  lo[(size_t)r * ldlo + c] = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+}
+}  // namespace fm
+
+extern "C" int fm_split_lo(const float* X, int64_t ldx, int rows, int cols, float* lo, int64_t ldlo, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(X && lo && rows >= 1 && cols >= 1 && ldx >= cols && ldlo >= cols && rows <= 65535, "fm_split_lo: bad args");
+  dim3 grid((unsigned)cdiv(cols, 256), (unsigned)rows);
+  split_lo_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, ldx, rows, cols, lo, ldlo);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }

@@ -100,7 +100,17 @@ def mean_update(acc, tsum, sbin, count, finalize_div=0):
                                      _stream()), "fm_mean_update")
 
 
-def gemm_tn(A, B, C_out=None, *, rscale=None, rbias=None, ksplit=1, workspace=None, upper_only=False, impl=0):
+def split_lo(X):
+    """lo plane of the 3xTF32 split of X (same shape and pitch policy as alloc_matrix)."""
+    _need(X, torch.float32, "X", 2)
+    lo = alloc_matrix(X.shape[0], X.shape[1], X.device)
+    check(_lib.load().fm_split_lo(ptr(X), X.stride(0), X.shape[0], X.shape[1], ptr(lo), lo.stride(0), _stream()),
+          "fm_split_lo")
+    return lo
+
+
+def gemm_tn(A, B, C_out=None, *, rscale=None, rbias=None, ksplit=1, workspace=None, upper_only=False, impl=0,
+            B_lo=None):
     """C[M,N] = rscale[m] * (A[M,K] @ B[N,K]^T) + rbias[m]; both operands K-contiguous float32.
     With ksplit > 1 the raw partial products go to `workspace` [ksplit, M, ldw] instead."""
     _need(A, torch.float32, "A", 2)
@@ -123,7 +133,11 @@ def gemm_tn(A, B, C_out=None, *, rscale=None, rbias=None, ksplit=1, workspace=No
         ldc = C_out.stride(0)
     _need(rscale, torch.float32, "rscale")
     _need(rbias, torch.float32, "rbias")
-    check(_lib.load().fm_gemm_tn(ptr(A), A.stride(0), ptr(B), B.stride(0), M, N, K, ptr(C_out), ldc, ptr(rscale),
+    _need(B_lo, torch.float32, "B_lo", 2)
+    if B_lo is not None and (tuple(B_lo.shape) != tuple(B.shape) or B_lo.stride(1) != 1):
+        raise FacemapB200Error("gemm_tn: B_lo must have B's shape")
+    check(_lib.load().fm_gemm_tn(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(B_lo),
+                                 B_lo.stride(0) if B_lo is not None else 0, M, N, K, ptr(C_out), ldc, ptr(rscale),
                                  ptr(rbias), int(ksplit), ptr(workspace), ldw, int(bool(upper_only)), int(impl),
                                  _stream()), "fm_gemm_tn")
 
@@ -175,6 +189,16 @@ class Solver:
         check(_lib.load().fm_syevd(self._h, ptr(G), n, ptr(lam), int(bool(use_fp32)), _stream()), "fm_syevd")
         return lam
 
+    def syevdx_top(self, G, k):
+        """Only the k largest eigenpairs: rows 0..k-1 of G (ascending), returns lam [k]."""
+        _need(G, torch.float64, "G", 2)
+        n = G.shape[0]
+        if G.shape[1] != n or not G.is_contiguous():
+            raise FacemapB200Error("syevdx_top: G must be a contiguous square matrix")
+        lam = torch.empty(n, dtype=torch.float64, device=G.device)
+        check(_lib.load().fm_syevdx_top(self._h, ptr(G), n, int(k), ptr(lam), _stream()), "fm_syevdx_top")
+        return lam[:k]
+
     def syevd_batched(self, G):
         """G: float64 [batch, n, n]; overwritten by eigenvectors (rows).  Returns lam [batch, n]."""
         _need(G, torch.float64, "G", 3)
@@ -197,18 +221,19 @@ class Solver:
             pass
 
 
-def topk_components(evec, lam, k, mean, Wt, want_scale=False):
+def topk_components(evec, lam, k, mean, Wt, want_scale=False, nev=None):
     """Top-k eigenpairs -> Wt[k, n] (sign-fixed, float32), sval[k], rbias[k], rscale[k] (if wanted).
     With want_scale the bias is pre-multiplied by rscale so that a GEMM epilogue
     `rscale*acc + rbias` yields (acc - w.mean)/sval."""
-    n = evec.shape[0]
+    n = evec.shape[1]
+    nev = n if nev is None else int(nev)
     dev = evec.device
     sval = torch.empty(k, dtype=torch.float32, device=dev)
     rbias = torch.empty(k, dtype=torch.float32, device=dev)
     rscale = torch.empty(k, dtype=torch.float32, device=dev) if want_scale else None
     if Wt.shape[0] < k or Wt.shape[1] < n:
         raise FacemapB200Error("topk_components: Wt too small")
-    check(_lib.load().fm_topk_components(ptr(evec), ptr(lam), n, int(k), ptr(mean), ptr(Wt), Wt.stride(0), ptr(sval),
+    check(_lib.load().fm_topk_components(ptr(evec), ptr(lam), n, nev, int(k), ptr(mean), ptr(Wt), Wt.stride(0), ptr(sval),
                                          ptr(rbias), ptr(rscale), _stream()), "fm_topk_components")
     return sval, rbias, rscale
 

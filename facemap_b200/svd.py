@@ -111,12 +111,14 @@ class SvdWorkspace:
         self._ws = None
         self._bufs = {}
 
-    def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm"):
+    def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm", B_lo=None):
         """C = rscale * (A @ B^T) + rbias with K chains of <= KCHAIN_GEMM reduced in float64."""
         ksplit = _gemm_ksplit(A.shape[1])
+        if self.gemm_impl != 0:
+            B_lo = None
         if ksplit == 1:
             with self.timer(label + ".mma"):
-                K.gemm_tn(A, B, C_out, rscale=rscale, rbias=rbias, impl=self.gemm_impl)
+                K.gemm_tn(A, B, C_out, rscale=rscale, rbias=rbias, impl=self.gemm_impl, B_lo=B_lo)
             return
         M, N = A.shape[0], B.shape[0]
         ld = max(32, K.round_up(N, 32))
@@ -127,7 +129,7 @@ class SvdWorkspace:
             self._bufs["splitk"] = buf
         part = buf[:need].view(ksplit, M, ld)
         with self.timer(label + ".mma"):
-            K.gemm_tn(A, B, ksplit=ksplit, workspace=part, impl=self.gemm_impl)
+            K.gemm_tn(A, B, ksplit=ksplit, workspace=part, impl=self.gemm_impl, B_lo=B_lo)
         with self.timer(label + ".reduce"):
             K.splitk_reduce(part, ksplit, C_out, rscale=rscale, rbias=rbias)
 
@@ -467,6 +469,9 @@ def stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, d
     kmax = max([Ut.shape[0] for m in mods for Ut in masks[m][0] if Ut is not None] + [1])
     rows_batch = projection_rows_per_batch(geo.p, kmax)
     X = {m: ws.matrix("X3." + m, rows_batch, geo.p) for m in mods}
+    # the masks are the B operand of every projection GEMM: split them once (lo plane), TMA stages both
+    with timer("stage3.split_masks"):
+        Ut_lo = {m: [None if Ut is None else K.split_lo(Ut) for Ut in masks[m][0]] for m in mods}
     carry = [[torch.zeros(n, dtype=torch.int32, device=device) for n in geo.npix_v] for _ in range(2)]
     have_carry = False
     flip = 0
@@ -532,12 +537,13 @@ def stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, d
             Uts = masks[m][0]
             Xm = X[m][:filled]
             if fullSVD and Uts[0] is not None:
-                ws.gemm(Xm, Uts[0], V[m][0][o:o + filled], label="stage3.project")
+                ws.gemm(Xm, Uts[0], V[m][0][o:o + filled], label="stage3.project", B_lo=Ut_lo[m][0])
             for j, (v, y0, y1, x0, x1) in enumerate(geo.mot_rois):
                 for r0 in range(0, filled, 32768):
                     r1 = min(filled, r0 + 32768)
                     Xr = ws.matrix("X3roi", r1 - r0, geo.roi_npix[j])
                     with timer("stage3.roi_gather"):
                         K.gather_roi(Xm[r0:r1], r1 - r0, geo.col0[v], int(geo.Lxb[v]), (y0, y1, x0, x1), Xr)
-                    ws.gemm(Xr, Uts[1 + j], V[m][1 + j][o + r0:o + r1], label="stage3.roi_project")
+                    ws.gemm(Xr, Uts[1 + j], V[m][1 + j][o + r0:o + r1], label="stage3.roi_project",
+                            B_lo=Ut_lo[m][1 + j])
     return V, E, E_roi

@@ -97,15 +97,21 @@ int fm_mean_update(float* acc, const long long* tsum, int64_t n, int sbin, int c
  * path: X @ U (facemap/process.py:485,495,503,510), and the GEMMs inside utils.svdecon
  * (facemap/utils.py:751-776 -> sklearn randomized_svd; here Gram + eigensolve, the formulation
  * of matlab/utils/svdecon.m:16-43).
+ *   B_lo            NULL, or the pre-computed lo plane of B (fm_split_lo): TMA then stages both B
+ *                   tiles and only A is split in the kernel (impl 0 only)
  *   rscale, rbias   float32 [M] or NULL
  *   ksplit >= 1: if > 1, `C` is ignored and raw partial products are written to
  *                workspace[ksplit, M, ldw] (no scale/bias); reduce with fm_gram_assemble.
  *   upper_only != 0: tiles entirely below the diagonal are skipped (symmetric Gram).
  *   impl: 0 = tcgen05 3xTF32 (product path), 1 = plain FP32 FFMA reference kernel (validation).
  */
-int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int K,
-               float* C, int64_t ldc, const float* rscale, const float* rbias,
+int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* B_lo, int64_t ldb_lo,
+               int M, int N, int K, float* C, int64_t ldc, const float* rscale, const float* rbias,
                int ksplit, float* workspace, int64_t ldw, int upper_only, int impl, void* stream);
+
+/* lo[r,c] = X[r,c] - tf32_trunc(X[r,c]): pre-computed second plane of a B operand that many GEMMs
+ * reuse (pass it as B_lo above). */
+int fm_split_lo(const float* X, int64_t ldx, int rows, int cols, float* lo, int64_t ldlo, void* stream);
 
 /*
  * Reduction of split-K partials: C[m,n] = rscale[m] * sum_s part[s,m,n] + rbias[m], summed in
@@ -138,22 +144,26 @@ typedef struct fm_solver fm_solver;
 int fm_solver_create(fm_solver** out);
 int fm_solver_destroy(fm_solver* s);
 int fm_syevd(fm_solver* s, double* G, int n, double* lam, int use_fp32, void* stream);
+/* Only the k largest eigenpairs (cusolverDnXsyevdx): rows 0..k-1 of G and lam[0..k) in ascending order. */
+int fm_syevdx_top(fm_solver* s, double* G, int n, int k, double* lam, void* stream);
 /* `batch` matrices stored back to back (cusolverDnXsyevBatched); lam is [batch, n]. */
 int fm_syevd_batched(fm_solver* s, double* G, int n, int batch, double* lam, void* stream);
 
 /*
  * Top-k extraction with the reference's sign rule (sklearn/utils/extmath.py:924-982,
  * u_based_decision=False: the largest-|.| entry of each right singular vector is positive):
- *   Wt[c, j]  = sgn_c * evec[n-1-c][j]                    float32 [k, ldwt]  (c = 0..k-1)
- *   sval[c]   = sqrt(max(lam[n-1-c], 0))                  float32 [k]
+ * evec/lam hold `nev` eigenpairs in ascending order (nev = n after fm_syevd, nev = k' after
+ * fm_syevdx_top), evec row-major with row length n:
+ *   Wt[c, j]  = sgn_c * evec[nev-1-c][j]                  float32 [k, ldwt]  (c = 0..k-1)
+ *   sval[c]   = sqrt(max(lam[nev-1-c], 0))                float32 [k]
  *   rscale[c] = 1 / sval[c] (0 if sval == 0)              float32 [k]   (may be NULL)
  *   rbias[c]  = - sum_j Wt[c, j] * mean[j]                float32 [k]   (centring of X^T W; may
  *               be NULL); when rscale is requested the bias is pre-multiplied by rscale[c] so
  *               that fm_gemm_tn's epilogue rscale*acc + rbias gives (acc - w.mean) / sval.
  */
-int fm_topk_components(const double* evec, const double* lam, int n, int k, const double* mean,
-                       float* Wt, int64_t ldwt, float* sval, float* rbias, float* rscale,
-                       void* stream);
+int fm_topk_components(const double* evec, const double* lam, int n, int nev, int k,
+                       const double* mean, float* Wt, int64_t ldwt, float* sval, float* rbias,
+                       float* rscale, void* stream);
 
 /* out[c, r] = in[r, c]  (rows x cols float32 -> cols x rows). */
 int fm_transpose(const float* in, int64_t ldin, int rows, int cols, float* out, int64_t ldout,

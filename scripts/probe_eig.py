@@ -50,3 +50,15 @@ try:
         print(f"XsyevBatched({n}) batch=1 fp64: {(time.perf_counter()-t)*1e3:.1f} ms", flush=True)
 except Exception as e:
     print("batched 3750 failed:", e)
+# range solve: only the top 500 of 3750
+try:
+    for rep in range(2):
+        G = G0.clone(); torch.cuda.synchronize(); t = time.perf_counter()
+        lam = s.syevdx_top(G, 500); torch.cuda.synchronize()
+        print(f"syevdx_top({n}, 500) fp64: {(time.perf_counter()-t)*1e3:.1f} ms", flush=True)
+    ref = torch.linalg.eigvalsh(G0)[-500:]
+    v = G[499]
+    print("  lam err", float((lam - ref).abs().max() / ref.abs().max()), " top eigvec residual", float((G0 @ v - lam[499] * v).norm() / lam[499]),
+          " orth", float((G[:500] @ G[:500].T - torch.eye(500, device=dev, dtype=torch.float64)).abs().max()))
+except Exception as e:
+    print("syevdx failed:", e)

@@ -32,15 +32,17 @@ def run(M, N, Kd, ksplit=1, show=False):
 ok = True
 for shp in [(128, 128, 32), (128, 256, 32), (128, 256, 64), (128, 256, 128), (256, 512, 256), (100, 90, 50), (250, 700, 999)]:
     ok &= run(*shp, show=True) < 1e-5
-if len(sys.argv) > 2:
+if len(sys.argv) > 2 and sys.argv[2] == "quick":
     sys.exit(0 if ok else 1)
 # timing on the production shapes
+PRESPLIT = len(sys.argv) > 2 and sys.argv[2] == "presplit"
 def bench(M, N, Kd, ksplit=1, reps=5, upper=False):
     A = K.alloc_matrix(M, Kd, dev); B = K.alloc_matrix(N, Kd, dev)
     A.normal_(); B.normal_()
+    Blo = K.split_lo(B) if PRESPLIT else None
     C = K.alloc_matrix(M, N, dev)
     ws = torch.empty((ksplit, M, K.round_up(N, 32)), device=dev) if ksplit > 1 else None
-    f = (lambda: K.gemm_tn(A, B, ksplit=ksplit, workspace=ws, upper_only=upper, impl=impl)) if ksplit > 1 else (lambda: K.gemm_tn(A, B, C, impl=impl, upper_only=upper))
+    f = (lambda: K.gemm_tn(A, B, ksplit=ksplit, workspace=ws, upper_only=upper, impl=impl, B_lo=Blo)) if ksplit > 1 else (lambda: K.gemm_tn(A, B, C, impl=impl, upper_only=upper, B_lo=Blo))
     for _ in range(2): f()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -50,6 +52,7 @@ def bench(M, N, Kd, ksplit=1, reps=5, upper=False):
     fl = 2.0 * M * N * Kd * (0.5 if upper else 1.0)
     print(f"impl {impl} M{M} N{N} K{Kd} ksplit{ksplit} upper{int(upper)}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s useful (x3 issued = {3*fl/ms/1e9:.0f})", flush=True)
 bench(18944, 500, 19200)
+bench(18944, 500, 19200, ksplit=8)
 bench(999, 999, 19200, ksplit=16, upper=True)
 bench(250, 19200, 999)
 bench(3750, 3750, 19200, ksplit=2, upper=True)

@@ -13,13 +13,13 @@ X = K.alloc_matrix(18944, p, dev); X.normal_()
 avg = torch.rand(p, device=dev)
 prev = torch.zeros(p, dtype=torch.int32, device=dev); last = torch.zeros_like(prev)
 energy = torch.zeros(T, dtype=torch.int64, device=dev)
-Ut = K.alloc_matrix(500, p, dev); Ut.normal_()
+Ut = K.alloc_matrix(500, p, dev); Ut.normal_(); Ut_lo = K.split_lo(Ut)
 V = torch.empty((18944, 500), device=dev)
 ws = torch.empty((8, 18944, 512), device=dev)
 for _ in range(3):
     K.bin_motion(frames, sbin, prev_sum=prev, avgmotion=avg, x_mot=X[:T], energy=energy, last_sum=last)
 for _ in range(3):
-    K.gemm_tn(X, Ut, ksplit=8, workspace=ws)
+    K.gemm_tn(X, Ut, ksplit=8, workspace=ws, B_lo=Ut_lo)
     K.splitk_reduce(ws, 8, V)
 torch.cuda.synchronize()
 print("ok")

@@ -26,7 +26,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 2, 3, 4, 5])
+@pytest.mark.parametrize("impl", [0, 2, 3, 4, 5, 7, 8])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm_matches_fp64(cuda_device, M, N, K, impl):
     from facemap_b200 import kernels as Kn
@@ -61,6 +61,29 @@ def test_tf32_operand_truncation_makes_hi_rewrite_redundant(cuda_device):
         Kn.gemm_tn(A, B, C1, impl=b)
         torch.cuda.synchronize()
         assert torch.equal(C0, C1)
+
+
+@pytest.mark.parametrize("M,N,K,ksplit", [(300, 500, 2049, 1), (1000, 100, 640, 1), (400, 500, 4100, 3)])
+def test_presplit_b_operand_is_bit_identical(cuda_device, M, N, K, ksplit):
+    """B_lo from fm_split_lo staged by TMA == the in-kernel split of B."""
+    from facemap_b200 import kernels as Kn
+
+    dev = cuda_device
+    A, B = _rand(M, K, dev, 21), _rand(N, K, dev, 22)
+    B_lo = Kn.split_lo(B)
+    tr = (B.view(torch.int32) & -8192).view(torch.float32)
+    assert torch.equal(B_lo, B - tr)
+    if ksplit == 1:
+        C0, C1 = Kn.alloc_matrix(M, N, dev), Kn.alloc_matrix(M, N, dev)
+        Kn.gemm_tn(A, B, C0)
+        Kn.gemm_tn(A, B, C1, B_lo=B_lo)
+    else:
+        C0 = torch.zeros((ksplit, M, Kn.round_up(N, 32)), device=dev)
+        C1 = torch.zeros_like(C0)
+        Kn.gemm_tn(A, B, ksplit=ksplit, workspace=C0)
+        Kn.gemm_tn(A, B, ksplit=ksplit, workspace=C1, B_lo=B_lo)
+    torch.cuda.synchronize()
+    assert torch.equal(C0, C1)
 
 
 def test_gemm_scale_bias_epilogue(cuda_device):
