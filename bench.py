@@ -139,6 +139,11 @@ def make_sources(rank, world, device, want_host):
                 self.dcache.start(lambda v, x, y: self.base[x - lo:y - lo], [(H, W)], priority, (a, b), dev)
                 self.h2d += self.dcache.bytes - before
 
+        def resident(self, t0, t1):
+            if self.on_host:
+                return self.dcache.covers(t0, t1)
+            return t0 >= lo and t1 <= hi
+
         def prefetch(self, t0, t1, dev):
             if self.on_host:
                 a, b = self.clamp(t0, t1)
@@ -260,9 +265,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(src, timing=None, keep=True):
+    def one_step(src, timing=None, keep=True, overlap=True):
         return process.process_source(src, sbin=SBIN, motSVD=True, movSVD=False, dist=shard, timing=timing,
-                                      keep_on_device=keep)
+                                      keep_on_device=keep, overlap_stage3=overlap)
 
     for _ in range(max(args.warmup, 3)):
         one_step(dev_src)
@@ -298,14 +303,23 @@ def main():
     for tm in timings:
         for k, v in tm["device_ms"].items():
             agg[k] = agg.get(k, 0.0) + v / len(timings)
+    # K1 runs on a side stream underneath the eigensolves in the timed steps; its own duration is taken from
+    # two extra passes with that overlap switched off (same kernels, same shapes, CUDA events)
+    k1_clean = []
+    for _ in range(2):
+        tm = {}
+        one_step(dev_src, timing=tm, overlap=False)
+        k1_clean.append(tm["device_ms"].get("stage3.bin", 0.0))
+    barrier()
     p = (H // SBIN) * (W // SBIN)
     f0, f1 = (0, total_frames) if shard is None else __import__("facemap_b200.parallel", fromlist=["x"]).frame_ranges(
         total_frames, world)[rank]
     rows3 = f1 - f0
-    k1_ms = agg.get("stage3.bin", 0.0)
+    k1_ms = min(k1_clean) if k1_clean else agg.get("stage3.bin", 0.0)
     k1_bytes = rows3 * (H * W + 4 * p)                       # algorithmic: read u8 frame once + write fp32 X
     k1 = {"kernel": "bin_motion_vec_kernel<4> (stage 3)", "bound": "hbm", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms else None,
-          "peak": hbm_peak, "unit": "GB/s", "ms_per_step": k1_ms, "algorithmic_bytes_per_frame": H * W + 4 * p}
+          "peak": hbm_peak, "unit": "GB/s", "ms_per_step": k1_ms, "algorithmic_bytes_per_frame": H * W + 4 * p,
+          "ms_per_step_overlapped_with_stage2": agg.get("stage3.bin", 0.0)}
     if k1["achieved"]:
         k1["frac"] = k1["achieved"] / hbm_peak
     mma_ms = agg.get("stage3.project.mma", 0.0)
@@ -332,8 +346,10 @@ def main():
         host_src.h2d = 0
         d2h = 0
         t0 = time.perf_counter()
+        e2e_tm = {}
         for _ in range(args.e2e_steps):
-            out = one_step(host_src, keep=False)
+            e2e_tm = {}
+            out = one_step(host_src, timing=e2e_tm, keep=False)
             d2h = sum(a.nbytes for key in ("avgframe", "avgmotion", "motion", "motMask", "motSVD") for a in out[key]) \
                 + out["motSv"].nbytes
         barrier()
@@ -344,7 +360,10 @@ def main():
         dt = float(tt.item())
         e2e = {"value": total_frames * args.e2e_steps / dt, "unit": "frames/s",
                "h2d_bytes_per_step": host_src.h2d // args.e2e_steps, "d2h_bytes_per_step": int(d2h),
-               "steps": args.e2e_steps, "api": "facemap_b200.process.process_source(HostArraySource-like pinned frames)"}
+               "steps": args.e2e_steps, "api": "facemap_b200.process.process_source(HostArraySource-like pinned frames)",
+               "upload_ms": round(host_src.dcache.upload_ms(), 1), "wall_s_last_step": round(e2e_tm.get("wall_s", 0.0), 4),
+               "assemble_wall_s": round(e2e_tm.get("assemble_wall_s", 0.0), 4),
+               "stage_ms": {k: round(v, 2) for k, v in sorted(e2e_tm.get("device_ms", {}).items()) if v > 1.0}}
 
     # ---- CPU baseline (rank 0, single GPU run only) ----
     cpu = None

@@ -36,6 +36,10 @@ class FrameSource:
         """list (one per view) of contiguous uint8 CUDA tensors [t1'-t0', H, W]."""
         raise NotImplementedError
 
+    def resident(self, t0, t1):
+        """True if fetch() of any sub-range of [t0, t1) is a zero-copy view of HBM-resident frames."""
+        return False
+
     def prefetch(self, t0, t1, device):
         """Hint that [t0, t1) is the next range to be fetched (host sources start the H2D copy on a
         side stream so it overlaps the kernels of the current range)."""
@@ -69,6 +73,9 @@ class DeviceArraySource(FrameSource):
     def fetch(self, t0, t1, device):
         a, b = self.clamp(t0, t1)
         return [v[a:b] for v in self.views]
+
+    def resident(self, t0, t1):
+        return True
 
 
 class _H2DPipe:
@@ -143,7 +150,10 @@ class DeviceFrameCache:
         order += [pc for pc in range(npieces) if pc not in seen]
         events = [None] * npieces
         self.stream.wait_stream(torch.cuda.current_stream())
+        self.ev_begin = torch.cuda.Event(enable_timing=True)
+        self.ev_end = torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(self.stream):
+            self.ev_begin.record(self.stream)
             for pc in order:
                 a, b = lo + pc * self.piece, min(hi, lo + (pc + 1) * self.piece)
                 for v in range(len(shapes)):
@@ -151,9 +161,14 @@ class DeviceFrameCache:
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
                 events[pc] = ev
+            self.ev_end.record(self.stream)
         self.bufs, self.events, self.home = bufs, events, (lo, hi)
         self.bytes += nbytes
         return True
+
+    def upload_ms(self):
+        """device time of the last upload (call after the pass has been synchronised)."""
+        return self.ev_begin.elapsed_time(self.ev_end) if self.home is not None else 0.0
 
     def covers(self, a, b):
         return self.home is not None and a >= self.home[0] and b <= self.home[1]
@@ -218,6 +233,9 @@ class HostArraySource(FrameSource):
 
     def h2d_bytes(self, nframes):
         return int(nframes) * sum(h * w for h, w in zip(self.Ly, self.Lx))
+
+    def resident(self, t0, t1):
+        return self._cache.covers(t0, t1)
 
     def _host_slices(self, a, b):
         out = []

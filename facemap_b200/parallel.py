@@ -110,11 +110,9 @@ class Shard:
                     full[m].append(out)
         return full, ks, nsegs
 
-    def stage3(self, source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, device, timer):
-        ranges = frame_ranges(source.nframes, self.world)
-        f0, f1 = ranges[self.rank]
-        V, E, E_roi = svd.stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, device, timer,
-                                         frame_range=(f0, f1))
+    def gather_stage3(self, V, E, E_roi, N, mods, timer):
+        """All-gather the per-rank projections / energies of frame_ranges(N, world) into full arrays."""
+        ranges = frame_ranges(N, self.world)
         with timer("stage3.allgather"):
             Vf = {m: [None if v is None else self.gather_rows(v, ranges) for v in V[m]] for m in mods}
             Ef = self.gather_rows(E.t().contiguous(), ranges).t().contiguous()

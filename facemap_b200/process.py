@@ -68,10 +68,13 @@ def _motion_from_energy(E_views, sbin, N):
 
 
 def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD=True, device=None,
-                   eig_fp32=False, gemm_impl=0, timing=None, dist=None, keep_on_device=False):
+                   eig_fp32=False, gemm_impl=0, timing=None, dist=None, keep_on_device=False,
+                   overlap_stage3=True):
     """Run the three stages on a FrameSource and return the proc-dict entries this path owns.
 
     timing: optional dict that receives per-stage device times (ms) and wall times.
+    overlap_stage3: run stage 3's bin/diff pass on a side stream underneath the stage-2 eigensolves
+            when the frames are HBM-resident (svd.Stage3.start_early).
     dist:   optional facemap_b200.parallel.Shard (frame-range sharding across ranks)."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     _lib.require_device(dev.index or 0)
@@ -111,6 +114,16 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         avgframe, avgmotion = dist.stage1(source, geo, dev, timer)
 
     mark("stage1")
+    # stage 3's bin phase depends on the averages only: start it underneath the stage-2 eigensolves
+    s3 = None
+    if mods and (fullSVD or nroi > 0):
+        fr = None
+        if dist is not None and dist.world > 1:
+            from .parallel import frame_ranges
+            fr = frame_ranges(N, dist.world)[dist.rank]
+        s3 = svd.Stage3(source, geo, avgframe, avgmotion, mods, fullSVD, ws, dev, timer, frame_range=fr)
+        if overlap_stage3:
+            s3.start_early()
     # ---- stage 2 ----
     masks = {}
     if (fullSVD or nroi > 0) and mods:
@@ -128,10 +141,9 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     # ---- stage 3 ----
     V, E, E_roi = {}, None, None
     if mods and masks:
-        if dist is None or dist.world == 1:
-            V, E, E_roi = svd.stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, dev, timer)
-        else:
-            V, E, E_roi = dist.stage3(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, dev, timer)
+        V, E, E_roi = s3.project(masks)
+        if dist is not None and dist.world > 1:
+            V, E, E_roi = dist.gather_stage3(V, E, E_roi, N, mods, timer)
 
     mark("stage3")
     # ---- assemble (device -> host) ----

@@ -174,10 +174,13 @@ def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
     n, p = X.shape
     mean, G = centred_gram(ws, X, timer, label)
     with timer(label + ".syevd"):
-        lam = ws.solver.syevd(G, use_fp32=ws.eig_fp32)
+        if ws.eig_fp32 or k == n:
+            lam, nev = ws.solver.syevd(G, use_fp32=ws.eig_fp32), n
+        else:
+            lam, nev = ws.solver.syevdx_top(G, k), k      # only the k largest eigenpairs (rows 0..k-1 of G)
     with timer(label + ".topk"):
         Wt = ws.matrix(label + ".Wt", k, n)
-        sval, rbias, rscale = K.topk_components(G, lam, k, mean, Wt, want_scale=want_scale)
+        sval, rbias, rscale = K.topk_components(G, lam, k, mean, Wt, want_scale=want_scale, nev=nev)
     return Wt, sval, rbias, rscale
 
 
@@ -446,104 +449,166 @@ def projection_rows_per_batch(p, k, budget_bytes=6 << 30):
     return int(min(rows, cap))
 
 
-def stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, device, timer,
-                   frame_range=None, fetch_frames=2368):
-    """Projection of every frame in [f0, f1) onto the masks (process.py:394-515).
+class Stage3:
+    """Projection of every frame in [f0, f1) onto the masks (process.py:394-515), in two phases:
 
-    Returns V[m] = list of [f1-f0, k] device tensors (index 0 full frame, 1+j ROI j), and the
-    integer energies E [nviews, f1-f0], E_roi [nroi, f1-f0] with row i <-> frame f0+i holding
-    sum |S_t - S_{t-1}| (row for frame 0 is zero).  Reference row conventions (Q1/Q2) are applied
-    by the caller, which sees the whole video."""
-    N = source.nframes
-    f0, f1 = (0, N) if frame_range is None else frame_range
-    nroi = len(geo.mot_rois)
-    nv = len(geo.Ly)
-    n_out = f1 - f0
-    V = {}
-    for m in mods:
-        Uts = masks[m][0]
-        V[m] = [None if Ut is None else torch.zeros((n_out, Ut.shape[0]), dtype=torch.float32, device=device)
-                for Ut in Uts]
-    E = torch.zeros((nv, n_out), dtype=torch.int64, device=device)
-    E_roi = torch.zeros((max(nroi, 1), n_out), dtype=torch.int64, device=device)
-    kmax = max([Ut.shape[0] for m in mods for Ut in masks[m][0] if Ut is not None] + [1])
-    rows_batch = projection_rows_per_batch(geo.p, kmax)
-    X = {m: ws.matrix("X3." + m, rows_batch, geo.p) for m in mods}
-    # the masks are the B operand of every projection GEMM: split them once (lo plane), TMA stages both
-    with timer("stage3.split_masks"):
-        Ut_lo = {m: [None if Ut is None else K.split_lo(Ut) for Ut in masks[m][0]] for m in mods}
-    carry = [[torch.zeros(n, dtype=torch.int32, device=device) for n in geo.npix_v] for _ in range(2)]
-    have_carry = False
-    flip = 0
-    # the frame before f0 seeds the carry so that a shard starting mid-video is seamless (1-frame halo)
-    if f0 > 0:
-        with timer("stage3.fetch"):
-            halo = source.fetch(f0 - 1, f0, device)
-        for v, fr in enumerate(halo):
-            K.bin_motion(fr, geo.sbin, last_sum=carry[flip][v])
-        have_carry = True
+      bin      K1 over the frames -> X rows (+ integer energies); needs only the stage-1 averages
+      project  X @ masks (K4) in whole-wave batches; needs the masks
 
-    # fetch plan: GEMM batches of <= rows_batch rows, each filled by several fetches
-    batches, t, have = [], f0, have_carry
-    while t < f1:
-        fetches, filled = [], 0
-        while t < f1 and filled < rows_batch:
-            n = min(fetch_frames, f1 - t, rows_batch - filled + (0 if have else 1))
-            rows = n if have else n - 1
-            fetches.append((t, n, rows, have))
-            filled += rows
-            t += n
-            have = True
-        batches.append(fetches)
-    flat = [f for b in batches for f in b]
-    pos = 0
-    for fetches in batches:
-        filled = 0
-        row_frame0 = None
+    When the frames are resident in HBM and all of X fits a budget, `start_early()` enqueues the whole
+    bin phase on a side stream right after stage 1, so it runs underneath the stage-2 eigensolves
+    (which leave the SMs mostly idle) and only the GEMMs remain on the critical path.  Otherwise the
+    two phases alternate batch by batch through one X buffer.
+
+    Results: V[m] = list of [f1-f0, k] tensors (0 = full frame, 1+j = ROI j); integer energies
+    E [nviews, f1-f0], E_roi [nroi, f1-f0], row i <-> frame f0+i holding sum |S_t - S_{t-1}| (row of
+    frame 0 stays zero).  The reference's row conventions (Q1/Q2) are applied by the caller."""
+
+    def __init__(self, source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer, frame_range=None,
+                 fetch_frames=2368, kmax=NCOMPS):
+        self.source, self.geo, self.avgframe, self.avgmotion = source, geo, avgframe, avgmotion
+        self.mods, self.fullSVD, self.ws, self.device, self.timer = mods, fullSVD, ws, device, timer
+        N = source.nframes
+        self.f0, self.f1 = (0, N) if frame_range is None else frame_range
+        self.n_out = self.f1 - self.f0
+        self.nroi, self.nv = len(geo.mot_rois), len(geo.Ly)
+        self.E = torch.zeros((self.nv, self.n_out), dtype=torch.int64, device=device)
+        self.E_roi = torch.zeros((max(self.nroi, 1), self.n_out), dtype=torch.int64, device=device)
+        self.carry = [[torch.zeros(n, dtype=torch.int32, device=device) for n in geo.npix_v] for _ in range(2)]
+        self.flip = 0
+        self.rows_batch = projection_rows_per_batch(geo.p, kmax)
+        # fetch plan: GEMM batches of <= rows_batch rows, each filled by several fetches
+        self.have0 = self.f0 > 0                         # a shard starting mid-video carries a 1-frame halo
+        self.batches, t, have = [], self.f0, self.have0
+        while t < self.f1:
+            fetches, filled = [], 0
+            while t < self.f1 and filled < self.rows_batch:
+                n = min(fetch_frames, self.f1 - t, self.rows_batch - filled + (0 if have else 1))
+                rows = n if have else n - 1
+                fetches.append((t, n, rows, have))
+                filled += rows
+                t += n
+                have = True
+            self.batches.append((fetches, filled))
+        self.flat = [f for b, _ in self.batches for f in b]
+        self.pos = 0
+        self.first_row_frame = self.f0 if self.have0 else self.f0 + 1
+        self.rows_total = max(0, self.f1 - self.first_row_frame)
+        self.X_full = None
+        self.early_done = None
+        self._halo_done = False
+
+    # ---- bin phase -------------------------------------------------------------------------------
+    def _seed_halo(self):
+        if self.have0 and not self._halo_done:
+            with self.timer("stage3.fetch"):
+                halo = self.source.fetch(self.f0 - 1, self.f0, self.device)
+            for v, fr in enumerate(halo):
+                K.bin_motion(fr, self.geo.sbin, last_sum=self.carry[self.flip][v])
+        self._halo_done = True
+
+    def _bin_fetches(self, fetches, X, row0):
+        """K1 for a list of fetches; rows land in X[m][row0 + ...]."""
+        geo, filled = self.geo, 0
         for (t, n, rows, have) in fetches:
-            with timer("stage3.fetch"):
-                frames = source.fetch(t, t + n, device)
-                if pos + 1 < len(flat):
-                    source.prefetch(flat[pos + 1][0], flat[pos + 1][0] + flat[pos + 1][1], device)
-            pos += 1
+            with self.timer("stage3.fetch"):
+                frames = self.source.fetch(t, t + n, self.device)
+                if self.pos + 1 < len(self.flat):
+                    nxt = self.flat[self.pos + 1]
+                    self.source.prefetch(nxt[0], nxt[0] + nxt[1], self.device)
+            self.pos += 1
             first_frame = t if have else t + 1
-            if row_frame0 is None:
-                row_frame0 = first_frame
-            with timer("stage3.bin"):
-                Xv = {m: X[m][filled:filled + rows] for m in mods} if rows > 0 else {m: None for m in mods}
-                o = first_frame - f0
-                energy = [E[v, o:o + rows] for v in range(nv)]
+            with self.timer("stage3.bin"):
+                r = row0 + filled
+                Xv = {m: X[m][r:r + rows] for m in self.mods} if rows > 0 else {m: None for m in self.mods}
+                o = first_frame - self.f0
+                energy = [self.E[v, o:o + rows] for v in range(self.nv)]
                 roi_e = []
-                for v in range(nv):
+                for v in range(self.nv):
                     js = geo.rois_on_view[v]
                     roi_e.append(None)
-                    if js:
-                        # ROI energies of one view must be contiguous [n_on_view, rows]
-                        roi_e[v] = torch.zeros((len(js), max(rows, 1)), dtype=torch.int64, device=device)
-                _bin_chunk(frames, geo, avgframe, avgmotion, mods if rows > 0 else [], Xv,
-                           prev=carry[flip] if have else None, last=carry[1 - flip],
+                    if js:      # ROI energies of one view must be contiguous [n_on_view, rows]
+                        roi_e[v] = torch.zeros((len(js), max(rows, 1)), dtype=torch.int64, device=self.device)
+                _bin_chunk(frames, geo, self.avgframe, self.avgmotion, self.mods if rows > 0 else [], Xv,
+                           prev=self.carry[self.flip] if have else None, last=self.carry[1 - self.flip],
                            energy=energy if rows > 0 else None,
-                           roi_energy=roi_e if (nroi and rows > 0) else None)
-                if nroi and rows > 0:
-                    for v in range(nv):
+                           roi_energy=roi_e if (self.nroi and rows > 0) else None)
+                if self.nroi and rows > 0:
+                    for v in range(self.nv):
                         for q, j in enumerate(geo.rois_on_view[v]):
-                            E_roi[j, o:o + rows] = roi_e[v][q, :rows]
-            flip = 1 - flip
+                            self.E_roi[j, o:o + rows] = roi_e[v][q, :rows]
+            self.flip = 1 - self.flip
             filled += rows
-        if filled == 0:
-            continue
-        o = row_frame0 - f0
+        return filled
+
+    def start_early(self, budget_bytes=24 << 30):
+        """Enqueue the whole bin phase on a side stream (see class docstring).  Returns True if taken."""
+        if self.rows_total == 0 or not self.mods or not self.source.resident(self.f0, self.f1):
+            return False
+        need = len(self.mods) * self.rows_total * max(32, K.round_up(self.geo.p, 32)) * 4
+        free, _ = torch.cuda.mem_get_info(self.device)
+        if need > budget_bytes or need > 0.5 * free:
+            return False
+        self.X_full = {m: self.ws.matrix("X3full." + m, self.rows_total, self.geo.p) for m in self.mods}
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._seed_halo()
+            row0 = 0
+            for fetches, filled in self.batches:
+                row0 += self._bin_fetches(fetches, self.X_full, row0)
+            self.early_done = torch.cuda.Event()
+            self.early_done.record(side)
+        self._side = side
+        return True
+
+    # ---- project phase ---------------------------------------------------------------------------
+    def project(self, masks):
+        geo, mods, ws, timer, device = self.geo, self.mods, self.ws, self.timer, self.device
+        V = {}
         for m in mods:
-            Uts = masks[m][0]
-            Xm = X[m][:filled]
-            if fullSVD and Uts[0] is not None:
-                ws.gemm(Xm, Uts[0], V[m][0][o:o + filled], label="stage3.project", B_lo=Ut_lo[m][0])
-            for j, (v, y0, y1, x0, x1) in enumerate(geo.mot_rois):
-                for r0 in range(0, filled, 32768):
-                    r1 = min(filled, r0 + 32768)
-                    Xr = ws.matrix("X3roi", r1 - r0, geo.roi_npix[j])
-                    with timer("stage3.roi_gather"):
-                        K.gather_roi(Xm[r0:r1], r1 - r0, geo.col0[v], int(geo.Lxb[v]), (y0, y1, x0, x1), Xr)
-                    ws.gemm(Xr, Uts[1 + j], V[m][1 + j][o + r0:o + r1], label="stage3.roi_project",
-                            B_lo=Ut_lo[m][1 + j])
-    return V, E, E_roi
+            V[m] = [None if Ut is None else torch.zeros((self.n_out, Ut.shape[0]), dtype=torch.float32, device=device)
+                    for Ut in masks[m][0]]
+        # the masks are the B operand of every projection GEMM: split them once (lo plane), TMA stages both
+        with timer("stage3.split_masks"):
+            Ut_lo = {m: [None if Ut is None else K.split_lo(Ut) for Ut in masks[m][0]] for m in mods}
+        if self.X_full is not None:
+            torch.cuda.current_stream().wait_event(self.early_done)
+            X = self.X_full
+        else:
+            X = {m: ws.matrix("X3." + m, self.rows_batch, geo.p) for m in mods}
+            self._seed_halo()
+        row0 = 0
+        for fetches, filled in self.batches:
+            if self.X_full is None:
+                self._bin_fetches(fetches, X, 0)
+                base = 0
+            else:
+                base = row0
+            if filled == 0:
+                continue
+            o = self.first_row_frame + row0 - self.f0
+            for m in mods:
+                Uts = masks[m][0]
+                Xm = X[m][base:base + filled]
+                if self.fullSVD and Uts[0] is not None:
+                    ws.gemm(Xm, Uts[0], V[m][0][o:o + filled], label="stage3.project", B_lo=Ut_lo[m][0])
+                for j, (v, y0, y1, x0, x1) in enumerate(geo.mot_rois):
+                    for r0 in range(0, filled, 32768):
+                        r1 = min(filled, r0 + 32768)
+                        Xr = ws.matrix("X3roi", r1 - r0, geo.roi_npix[j])
+                        with timer("stage3.roi_gather"):
+                            K.gather_roi(Xm[r0:r1], r1 - r0, geo.col0[v], int(geo.Lxb[v]), (y0, y1, x0, x1), Xr)
+                        ws.gemm(Xr, Uts[1 + j], V[m][1 + j][o + r0:o + r1], label="stage3.roi_project",
+                                B_lo=Ut_lo[m][1 + j])
+            row0 += filled
+        return V, self.E, self.E_roi
+
+
+def stage3_project(source, geo, avgframe, avgmotion, masks, mods, fullSVD, ws, device, timer, frame_range=None,
+                   fetch_frames=2368):
+    """One-shot form of Stage3 (bin and project alternating batch by batch)."""
+    kmax = max([Ut.shape[0] for m in mods for Ut in masks[m][0] if Ut is not None] + [1])
+    return Stage3(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer, frame_range, fetch_frames,
+                  kmax).project(masks)
