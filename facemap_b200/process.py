@@ -67,6 +67,34 @@ def _motion_from_energy(E_views, sbin, N):
     return out
 
 
+class _HostSink:
+    """Asynchronous device->host copies into page-locked arrays on a private stream: results leave
+    the GPU while later batches are still being computed, and land in pinned memory (fast DMA)."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device)
+
+    @staticmethod
+    def alloc(shape, dtype=torch.float32):
+        return torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+
+    def copy(self, dev_tensor, host_tensor):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            host_tensor.copy_(dev_tensor, non_blocking=True)
+        dev_tensor.record_stream(self.stream)
+
+    def to_host(self, dev_tensor):
+        h = self.alloc(dev_tensor.shape, dev_tensor.dtype)
+        self.copy(dev_tensor, h)
+        return h
+
+    def wait(self):
+        self.stream.synchronize()
+
+
 def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD=True, device=None,
                    eig_fp32=False, gemm_impl=0, timing=None, dist=None, keep_on_device=False,
                    overlap_stage3=True):
@@ -139,10 +167,16 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     nc_plan = svd.stage2_plan(N)[2]
 
     # ---- stage 3 ----
+    sink = None if keep_on_device else _HostSink(dev)
+    pending_masks = {}
     V, E, E_roi = {}, None, None
     if mods and masks:
-        V, E, E_roi = s3.project(masks)
-        if dist is not None and dist.world > 1:
+        single = dist is None or dist.world == 1
+        if sink is not None:
+            # masks and singular values leave while stage 3 runs; projections leave batch by batch
+            pending_masks = {m: ([sink.to_host(u) for u in masks[m][1]], sink.to_host(masks[m][2])) for m in masks}
+        V, E, E_roi = s3.project(masks, sink=sink if single else None)
+        if not single:
             V, E, E_roi = dist.gather_stage3(V, E, E_roi, N, mods, timer)
 
     mark("stage3")
@@ -167,7 +201,12 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     }
 
     def host(t):
-        return t if keep_on_device else t.cpu().numpy()
+        if keep_on_device:
+            return t
+        return t.numpy() if not t.is_cuda else sink.to_host(t)       # pinned tensors are unwrapped below
+
+    def unwrap(x):
+        return x.numpy() if torch.is_tensor(x) and not x.is_cuda else x
 
     U_out = {"mot": [], "mov": []}
     U_resh = {"mot": [], "mov": []}
@@ -179,13 +218,21 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
             if m in masks:
                 _, Us, sv = masks[m]
                 with timer("assemble.d2h"):
-                    U_out[m] = [host(u) for u in Us]
-                    S_out[m] = host(sv)
+                    if m in pending_masks:
+                        U_out[m], S_out[m] = pending_masks[m]
+                    else:
+                        U_out[m] = [host(u) for u in Us]
+                        S_out[m] = host(sv)
             elif m not in mods:
                 # quirk Q7: ROI placeholders exist for a modality that is switched off
                 for (_, y0, y1, x0, x1) in geo.mot_rois:
                     n = (y1 - y0) * (x1 - x0)
                     U_out[m].append(np.zeros((n, nsegs_plan * min(nc_plan, n)), np.float32))
+        if sink is not None:
+            sink.wait()
+            for m in ("mot", "mov"):
+                U_out[m] = [unwrap(u) for u in U_out[m]]
+                S_out[m] = unwrap(S_out[m])
         for m in ("mot", "mov"):
             U_resh[m] = list(U_out[m])
             if m in mods and not keep_on_device:
@@ -201,10 +248,15 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                 if v is None:
                     V_out[m].append(np.zeros((0, 1), np.float32))
                     continue
+                if v.is_cuda and not keep_on_device:
+                    with timer("assemble.d2h"):
+                        v = sink.to_host(v)
+                        sink.wait()
+                if torch.is_tensor(v) and not v.is_cuda:
+                    v = v.numpy()
                 if N > 1:
-                    v[0].copy_(v[1])                    # quirk Q2: first projected row duplicated
-                with timer("assemble.d2h"):
-                    V_out[m].append(host(v))
+                    v[0] = v[1]                         # quirk Q2: first projected row duplicated
+                V_out[m].append(v)
         if fullSVD:
             M.append(_motion_from_energy([E_h[v] for v in range(len(Ly))], sbin, N) if motSVD
                      else np.zeros(N, np.float32))

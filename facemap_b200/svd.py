@@ -70,8 +70,10 @@ class StageTimer:
 # tcgen05 accumulates in float32 with truncation: every MMA into a running sum loses up to one ulp
 # of it, always in the same direction, so the relative bias grows with the length of the K chain.
 # Contractions are therefore cut into short chains (split-K) that are reduced exactly in float64.
-KCHAIN_GRAM = 640     # Gram matrices feed an eigensolve: keep the bias ~1e-5 of an entry
-KCHAIN_GEMM = 2400    # projections / left vectors: ~3e-5, far inside the 1e-3 trace tolerance
+# (measured on B200: -5.4e-8 relative per accumulation, toward zero; scripts/probe_trunc.py)
+KCHAIN_GRAM = 320     # Gram matrices feed an eigensolve: 120 accumulations -> ~6e-6 of an entry
+KCHAIN_LEFT = 256     # left singular vectors (small GEMMs): ~5e-6
+KCHAIN_GEMM = 1200    # projection of every frame: ~2.4e-5 of the largest term (trace tolerance 1e-3)
 
 
 def _gram_ksplit(n, kdim):
@@ -83,8 +85,8 @@ def _gram_ksplit(n, kdim):
     return int(max(1, min(want, math.ceil(kdim / 32), 64)))
 
 
-def _gemm_ksplit(kdim):
-    return int(max(1, math.ceil(kdim / KCHAIN_GEMM)))
+def _gemm_ksplit(kdim, chain=None):
+    return int(max(1, math.ceil(kdim / (chain or KCHAIN_GEMM))))
 
 
 _SOLVERS = {}
@@ -111,9 +113,9 @@ class SvdWorkspace:
         self._ws = None
         self._bufs = {}
 
-    def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm", B_lo=None):
-        """C = rscale * (A @ B^T) + rbias with K chains of <= KCHAIN_GEMM reduced in float64."""
-        ksplit = _gemm_ksplit(A.shape[1])
+    def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm", B_lo=None, chain=None):
+        """C = rscale * (A @ B^T) + rbias with K chains of <= `chain` (KCHAIN_GEMM) reduced in float64."""
+        ksplit = _gemm_ksplit(A.shape[1], chain)
         if self.gemm_impl != 0:
             B_lo = None
         if ksplit == 1:
@@ -193,7 +195,7 @@ def left_components(ws, X, evec, lam, mean, k, out_Yt, timer, label):
     with timer(label + ".transpose"):
         Xt = ws.matrix(label + ".Xt", p, n)
         K.transpose(X, Xt)
-    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left")
+    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left", chain=KCHAIN_LEFT)
 
 
 def chunk_components(ws, X, k, out_Yt, timer, label="chunk"):
@@ -214,7 +216,7 @@ def merge_components(ws, Yt, k, timer, label="merge"):
         Y = ws.matrix(label + ".Y", p, c)
         K.transpose(Yt, Y)
     Ut = K.alloc_matrix(k, p, Yt.device)
-    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left")
+    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left", chain=KCHAIN_LEFT)
     with timer(label + ".transpose"):
         U = torch.empty((p, k), dtype=torch.float32, device=Yt.device)
         K.transpose(Ut, U)
@@ -564,12 +566,19 @@ class Stage3:
         return True
 
     # ---- project phase ---------------------------------------------------------------------------
-    def project(self, masks):
+    def project(self, masks, sink=None):
+        """sink: optional host sink (process._HostSink); the projections are then copied to pinned host
+        arrays batch by batch on its stream and returned as CPU tensors."""
         geo, mods, ws, timer, device = self.geo, self.mods, self.ws, self.timer, self.device
-        V = {}
+        V, V_host = {}, {}
         for m in mods:
             V[m] = [None if Ut is None else torch.zeros((self.n_out, Ut.shape[0]), dtype=torch.float32, device=device)
                     for Ut in masks[m][0]]
+            if sink is not None:
+                V_host[m] = [None if v is None else sink.alloc(v.shape) for v in V[m]]
+                for h in V_host[m]:
+                    if h is not None and self.first_row_frame > self.f0:
+                        h[:self.first_row_frame - self.f0].zero_()      # frame 0 has no difference row
         # the masks are the B operand of every projection GEMM: split them once (lo plane), TMA stages both
         with timer("stage3.split_masks"):
             Ut_lo = {m: [None if Ut is None else K.split_lo(Ut) for Ut in masks[m][0]] for m in mods}
@@ -594,6 +603,8 @@ class Stage3:
                 Xm = X[m][base:base + filled]
                 if self.fullSVD and Uts[0] is not None:
                     ws.gemm(Xm, Uts[0], V[m][0][o:o + filled], label="stage3.project", B_lo=Ut_lo[m][0])
+                    if sink is not None:
+                        sink.copy(V[m][0][o:o + filled], V_host[m][0][o:o + filled])
                 for j, (v, y0, y1, x0, x1) in enumerate(geo.mot_rois):
                     for r0 in range(0, filled, 32768):
                         r1 = min(filled, r0 + 32768)
@@ -602,7 +613,11 @@ class Stage3:
                             K.gather_roi(Xm[r0:r1], r1 - r0, geo.col0[v], int(geo.Lxb[v]), (y0, y1, x0, x1), Xr)
                         ws.gemm(Xr, Uts[1 + j], V[m][1 + j][o + r0:o + r1], label="stage3.roi_project",
                                 B_lo=Ut_lo[m][1 + j])
+                        if sink is not None:
+                            sink.copy(V[m][1 + j][o + r0:o + r1], V_host[m][1 + j][o + r0:o + r1])
             row0 += filled
+        if sink is not None:
+            return V_host, self.E, self.E_roi
         return V, self.E, self.E_roi
 
 
