@@ -282,10 +282,13 @@ class HostArraySource(FrameSource):
 class VideoFileSource(FrameSource):
     """filenames: 2-D list [[view0, view1, ...] per sequential block] (facemap/process.py:652-654).
     Decoding stays on the host (OpenCV); decode failures repeat the previous frame like
-    utils.get_frames (facemap/utils.py:545-547)."""
+    utils.get_frames (facemap/utils.py:545-547).  Every view has its own decode thread (OpenCV
+    releases the GIL), decoding into pinned buffers; `prefetch` starts the next range while the GPU
+    works on the current one, and the H2D copy is asynchronous on a side stream."""
 
     def __init__(self, filenames):
         import cv2
+        from concurrent.futures import ThreadPoolExecutor
 
         self._cv2 = cv2
         self.filenames = filenames
@@ -307,13 +310,18 @@ class VideoFileSource(FrameSource):
         self.cumframes = np.array(cum).astype(int)
         self.nframes = int(cum[-1])
         self.block_frames = [int(x) for x in np.diff(self.cumframes)]
+        self._workers = [ThreadPoolExecutor(max_workers=1) for _ in self.Ly]   # one decoder per view
+        self._jobs = {}
+        self._pipe = _H2DPipe()
+        self.h2d = 0
 
     def h2d_bytes(self, nframes):
         return int(nframes) * sum(h * w for h, w in zip(self.Ly, self.Lx))
 
-    def _read(self, view, a, b):
+    def _read(self, view, a, b, out=None):
         cv2 = self._cv2
-        out = np.zeros((b - a, self.Ly[view], self.Lx[view]), np.uint8)
+        if out is None:
+            out = np.zeros((b - a, self.Ly[view], self.Lx[view]), np.uint8)
         k = 0
         for blk in range(len(self.caps)):
             lo, hi = max(a, self.cumframes[blk]), min(b, self.cumframes[blk + 1])
@@ -329,15 +337,35 @@ class VideoFileSource(FrameSource):
                     out[k] = frame if frame.ndim == 2 else cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
                 elif k > 0:
                     out[k] = out[k - 1]
+                else:
+                    out[k] = 0
                 k += 1
         return out
 
+    def _decode_pinned(self, view, a, b):
+        buf = torch.empty((b - a, self.Ly[view], self.Lx[view]), dtype=torch.uint8, pin_memory=True)
+        self._read(view, a, b, out=buf.numpy())
+        return buf
+
+    def _submit(self, a, b):
+        if (a, b) not in self._jobs:
+            self._jobs[(a, b)] = [w.submit(self._decode_pinned, v, a, b) for v, w in enumerate(self._workers)]
+
+    def prefetch(self, t0, t1, device):
+        a, b = self.clamp(t0, t1)
+        self._submit(a, b)
+
     def fetch(self, t0, t1, device):
         a, b = self.clamp(t0, t1)
-        return [torch.from_numpy(self._read(v, a, b)).pin_memory().to(device, non_blocking=True)
-                for v in range(len(self.Ly))]
+        self._submit(a, b)
+        host = [f.result() for f in self._jobs.pop((a, b))]
+        self.h2d += self.h2d_bytes(b - a)
+        self._pipe.issue((a, b), host, device)
+        return self._pipe.take((a, b))
 
     def close(self):
+        for w in self._workers:
+            w.shutdown(wait=True)
         for caps in self.caps:
             for c in caps:
                 c.release()

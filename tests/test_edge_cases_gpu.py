@@ -1,0 +1,119 @@
+"""Edge cases of the frame count / geometry against the live oracle (exact svdecon): videos shorter than
+one SVD chunk, exactly on and just past the 500 / 1000 / 2000-frame boundaries of the reference's chunking
+(process.py:134-141, 394-395), frame sizes that do not divide by sbin, sbin == 1, three views."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import facemap_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _video(T, H, W, seed):
+    from facemap_b200.synth import SynthVideo
+
+    return SynthVideo(H, W, T, seed=seed, nmodes=12).all_frames()
+
+
+def _compare(p, o, motSVD=True, movSVD=False, s_floor=1e-2):
+    for key in ("avgframe", "avgmotion", "motion"):
+        assert len(p[key]) == len(o[key]), key
+        for a, b in zip(p[key], o[key]):
+            assert a.shape == b.shape and np.array_equal(a, b), key
+    for on, mk, vk, sk in ((motSVD, "motMask", "motSVD", "motSv"), (movSVD, "movMask", "movSVD", "movSv")):
+        assert len(p[mk]) == len(o[mk]) and len(p[vk]) == len(o[vk])
+        assert np.asarray(p[sk]).shape == np.asarray(o[sk]).shape
+        if not on:
+            continue
+        for U, Ur, V, Vr in zip(p[mk], o[mk], p[vk], o[vk]):
+            assert U.shape == Ur.shape and V.shape == Vr.shape, (mk, U.shape, Ur.shape, V.shape, Vr.shape)
+            nrm, nrm_r = np.linalg.norm(U.astype(np.float64), axis=0), np.linalg.norm(Ur.astype(np.float64), axis=0)
+            k = min(3, U.shape[1])
+            cos = np.abs((U[:, :k].astype(np.float64) * Ur[:, :k]).sum(axis=0)) / (nrm[:k] * nrm_r[:k])
+            assert np.abs(cos - 1).max() < 1e-5, (mk, cos)
+            err = np.abs(np.abs(V[:, :k]) - np.abs(Vr[:, :k])).max()
+            assert err <= 1e-3 * np.abs(Vr[:, :k]).max(), (vk, err)
+        S, Sr = np.asarray(p[sk], np.float64), np.asarray(o[sk], np.float64)
+        if np.any(Sr):
+            big = Sr >= s_floor * Sr[0]
+            assert (np.abs(S - Sr)[big] / Sr[big]).max() <= 1e-4, sk
+
+
+@pytest.mark.parametrize("N", [120, 499, 500, 501, 999, 1000, 1001, 1999, 2000, 2001, 3217])
+def test_frame_count_boundaries(cuda_device, N):
+    from facemap_b200 import process
+    from facemap_b200.frames import DeviceArraySource
+
+    v = _video(N, 32, 48, seed=N % 7)
+    o = orc.run_oracle([v], sbin=2, motSVD=True, movSVD=True, svd="exact")
+    p = process.process_source(DeviceArraySource([torch.from_numpy(v).to(cuda_device)]), sbin=2, motSVD=True, movSVD=True)
+    _compare(p, o, True, True)
+    assert p["motion"][0].shape == (N,) and p["motSVD"][0].shape[0] == N
+    if N > 1:
+        assert np.array_equal(p["motSVD"][0][0], p["motSVD"][0][1])
+
+
+@pytest.mark.parametrize("H,W,sbin", [(33, 47, 2), (50, 70, 3), (41, 64, 4), (24, 32, 1), (64, 48, 8), (37, 53, 5)])
+def test_odd_geometry_and_bin_factors(cuda_device, H, W, sbin):
+    from facemap_b200 import process
+    from facemap_b200.frames import DeviceArraySource
+    from tests.helpers import ulp_distance
+
+    N = 2100
+    v = _video(N, H, W, seed=H)
+    o = orc.run_oracle([v], sbin=sbin, motSVD=True, movSVD=False, svd="exact")
+    p = process.process_source(DeviceArraySource([torch.from_numpy(v).to(cuda_device)]), sbin=sbin, motSVD=True, movSVD=False)
+    if sbin & (sbin - 1) == 0:
+        _compare(p, o)
+    else:   # non power-of-two bins: float64 means of means in the reference, <= 1 ulp here
+        for key in ("avgframe", "avgmotion"):
+            assert ulp_distance(p[key][0], o[key][0]) <= 1, key
+        assert np.allclose(p["motion"][0], o["motion"][0], rtol=3e-7, atol=0)
+        S, Sr = p["motSv"].astype(np.float64), o["motSv"].astype(np.float64)
+        big = Sr >= 1e-2 * Sr[0]
+        assert (np.abs(S - Sr)[big] / Sr[big]).max() <= 1e-4
+
+
+def test_three_views_canvas(cuda_device):
+    """3 simultaneous views of different sizes: concatenated pixel axis + 1x2 canvas rule (utils.py:703-748)."""
+    from facemap_b200 import process
+    from facemap_b200.frames import DeviceArraySource
+
+    N = 2050
+    vids = [_video(N, 32, 48, 1), _video(N, 40, 40, 2), _video(N, 24, 64, 3)]
+    o = orc.run_oracle(vids, sbin=2, motSVD=True, movSVD=False, svd="exact")
+    p = process.process_source(DeviceArraySource([torch.from_numpy(v).to(cuda_device) for v in vids]), sbin=2)
+    _compare(p, o)
+    for key in ("sybin", "sxbin", "Lybin", "Lxbin"):
+        assert np.array_equal(np.asarray(p[key]), np.asarray(o[key])), key
+    assert int(p["LYbin"]) == int(o["LYbin"]) and int(p["LXbin"]) == int(o["LXbin"])
+    assert p["motMask_reshape"][0].shape == o["motMask_reshape"][0].shape
+    assert np.array_equal(p["avgframe_reshape"], o["avgframe_reshape"])
+    # the canvas of the first mask is the scatter of its rows
+    k0 = np.abs(p["motMask_reshape"][0][..., 0]).sum()
+    assert np.isclose(k0, np.abs(p["motMask"][0][:, 0]).sum(), rtol=1e-6)
+
+
+def test_fullsvd_off_with_roi(cuda_device):
+    """fullSVD=False + one motion ROI: placeholders of process.py:153-160, 336-339 and the ROI outputs."""
+    import copy
+
+    from facemap_b200 import process
+    from facemap_b200.frames import DeviceArraySource
+    from tests.helpers import motion_roi
+
+    N = 2100
+    v = _video(N, 48, 64, 5)
+    rois = [motion_roi(0, 4, 40, 6, 50)]
+    o = orc.run_oracle([v], sbin=2, motSVD=True, movSVD=False, rois=copy.deepcopy(rois), fullSVD=False, svd="exact")
+    p = process.process_source(DeviceArraySource([torch.from_numpy(v).to(cuda_device)]), sbin=2, motSVD=True,
+                               movSVD=False, rois=copy.deepcopy(rois), fullSVD=False)
+    assert p["motMask"][0].shape == (0, 1) and p["motSVD"][0].shape == (0, 1) and p["motion"][0].shape == (0,)
+    assert p["motMask"][1].shape == o["motMask"][1].shape and p["motSVD"][1].shape == o["motSVD"][1].shape
+    assert np.array_equal(p["motion"][1], o["motion"][1])
+    S, Sr = p["motSv"].astype(np.float64), o["motSv"].astype(np.float64)
+    big = Sr >= 1e-2 * Sr[0]
+    assert S.shape == Sr.shape and (np.abs(S - Sr)[big] / Sr[big]).max() <= 1e-4
+    U, Ur = p["motMask"][1][:, :3].astype(np.float64), o["motMask"][1][:, :3].astype(np.float64)
+    assert np.abs(np.abs((U * Ur).sum(axis=0)) - 1).max() < 1e-5
