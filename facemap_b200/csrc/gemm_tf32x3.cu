@@ -143,10 +143,15 @@ struct GemmCfg {
 // B operand is the mask matrix, constant over all frames and L2-resident), so TMA fills both B tiles and
 // the splitter warps only touch the A tile — a third of the LDS/STS traffic on the shared-memory pipe
 // that ncu shows to be the limiter of the in-kernel split.
-template <int BN, int BK, bool HI_INPLACE, bool B_PRESPLIT>
+// A_PRESPLIT (needs B_PRESPLIT): A's lo plane comes from global memory too (the Gram matrices, where
+// A = B = X and one fm_split_lo pass serves both operands): no splitter stage at all, the MMA thread
+// consumes the TMA barrier directly — a plain TMA -> tcgen05 pipeline.
+template <int BN, int BK, bool HI_INPLACE, bool B_PRESPLIT, bool A_PRESPLIT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+                   const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
+                   const GemmParams p) {
+  static_assert(!A_PRESPLIT || B_PRESPLIT, "A_PRESPLIT requires B_PRESPLIT");
   using Cfg = GemmCfg<BN, BK>;
   constexpr int STAGES = Cfg::STAGES;
   const int m0 = blockIdx.y * BM;
@@ -203,9 +208,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), (uint32_t)(Cfg::HI_BYTES + (B_PRESPLIT ? BN * BK * 4 : 0)));
+        mbar_expect_tx(full_bar(s), (uint32_t)(Cfg::HI_BYTES + (B_PRESPLIT ? BN * BK * 4 : 0) +
+                                               (A_PRESPLIT ? BM * BK * 4 : 0)));
         tma_load_2d(stage, &tmA, full_bar(s), (kb0 + i) * BK, m0);
         tma_load_2d(stage + BM * BK * 4, &tmB, full_bar(s), (kb0 + i) * BK, n0);
+        if constexpr (A_PRESPLIT) tma_load_2d(stage + Cfg::HI_BYTES, &tmAlo, full_bar(s), (kb0 + i) * BK, m0);
         if constexpr (B_PRESPLIT)
           tma_load_2d(stage + Cfg::HI_BYTES + BM * BK * 4, &tmBlo, full_bar(s), (kb0 + i) * BK, n0);
       }
@@ -219,7 +226,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(split_bar(s), ph);
+        mbar_wait(A_PRESPLIT ? full_bar(s) : split_bar(s), ph);
         tcgen05_fence_after();
         const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
         const uint64_t a_hi = make_desc_kmajor<BK>(stage);
@@ -240,7 +247,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else {
     // ===== splitter, then epilogue =====
     const int st = threadIdx.x - 64;  // 0 .. 255
-    for (int i = 0; i < nkb; ++i) {
+    for (int i = 0; i < (A_PRESPLIT ? 0 : nkb); ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
       mbar_wait(full_bar(s), ph);
@@ -649,10 +656,11 @@ static int make_map(CUtensorMap* map, const float* base, int64_t ld, int rows, i
   return FM_OK;
 }
 
-template <int BN, int BK, bool HI_INPLACE, bool B_PRESPLIT = false>
+template <int BN, int BK, bool HI_INPLACE, bool B_PRESPLIT = false, bool A_PRESPLIT = false>
 static int launch_tc(const float* A, int64_t lda, const float* B, int64_t ldb, const GemmParams& p, cudaStream_t st,
-                     const float* B_lo = nullptr, int64_t ldb_lo = 0) {
-  CUtensorMap ta, tb, tblo;
+                     const float* B_lo = nullptr, int64_t ldb_lo = 0, const float* A_lo = nullptr,
+                     int64_t lda_lo = 0) {
+  CUtensorMap ta, tb, talo, tblo;
   int rc;
   if ((rc = make_map(&ta, A, lda, p.M, p.K, BM, BK)) != FM_OK) return rc;
   if ((rc = make_map(&tb, B, ldb, p.N, p.K, BN, BK)) != FM_OK) return rc;
@@ -661,15 +669,20 @@ static int launch_tc(const float* A, int64_t lda, const float* B, int64_t ldb, c
   } else {
     tblo = tb;
   }
+  if (A_PRESPLIT) {
+    if ((rc = make_map(&talo, A_lo, lda_lo, p.M, p.K, BM, BK)) != FM_OK) return rc;
+  } else {
+    talo = ta;
+  }
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, BK, HI_INPLACE, B_PRESPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, BK, HI_INPLACE, B_PRESPLIT, A_PRESPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     GemmCfg<BN, BK>::SMEM_BYTES);
   });
   FM_CUDA_TRY(attr_err);
   dim3 grid((unsigned)cdiv(p.N, BN), (unsigned)cdiv(p.M, BM), (unsigned)p.ksplit);
-  gemm_tf32x3_kernel<BN, BK, HI_INPLACE, B_PRESPLIT><<<grid, GEMM_THREADS, GemmCfg<BN, BK>::SMEM_BYTES, st>>>(ta, tb, tblo, p);
+  gemm_tf32x3_kernel<BN, BK, HI_INPLACE, B_PRESPLIT, A_PRESPLIT><<<grid, GEMM_THREADS, GemmCfg<BN, BK>::SMEM_BYTES, st>>>(ta, tb, talo, tblo, p);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }
@@ -701,8 +714,9 @@ extern "C" int64_t fm_gemm_workspace_bytes(int M, int64_t ldw, int ksplit) {
   return (int64_t)ksplit * M * ldw * 4;
 }
 
-extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* B_lo,
-                          int64_t ldb_lo, int M, int N, int K, float* C, int64_t ldc, const float* rscale,
+extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* A_lo, int64_t lda_lo, const float* B,
+                          int64_t ldb, const float* B_lo, int64_t ldb_lo, int M, int N, int K, float* C,
+                          int64_t ldc, const float* rscale,
                           const float* rbias, int ksplit, float* workspace, int64_t ldw, int upper_only, int impl,
                           void* stream) {
   using namespace fm;
@@ -743,8 +757,15 @@ extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
   if (B_lo != nullptr) {
     FM_REQUIRE(ldb_lo >= K && ldb_lo % 4 == 0 && (reinterpret_cast<uintptr_t>(B_lo) & 15) == 0,
                "fm_gemm_tn: B_lo needs a 16-byte aligned base and ldb_lo %% 4 == 0");
+    if (A_lo != nullptr) {
+      FM_REQUIRE(lda_lo >= K && lda_lo % 4 == 0 && (reinterpret_cast<uintptr_t>(A_lo) & 15) == 0,
+                 "fm_gemm_tn: A_lo needs a 16-byte aligned base and lda_lo %% 4 == 0");
+      return (N > 128) ? launch_tc<256, 16, false, true, true>(A, lda, B, ldb, p, st, B_lo, ldb_lo, A_lo, lda_lo)
+                       : launch_tc<128, 32, false, true, true>(A, lda, B, ldb, p, st, B_lo, ldb_lo, A_lo, lda_lo);
+    }
     return (N > 128) ? launch_tc<256, 16, false, true>(A, lda, B, ldb, p, st, B_lo, ldb_lo)
                      : launch_tc<128, 32, false, true>(A, lda, B, ldb, p, st, B_lo, ldb_lo);
   }
+  FM_REQUIRE(A_lo == nullptr, "fm_gemm_tn: A_lo is only accepted together with B_lo");
   return (N > 128) ? launch_tc<256, 16, false>(A, lda, B, ldb, p, st) : launch_tc<128, 32, false>(A, lda, B, ldb, p, st);
 }

@@ -100,17 +100,19 @@ def mean_update(acc, tsum, sbin, count, finalize_div=0):
                                      _stream()), "fm_mean_update")
 
 
-def split_lo(X):
+def split_lo(X, out=None):
     """lo plane of the 3xTF32 split of X (same shape and pitch policy as alloc_matrix)."""
     _need(X, torch.float32, "X", 2)
-    lo = alloc_matrix(X.shape[0], X.shape[1], X.device)
+    lo = alloc_matrix(X.shape[0], X.shape[1], X.device) if out is None else out
+    if tuple(lo.shape) != tuple(X.shape) or lo.stride(1) != 1:
+        raise FacemapB200Error("split_lo: out must have X's shape")
     check(_lib.load().fm_split_lo(ptr(X), X.stride(0), X.shape[0], X.shape[1], ptr(lo), lo.stride(0), _stream()),
           "fm_split_lo")
     return lo
 
 
 def gemm_tn(A, B, C_out=None, *, rscale=None, rbias=None, ksplit=1, workspace=None, upper_only=False, impl=0,
-            B_lo=None):
+            B_lo=None, A_lo=None):
     """C[M,N] = rscale[m] * (A[M,K] @ B[N,K]^T) + rbias[m]; both operands K-contiguous float32.
     With ksplit > 1 the raw partial products go to `workspace` [ksplit, M, ldw] instead."""
     _need(A, torch.float32, "A", 2)
@@ -136,7 +138,11 @@ def gemm_tn(A, B, C_out=None, *, rscale=None, rbias=None, ksplit=1, workspace=No
     _need(B_lo, torch.float32, "B_lo", 2)
     if B_lo is not None and (tuple(B_lo.shape) != tuple(B.shape) or B_lo.stride(1) != 1):
         raise FacemapB200Error("gemm_tn: B_lo must have B's shape")
-    check(_lib.load().fm_gemm_tn(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(B_lo),
+    _need(A_lo, torch.float32, "A_lo", 2)
+    if A_lo is not None and (tuple(A_lo.shape) != tuple(A.shape) or A_lo.stride(1) != 1 or B_lo is None):
+        raise FacemapB200Error("gemm_tn: A_lo must have A's shape and needs B_lo")
+    check(_lib.load().fm_gemm_tn(ptr(A), A.stride(0), ptr(A_lo), A_lo.stride(0) if A_lo is not None else 0,
+                                 ptr(B), B.stride(0), ptr(B_lo),
                                  B_lo.stride(0) if B_lo is not None else 0, M, N, K, ptr(C_out), ldc, ptr(rscale),
                                  ptr(rbias), int(ksplit), ptr(workspace), ldw, int(bool(upper_only)), int(impl),
                                  _stream()), "fm_gemm_tn")

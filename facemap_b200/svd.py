@@ -159,11 +159,16 @@ def centred_gram(ws: SvdWorkspace, X, timer, label, out=None):
         mean = K.row_means(X)
     ksplit = _gram_ksplit(n, p)
     part = ws.workspace(ksplit, n)
+    # A = B = X: one lo plane serves both operands, TMA stages all four tiles (no in-kernel split)
+    X_lo = None
+    if ws.gemm_impl == 0:
+        with timer(label + ".gram.split"):
+            X_lo = K.split_lo(X, out=ws.matrix("gram.lo", n, p))
     with timer(label + ".gram.mma"):
         if ksplit > 1:
-            K.gemm_tn(X, X, ksplit=ksplit, workspace=part, upper_only=True, impl=ws.gemm_impl)
+            K.gemm_tn(X, X, ksplit=ksplit, workspace=part, upper_only=True, impl=ws.gemm_impl, B_lo=X_lo, A_lo=X_lo)
         else:
-            K.gemm_tn(X, X, part[0], upper_only=True, impl=ws.gemm_impl)
+            K.gemm_tn(X, X, part[0], upper_only=True, impl=ws.gemm_impl, B_lo=X_lo, A_lo=X_lo)
     with timer(label + ".gram.assemble"):
         G = K.gram_assemble(part, ksplit, n, mean, p, True, out=out)
     return mean, G
@@ -195,7 +200,8 @@ def left_components(ws, X, evec, lam, mean, k, out_Yt, timer, label):
     with timer(label + ".transpose"):
         Xt = ws.matrix(label + ".Xt", p, n)
         K.transpose(X, Xt)
-    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left", chain=KCHAIN_LEFT)
+        Xt_lo = K.split_lo(Xt, out=ws.matrix(label + ".Xt_lo", p, n)) if ws.gemm_impl == 0 else None
+    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left", chain=KCHAIN_LEFT, B_lo=Xt_lo)
 
 
 def chunk_components(ws, X, k, out_Yt, timer, label="chunk"):
@@ -215,8 +221,9 @@ def merge_components(ws, Yt, k, timer, label="merge"):
     with timer(label + ".transpose"):
         Y = ws.matrix(label + ".Y", p, c)
         K.transpose(Yt, Y)
+        Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p, c)) if ws.gemm_impl == 0 else None
     Ut = K.alloc_matrix(k, p, Yt.device)
-    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left", chain=KCHAIN_LEFT)
+    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left", chain=KCHAIN_LEFT, B_lo=Y_lo)
     with timer(label + ".transpose"):
         U = torch.empty((p, k), dtype=torch.float32, device=Yt.device)
         K.transpose(Ut, U)

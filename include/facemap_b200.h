@@ -99,14 +99,16 @@ int fm_mean_update(float* acc, const long long* tsum, int64_t n, int sbin, int c
  * of matlab/utils/svdecon.m:16-43).
  *   B_lo            NULL, or the pre-computed lo plane of B (fm_split_lo): TMA then stages both B
  *                   tiles and only A is split in the kernel (impl 0 only)
+ *   A_lo            NULL, or the lo plane of A (only together with B_lo): no in-kernel split at all
  *   rscale, rbias   float32 [M] or NULL
  *   ksplit >= 1: if > 1, `C` is ignored and raw partial products are written to
  *                workspace[ksplit, M, ldw] (no scale/bias); reduce with fm_gram_assemble.
  *   upper_only != 0: tiles entirely below the diagonal are skipped (symmetric Gram).
  *   impl: 0 = tcgen05 3xTF32 (product path), 1 = plain FP32 FFMA reference kernel (validation).
  */
-int fm_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, const float* B_lo, int64_t ldb_lo,
-               int M, int N, int K, float* C, int64_t ldc, const float* rscale, const float* rbias,
+int fm_gemm_tn(const float* A, int64_t lda, const float* A_lo, int64_t lda_lo, const float* B, int64_t ldb,
+               const float* B_lo, int64_t ldb_lo, int M, int N, int K, float* C, int64_t ldc,
+               const float* rscale, const float* rbias,
                int ksplit, float* workspace, int64_t ldw, int upper_only, int impl, void* stream);
 
 /* lo[r,c] = X[r,c] - tf32_trunc(X[r,c]): pre-computed second plane of a B operand that many GEMMs

@@ -40,9 +40,10 @@ def bench(M, N, Kd, ksplit=1, reps=5, upper=False):
     A = K.alloc_matrix(M, Kd, dev); B = K.alloc_matrix(N, Kd, dev)
     A.normal_(); B.normal_()
     Blo = K.split_lo(B) if PRESPLIT else None
+    Alo = K.split_lo(A) if (len(sys.argv) > 3 and sys.argv[3] == "both") else None
     C = K.alloc_matrix(M, N, dev)
     ws = torch.empty((ksplit, M, K.round_up(N, 32)), device=dev) if ksplit > 1 else None
-    f = (lambda: K.gemm_tn(A, B, ksplit=ksplit, workspace=ws, upper_only=upper, impl=impl, B_lo=Blo)) if ksplit > 1 else (lambda: K.gemm_tn(A, B, C, impl=impl, upper_only=upper, B_lo=Blo))
+    f = (lambda: K.gemm_tn(A, B, ksplit=ksplit, workspace=ws, upper_only=upper, impl=impl, B_lo=Blo, A_lo=Alo)) if ksplit > 1 else (lambda: K.gemm_tn(A, B, C, impl=impl, upper_only=upper, B_lo=Blo, A_lo=Alo))
     for _ in range(2): f()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()

@@ -86,6 +86,29 @@ def test_presplit_b_operand_is_bit_identical(cuda_device, M, N, K, ksplit):
     assert torch.equal(C0, C1)
 
 
+def test_fully_presplit_gram_is_bit_identical(cuda_device):
+    """A_lo = B_lo = split_lo(X) staged by TMA (no splitter warps) == in-kernel split, for the Gram shape."""
+    from facemap_b200 import kernels as Kn
+
+    dev = cuda_device
+    n, K, ksplit = 999, 4100, 5
+    X = _rand(n, K, dev, 31)
+    X_lo = Kn.split_lo(X)
+    ld = Kn.round_up(n, 32)
+    W0 = torch.zeros((ksplit, n, ld), device=dev)
+    W1 = torch.zeros_like(W0)
+    Kn.gemm_tn(X, X, ksplit=ksplit, workspace=W0, upper_only=True)
+    Kn.gemm_tn(X, X, ksplit=ksplit, workspace=W1, upper_only=True, B_lo=X_lo, A_lo=X_lo)
+    torch.cuda.synchronize()
+    assert torch.equal(W0, W1)
+    A, B = _rand(300, 777, dev, 32), _rand(200, 777, dev, 33)
+    C0, C1 = Kn.alloc_matrix(300, 200, dev), Kn.alloc_matrix(300, 200, dev)
+    Kn.gemm_tn(A, B, C0)
+    Kn.gemm_tn(A, B, C1, B_lo=Kn.split_lo(B), A_lo=Kn.split_lo(A))
+    torch.cuda.synchronize()
+    assert torch.equal(C0, C1)
+
+
 def test_gemm_scale_bias_epilogue(cuda_device):
     from facemap_b200 import kernels as Kn
 
