@@ -55,6 +55,9 @@ SIGNATURES = {
     "fm_gemm_workspace_bytes": (_L, [_I, _L, _I]),
     "fm_row_means": (_I, [_P, _L, _I, _L, _P, _P]),
     "fm_gram_assemble": (_I, [_P, _I, _I, _L, _P, _L, _I, _P, _P]),
+    "fm_row_dot": (_I, [_P, _L, _I, _L, _P, _P, _P]),
+    "fm_gram_assemble_rowside": (_I, [_P, _I, _I, _L, _P, _P, _I, _I, _P, _P]),
+    "fm_sign_from_right": (_I, [_P, _L, _I, _I, _P, _P, _L, _I, _P]),
     "fm_solver_create": (_I, [C.POINTER(_P)]),
     "fm_solver_destroy": (_I, [_P]),
     "fm_syevd": (_I, [_P, _P, _I, _P, _I, _P]),

@@ -270,3 +270,122 @@ extern "C" int fm_split_lo(const float* X, int64_t ldx, int rows, int cols, floa
   FM_LAUNCH_CHECK();
   return FM_OK;
 }
+
+// ---- row-side Gram for wide matrices (merge of an ROI: p pixels < c stacked components) -------
+// svdecon(Y [p, c]) with PCA column centring Yc = Y - 1 mu^T:
+//   Yc Yc^T = Y Y^T - q 1^T - 1 q^T + (mu.mu) 1 1^T,   q = Y mu
+// Its eigenvectors ARE the left singular vectors; the sign rule needs the right ones,
+//   V S = Yc^T U = Y^T U - mu (1^T U).
+namespace fm {
+// q[r] = sum_c Y[r,c] * w[c]   (float64), one block per row
+__global__ void __launch_bounds__(256) row_dot_kernel(const float* __restrict__ Y, int64_t ldy, int64_t ncols,
+                                                      const double* __restrict__ w, double* __restrict__ q) {
+  __shared__ double sh[8];
+  const float* row = Y + (size_t)blockIdx.x * ldy;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < ncols; i += 256) acc += (double)row[i] * w[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int i = 0; i < 8; ++i) v += sh[i];
+    q[blockIdx.x] = v;
+  }
+}
+
+__global__ void gram_assemble_rowside_kernel(const float* __restrict__ part, int ksplit, int n, int64_t ldw,
+                                             const double* __restrict__ q, const double* __restrict__ mu, int nmu,
+                                             int upper_only, double* __restrict__ G) {
+  __shared__ double s_mumu;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    double a = 0.0;
+    for (int i = 0; i < nmu; ++i) a += mu[i] * mu[i];
+    s_mumu = a;
+  }
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n || j >= n) return;
+  int si = i, sj = j;
+  if (upper_only && i > j) { si = j; sj = i; }
+  double acc = 0.0;
+  const size_t plane = (size_t)n * ldw;
+  for (int s = 0; s < ksplit; ++s) acc += (double)part[(size_t)s * plane + (size_t)si * ldw + sj];
+  G[(size_t)i * n + j] = acc - (q[i] + q[j]) + s_mumu;
+}
+
+// one block per component: sign of the largest-|.| entry of its RIGHT singular vector
+//   v[j] = T[c,j] - mu[j] * sum_a Ut[c,a];  negative -> flip row c of Ut
+__global__ void __launch_bounds__(256) sign_from_right_kernel(const float* __restrict__ T, int64_t ldt, int ncols,
+                                                              const double* __restrict__ mu, float* __restrict__ Ut,
+                                                              int64_t ldu, int p) {
+  __shared__ double s_val[256];
+  __shared__ double s_abs[256];
+  __shared__ int s_idx[256];
+  __shared__ double s_su;
+  const int c = blockIdx.x;
+  float* u = Ut + (size_t)c * ldu;
+  double su = 0.0;
+  for (int a = threadIdx.x; a < p; a += 256) su += (double)u[a];
+  s_val[threadIdx.x] = su;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_val[threadIdx.x] += s_val[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s_su = s_val[0];
+  __syncthreads();
+  su = s_su;
+  double best = -1.0, bval = 0.0;
+  int bidx = 0;
+  for (int j = threadIdx.x; j < ncols; j += 256) {
+    const double v = (double)T[(size_t)c * ldt + j] - mu[j] * su;
+    if (fabs(v) > best) { best = fabs(v); bval = v; bidx = j; }
+  }
+  __syncthreads();
+  s_abs[threadIdx.x] = best; s_val[threadIdx.x] = bval; s_idx[threadIdx.x] = bidx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double a = s_abs[threadIdx.x + o];
+      if (a > s_abs[threadIdx.x] || (a == s_abs[threadIdx.x] && s_idx[threadIdx.x + o] < s_idx[threadIdx.x])) {
+        s_abs[threadIdx.x] = a; s_val[threadIdx.x] = s_val[threadIdx.x + o]; s_idx[threadIdx.x] = s_idx[threadIdx.x + o];
+      }
+    }
+    __syncthreads();
+  }
+  const bool flip = s_val[0] < 0.0;
+  if (flip)
+    for (int a = threadIdx.x; a < p; a += 256) u[a] = -u[a];
+}
+}  // namespace fm
+
+extern "C" int fm_row_dot(const float* Y, int64_t ldy, int rows, int64_t ncols, const double* w, double* q,
+                          void* stream) {
+  using namespace fm;
+  FM_REQUIRE(Y && w && q && rows >= 1 && ncols >= 1 && ldy >= ncols, "fm_row_dot: bad args");
+  row_dot_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(Y, ldy, ncols, w, q);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+extern "C" int fm_gram_assemble_rowside(const float* part, int ksplit, int n, int64_t ldw, const double* q,
+                                        const double* mu, int nmu, int upper_only, double* G, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(part && q && mu && G && ksplit >= 1 && n >= 1 && nmu >= 1 && ldw >= n, "fm_gram_assemble_rowside: bad args");
+  dim3 block(32, 8), grid((unsigned)cdiv(n, 32), (unsigned)cdiv(n, 8));
+  gram_assemble_rowside_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part, ksplit, n, ldw, q, mu,
+                                                                                          nmu, upper_only, G);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+extern "C" int fm_sign_from_right(const float* T, int64_t ldt, int k, int ncols, const double* mu, float* Ut,
+                                  int64_t ldu, int p, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(T && mu && Ut && k >= 1 && ncols >= 1 && p >= 1 && ldt >= ncols && ldu >= p, "fm_sign_from_right: bad args");
+  sign_from_right_kernel<<<k, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(T, ldt, ncols, mu, Ut, ldu, p);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}

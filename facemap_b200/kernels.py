@@ -177,6 +177,29 @@ def gram_assemble(workspace, ksplit, n, mean, ncols, upper_only, out=None):
     return out
 
 
+def row_dot(Y, w):
+    """q[r] = sum_c Y[r,c] * w[c] in float64."""
+    _need(Y, torch.float32, "Y", 2)
+    _need(w, torch.float64, "w")
+    q = torch.empty(Y.shape[0], dtype=torch.float64, device=Y.device)
+    check(_lib.load().fm_row_dot(ptr(Y), Y.stride(0), Y.shape[0], Y.shape[1], ptr(w), ptr(q), _stream()), "fm_row_dot")
+    return q
+
+
+def gram_assemble_rowside(workspace, ksplit, n, q, mu, upper_only):
+    G = torch.empty((n, n), dtype=torch.float64, device=workspace.device)
+    check(_lib.load().fm_gram_assemble_rowside(ptr(workspace), int(ksplit), int(n), workspace.stride(-2), ptr(q), ptr(mu),
+                                               mu.numel(), int(bool(upper_only)), ptr(G), _stream()),
+          "fm_gram_assemble_rowside")
+    return G
+
+
+def sign_from_right(T, mu, Ut):
+    """flip rows of Ut [k, p] by the sign rule on the right singular vectors; T = Ut @ Y [k, c]."""
+    check(_lib.load().fm_sign_from_right(ptr(T), T.stride(0), Ut.shape[0], T.shape[1], ptr(mu), ptr(Ut), Ut.stride(0),
+                                         Ut.shape[1], _stream()), "fm_sign_from_right")
+
+
 class Solver:
     """cuSOLVER handle + workspaces (fm_solver)."""
 

@@ -236,7 +236,10 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         for m in ("mot", "mov"):
             U_resh[m] = list(U_out[m])
             if m in mods and not keep_on_device:
-                if fullSVD:
+                if fullSVD and len(Ly) == 1:
+                    # one view: the canvas IS the mask matrix seen as (Lyb, Lxb, ncomp) — no copy
+                    U_resh[m][0] = U_out[m][0].reshape(int(Lybin[0]), int(Lxbin[0]), -1)
+                elif fullSVD:
                     U_resh[m][0] = multivideo_reshape(U_out[m][0], LYbin, LXbin, sybin, sxbin, Lybin, Lxbin, iinds)
                 for j, (_, y0, y1, x0, x1) in enumerate(geo.mot_rois):
                     U_resh[m][1 + j] = U_out[m][1 + j].copy().reshape(y1 - y0, x1 - x0, -1)

@@ -213,10 +213,51 @@ def chunk_components(ws, X, k, out_Yt, timer, label="chunk"):
     left_components(ws, X, G, lam, mean, k, out_Yt, timer, label)
 
 
+def merge_components_rowside(ws, Yt, k, timer, label="merge"):
+    """svdecon(Y, k) when Y [p, c] is wide (p < c: the merge of a small ROI): eigensolve of the p x p
+    matrix Yc Yc^T, whose eigenvectors are the masks themselves; the sign comes from the right vectors."""
+    c, p = Yt.shape
+    with timer(label + ".colmean"):
+        mu = K.row_means(Yt)                                   # column means of Y = row means of Yt
+    with timer(label + ".transpose"):
+        Y = ws.matrix(label + ".Y", p, c)
+        K.transpose(Yt, Y)
+        Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p, c)) if ws.gemm_impl == 0 else None
+    ksplit = _gram_ksplit(p, c)
+    part = ws.workspace(ksplit, p)
+    with timer(label + ".gram.mma"):
+        if ksplit > 1:
+            K.gemm_tn(Y, Y, ksplit=ksplit, workspace=part, upper_only=True, impl=ws.gemm_impl, B_lo=Y_lo, A_lo=Y_lo)
+        else:
+            K.gemm_tn(Y, Y, part[0], upper_only=True, impl=ws.gemm_impl, B_lo=Y_lo, A_lo=Y_lo)
+    with timer(label + ".gram.assemble"):
+        q = K.row_dot(Y, mu)
+        G = K.gram_assemble_rowside(part, ksplit, p, q, mu, True)
+    with timer(label + ".syevd"):
+        if ws.eig_fp32 or k == p:
+            lam, nev = ws.solver.syevd(G, use_fp32=ws.eig_fp32), p
+        else:
+            lam, nev = ws.solver.syevdx_top(G, k), k
+    with timer(label + ".topk"):
+        Ut = K.alloc_matrix(k, p, Yt.device)
+        sval, _, _ = K.topk_components(G, lam, k, None, Ut, want_scale=False, nev=nev)
+    # sign rule on the right singular vectors: T = Ut Y  (V S = T^T - mu (1^T U))
+    T = ws.matrix(label + ".T", k, c)
+    ws.gemm(Ut, Yt, T, label=label + ".left", chain=KCHAIN_LEFT)
+    with timer(label + ".topk"):
+        K.sign_from_right(T, mu, Ut)
+    with timer(label + ".transpose"):
+        U = torch.empty((p, k), dtype=torch.float32, device=Yt.device)
+        K.transpose(Ut, U)
+    return Ut, U, sval
+
+
 def merge_components(ws, Yt, k, timer, label="merge"):
     """svdecon(Y, k) for Y = [U_1 S_1 ... ] given as Yt [c, p] (facemap/process.py:264-295).
     Returns (Ut [k, p], U [p, k], sval [k])."""
     c, p = Yt.shape
+    if p < c:
+        return merge_components_rowside(ws, Yt, k, timer, label)
     Wt, sval, rbias, rscale = gram_eig(ws, Yt, k, timer, True, label)
     with timer(label + ".transpose"):
         Y = ws.matrix(label + ".Y", p, c)

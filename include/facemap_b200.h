@@ -137,6 +137,20 @@ int fm_gram_assemble(const float* part, int ksplit, int n, int64_t ldw, const do
                      int64_t ncols, int upper_only, double* G, void* stream);
 
 /*
+ * Row-side form of the same PCA for wide matrices (merge of a small ROI: p pixels < c stacked
+ * components, facemap/process.py:276-295): with mu = column means of Y [p, c] and q = Y mu,
+ *   fm_row_dot : q[r] = sum_c Y[r,c] * w[c]
+ *   fm_gram_assemble_rowside : G = sum_s part[s] - q 1^T - 1 q^T + (mu.mu) 1 1^T   (= Yc Yc^T, p x p)
+ *   fm_sign_from_right : the sign rule needs the RIGHT vectors, V S = Y^T U - mu (1^T U); given
+ *       T[k, c] = Ut Y (fm_gemm_tn) it flips the rows of Ut whose largest-|.| right entry is negative.
+ */
+int fm_row_dot(const float* Y, int64_t ldy, int rows, int64_t ncols, const double* w, double* q, void* stream);
+int fm_gram_assemble_rowside(const float* part, int ksplit, int n, int64_t ldw, const double* q,
+                             const double* mu, int nmu, int upper_only, double* G, void* stream);
+int fm_sign_from_right(const float* T, int64_t ldt, int k, int ncols, const double* mu, float* Ut,
+                       int64_t ldu, int p, void* stream);
+
+/*
  * Symmetric eigensolve (cuSOLVER syevd — the one library call on the path; timed separately,
  * not claimed as a kernel).  G is float64 n x n, overwritten with eigenvectors (row j =
  * eigenvector of the j-th smallest eigenvalue); lam[n] ascending.  `use_fp32` solves in float32
