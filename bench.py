@@ -281,15 +281,18 @@ def main():
         torch.cuda.synchronize()
 
     def one_step(src, timing=None, keep=True, overlap=True):
+        # every rank keeps the projections of its own frame range (north_star: "each rank projects its own
+        # frames with no further communication"); the gather for the file is process.run's business
         return process.process_source(src, sbin=SBIN, motSVD=True, movSVD=False, dist=shard, timing=timing,
-                                      keep_on_device=keep, overlap_stage3=overlap)
+                                      keep_on_device=keep, overlap_stage3=overlap, gather_outputs=False)
 
-    for _ in range(max(args.warmup, 3)):
+    nwarm = max(args.warmup, 3)
+    clocks = ClockSampler(local)
+    for i in range(nwarm):
+        if i == nwarm - 1 and rank == 0:
+            clocks.start()                       # one sampler (rank 0's GPU), spawned outside the timed region
         one_step(dev_src)
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
-    time.sleep(0.3)
     timings = []
     n0 = kernels.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -305,7 +308,7 @@ def main():
     barrier()
     w1 = time.perf_counter()
     launches = kernels.launch_count() - n0
-    clk = clocks.stop(w0, w1)
+    clk = clocks.stop(w0, w1) if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if world > 1:
@@ -373,8 +376,11 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
+        io = torch.tensor([host_src.h2d // args.e2e_steps, int(d2h)], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(io, op=dist.ReduceOp.SUM)          # bytes of the whole job, all ranks
         e2e = {"value": total_frames * args.e2e_steps / dt, "unit": "frames/s",
-               "h2d_bytes_per_step": host_src.h2d // args.e2e_steps, "d2h_bytes_per_step": int(d2h),
+               "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
                "steps": args.e2e_steps, "api": "facemap_b200.process.process_source(HostArraySource-like pinned frames)",
                "upload_ms": round(host_src.dcache.upload_ms(), 1), "wall_s_last_step": round(e2e_tm.get("wall_s", 0.0), 4),
                "assemble_wall_s": round(e2e_tm.get("assemble_wall_s", 0.0), 4),

@@ -49,21 +49,27 @@ def save(proc, savepath=None):
     return savename
 
 
-def _motion_from_energy(E_views, sbin, N):
+def _motion_from_energy(E_views, sbin, N, f0=0):
     """Reference float semantics of `M[.] += imbin_mot.sum(-1)` per view (process.py:460) applied
     to exact integer energies, then the chunk-0 layout (quirk Q1): entries [0, nt1-1) hold the
-    diffs of frames 1..nt1-1, entry nt1-1 stays 0."""
+    diffs of frames 1..nt1-1, entry nt1-1 stays 0.  E_views cover frames [f0, f0 + len) of an
+    N-frame video (a rank's shard when the outputs are not gathered)."""
     s2 = float(sbin * sbin)
-    acc = np.zeros(N, np.float32)
+    n = len(E_views[0])
+    acc = np.zeros(n, np.float32)
     for e in E_views:
         if sbin == 1:
             acc = acc + e.astype(np.float32)                    # float32 sums in the reference
         else:
             acc = (acc.astype(np.float64) + e.astype(np.float64) / s2).astype(np.float32)
     nt1 = min(500, N)
-    out = np.zeros(N, np.float32)
-    out[:nt1 - 1] = acc[1:nt1]
-    out[nt1:] = acc[nt1:]
+    out = acc.copy()
+    if f0 < nt1:                                                # this range holds (part of) the first chunk
+        hi = min(nt1 - 1, f0 + n - 1)                           # global frames f0 .. hi-1 take the next frame's energy
+        if hi > f0:
+            out[:hi - f0] = acc[1:hi - f0 + 1]
+        if nt1 - 1 - f0 < n:
+            out[nt1 - 1 - f0] = 0
     return out
 
 
@@ -97,10 +103,12 @@ class _HostSink:
 
 def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD=True, device=None,
                    eig_fp32=False, gemm_impl=0, timing=None, dist=None, keep_on_device=False,
-                   overlap_stage3=True):
+                   overlap_stage3=True, gather_outputs=True):
     """Run the three stages on a FrameSource and return the proc-dict entries this path owns.
 
     timing: optional dict that receives per-stage device times (ms) and wall times.
+    gather_outputs: with `dist`, all-gather projections / energies so every rank returns the whole video
+            (what `run` needs for the file); False keeps each rank's frame range only (proc["frame_range"]).
     overlap_stage3: run stage 3's bin/diff pass on a side stream underneath the stage-2 eigensolves
             when the frames are HBM-resident (svd.Stage3.start_early).
     dist:   optional facemap_b200.parallel.Shard (frame-range sharding across ranks)."""
@@ -171,7 +179,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     pending_masks = {}
     V, E, E_roi = {}, None, None
     if mods and masks:
-        single = dist is None or dist.world == 1
+        single = dist is None or dist.world == 1 or not gather_outputs
         if sink is not None:
             # masks and singular values leave while stage 3 runs; projections leave batch by batch
             pending_masks = {m: ([sink.to_host(u) for u in masks[m][1]], sink.to_host(masks[m][2])) for m in masks}
@@ -181,6 +189,9 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
 
     mark("stage3")
     # ---- assemble (device -> host) ----
+    f0_out = 0
+    if dist is not None and dist.world > 1 and not gather_outputs and s3 is not None:
+        f0_out = s3.f0
     t_asm = time.perf_counter()
     with timer("assemble.d2h"):
         avgframe_h = avgframe.cpu().numpy()
@@ -199,6 +210,8 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                                                            Lybin, Lxbin, iinds)),
         "rois": rois,
     }
+    if f0_out or (dist is not None and dist.world > 1 and not gather_outputs and s3 is not None):
+        proc["frame_range"] = (s3.f0, s3.f1)     # motSVD / movSVD / motion rows cover this range only
 
     def host(t):
         if keep_on_device:
@@ -257,16 +270,17 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                         sink.wait()
                 if torch.is_tensor(v) and not v.is_cuda:
                     v = v.numpy()
-                if N > 1:
+                if N > 1 and f0_out == 0 and v.shape[0] > 1:
                     v[0] = v[1]                         # quirk Q2: first projected row duplicated
                 V_out[m].append(v)
         if fullSVD:
-            M.append(_motion_from_energy([E_h[v] for v in range(len(Ly))], sbin, N) if motSVD
-                     else np.zeros(N, np.float32))
+            M.append(_motion_from_energy([E_h[v] for v in range(len(Ly))], sbin, N, f0_out) if motSVD
+                     else np.zeros(E_h.shape[1], np.float32))
         else:
             M.append(np.zeros((0,), np.float32))
         for j in range(nroi):
-            M.append(_motion_from_energy([E_roi_h[j]], sbin, N) if motSVD else np.zeros(N, np.float32))
+            M.append(_motion_from_energy([E_roi_h[j]], sbin, N, f0_out) if motSVD
+                     else np.zeros(E_roi_h.shape[1], np.float32))
         # quirk Q4: the avg arrays of a view carrying a motion ROI are saved 2-D
         for v in range(len(Ly)):
             if geo.rois_on_view[v]:

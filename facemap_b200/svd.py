@@ -29,6 +29,7 @@ CHUNK_SVD = 1000    # process.py:134
 BUDGET_SVD = 15000  # process.py:135
 NC_CHUNK = 250      # process.py:136
 NUM_SMS = 148
+BATCHED_EIG_MIN = 5
 
 
 class StageTimer:
@@ -449,7 +450,9 @@ def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, t
                     mean, _ = centred_gram(ws, Xt, timer, label, out=G[len(jobs)])
                     jobs.append((slot, m, idx, Xt, mean, label))
         with timer("stage2.chunk.syevd"):
-            if ws.eig_fp32 or len(jobs) == 1:
+            # the batched solver carries ~50 ms of fixed cost on B200 (15 x 999^2: 68 ms, 2 x 999^2: 53 ms)
+            # against 12 ms per serial syevd: it pays off from 5 matrices on
+            if ws.eig_fp32 or len(jobs) < BATCHED_EIG_MIN:
                 lam = torch.stack([ws.solver.syevd(G[i], use_fp32=ws.eig_fp32) for i in range(len(jobs))])
             else:
                 lam = ws.solver.syevd_batched(G)
