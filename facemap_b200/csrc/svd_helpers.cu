@@ -115,10 +115,11 @@ __global__ void __launch_bounds__(256) topk_kernel(const double* __restrict__ ev
   }
 }
 
+template <bool SWAP_GRID>
 __global__ void transpose_kernel(const float* __restrict__ in, int64_t ldin, int rows, int cols,
                                  float* __restrict__ out, int64_t ldout) {
   __shared__ float tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int c0 = (SWAP_GRID ? blockIdx.y : blockIdx.x) * 32, r0 = (SWAP_GRID ? blockIdx.x : blockIdx.y) * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int r = r0 + i, c = c0 + threadIdx.x;
     tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * ldin + c] : 0.f;
@@ -178,9 +179,15 @@ extern "C" int fm_transpose(const float* in, int64_t ldin, int rows, int cols, f
   using namespace fm;
   FM_REQUIRE(in && out && rows >= 0 && cols >= 0 && ldin >= cols && ldout >= rows, "fm_transpose: bad args");
   if (rows == 0 || cols == 0) return FM_OK;
+  // the longer dimension goes on grid.x (2^31 blocks), the shorter on grid.y (65535 blocks = 2M elements)
   dim3 block(32, 8), grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32));
-  FM_REQUIRE(grid.y <= 65535, "fm_transpose: too many rows (%d)", rows);
-  transpose_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, ldin, rows, cols, out, ldout);
+  const bool swap = grid.y > 65535;
+  if (swap) grid = dim3((unsigned)cdiv(rows, 32), (unsigned)cdiv(cols, 32));
+  FM_REQUIRE(grid.y <= 65535, "fm_transpose: matrix too large (%d x %d)", rows, cols);
+  if (swap)
+    transpose_kernel<true><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, ldin, rows, cols, out, ldout);
+  else
+    transpose_kernel<false><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, ldin, rows, cols, out, ldout);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }
@@ -255,17 +262,18 @@ namespace fm {
 __global__ void split_lo_kernel(const float* __restrict__ X, int64_t ldx, int rows, int cols, float* __restrict__ lo,
                                 int64_t ldlo) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = blockIdx.y;
   if (c >= cols) return;
-  const float x = X[(size_t)r * ldx + c];
-  lo[(size_t)r * ldlo + c] = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float x = X[(size_t)r * ldx + c];
+    lo[(size_t)r * ldlo + c] = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  }
 }
 }  // namespace fm
 
 extern "C" int fm_split_lo(const float* X, int64_t ldx, int rows, int cols, float* lo, int64_t ldlo, void* stream) {
   using namespace fm;
-  FM_REQUIRE(X && lo && rows >= 1 && cols >= 1 && ldx >= cols && ldlo >= cols && rows <= 65535, "fm_split_lo: bad args");
-  dim3 grid((unsigned)cdiv(cols, 256), (unsigned)rows);
+  FM_REQUIRE(X && lo && rows >= 1 && cols >= 1 && ldx >= cols && ldlo >= cols, "fm_split_lo: bad args");
+  dim3 grid((unsigned)cdiv(cols, 256), (unsigned)(rows < 65535 ? rows : 65535));
   split_lo_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, ldx, rows, cols, lo, ldlo);
   FM_LAUNCH_CHECK();
   return FM_OK;
