@@ -1,6 +1,6 @@
 #!/bin/bash
 # first GPU contact: environment, K1 parity, GEMM bring-up, pipeline with both GEMM paths
-mkdir -p gpurun_out; cd "$(dirname "$0")/.."
+mkdir -p gpurun_out; cd "$(dirname "$0")/../.."
 { nvidia-smi; nproc; free -g; python -c "import os;print('cpus',os.cpu_count())"; } > gpurun_out/env.log 2>&1
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 timeout 600 python -m pytest tests/test_k1_gpu.py -q -x > gpurun_out/k1.log 2>&1; echo "k1 rc $?" >> gpurun_out/summary.log

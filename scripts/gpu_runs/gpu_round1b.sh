@@ -1,6 +1,6 @@
 #!/bin/bash
 # second GPU contact: full gpu test suite, accuracy probe, eig variants, bench, ncu evidence
-mkdir -p gpurun_out; cd "$(dirname "$0")/.."
+mkdir -p gpurun_out; cd "$(dirname "$0")/../.."
 rm -f gpurun_out/summary.log
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest gpu rc $?" >> gpurun_out/summary.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # N GPUs: multi-GPU correctness + bench at N
-mkdir -p gpurun_out; cd "$(dirname "$0")/.."
+mkdir -p gpurun_out; cd "$(dirname "$0")/../.."
 N=${1:-2}
 rm -f gpurun_out/summary.log
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1

@@ -1,5 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out; cd "$(dirname "$0")/.."
+mkdir -p gpurun_out; cd "$(dirname "$0")/../.."
 rm -f gpurun_out/summary.log
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 for impl in 7 8; do timeout 180 python scripts/probe_gemm.py $impl > gpurun_out/gemm_impl$impl.log 2>&1; echo "gemm impl $impl rc $?" >> gpurun_out/summary.log; done

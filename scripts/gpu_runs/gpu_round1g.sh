@@ -1,5 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out; cd "$(dirname "$0")/.."
+mkdir -p gpurun_out; cd "$(dirname "$0")/../.."
 rm -f gpurun_out/summary.log
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 timeout 180 python scripts/probe_gemm.py 0 > gpurun_out/gemm_impl0.log 2>&1

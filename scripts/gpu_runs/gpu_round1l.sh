@@ -1,6 +1,6 @@
 #!/bin/bash
 # multi-GPU scaling: bench at N=4 and N=8 (and the dist check at 8)
-mkdir -p gpurun_out; cd "$(dirname "$0")/.."
+mkdir -p gpurun_out; cd "$(dirname "$0")/../.."
 rm -f gpurun_out/summary.log
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 free -g > gpurun_out/env8.log; nproc >> gpurun_out/env8.log; nvidia-smi topo -m >> gpurun_out/env8.log 2>&1
