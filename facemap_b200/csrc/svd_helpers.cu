@@ -42,19 +42,44 @@ __global__ void __launch_bounds__(256) row_means_kernel(const float* __restrict_
 
 // G[i,j] = sum_s part[s,i,j] - ncols*mean[i]*mean[j]; with upper_only the (i>j) entries are read
 // from (j,i).
+// A thread reduces 4 adjacent columns of the UPPER triangle (float4 loads over the split planes) and
+// writes both G[i,j] and its mirror G[j,i], so the lower triangle is never read.
 __global__ void gram_assemble_kernel(const float* __restrict__ part, int ksplit, int n, int64_t ldw,
                                      const double* __restrict__ mean, double ncols, int upper_only,
                                      double* __restrict__ G) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int i = blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= n || j >= n) return;
-  int si = i, sj = j;
-  if (upper_only && i > j) { si = j; sj = i; }
-  double acc = 0.0;
+  if (i >= n || j0 >= n) return;
+  if (upper_only && j0 + 3 < i) return;                     // entirely below the diagonal: mirrored from above
   const size_t plane = (size_t)n * ldw;
-  for (int s = 0; s < ksplit; ++s) acc += (double)part[(size_t)s * plane + (size_t)si * ldw + sj];
-  if (mean) acc -= ncols * (mean[i] * mean[j]);  // commutative product: G stays exactly symmetric
-  G[(size_t)i * n + j] = acc;
+  const float* src = part + (size_t)i * ldw + j0;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (j0 + 4 <= n && (ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(part) & 15) == 0)) {
+#pragma unroll 4
+    for (int s = 0; s < ksplit; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (size_t)s * plane);
+      a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+    }
+  } else {
+    for (int s = 0; s < ksplit; ++s) {
+      const float* q = src + (size_t)s * plane;
+      a0 += q[0];
+      if (j0 + 1 < n) a1 += q[1];
+      if (j0 + 2 < n) a2 += q[2];
+      if (j0 + 3 < n) a3 += q[3];
+    }
+  }
+  const double acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int j = j0 + t;
+    if (j >= n) break;
+    if (upper_only && j < i) continue;
+    double v = acc[t];
+    if (mean) v -= ncols * (mean[i] * mean[j]);  // commutative product: G stays exactly symmetric
+    G[(size_t)i * n + j] = v;
+    if (upper_only && j != i) G[(size_t)j * n + i] = v;
+  }
 }
 
 // one block per component c
@@ -155,7 +180,7 @@ extern "C" int fm_gram_assemble(const float* part, int ksplit, int n, int64_t ld
                                 int64_t ncols, int upper_only, double* G, void* stream) {
   using namespace fm;
   FM_REQUIRE(part && G && ksplit >= 1 && n >= 1 && ldw >= n, "fm_gram_assemble: bad args");
-  dim3 block(32, 8), grid((unsigned)cdiv(n, 32), (unsigned)cdiv(n, 8));
+  dim3 block(32, 8), grid((unsigned)cdiv(cdiv(n, 4), 32), (unsigned)cdiv(n, 8));
   gram_assemble_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       part, ksplit, n, ldw, mean, (double)ncols, upper_only, G);
   FM_LAUNCH_CHECK();
@@ -261,11 +286,25 @@ extern "C" int fm_splitk_reduce(const float* part, int ksplit, int M, int N, int
 namespace fm {
 __global__ void split_lo_kernel(const float* __restrict__ X, int64_t ldx, int rows, int cols, float* __restrict__ lo,
                                 int64_t ldlo) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= cols) return;
+  const bool v4 = (c + 4 <= cols) && (ldx % 4 == 0) && (ldlo % 4 == 0) &&
+                  (((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0);
   for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-    const float x = X[(size_t)r * ldx + c];
-    lo[(size_t)r * ldlo + c] = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    if (v4) {
+      const float4 x = *reinterpret_cast<const float4*>(X + (size_t)r * ldx + c);
+      float4 l;
+      l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+      l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+      l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+      l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+      *reinterpret_cast<float4*>(lo + (size_t)r * ldlo + c) = l;
+    } else {
+      for (int t = 0; t < 4 && c + t < cols; ++t) {
+        const float x = X[(size_t)r * ldx + c + t];
+        lo[(size_t)r * ldlo + c + t] = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+      }
+    }
   }
 }
 }  // namespace fm
@@ -273,7 +312,7 @@ __global__ void split_lo_kernel(const float* __restrict__ X, int64_t ldx, int ro
 extern "C" int fm_split_lo(const float* X, int64_t ldx, int rows, int cols, float* lo, int64_t ldlo, void* stream) {
   using namespace fm;
   FM_REQUIRE(X && lo && rows >= 1 && cols >= 1 && ldx >= cols && ldlo >= cols, "fm_split_lo: bad args");
-  dim3 grid((unsigned)cdiv(cols, 256), (unsigned)(rows < 65535 ? rows : 65535));
+  dim3 grid((unsigned)cdiv(cdiv(cols, 4), 256), (unsigned)(rows < 65535 ? rows : 65535));
   split_lo_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, ldx, rows, cols, lo, ldlo);
   FM_LAUNCH_CHECK();
   return FM_OK;
