@@ -189,7 +189,8 @@ class HostArraySource(FrameSource):
     fetch is a direct DMA from the caller's buffer; if registration is refused the copy goes
     through a pinned staging buffer.  `prefetch` overlaps the next copy with the current kernels."""
 
-    def __init__(self, views, block_frames=None, pin=True):
+    def __init__(self, views, block_frames=None, pin=True, cache_on_device=True):
+        self.cache_on_device = cache_on_device      # False forces the streaming path (videos larger than HBM)
         self.views = []
         for v in views:
             t = v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v))
@@ -213,7 +214,7 @@ class HostArraySource(FrameSource):
     def plan_access(self, priority, home, device):
         self._ensure_pinned()
         self._cache.drop()
-        if all(self._pinned):
+        if self.cache_on_device and all(self._pinned):
             before = self._cache.bytes
             self._cache.start(lambda v, a, b: self.views[v][a:b], list(zip(self.Ly, self.Lx)), priority, home, device)
             self.h2d += self._cache.bytes - before

@@ -225,6 +225,47 @@ def test_host_source_equals_device_source(cuda_device):
     assert np.array_equal(a["motSv"], b["motSv"])
 
 
+def test_streaming_host_source_equals_cached(cuda_device):
+    """Videos that do not fit HBM stream through pinned buffers chunk by chunk (prefetch on a copy stream);
+    forcing that path must give bit-identical outputs to the upload-once cache."""
+    from facemap_b200 import process
+    from facemap_b200.frames import HostArraySource
+
+    views, N, sbin, mot, mov, _ = CASES["single_s2"]
+    vids = case_videos("single_s2")
+    outs = []
+    for cache in (True, False):
+        src = HostArraySource(vids, cache_on_device=cache)
+        outs.append(process.process_source(src, sbin=sbin, motSVD=mot, movSVD=mov))
+        assert src.h2d > 0
+        src.close()
+    for key in ("avgframe", "avgmotion", "motion", "motMask", "motSVD", "movMask", "movSVD"):
+        for x, y in zip(outs[0][key], outs[1][key]):
+            assert np.array_equal(x, y), key
+
+
+def test_run_with_proc_settings_and_mat_output(cuda_device, tmp_path):
+    """`proc=` overrides the keyword arguments (process.py:701-708) and save_mat writes the flattened .mat
+    (process.py:615-634)."""
+    import scipy.io
+
+    from facemap_b200 import process
+    from tests.helpers import motion_roi
+
+    vids = case_videos("short_s2")
+    settings = {"sbin": 2, "fullSVD": True, "save_mat": True, "rois": [motion_roi(0, 4, 30, 6, 40)], "sy": 3, "sx": 5,
+                "savepath": str(tmp_path)}
+    name = process.run([torch.from_numpy(v) for v in vids], sbin=7, motSVD=True, movSVD=False, proc=settings)
+    d = np.load(name, allow_pickle=True).item()
+    assert d["sbin"] == 2 and d["sy"] == 3 and d["sx"] == 5 and d["save_mat"] is True
+    assert len(d["motMask"]) == 2 and len(d["motSVD"]) == 2 and len(d["motion"]) == 2
+    assert "yrange_bin" in d["rois"][0] and d["avgmotion"][0].ndim == 2          # quirks: rois mutated, Q4
+    mat = scipy.io.loadmat(os.path.join(str(tmp_path), "array_input_proc.mat"))
+    for key in ("motSVD_0", "motSVD_1", "motMask_0", "motion_0", "avgframe_0", "motSv"):
+        assert key in mat, key
+    assert mat["motSVD_0"].shape == d["motSVD"][0].shape
+
+
 def test_run_writes_reference_proc_file(cuda_device, tmp_path):
     """process.run: same signature / file naming / keys as facemap.process.run (process.py:605-647, 859-892)."""
     from facemap_b200 import process
