@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=2000)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -366,7 +366,8 @@ def main():
     # ---- e2e: host-resident frames through the public API ----
     e2e = None
     if want_host:
-        one_step(host_src, keep=False)                       # warm-up (fills the host cache of sample chunks)
+        for _ in range(2):                                   # warm-up (host cache of sample chunks, pinned pools)
+            one_step(host_src, timing={}, keep=False)
         barrier()
         host_src.h2d = 0
         d2h = 0
@@ -391,7 +392,9 @@ def main():
                "steps": args.e2e_steps, "api": "facemap_b200.process.process_source(HostArraySource-like pinned frames)",
                "upload_ms": round(host_src.dcache.upload_ms(), 1), "wall_s_last_step": round(e2e_tm.get("wall_s", 0.0), 4),
                "assemble_wall_s": round(e2e_tm.get("assemble_wall_s", 0.0), 4),
-               "stage_ms": {k: round(v, 2) for k, v in sorted(e2e_tm.get("device_ms", {}).items()) if v > 1.0}}
+               "stage_ms": {k: round(v, 2) for k, v in sorted(e2e_tm.get("device_ms", {}).items()) if v > 1.0},
+               "timeline_ms": {k: round(v, 1) for k, v in sorted(e2e_tm.get("timeline_ms", {}).items(), key=lambda kv: kv[1])
+                               if k.split(".")[-1] in ("fetch", "syevd", "mma", "bin", "d2h")}}
 
     # ---- CPU baseline (rank 0, single GPU run only) ----
     cpu = None

@@ -299,6 +299,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         if marks:
             timing["wall_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks[:-1], marks[1:])}
         timing["device_ms"] = timer.report()
+        timing["timeline_ms"] = timer.timeline()
         timing["wall_s"] = time.perf_counter() - wall0
         timing["assemble_wall_s"] = time.perf_counter() - t_asm
     return proc

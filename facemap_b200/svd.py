@@ -39,6 +39,10 @@ class StageTimer:
     def __init__(self, enabled=True):
         self.enabled = enabled
         self.spans = []
+        self.origin = None
+        if enabled:
+            self.origin = torch.cuda.Event(enable_timing=True)
+            self.origin.record()
 
     class _Span:
         def __init__(self, owner, name):
@@ -65,6 +69,15 @@ class StageTimer:
         out = {}
         for name, a, b in self.spans:
             out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+    def timeline(self):
+        """device-time offset (ms since construction) at which the LAST span of every label ended."""
+        torch.cuda.synchronize()
+        out = {}
+        if self.origin is not None:
+            for name, a, b in self.spans:
+                out[name] = max(out.get(name, 0.0), self.origin.elapsed_time(b))
         return out
 
 
