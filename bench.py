@@ -415,7 +415,8 @@ def main():
         line = {
             "metric": "motion-SVD frames/sec (bin+diff+cov+SVD+proj)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": nwarm, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 products, f64 eigensolve)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "dtype_detail": "u8 frames, integer block sums / energies, f32 operands as 3xTF32 tensor-core products with f64 chain reduction, f64 eigensolve",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_total": total_frames, "frame_bytes": H * W,
                        "l2": "inputs (30.7 GB per GPU) exceed L2; no flush needed", "parallelism": f"frame-range x{world}"},
