@@ -135,6 +135,10 @@ def make_sources(rank, world, device, want_host):
             if self.on_host:
                 self.dcache.drop()
                 a, b = max(home[0], lo), min(home[1], hi)       # the part of `home` this rank holds in host memory
+                for (x, y) in priority:                        # sample ranges outside the shard go first: the H2D
+                    x, y = self.clamp(x, y)                    # engine serves copies in submission order
+                    if not (x >= a and y <= b):
+                        self.pipe.issue((x, y), [self._range(x, y)], dev)
                 before = self.dcache.bytes
                 self.dcache.start(lambda v, x, y: self.base[x - lo:y - lo], [(H, W)], priority, (a, b), dev)
                 self.h2d += self.dcache.bytes - before

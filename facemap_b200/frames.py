@@ -215,6 +215,10 @@ class HostArraySource(FrameSource):
         self._ensure_pinned()
         self._cache.drop()
         if self.cache_on_device and all(self._pinned):
+            for (x, y) in priority:      # sample ranges outside `home` (multi-rank) are copied first: the H2D
+                x, y = self.clamp(x, y)  # engine serves copies in submission order
+                if not (x >= home[0] and y <= home[1]):
+                    self._pipe.issue((x, y), self._host_slices(x, y), device)
             before = self._cache.bytes
             self._cache.start(lambda v, a, b: self.views[v][a:b], list(zip(self.Ly, self.Lx)), priority, home, device)
             self.h2d += self._cache.bytes - before

@@ -104,7 +104,10 @@ int fm_mean_update(float* acc, const long long* tsum, int64_t n, int sbin, int c
  *   ksplit >= 1: if > 1, `C` is ignored and raw partial products are written to
  *                workspace[ksplit, M, ldw] (no scale/bias); reduce with fm_gram_assemble.
  *   upper_only != 0: tiles entirely below the diagonal are skipped (symmetric Gram).
- *   impl: 0 = tcgen05 3xTF32 (product path), 1 = plain FP32 FFMA reference kernel (validation).
+ *   impl: 0 = tcgen05 3xTF32 (product path), 1 = plain FP32 FFMA reference kernel (validation);
+ *         2..8 = tile-shape / CTA-pair (cta_group::2) variants of the tensor-core kernel kept for the
+ *         tests and tuning runs (same results, see csrc/gemm_tf32x3.cu).
+ *   ksplit > 1 with ldw: reduce with fm_splitk_reduce (general) or fm_gram_assemble (Gram).
  */
 int fm_gemm_tn(const float* A, int64_t lda, const float* A_lo, int64_t lda_lo, const float* B, int64_t ldb,
                const float* B_lo, int64_t ldb_lo, int M, int N, int K, float* C, int64_t ldc,
