@@ -325,6 +325,222 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// Chained-accumulation variant: one CTA walks its whole K range in CHAINS of CH k-blocks.  The MMA
+// thread alternates between two 256-column TMEM accumulators (all 512 columns); while chain c+1 is
+// being accumulated, the splitter/epilogue warps drain chain c with tcgen05.ld and add it into
+// float32 REGISTER accumulators (128 per thread) with round-to-nearest.  The tensor cores truncate
+// the fp32 accumulator on every MMA (-5.4e-8 relative, always toward zero); bounding every TMEM chain
+// to CH*BK/8*3 = 48 accumulations caps that bias at ~2.6e-6 of an entry without any split-K workspace,
+// partial-sum traffic or reduction kernel.
+//   SPLIT_MODE 0: A and B split in the kernel; 1: B pre-split (TMA stages B_lo), A split in the kernel;
+//              2: both pre-split (no split work; the warps only drain).
+// ---------------------------------------------------------------------------------------------
+template <int BK, int SPLIT_MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32x3_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
+                         const GemmParams p) {
+  constexpr int BN = 256;
+  constexpr int CH = 8;                       // k-blocks per TMEM chain
+  using Cfg = GemmCfg<BN, BK>;
+  constexpr int STAGES = Cfg::STAGES;
+  static_assert(CH > STAGES, "a chain must outlast the stage ring (drain scheduling)");
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  if (p.upper_only && n0 + BN - 1 < m0) return;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto split_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto accfull_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
+  auto accempty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int KB = (p.K + BK - 1) / BK;
+  const int kb0 = (int)(((long long)blockIdx.z * KB) / p.ksplit);
+  const int kb1 = (int)(((long long)(blockIdx.z + 1) * KB) / p.ksplit);
+  const int nkb = kb1 - kb0;
+  const int nchains = (nkb + CH - 1) / CH;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(split_bar(s), NUM_SPLIT_WARPS);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accfull_bar(b), 1);
+      mbar_init(accempty_bar(b), NUM_SPLIT_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(full_bar(s), (uint32_t)(Cfg::HI_BYTES + (SPLIT_MODE >= 1 ? BN * BK * 4 : 0) +
+                                               (SPLIT_MODE == 2 ? BM * BK * 4 : 0)));
+        tma_load_2d(stage, &tmA, full_bar(s), (kb0 + i) * BK, m0);
+        tma_load_2d(stage + BM * BK * 4, &tmB, full_bar(s), (kb0 + i) * BK, n0);
+        if constexpr (SPLIT_MODE == 2) tma_load_2d(stage + Cfg::HI_BYTES, &tmAlo, full_bar(s), (kb0 + i) * BK, m0);
+        if constexpr (SPLIT_MODE >= 1)
+          tma_load_2d(stage + Cfg::HI_BYTES + BM * BK * 4, &tmBlo, full_bar(s), (kb0 + i) * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+      int i = 0;
+      for (int c = 0; c < nchains; ++c) {
+        const int buf = c & 1;
+        mbar_wait(accempty_bar(buf), (((uint32_t)(c >> 1)) & 1u) ^ 1u);   // drained by the epilogue warps
+        tcgen05_fence_after();
+        const uint32_t acc = tmem_acc + (uint32_t)(buf * BN);
+        const int len = min(CH, nkb - c * CH);
+        for (int j = 0; j < len; ++j, ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+          mbar_wait(SPLIT_MODE == 2 ? full_bar(s) : split_bar(s), ph);
+          tcgen05_fence_after();
+          const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
+          const uint64_t a_hi = make_desc_kmajor<BK>(stage);
+          const uint64_t b_hi = make_desc_kmajor<BK>(stage + BM * BK * 4);
+          const uint64_t a_lo = make_desc_kmajor<BK>(stage + Cfg::HI_BYTES);
+          const uint64_t b_lo = make_desc_kmajor<BK>(stage + Cfg::HI_BYTES + BM * BK * 4);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
+            umma_tf32(acc, a_lo + adv, b_hi + adv, IDESC, (j > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(acc, a_hi + adv, b_lo + adv, IDESC, 1u);
+            umma_tf32(acc, a_hi + adv, b_hi + adv, IDESC, 1u);
+          }
+          tcgen05_commit(empty_bar(s));
+        }
+        tcgen05_commit(accfull_bar(buf));
+      }
+    }
+  } else {
+    const int st = threadIdx.x - 64;
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float acc[BN / 2];
+#pragma unroll
+    for (int j = 0; j < BN / 2; ++j) acc[j] = 0.f;
+    int drained = 0;
+    auto drain = [&](int c) {
+      const int buf = c & 1;
+      mbar_wait(accfull_bar(buf), ((uint32_t)(c >> 1)) & 1u);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < BN / 2; cc += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * (BN / 2) + cc);
+        TMEM_LD_32x32b_X32(taddr, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[cc + j] += __uint_as_float(r[j]);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accempty_bar(buf));
+    };
+    if constexpr (SPLIT_MODE == 2) {
+      for (int c = 0; c < nchains; ++c) drain(c);
+    } else {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        const float4* hi = reinterpret_cast<const float4*>(smem_gen + s * Cfg::STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem_gen + s * Cfg::STAGE_BYTES + Cfg::HI_BYTES);
+        constexpr int NV = (SPLIT_MODE == 1 ? BM * BK * 4 : Cfg::HI_BYTES) / 16;
+#pragma unroll 4
+        for (int v = st; v < NV; v += 32 * NUM_SPLIT_WARPS) {
+          const float4 x = hi[v];
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          lo[v] = l;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(s));
+        // chain `drained` ended at k-block (drained+1)*CH-1; once the ring has wrapped past it its MMAs are
+        // complete (their stage was re-filled), so the wait below is (almost) free
+        if (drained < nchains && (drained + 1) * CH - 1 + STAGES <= i) {
+          drain(drained);
+          ++drained;
+        }
+      }
+      for (; drained < nchains; ++drained) drain(drained);
+    }
+
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < p.M;
+    float scale = 1.f, bias = 0.f;
+    float* dst_row;
+    if (p.ksplit > 1) {
+      dst_row = p.workspace + ((size_t)blockIdx.z * p.M + (size_t)(row_ok ? m : 0)) * p.ldw;
+    } else {
+      dst_row = p.C + (size_t)(row_ok ? m : 0) * p.ldc;
+      if (row_ok && p.rscale) scale = p.rscale[m];
+      if (row_ok && p.rbias) bias = p.rbias[m];
+    }
+    const bool vec_ok = ((p.ksplit > 1 ? p.ldw : p.ldc) % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.ksplit > 1 ? p.workspace : p.C) & 15) == 0);
+    const int nbase = n0 + half * (BN / 2);
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < BN / 2; j += 4) {
+        const int n = nbase + j;
+        if (vec_ok && n + 4 <= p.N) {
+          float4 o;
+          o.x = fmaf(acc[j + 0], scale, bias);
+          o.y = fmaf(acc[j + 1], scale, bias);
+          o.z = fmaf(acc[j + 2], scale, bias);
+          o.w = fmaf(acc[j + 3], scale, bias);
+          *reinterpret_cast<float4*>(dst_row + n) = o;
+        } else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (n + t < p.N) dst_row[n + t] = fmaf(acc[j + t], scale, bias);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(2 * BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2): two CTAs of a cluster on one TPC compute a 256 x 256 tile.
 // Each CTA stages its own 128 rows of A and HALF of the B tile (128 rows), so per-SM shared-memory
 // traffic for B (TMA fill, lo split, tensor-core operand reads) is halved — shared-memory
@@ -687,6 +903,31 @@ static int launch_tc(const float* A, int64_t lda, const float* B, int64_t ldb, c
   return FM_OK;
 }
 
+template <int BK, int SPLIT_MODE>
+static int launch_chain(const float* A, int64_t lda, const float* B, int64_t ldb, const GemmParams& p, cudaStream_t st,
+                        const float* B_lo, int64_t ldb_lo, const float* A_lo, int64_t lda_lo) {
+  constexpr int BN = 256;
+  CUtensorMap ta, tb, talo, tblo;
+  int rc;
+  if ((rc = make_map(&ta, A, lda, p.M, p.K, BM, BK)) != FM_OK) return rc;
+  if ((rc = make_map(&tb, B, ldb, p.N, p.K, BN, BK)) != FM_OK) return rc;
+  tblo = tb;
+  talo = ta;
+  if (SPLIT_MODE >= 1 && (rc = make_map(&tblo, B_lo, ldb_lo, p.N, p.K, BN, BK)) != FM_OK) return rc;
+  if (SPLIT_MODE == 2 && (rc = make_map(&talo, A_lo, lda_lo, p.M, p.K, BM, BK)) != FM_OK) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tf32x3_chain_kernel<BK, SPLIT_MODE>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, BK>::SMEM_BYTES);
+  });
+  FM_CUDA_TRY(attr_err);
+  dim3 grid((unsigned)cdiv(p.N, BN), (unsigned)cdiv(p.M, BM), (unsigned)p.ksplit);
+  gemm_tf32x3_chain_kernel<BK, SPLIT_MODE><<<grid, GEMM_THREADS, GemmCfg<BN, BK>::SMEM_BYTES, st>>>(ta, tb, talo, tblo, p);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
 template <int BK>
 static int launch_pair(const float* A, int64_t lda, const float* B, int64_t ldb, const GemmParams& p, cudaStream_t st) {
   CUtensorMap ta, tb;
@@ -739,10 +980,15 @@ extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* A_lo, int64_
     FM_LAUNCH_CHECK();
     return FM_OK;
   }
-  FM_REQUIRE(impl == 0 || (impl >= 2 && impl <= 8), "fm_gemm_tn: unknown impl %d", impl);
+  FM_REQUIRE(impl == 0 || (impl >= 2 && impl <= 9), "fm_gemm_tn: unknown impl %d", impl);
   FM_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
              "fm_gemm_tn: TMA operands need 16-byte aligned bases and ld %% 4 == 0 (lda=%lld ldb=%lld)",
              (long long)lda, (long long)ldb);
+  if (impl == 9) {   // chained accumulation: TMEM chains of 128 K drained into register accumulators
+    if (B_lo != nullptr && A_lo != nullptr) return launch_chain<16, 2>(A, lda, B, ldb, p, st, B_lo, ldb_lo, A_lo, lda_lo);
+    if (B_lo != nullptr) return launch_chain<16, 1>(A, lda, B, ldb, p, st, B_lo, ldb_lo, nullptr, 0);
+    return launch_chain<16, 0>(A, lda, B, ldb, p, st, nullptr, 0, nullptr, 0);
+  }
   // impl 0: product configuration; 2..4: tile-shape variants kept for tuning runs
   switch (impl) {
     case 2: return launch_tc<256, 32, false>(A, lda, B, ldb, p, st);

@@ -130,7 +130,7 @@ class SvdWorkspace:
     def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm", B_lo=None, chain=None):
         """C = rscale * (A @ B^T) + rbias with K chains of <= `chain` (KCHAIN_GEMM) reduced in float64."""
         ksplit = _gemm_ksplit(A.shape[1], chain)
-        if self.gemm_impl != 0:
+        if self.gemm_impl not in (0, 9):
             B_lo = None
         if ksplit == 1:
             with self.timer(label + ".mma"):

@@ -53,7 +53,7 @@ def bench(M, N, Kd, ksplit=1, reps=5, upper=False):
     fl = 2.0 * M * N * Kd * (0.5 if upper else 1.0)
     print(f"impl {impl} M{M} N{N} K{Kd} ksplit{ksplit} upper{int(upper)}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s useful (x3 issued = {3*fl/ms/1e9:.0f})", flush=True)
 bench(18944, 500, 19200)
-bench(18944, 500, 19200, ksplit=8)
+bench(18944, 500, 19200, ksplit=16)
 bench(999, 999, 19200, ksplit=16, upper=True)
 bench(250, 19200, 999)
 bench(3750, 3750, 19200, ksplit=2, upper=True)

@@ -26,7 +26,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 2, 3, 4, 5, 7, 8])
+@pytest.mark.parametrize("impl", [0, 2, 3, 4, 5, 7, 8, 9])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm_matches_fp64(cuda_device, M, N, K, impl):
     from facemap_b200 import kernels as Kn
@@ -107,6 +107,47 @@ def test_fully_presplit_gram_is_bit_identical(cuda_device):
     Kn.gemm_tn(A, B, C1, B_lo=Kn.split_lo(B), A_lo=Kn.split_lo(A))
     torch.cuda.synchronize()
     assert torch.equal(C0, C1)
+
+
+@pytest.mark.parametrize("mode", ["split", "b_lo", "both"])
+def test_chained_accumulation_removes_truncation_bias(cuda_device, mode):
+    """impl 9 bounds every TMEM chain to 128 K and sums chains in float32 registers with round-to-nearest:
+    on an all-positive 19200-long contraction (the worst case for the truncating accumulator) the relative
+    error must stay below 5e-6, where one plain chain (impl 0) is off by more than 1e-4."""
+    from facemap_b200 import kernels as Kn
+
+    dev = cuda_device
+    M, N, K = 256, 512, 19200
+    g = torch.Generator().manual_seed(5)
+    A, B = Kn.alloc_matrix(M, K, dev), Kn.alloc_matrix(N, K, dev)
+    A.copy_(torch.rand((M, K), generator=g) + 0.5)
+    B.copy_(torch.rand((N, K), generator=g) + 0.5)
+    kw = {}
+    if mode in ("b_lo", "both"):
+        kw["B_lo"] = Kn.split_lo(B)
+    if mode == "both":
+        kw["A_lo"] = Kn.split_lo(A)
+    C9, C0 = Kn.alloc_matrix(M, N, dev), Kn.alloc_matrix(M, N, dev)
+    Kn.gemm_tn(A, B, C9, impl=9, **kw)
+    Kn.gemm_tn(A, B, C0, impl=0, **kw)
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().T
+    e9 = float(((C9.double() - ref).abs() / ref).max())
+    e0 = float(((C0.double() - ref).abs() / ref).max())
+    assert e9 < 5e-6, e9
+    assert e0 > 1e-4, e0          # documents why the chains exist
+    # ragged shape, scale / bias epilogue, split over blockIdx.z
+    A, B = _rand(333, 2500, dev, 41), _rand(700, 2500, dev, 42)
+    rs, rb = torch.rand(333, device=dev) + 0.5, torch.randn(333, device=dev)
+    C = Kn.alloc_matrix(333, 700, dev)
+    Kn.gemm_tn(A, B, C, rscale=rs, rbias=rb, impl=9)
+    ws = torch.full((3, 333, 704), float("nan"), device=dev)
+    Kn.gemm_tn(A, B, ksplit=3, workspace=ws, impl=9)
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().T
+    bound = (A.double().abs() @ B.double().abs().T) * 3e-6
+    assert bool(((C.double() - (ref * rs.double()[:, None] + rb.double()[:, None])).abs() <= bound * 2 + 1e-6).all())
+    assert bool(((ws[:, :, :700].double().sum(0) - ref).abs() <= bound).all())
 
 
 def test_gemm_scale_bias_epilogue(cuda_device):
