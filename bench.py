@@ -346,7 +346,7 @@ def main():
         k1["frac"] = k1["achieved"] / hbm_peak
     mma_ms = agg.get("stage3.project.mma", 0.0)
     flops = 2.0 * rows3 * p * NCOMP                          # algorithmic (a 3xTF32 split issues 3x this)
-    mm = {"kernel": "gemm_tf32x3_kernel<256,16> (stage 3 projection)", "bound": "tensor",
+    mm = {"kernel": "gemm_tf32x3_chain_kernel<16,1> (stage 3 projection)", "bound": "tensor",
           "achieved": flops / (mma_ms * 1e-3) / 1e12 if mma_ms else None, "peak": tc_peak, "unit": "TFLOP/s",
           "ms_per_step": mma_ms, "algorithmic_flop_per_frame": 2.0 * p * NCOMP,
           "note": "peak = measured dense bf16; the kernel runs kind::tf32 (half the bf16 rate) and issues 3 MMAs per "
@@ -361,7 +361,7 @@ def main():
         traffic = tj["gemm_tf32x3_projection" if dominant is mm else "bin_motion_vec_kernel"]["bytes_per_launch"]
     except Exception:
         pass
-    mm["algorithmic_bytes_per_launch"] = 4 * (18944 * p + NCOMP * p) + 4 * 16 * 18944 * 512
+    mm["algorithmic_bytes_per_launch"] = 4 * (18944 * p + NCOMP * p + 18944 * NCOMP)
     roofline = {"bound": dominant["bound"], "achieved": dominant["achieved"], "peak": dominant["peak"],
                 "unit": dominant["unit"], "frac": dominant.get("frac"), "traffic": traffic, "kernel": dominant["kernel"],
                 "peak_source": peak_src, "detail": dominant, "other_kernel": other}

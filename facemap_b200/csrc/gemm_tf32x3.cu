@@ -984,34 +984,37 @@ extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* A_lo, int64_
   FM_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
              "fm_gemm_tn: TMA operands need 16-byte aligned bases and ld %% 4 == 0 (lda=%lld ldb=%lld)",
              (long long)lda, (long long)ldb);
-  if (impl == 9) {   // chained accumulation: TMEM chains of 128 K drained into register accumulators
+  if (B_lo != nullptr)
+    FM_REQUIRE(ldb_lo >= K && ldb_lo % 4 == 0 && (reinterpret_cast<uintptr_t>(B_lo) & 15) == 0,
+               "fm_gemm_tn: B_lo needs a 16-byte aligned base and ldb_lo %% 4 == 0");
+  if (A_lo != nullptr)
+    FM_REQUIRE(B_lo != nullptr && lda_lo >= K && lda_lo % 4 == 0 && (reinterpret_cast<uintptr_t>(A_lo) & 15) == 0,
+               "fm_gemm_tn: A_lo needs B_lo, a 16-byte aligned base and lda_lo %% 4 == 0");
+  // impl 0 = product configuration: chained accumulation (TMEM chains of 128 K drained into register
+  // accumulators) on 128 x 256 tiles; outputs at most 128 wide use the 128 x 128 single-accumulator kernel
+  if (impl == 0 && N > 128) {
     if (B_lo != nullptr && A_lo != nullptr) return launch_chain<16, 2>(A, lda, B, ldb, p, st, B_lo, ldb_lo, A_lo, lda_lo);
     if (B_lo != nullptr) return launch_chain<16, 1>(A, lda, B, ldb, p, st, B_lo, ldb_lo, nullptr, 0);
     return launch_chain<16, 0>(A, lda, B, ldb, p, st, nullptr, 0, nullptr, 0);
   }
-  // impl 0: product configuration; 2..4: tile-shape variants kept for tuning runs
+  // 2..8: tile-shape / CTA-pair variants, 9: the single-accumulator kernel (one TMEM chain per launch);
+  // kept for the tests and tuning runs
   switch (impl) {
     case 2: return launch_tc<256, 32, false>(A, lda, B, ldb, p, st);
     case 3: return launch_tc<128, 32, false>(A, lda, B, ldb, p, st);
     case 4: return launch_tc<128, 16, false>(A, lda, B, ldb, p, st);
-    case 5: return launch_tc<256, 16, true>(A, lda, B, ldb, p, st);   // explicit hi rewrite (== impl 0 bit for bit)
+    case 5: return launch_tc<256, 16, true>(A, lda, B, ldb, p, st);   // explicit hi rewrite (== impl 9 bit for bit)
     case 6: return launch_tc<128, 32, true>(A, lda, B, ldb, p, st);
     case 7: return launch_pair<16>(A, lda, B, ldb, p, st);            // CTA pair, cta_group::2
     case 8: return launch_pair<32>(A, lda, B, ldb, p, st);
     default: break;
   }
   if (B_lo != nullptr) {
-    FM_REQUIRE(ldb_lo >= K && ldb_lo % 4 == 0 && (reinterpret_cast<uintptr_t>(B_lo) & 15) == 0,
-               "fm_gemm_tn: B_lo needs a 16-byte aligned base and ldb_lo %% 4 == 0");
-    if (A_lo != nullptr) {
-      FM_REQUIRE(lda_lo >= K && lda_lo % 4 == 0 && (reinterpret_cast<uintptr_t>(A_lo) & 15) == 0,
-                 "fm_gemm_tn: A_lo needs a 16-byte aligned base and lda_lo %% 4 == 0");
+    if (A_lo != nullptr)
       return (N > 128) ? launch_tc<256, 16, false, true, true>(A, lda, B, ldb, p, st, B_lo, ldb_lo, A_lo, lda_lo)
                        : launch_tc<128, 32, false, true, true>(A, lda, B, ldb, p, st, B_lo, ldb_lo, A_lo, lda_lo);
-    }
     return (N > 128) ? launch_tc<256, 16, false, true>(A, lda, B, ldb, p, st, B_lo, ldb_lo)
                      : launch_tc<128, 32, false, true>(A, lda, B, ldb, p, st, B_lo, ldb_lo);
   }
-  FM_REQUIRE(A_lo == nullptr, "fm_gemm_tn: A_lo is only accepted together with B_lo");
   return (N > 128) ? launch_tc<256, 16, false>(A, lda, B, ldb, p, st) : launch_tc<128, 32, false>(A, lda, B, ldb, p, st);
 }

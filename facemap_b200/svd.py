@@ -82,25 +82,33 @@ class StageTimer:
 
 
 # tcgen05 accumulates in float32 with truncation: every MMA into a running sum loses up to one ulp
-# of it, always in the same direction, so the relative bias grows with the length of the K chain.
-# Contractions are therefore cut into short chains (split-K) that are reduced exactly in float64.
-# (measured on B200: -5.4e-8 relative per accumulation, toward zero; scripts/probe_trunc.py)
-KCHAIN_GRAM = 320     # Gram matrices feed an eigensolve: 120 accumulations -> ~6e-6 of an entry
-KCHAIN_LEFT = 256     # left singular vectors (small GEMMs): ~5e-6
-KCHAIN_GEMM = 1200    # projection of every frame: ~2.4e-5 of the largest term (trace tolerance 1e-3)
+# of it, always toward zero (measured on B200: -5.4e-8 relative per accumulation, scripts/probe_trunc.py),
+# so the bias grows with the length of a K chain.  The product GEMM (impl 0, outputs wider than 128) bounds
+# its TMEM chains to 128 K inside the kernel and sums them in float32 registers with round-to-nearest;
+# split-K over CTAs is then only needed to fill the machine.  Narrow outputs (<= 128 columns) run the
+# single-accumulator kernel and are cut into K chains here, reduced in float64.
+KCHAIN_NARROW = 256
+
+
+def _fill_ksplit(tiles, kdim):
+    """split-K factor that only serves parallelism: ~2 waves of CTAs, at least 1024 K elements each."""
+    want = math.ceil(2 * NUM_SMS / max(tiles, 1)) if tiles < NUM_SMS else 1
+    return int(max(1, min(want, kdim // 1024 if kdim >= 2048 else 1, 64)))
 
 
 def _gram_ksplit(n, kdim):
-    """split-K factor for an n x n upper-triangular Gram over `kdim`: K chains of <= KCHAIN_GRAM and
-    at least ~2 waves of CTAs."""
+    """split-K factor for an n x n upper-triangular Gram over `kdim`."""
+    if n <= 128:
+        return int(max(1, min(math.ceil(kdim / KCHAIN_NARROW), 64)))
     mt, nt = math.ceil(n / 128), math.ceil(n / 256)
     tiles = sum(1 for i in range(mt) for j in range(nt) if (j + 1) * 256 - 1 >= i * 128)
-    want = max(math.ceil(kdim / KCHAIN_GRAM), math.ceil(2 * NUM_SMS / max(tiles, 1)))
-    return int(max(1, min(want, math.ceil(kdim / 32), 64)))
+    return _fill_ksplit(tiles, kdim)
 
 
-def _gemm_ksplit(kdim, chain=None):
-    return int(max(1, math.ceil(kdim / (chain or KCHAIN_GEMM))))
+def _gemm_ksplit(M, N, kdim):
+    if N <= 128:
+        return int(max(1, min(math.ceil(kdim / KCHAIN_NARROW), 64)))
+    return _fill_ksplit(math.ceil(M / 128) * math.ceil(N / 256), kdim)
 
 
 _SOLVERS = {}
@@ -127,9 +135,10 @@ class SvdWorkspace:
         self._ws = None
         self._bufs = {}
 
-    def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm", B_lo=None, chain=None):
-        """C = rscale * (A @ B^T) + rbias with K chains of <= `chain` (KCHAIN_GEMM) reduced in float64."""
-        ksplit = _gemm_ksplit(A.shape[1], chain)
+    def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm", B_lo=None):
+        """C = rscale * (A @ B^T) + rbias; split over K only where the tile count cannot fill the GPU (the
+        partials are then reduced in float64)."""
+        ksplit = _gemm_ksplit(A.shape[0], B.shape[0], A.shape[1])
         if self.gemm_impl not in (0, 9):
             B_lo = None
         if ksplit == 1:
@@ -215,7 +224,7 @@ def left_components(ws, X, evec, lam, mean, k, out_Yt, timer, label):
         Xt = ws.matrix(label + ".Xt", p, n)
         K.transpose(X, Xt)
         Xt_lo = K.split_lo(Xt, out=ws.matrix(label + ".Xt_lo", p, n)) if ws.gemm_impl == 0 else None
-    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left", chain=KCHAIN_LEFT, B_lo=Xt_lo)
+    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left", B_lo=Xt_lo)
 
 
 def chunk_components(ws, X, k, out_Yt, timer, label="chunk"):
@@ -257,7 +266,7 @@ def merge_components_rowside(ws, Yt, k, timer, label="merge"):
         sval, _, _ = K.topk_components(G, lam, k, None, Ut, want_scale=False, nev=nev)
     # sign rule on the right singular vectors: T = Ut Y  (V S = T^T - mu (1^T U))
     T = ws.matrix(label + ".T", k, c)
-    ws.gemm(Ut, Yt, T, label=label + ".left", chain=KCHAIN_LEFT)
+    ws.gemm(Ut, Yt, T, label=label + ".left")
     with timer(label + ".topk"):
         K.sign_from_right(T, mu, Ut)
     with timer(label + ".transpose"):
@@ -278,7 +287,7 @@ def merge_components(ws, Yt, k, timer, label="merge"):
         K.transpose(Yt, Y)
         Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p, c)) if ws.gemm_impl == 0 else None
     Ut = K.alloc_matrix(k, p, Yt.device)
-    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left", chain=KCHAIN_LEFT, B_lo=Y_lo)
+    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left", B_lo=Y_lo)
     with timer(label + ".transpose"):
         U = torch.empty((p, k), dtype=torch.float32, device=Yt.device)
         K.transpose(Ut, U)

@@ -1,6 +1,6 @@
 """Launches the two O(N) kernels at production shape (config C2) a few times: the target of the
 `ncu --set full` captures.  K1: 2368 frames of 640x480 (sbin 4); projection GEMM: 18944 x 500 x 19200
-as 16 K chains + reduction."""
+chained accumulation, pre-split masks."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,11 +15,9 @@ prev = torch.zeros(p, dtype=torch.int32, device=dev); last = torch.zeros_like(pr
 energy = torch.zeros(T, dtype=torch.int64, device=dev)
 Ut = K.alloc_matrix(500, p, dev); Ut.normal_(); Ut_lo = K.split_lo(Ut)
 V = torch.empty((18944, 500), device=dev)
-ws = torch.empty((16, 18944, 512), device=dev)   # 16 K chains of 1200 = svd.KCHAIN_GEMM
 for _ in range(3):
     K.bin_motion(frames, sbin, prev_sum=prev, avgmotion=avg, x_mot=X[:T], energy=energy, last_sum=last)
 for _ in range(3):
-    K.gemm_tn(X, Ut, ksplit=16, workspace=ws, B_lo=Ut_lo)
-    K.splitk_reduce(ws, 16, V)
+    K.gemm_tn(X, Ut, V, B_lo=Ut_lo)
 torch.cuda.synchronize()
 print("ok")

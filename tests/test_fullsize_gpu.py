@@ -71,7 +71,7 @@ def test_projection_and_energy_recomputed_on_windows(full_run):
     for (t0, t1) in [(1, 40), (480, 520), (18900, 18990), (50000, 50032), (N - 40, N)]:
         Vw, Ew = _window_reference(video, t0, t1, am, U)
         got = V[t0:t1].astype(np.float64)
-        assert np.abs(got - Vw).max() <= 6e-5 * np.abs(Vw).max(), (t0, t1)
+        assert np.abs(got - Vw).max() <= 1e-5 * np.abs(Vw).max(), (t0, t1)
         # motion: exact (integer energy / 16 -> float32), with the first-chunk shift of Q1
         for i, t in enumerate(range(t0, t1)):
             idx = t - 1 if t < 500 else t

@@ -211,8 +211,8 @@ def test_against_live_oracle_all_components(cuda_device):
     X = (np.abs(np.diff(b, axis=0)) - o["avgmotion"][0]).astype(np.float32).astype(np.float64)
     Vw = X @ U.astype(np.float64)
     got = p["motSVD"][0][1000:1031].astype(np.float64)
-    # K chains of 2400: ~900 truncating accumulations x 5.4e-8 -> up to ~5e-5 of the largest term
-    assert np.abs(got - Vw).max() <= 6e-5 * np.abs(Vw).max()
+    # in-kernel chains of 128 K (48 truncating accumulations x 5.4e-8) + float32 rounding of the register sums
+    assert np.abs(got - Vw).max() <= 1e-5 * np.abs(Vw).max()
 
 
 def test_host_source_equals_device_source(cuda_device):
