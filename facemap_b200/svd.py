@@ -87,7 +87,11 @@ class StageTimer:
 # its TMEM chains to 128 K inside the kernel and sums them in float32 registers with round-to-nearest;
 # split-K over CTAs is then only needed to fill the machine.  Narrow outputs (<= 128 columns) run the
 # single-accumulator kernel and are cut into K chains here, reduced in float64.
+# Gram matrices feed an eigensolve whose SMALL eigenvalues are sensitive to unstructured error: their K range is
+# still cut into many short partial sums reduced in float64 (fm_gram_assemble), so that at most 2-3 chains are
+# added in float32 before the exact reduction.
 KCHAIN_NARROW = 256
+KCHAIN_GRAM = 320
 
 
 def _fill_ksplit(tiles, kdim):
@@ -102,7 +106,7 @@ def _gram_ksplit(n, kdim):
         return int(max(1, min(math.ceil(kdim / KCHAIN_NARROW), 64)))
     mt, nt = math.ceil(n / 128), math.ceil(n / 256)
     tiles = sum(1 for i in range(mt) for j in range(nt) if (j + 1) * 256 - 1 >= i * 128)
-    return _fill_ksplit(tiles, kdim)
+    return int(max(_fill_ksplit(tiles, kdim), min(math.ceil(kdim / KCHAIN_GRAM), 64)))
 
 
 def _gemm_ksplit(M, N, kdim):
