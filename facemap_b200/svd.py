@@ -92,6 +92,10 @@ class StageTimer:
 # added in float32 before the exact reduction.
 KCHAIN_NARROW = 256
 KCHAIN_GRAM = 320
+# The left singular vectors (U S = X^T W, U = Y W / S) feed the next Gram / are the masks themselves: their small
+# components come out of large cancelling sums, so they too keep float64-reduced partials (2 in-kernel chains each).
+# The projection of every frame (trace tolerance 1e-3) runs as one launch: 150 chains summed in registers.
+KCHAIN_LEFT = 256
 
 
 def _fill_ksplit(tiles, kdim):
@@ -109,9 +113,9 @@ def _gram_ksplit(n, kdim):
     return int(max(_fill_ksplit(tiles, kdim), min(math.ceil(kdim / KCHAIN_GRAM), 64)))
 
 
-def _gemm_ksplit(M, N, kdim):
-    if N <= 128:
-        return int(max(1, min(math.ceil(kdim / KCHAIN_NARROW), 64)))
+def _gemm_ksplit(M, N, kdim, chain=None):
+    if chain is not None or N <= 128:
+        return int(max(1, min(math.ceil(kdim / (chain or KCHAIN_NARROW)), 64)))
     return _fill_ksplit(math.ceil(M / 128) * math.ceil(N / 256), kdim)
 
 
@@ -139,10 +143,10 @@ class SvdWorkspace:
         self._ws = None
         self._bufs = {}
 
-    def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm", B_lo=None):
-        """C = rscale * (A @ B^T) + rbias; split over K only where the tile count cannot fill the GPU (the
-        partials are then reduced in float64)."""
-        ksplit = _gemm_ksplit(A.shape[0], B.shape[0], A.shape[1])
+    def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm", B_lo=None, chain=None):
+        """C = rscale * (A @ B^T) + rbias.  `chain` cuts K into partial sums of that length reduced in float64;
+        without it K is split only where the tile count cannot fill the GPU."""
+        ksplit = _gemm_ksplit(A.shape[0], B.shape[0], A.shape[1], chain)
         if self.gemm_impl not in (0, 9):
             B_lo = None
         if ksplit == 1:
@@ -228,7 +232,7 @@ def left_components(ws, X, evec, lam, mean, k, out_Yt, timer, label):
         Xt = ws.matrix(label + ".Xt", p, n)
         K.transpose(X, Xt)
         Xt_lo = K.split_lo(Xt, out=ws.matrix(label + ".Xt_lo", p, n)) if ws.gemm_impl == 0 else None
-    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left", B_lo=Xt_lo)
+    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left", B_lo=Xt_lo, chain=KCHAIN_LEFT)
 
 
 def chunk_components(ws, X, k, out_Yt, timer, label="chunk"):
@@ -270,7 +274,7 @@ def merge_components_rowside(ws, Yt, k, timer, label="merge"):
         sval, _, _ = K.topk_components(G, lam, k, None, Ut, want_scale=False, nev=nev)
     # sign rule on the right singular vectors: T = Ut Y  (V S = T^T - mu (1^T U))
     T = ws.matrix(label + ".T", k, c)
-    ws.gemm(Ut, Yt, T, label=label + ".left")
+    ws.gemm(Ut, Yt, T, label=label + ".left", chain=KCHAIN_LEFT)
     with timer(label + ".topk"):
         K.sign_from_right(T, mu, Ut)
     with timer(label + ".transpose"):
@@ -291,7 +295,7 @@ def merge_components(ws, Yt, k, timer, label="merge"):
         K.transpose(Yt, Y)
         Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p, c)) if ws.gemm_impl == 0 else None
     Ut = K.alloc_matrix(k, p, Yt.device)
-    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left", B_lo=Y_lo)
+    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left", B_lo=Y_lo, chain=KCHAIN_LEFT)
     with timer(label + ".transpose"):
         U = torch.empty((p, k), dtype=torch.float32, device=Yt.device)
         K.transpose(Ut, U)

@@ -65,7 +65,7 @@ def test_merge_components_row_side_equals_column_side(cuda_device, p, c, k):
     Ymat = K.alloc_matrix(p, c, cuda_device)
     K.transpose(Yt, Ymat)
     Ut_c = K.alloc_matrix(k, p, cuda_device)
-    ws.gemm(Wt, Ymat, Ut_c, rscale=rscale, rbias=rbias)
+    ws.gemm(Wt, Ymat, Ut_c, rscale=rscale, rbias=rbias, chain=svd.KCHAIN_LEFT)
     torch.cuda.synchronize()
     lead = min(20, k)
     a, b = Ut_r[:lead].double(), Ut_c[:lead].double()
