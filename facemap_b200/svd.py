@@ -96,6 +96,7 @@ KCHAIN_GRAM = 320
 # components come out of large cancelling sums, so they too keep float64-reduced partials (2 in-kernel chains each).
 # The projection of every frame (trace tolerance 1e-3) runs as one launch: 150 chains summed in registers.
 KCHAIN_LEFT = 256
+KCHAIN_PROJ = 1200    # only when the projection runs the single-accumulator kernel (impl 9)
 
 
 def _fill_ksplit(tiles, kdim):
@@ -138,20 +139,26 @@ class SvdWorkspace:
         self.device = device
         self.timer = timer if timer is not None else StageTimer(enabled=False)
         self.solver = get_solver(device)
+        # per-role kernel choice (tuning / tests): 0 = chained accumulation, 9 = one TMEM chain per partial
+        import os as _os
+        self.gram_impl = int(_os.environ.get("FM_GRAM_IMPL", gemm_impl))
+        self.left_impl = int(_os.environ.get("FM_LEFT_IMPL", gemm_impl))
+        self.proj_impl = int(_os.environ.get("FM_PROJ_IMPL", gemm_impl))
         self.eig_fp32 = eig_fp32
         self.gemm_impl = gemm_impl
         self._ws = None
         self._bufs = {}
 
-    def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm", B_lo=None, chain=None):
+    def gemm(self, A, B, C_out, rscale=None, rbias=None, label="gemm", B_lo=None, chain=None, impl=None):
         """C = rscale * (A @ B^T) + rbias.  `chain` cuts K into partial sums of that length reduced in float64;
         without it K is split only where the tile count cannot fill the GPU."""
         ksplit = _gemm_ksplit(A.shape[0], B.shape[0], A.shape[1], chain)
-        if self.gemm_impl not in (0, 9):
+        impl = self.gemm_impl if impl is None else impl
+        if impl not in (0, 9):
             B_lo = None
         if ksplit == 1:
             with self.timer(label + ".mma"):
-                K.gemm_tn(A, B, C_out, rscale=rscale, rbias=rbias, impl=self.gemm_impl, B_lo=B_lo)
+                K.gemm_tn(A, B, C_out, rscale=rscale, rbias=rbias, impl=impl, B_lo=B_lo)
             return
         M, N = A.shape[0], B.shape[0]
         ld = max(32, K.round_up(N, 32))
@@ -162,7 +169,7 @@ class SvdWorkspace:
             self._bufs["splitk"] = buf
         part = buf[:need].view(ksplit, M, ld)
         with self.timer(label + ".mma"):
-            K.gemm_tn(A, B, ksplit=ksplit, workspace=part, impl=self.gemm_impl, B_lo=B_lo)
+            K.gemm_tn(A, B, ksplit=ksplit, workspace=part, impl=impl, B_lo=B_lo)
         with self.timer(label + ".reduce"):
             K.splitk_reduce(part, ksplit, C_out, rscale=rscale, rbias=rbias)
 
@@ -192,14 +199,14 @@ def centred_gram(ws: SvdWorkspace, X, timer, label, out=None):
     part = ws.workspace(ksplit, n)
     # A = B = X: one lo plane serves both operands, TMA stages all four tiles (no in-kernel split)
     X_lo = None
-    if ws.gemm_impl == 0:
+    if ws.gram_impl in (0, 9):
         with timer(label + ".gram.split"):
             X_lo = K.split_lo(X, out=ws.matrix("gram.lo", n, p))
     with timer(label + ".gram.mma"):
         if ksplit > 1:
-            K.gemm_tn(X, X, ksplit=ksplit, workspace=part, upper_only=True, impl=ws.gemm_impl, B_lo=X_lo, A_lo=X_lo)
+            K.gemm_tn(X, X, ksplit=ksplit, workspace=part, upper_only=True, impl=ws.gram_impl, B_lo=X_lo, A_lo=X_lo)
         else:
-            K.gemm_tn(X, X, part[0], upper_only=True, impl=ws.gemm_impl, B_lo=X_lo, A_lo=X_lo)
+            K.gemm_tn(X, X, part[0], upper_only=True, impl=ws.gram_impl, B_lo=X_lo, A_lo=X_lo)
     with timer(label + ".gram.assemble"):
         G = K.gram_assemble(part, ksplit, n, mean, p, True, out=out)
     return mean, G
@@ -231,8 +238,8 @@ def left_components(ws, X, evec, lam, mean, k, out_Yt, timer, label):
     with timer(label + ".transpose"):
         Xt = ws.matrix(label + ".Xt", p, n)
         K.transpose(X, Xt)
-        Xt_lo = K.split_lo(Xt, out=ws.matrix(label + ".Xt_lo", p, n)) if ws.gemm_impl == 0 else None
-    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left", B_lo=Xt_lo, chain=KCHAIN_LEFT)
+        Xt_lo = K.split_lo(Xt, out=ws.matrix(label + ".Xt_lo", p, n)) if ws.left_impl in (0, 9) else None
+    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left", B_lo=Xt_lo, chain=KCHAIN_LEFT, impl=ws.left_impl)
 
 
 def chunk_components(ws, X, k, out_Yt, timer, label="chunk"):
@@ -253,14 +260,14 @@ def merge_components_rowside(ws, Yt, k, timer, label="merge"):
     with timer(label + ".transpose"):
         Y = ws.matrix(label + ".Y", p, c)
         K.transpose(Yt, Y)
-        Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p, c)) if ws.gemm_impl == 0 else None
+        Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p, c)) if ws.gram_impl in (0, 9) else None
     ksplit = _gram_ksplit(p, c)
     part = ws.workspace(ksplit, p)
     with timer(label + ".gram.mma"):
         if ksplit > 1:
-            K.gemm_tn(Y, Y, ksplit=ksplit, workspace=part, upper_only=True, impl=ws.gemm_impl, B_lo=Y_lo, A_lo=Y_lo)
+            K.gemm_tn(Y, Y, ksplit=ksplit, workspace=part, upper_only=True, impl=ws.gram_impl, B_lo=Y_lo, A_lo=Y_lo)
         else:
-            K.gemm_tn(Y, Y, part[0], upper_only=True, impl=ws.gemm_impl, B_lo=Y_lo, A_lo=Y_lo)
+            K.gemm_tn(Y, Y, part[0], upper_only=True, impl=ws.gram_impl, B_lo=Y_lo, A_lo=Y_lo)
     with timer(label + ".gram.assemble"):
         q = K.row_dot(Y, mu)
         G = K.gram_assemble_rowside(part, ksplit, p, q, mu, True)
@@ -274,7 +281,7 @@ def merge_components_rowside(ws, Yt, k, timer, label="merge"):
         sval, _, _ = K.topk_components(G, lam, k, None, Ut, want_scale=False, nev=nev)
     # sign rule on the right singular vectors: T = Ut Y  (V S = T^T - mu (1^T U))
     T = ws.matrix(label + ".T", k, c)
-    ws.gemm(Ut, Yt, T, label=label + ".left", chain=KCHAIN_LEFT)
+    ws.gemm(Ut, Yt, T, label=label + ".left", chain=KCHAIN_LEFT, impl=ws.left_impl)
     with timer(label + ".topk"):
         K.sign_from_right(T, mu, Ut)
     with timer(label + ".transpose"):
@@ -293,9 +300,10 @@ def merge_components(ws, Yt, k, timer, label="merge"):
     with timer(label + ".transpose"):
         Y = ws.matrix(label + ".Y", p, c)
         K.transpose(Yt, Y)
-        Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p, c)) if ws.gemm_impl == 0 else None
+        Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p, c)) if ws.left_impl in (0, 9) else None
     Ut = K.alloc_matrix(k, p, Yt.device)
-    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left", B_lo=Y_lo, chain=KCHAIN_LEFT)
+    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left", B_lo=Y_lo, chain=KCHAIN_LEFT,
+            impl=ws.left_impl)
     with timer(label + ".transpose"):
         U = torch.empty((p, k), dtype=torch.float32, device=Yt.device)
         K.transpose(Ut, U)
@@ -683,7 +691,8 @@ class Stage3:
                 Uts = masks[m][0]
                 Xm = X[m][base:base + filled]
                 if self.fullSVD and Uts[0] is not None:
-                    ws.gemm(Xm, Uts[0], V[m][0][o:o + filled], label="stage3.project", B_lo=Ut_lo[m][0])
+                    ws.gemm(Xm, Uts[0], V[m][0][o:o + filled], label="stage3.project", B_lo=Ut_lo[m][0], impl=ws.proj_impl,
+                            chain=KCHAIN_PROJ if ws.proj_impl == 9 else None)
                     if sink is not None:
                         sink.copy(V[m][0][o:o + filled], V_host[m][0][o:o + filled])
                 for j, (v, y0, y1, x0, x1) in enumerate(geo.mot_rois):
@@ -693,7 +702,8 @@ class Stage3:
                         with timer("stage3.roi_gather"):
                             K.gather_roi(Xm[r0:r1], r1 - r0, geo.col0[v], int(geo.Lxb[v]), (y0, y1, x0, x1), Xr)
                         ws.gemm(Xr, Uts[1 + j], V[m][1 + j][o + r0:o + r1], label="stage3.roi_project",
-                                B_lo=Ut_lo[m][1 + j])
+                                B_lo=Ut_lo[m][1 + j], impl=ws.proj_impl,
+                                chain=KCHAIN_PROJ if ws.proj_impl == 9 else None)
                         if sink is not None:
                             sink.copy(V[m][1 + j][o + r0:o + r1], V_host[m][1 + j][o + r0:o + r1])
             row0 += filled
