@@ -91,7 +91,7 @@ class StageTimer:
 # still cut into many short partial sums reduced in float64 (fm_gram_assemble), so that at most 2-3 chains are
 # added in float32 before the exact reduction.
 KCHAIN_NARROW = 256
-KCHAIN_GRAM = 320
+KCHAIN_GRAM = int(__import__('os').environ.get('FM_KCHAIN_GRAM', 128))   # one TMEM chain per float64-reduced partial
 # The left singular vectors (U S = X^T W, U = Y W / S) feed the next Gram / are the masks themselves: their small
 # components come out of large cancelling sums, so they too keep float64-reduced partials (2 in-kernel chains each).
 # The projection of every frame (trace tolerance 1e-3) runs as one launch: 150 chains summed in registers.
@@ -111,7 +111,8 @@ def _gram_ksplit(n, kdim):
         return int(max(1, min(math.ceil(kdim / KCHAIN_NARROW), 64)))
     mt, nt = math.ceil(n / 128), math.ceil(n / 256)
     tiles = sum(1 for i in range(mt) for j in range(nt) if (j + 1) * 256 - 1 >= i * 128)
-    return int(max(_fill_ksplit(tiles, kdim), min(math.ceil(kdim / KCHAIN_GRAM), 64)))
+    fill = math.ceil(2 * NUM_SMS / max(tiles, 1)) if tiles < NUM_SMS else 1
+    return int(max(1, min(max(fill, math.ceil(kdim / KCHAIN_GRAM)), math.ceil(kdim / 32), 192)))
 
 
 def _gemm_ksplit(M, N, kdim, chain=None):
