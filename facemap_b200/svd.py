@@ -91,7 +91,7 @@ class StageTimer:
 # still cut into many short partial sums reduced in float64 (fm_gram_assemble), so that at most 2-3 chains are
 # added in float32 before the exact reduction.
 KCHAIN_NARROW = 256
-KCHAIN_GRAM = int(__import__('os').environ.get('FM_KCHAIN_GRAM', 128))   # one TMEM chain per float64-reduced partial
+KCHAIN_GRAM = 320     # <= 3 in-kernel chains per float64-reduced partial
 # The left singular vectors (U S = X^T W, U = Y W / S) feed the next Gram / are the masks themselves: their small
 # components come out of large cancelling sums, so they too keep float64-reduced partials (2 in-kernel chains each).
 # The projection of every frame (trace tolerance 1e-3) runs as one launch: 150 chains summed in registers.

@@ -36,8 +36,9 @@ def _compare(p, o, motSVD=True, movSVD=False, s_floor=1e-2):
             assert err <= 1e-3 * np.abs(Vr[:, :k]).max(), (vk, err)
         S, Sr = np.asarray(p[sk], np.float64), np.asarray(o[sk], np.float64)
         if np.any(Sr):
+            # 1e-4 relative, with the float32 floor of the data path (a few eps of the top singular value)
             big = Sr >= s_floor * Sr[0]
-            assert (np.abs(S - Sr)[big] / Sr[big]).max() <= 1e-4, sk
+            assert np.all(np.abs(S - Sr)[big] <= np.maximum(1e-4 * Sr[big], 4e-6 * Sr[0])), sk
 
 
 @pytest.mark.parametrize("N", [120, 499, 500, 501, 999, 1000, 1001, 1999, 2000, 2001, 3217])
@@ -72,7 +73,7 @@ def test_odd_geometry_and_bin_factors(cuda_device, H, W, sbin):
         assert np.allclose(p["motion"][0], o["motion"][0], rtol=3e-7, atol=0)
         S, Sr = p["motSv"].astype(np.float64), o["motSv"].astype(np.float64)
         big = Sr >= 1e-2 * Sr[0]
-        assert (np.abs(S - Sr)[big] / Sr[big]).max() <= 1e-4
+        assert np.all(np.abs(S - Sr)[big] <= np.maximum(1e-4 * Sr[big], 4e-6 * Sr[0]))
 
 
 def test_three_views_canvas(cuda_device):
