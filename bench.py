@@ -298,6 +298,9 @@ def main():
         one_step(dev_src, timing={})             # same code path as the timed steps (CUDA-event timers on)
     barrier()
     timings = []
+    import gc
+    gc.collect()
+    gc.disable()                                 # no collector pauses inside the timed region
     n0 = kernels.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
@@ -311,6 +314,7 @@ def main():
     ev1.record()
     barrier()
     w1 = time.perf_counter()
+    gc.enable()
     launches = kernels.launch_count() - n0
     clk = clocks.stop(w0, w1) if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
@@ -430,6 +434,8 @@ def main():
             "stage_ms": {k: round(v, 3) for k, v in sorted(agg.items())},
             "cusolver_ms_per_step": solver_ms,
             "host_ms_per_step": [round(tm["host_ms"], 1) for tm in timings],
+            "cusolver_ms_each_step": [round(sum(v for k, v in tm["device_ms"].items() if k.endswith(".syevd")), 1)
+                                      for tm in timings],
             "kernels_only_frames_per_s": total_frames / ((ms_step - solver_ms) / 1e3) if ms_step > solver_ms else None,
         }
         print(json.dumps(line), flush=True)
