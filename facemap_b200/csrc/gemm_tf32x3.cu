@@ -6,7 +6,13 @@
 // 503, 510) and the products inside utils.svdecon (facemap/utils.py:751-776), here in the Gram
 // formulation (matlab/utils/svdecon.m:16-43).
 //
-// One CTA computes a 128 x BN tile over one K range (split-K over blockIdx.z):
+// Kernels in this file (fm_gemm_tn's `impl`):
+//   gemm_tf32x3_chain_kernel   impl 0, the product configuration: 128 x 256 tiles, two TMEM accumulators used
+//                              alternately in chains of 128 K, drained into float32 register accumulators
+//   gemm_tf32x3_kernel         one TMEM chain per launch (impl 9; also serves outputs <= 128 wide), tile variants 2..6
+//   gemm_tf32x3_pair_kernel    CTA pair, cta_group::2 (impl 7/8)
+//   gemm_fp32_ref_kernel       plain FFMA reference for the tests (impl 1)
+// Common structure — one CTA computes a 128 x BN tile over one K range (split-K over blockIdx.z):
 //   warp 0        TMA producer: raw fp32 tiles of A (128x32) and B (BNx32) per stage
 //   warps 2..9    splitter: lo = x - (x & 0xffffe000) into a second buffer (kind::tf32 reads only the
 //                 top 19 bits of an operand word, so the raw tile itself is the hi operand), then
