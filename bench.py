@@ -36,52 +36,60 @@ WORKLOAD = "1-camera 640x480 uint8, 100k frames per GPU, sbin=4, motSVD 500 comp
 # clocks sampling
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region.  NVML from a thread
+    (pynvml; its calls release the GIL and cost microseconds) — a looping `nvidia-smi` subprocess stalls
+    the CUDA driver for 100-200 ms at a time on this platform, which showed up as outlier steps."""
 
-    def __init__(self, gpu_index):
-        self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index, period_s=0.1):
+        self.idx, self.period = gpu_index, period_s
+        self.samples, self.stop_flag, self.thread, self.nvml = [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "250"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
+            self.nvml = None
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+    def _loop(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.perf_counter(), sm, rs))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        for ts, line in self.lines:
-            if ts < t0 or ts > t1:
-                continue
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax = float(f[2])
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self.stop_flag = True
+        if self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.thread.join(1.0)
+        nv = self.nvml
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sm = sorted(s[1] for s in self.samples if t0 <= s[0] <= t1)
+        reasons = set()
+        for ts, _, rs in self.samples:
+            if t0 <= ts <= t1:
+                for k, bit in names.items():
+                    if rs & bit:
+                        reasons.add(k)
+        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.smax),
+                "reasons": sorted(reasons), "samples": len(sm), "how": "NVML, 100 ms period, rank-0 GPU"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -302,6 +310,7 @@ def main():
     gc.collect()
     gc.disable()                                 # no collector pauses inside the timed region
     n0 = kernels.launch_count()
+    mem0 = torch.cuda.memory_stats(device)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     ev0.record()
@@ -316,6 +325,8 @@ def main():
     w1 = time.perf_counter()
     gc.enable()
     launches = kernels.launch_count() - n0
+    mem1 = torch.cuda.memory_stats(device)
+    alloc_diag = {k: int(mem1.get(k, 0) - mem0.get(k, 0)) for k in ("num_device_alloc", "num_device_free", "num_alloc_retries")}
     clk = clocks.stop(w0, w1) if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
@@ -434,6 +445,7 @@ def main():
             "stage_ms": {k: round(v, 3) for k, v in sorted(agg.items())},
             "cusolver_ms_per_step": solver_ms,
             "host_ms_per_step": [round(tm["host_ms"], 1) for tm in timings],
+            "allocator_in_timed_region": alloc_diag,
             "cusolver_ms_each_step": [round(sum(v for k, v in tm["device_ms"].items() if k.endswith(".syevd")), 1)
                                       for tm in timings],
             "kernels_only_frames_per_s": total_frames / ((ms_step - solver_ms) / 1e3) if ms_step > solver_ms else None,
