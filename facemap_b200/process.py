@@ -132,11 +132,16 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     wall0 = time.perf_counter()
     marks = []
 
+    hmarks = []
+
     def mark(name):
-        """diagnostic wall-clock checkpoints (synchronising) when timing["sync"] is set"""
-        if timing is not None and timing.get("sync"):
-            torch.cuda.synchronize()
-            marks.append((name, time.perf_counter()))
+        """host timestamps per stage (timing["host_marks_ms"]); with timing["sync"] the device is
+        synchronised first, which turns them into per-stage wall times (diagnostic)"""
+        if timing is not None:
+            hmarks.append((name, time.perf_counter()))
+            if timing.get("sync"):
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
 
     mark("start")
     ws = svd.SvdWorkspace(dev, eig_fp32=eig_fp32, gemm_impl=gemm_impl, timer=timer)
@@ -298,6 +303,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     if timing is not None:
         if marks:
             timing["wall_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks[:-1], marks[1:])}
+        timing["host_marks_ms"] = {b[0]: round(1e3 * (b[1] - a[1]), 2) for a, b in zip(hmarks[:-1], hmarks[1:])}
         timing["device_ms"] = timer.report()
         timing["timeline_ms"] = timer.timeline()
         timing["wall_s"] = time.perf_counter() - wall0
