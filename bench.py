@@ -393,7 +393,7 @@ def main():
         t0 = time.perf_counter()
         e2e_tm = {}
         for _ in range(args.e2e_steps):
-            e2e_tm = {}
+            e2e_tm = {"timeline": True}
             out = one_step(host_src, timing=e2e_tm, keep=False)
             d2h = sum(a.nbytes for key in ("avgframe", "avgmotion", "motion", "motMask", "motSVD") for a in out[key]) \
                 + out["motSv"].nbytes

@@ -305,7 +305,9 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
             timing["wall_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks[:-1], marks[1:])}
         timing["host_marks_ms"] = {b[0]: round(1e3 * (b[1] - a[1]), 2) for a, b in zip(hmarks[:-1], hmarks[1:])}
         timing["device_ms"] = timer.report()
-        timing["timeline_ms"] = timer.timeline()
+        if timing.get("timeline"):
+            timing["timeline_ms"] = timer.timeline()
+        timer.release()
         timing["wall_s"] = time.perf_counter() - wall0
         timing["assemble_wall_s"] = time.perf_counter() - t_asm
     return proc

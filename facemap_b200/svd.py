@@ -34,15 +34,22 @@ BATCHED_EIG_MIN = 5
 
 class StageTimer:
     """CUDA-event stopwatch: `with timer("name"):` accumulates device time per label; nothing is
-    synchronised until report()."""
+    synchronised until report().  Events come from a process-wide pool (creating and destroying ~600
+    events per pass showed up as host-side stalls)."""
+
+    _pool = []
 
     def __init__(self, enabled=True):
         self.enabled = enabled
         self.spans = []
         self.origin = None
         if enabled:
-            self.origin = torch.cuda.Event(enable_timing=True)
+            self.origin = self._event()
             self.origin.record()
+
+    @classmethod
+    def _event(cls):
+        return cls._pool.pop() if cls._pool else torch.cuda.Event(enable_timing=True)
 
     class _Span:
         def __init__(self, owner, name):
@@ -50,8 +57,8 @@ class StageTimer:
 
         def __enter__(self):
             if self.owner.enabled:
-                self.a = torch.cuda.Event(enable_timing=True)
-                self.b = torch.cuda.Event(enable_timing=True)
+                self.a = self.owner._event()
+                self.b = self.owner._event()
                 self.a.record()
             return self
 
@@ -79,6 +86,15 @@ class StageTimer:
             for name, a, b in self.spans:
                 out[name] = max(out.get(name, 0.0), self.origin.elapsed_time(b))
         return out
+
+    def release(self):
+        """hand the events back to the pool (call after report / timeline)."""
+        for _, a, b in self.spans:
+            StageTimer._pool.append(a)
+            StageTimer._pool.append(b)
+        if self.origin is not None:
+            StageTimer._pool.append(self.origin)
+        self.spans, self.origin = [], None
 
 
 # tcgen05 accumulates in float32 with truncation: every MMA into a running sum loses up to one ulp
