@@ -40,9 +40,10 @@ class ClockSampler:
     (pynvml; its calls release the GIL and cost microseconds) — a looping `nvidia-smi` subprocess stalls
     the CUDA driver for 100-200 ms at a time on this platform, which showed up as outlier steps."""
 
-    def __init__(self, gpu_index, period_s=0.1):
+    def __init__(self, gpu_index, period_s=0.4):
         self.idx, self.period = gpu_index, period_s
         self.samples, self.stop_flag, self.thread, self.nvml = [], False, None, None
+        self.call_ms = (0.0, 0.0)
 
     def start(self):
         try:
@@ -61,12 +62,16 @@ class ClockSampler:
         nv = self.nvml
         while not self.stop_flag:
             try:
+                t0 = time.perf_counter()
                 sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                t1 = time.perf_counter()
                 try:
                     rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 except Exception:
                     rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                self.samples.append((time.perf_counter(), sm, rs))
+                t2 = time.perf_counter()
+                self.samples.append((t2, sm, rs))
+                self.call_ms = (max(self.call_ms[0], 1e3 * (t1 - t0)), max(self.call_ms[1], 1e3 * (t2 - t1)))
             except Exception:
                 pass
             time.sleep(self.period)
@@ -89,7 +94,8 @@ class ClockSampler:
                     if rs & bit:
                         reasons.add(k)
         return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.smax),
-                "reasons": sorted(reasons), "samples": len(sm), "how": "NVML, 100 ms period, rank-0 GPU"}
+                "reasons": sorted(reasons), "samples": len(sm), "how": f"NVML every {self.period} s, rank-0 GPU",
+                "nvml_call_ms_max": {"clock": round(self.call_ms[0], 2), "reasons": round(self.call_ms[1], 2)}}
 
 
 # ---------------------------------------------------------------------------------------------
