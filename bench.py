@@ -452,6 +452,7 @@ def main():
             "cusolver_ms_per_step": solver_ms,
             "host_ms_per_step": [round(tm["host_ms"], 1) for tm in timings],
             "allocator_in_timed_region": alloc_diag,
+            "report_ms_each_step": [(tm.get("final_sync_ms"), tm.get("report_ms")) for tm in timings],
             "host_marks_ms_slowest_step": max(timings, key=lambda tm: tm["host_ms"]).get("host_marks_ms"),
             "host_marks_ms_fastest_step": min(timings, key=lambda tm: tm["host_ms"]).get("host_marks_ms"),
             "cusolver_ms_each_step": [round(sum(v for k, v in tm["device_ms"].items() if k.endswith(".syevd")), 1)

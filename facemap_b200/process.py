@@ -304,7 +304,11 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         if marks:
             timing["wall_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks[:-1], marks[1:])}
         timing["host_marks_ms"] = {b[0]: round(1e3 * (b[1] - a[1]), 2) for a, b in zip(hmarks[:-1], hmarks[1:])}
+        t_rep = time.perf_counter()
+        torch.cuda.synchronize()
+        timing["final_sync_ms"] = round(1e3 * (time.perf_counter() - t_rep), 2)
         timing["device_ms"] = timer.report()
+        timing["report_ms"] = round(1e3 * (time.perf_counter() - t_rep), 2)
         if timing.get("timeline"):
             timing["timeline_ms"] = timer.timeline()
         timer.release()
