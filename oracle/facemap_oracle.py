@@ -321,10 +321,12 @@ def stage2_masks(video, sbin, avgframe, avgmotion, motSVD=True, movSVD=False, ro
 # stage 3
 # ------------------------------------------------------------------------------------------
 def stage3_project(video, sbin, avgframe, avgmotion, U_mot, U_mov, motSVD=True, movSVD=False,
-                   rois=None, fullSVD=True):
+                   rois=None, fullSVD=True, fullres=None):
     """facemap/process.py:302-530 (SVD/motion parts) — all frames in chunks of 500 with a
     one-frame carry; first projected row duplicated (Q2); motion[499] hole (Q1);
-    avg arrays reshaped in place when a motion ROI sits on the view (Q4)."""
+    avg arrays reshaped in place when a motion ROI sits on the view (Q4).
+    `fullres` (oracle/roi_oracle.FullResRois) processes pupil/blink/running ROIs on each chunk
+    first and paints the chunk in place (process.py:410-425, 543, 567), which the binning sees."""
     N = video.N
     Lyb, Lxb, cols = binned_geometry(video.Ly, video.Lx, sbin)
     p = int((Lyb.astype(np.int64) * Lxb).sum())
@@ -350,6 +352,9 @@ def stage3_project(video, sbin, avgframe, avgmotion, U_mot, U_mov, motSVD=True, 
     for n in range(nseg):
         ims = video.get(t, CHUNK_PROJ)
         nt1 = ims[0].shape[0]
+        if fullres is not None and fullres.any:
+            ims = [im.copy() for im in ims]
+            fullres.chunk(t, ims, first=(n == 0))
         rows = nt1 if n > 0 else nt1 - 1
         if fullSVD:
             X_mot = np.zeros((rows, p), np.float32)
@@ -463,7 +468,12 @@ def run_oracle(views, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD=True
                  "motMask_reshape": U_mot_r, "movMask_reshape": U_mov_r})
     if "proj" not in stages:
         return proc
+    from .roi_oracle import FullResRois
+
+    fullres = FullResRois(rois, video.N)
     V_mot, V_mov, M = stage3_project(video, sbin, avgframe, avgmotion, U_mot, U_mov, motSVD,
-                                     movSVD, rois, fullSVD)
-    proc.update({"motion": M, "motSVD": V_mot, "movSVD": V_mov})
+                                     movSVD, rois, fullSVD, fullres)
+    pups, blinks, runs = fullres.finish()
+    proc.update({"motion": M, "motSVD": V_mot, "movSVD": V_mov,
+                 "pupil": pups, "blink": blinks, "running": runs})
     return proc

@@ -77,3 +77,96 @@ def sign_align(A, B):
     sg = np.sign(np.sum(np.asarray(A, np.float64) * np.asarray(B, np.float64), axis=0))
     sg[sg == 0] = 1.0
     return A * sg[None, :], sg
+
+
+# ---------------------------------------------------------------------------------------------
+# full-resolution ROI cases (pupil / blink / running) — shared with scripts/make_golden_fullres.py
+# ---------------------------------------------------------------------------------------------
+def ellipse_mask(ny, nx):
+    """Boolean ellipse inscribed in an ny x nx rectangle (what facemap/roi.py:254-259 draws)."""
+    y, x = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    return ((y - ny / 2) ** 2 / (ny / 2) ** 2 + (x - nx / 2) ** 2 / (nx / 2) ** 2) <= 1
+
+
+def eye_video(H, W, N, seed=0, wheel=True):
+    """uint8 (N, H, W): bright noisy background, a dark disc that drifts and pulses (pupil) with a
+    small bright reflection on it, slow lid closures (blinks), and a drifting texture band at the
+    bottom (running wheel).  Deterministic for a seed."""
+    rs = np.random.RandomState(seed)
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    t = np.arange(N)
+    cy = H * 0.35 + 3.0 * np.sin(t / 37.0) + rs.randn(N).cumsum() * 0.05
+    cx = W * 0.40 + 4.0 * np.cos(t / 53.0) + rs.randn(N).cumsum() * 0.05
+    rad = min(H, W) * (0.10 + 0.03 * np.sin(t / 91.0))
+    lid = np.clip(np.sin(t / 140.0) * 4 - 3, 0, 1)                       # 0 open .. 1 closed
+    tex = rs.randint(0, 256, size=(H, 4 * W)).astype(np.int32)
+    shift = np.cumsum(rs.randint(0, 4, size=N))
+    out = np.empty((N, H, W), np.uint8)
+    for i in range(N):
+        f = 170 + 25 * np.sin(yy / 9.0 + i / 300.0) + rs.randint(-6, 7, size=(H, W))
+        r2 = (yy - cy[i]) ** 2 + (xx - cx[i]) ** 2
+        f = np.where(r2 <= rad[i] ** 2, 25 + rs.randint(0, 12, size=(H, W)), f)
+        f = np.where((yy - cy[i] + 2) ** 2 + (xx - cx[i] - 3) ** 2 <= 4, 250, f)
+        f = f * (1 - 0.6 * lid[i] * (yy < H * 0.6))
+        if wheel:
+            band = yy >= int(H * 0.7)
+            s = int(shift[i]) % (3 * W)
+            f = np.where(band, tex[:, s:s + W] // 2 + 60, f)
+        out[i] = np.clip(f, 0, 255).astype(np.uint8)
+    if N > 600:      # degenerate frames: nothing dark, everything dark, one dark pixel, two far dark pixels
+        out[505] = 255
+        out[506] = 0
+        out[507] = 255
+        out[507, int(H * 0.3), int(W * 0.4)] = 3
+        out[508] = 255
+        out[508, int(H * 0.2), int(W * 0.3)] = 0
+        out[508, int(H * 0.4), int(W * 0.5)] = 10
+    return out
+
+
+def pupil_roi(ivid, y0, y1, x0, x1, saturation, sigma=2.0, reflector=None):
+    r = {"rind": 0, "rtype": "Pupil", "iROI": 0, "ivid": ivid, "color": (0, 0, 0),
+         "yrange": np.arange(y0, y1), "xrange": np.arange(x0, x1), "saturation": saturation,
+         "pupil_sigma": sigma, "ellipse": ellipse_mask(y1 - y0, x1 - x0)}
+    if reflector is not None:
+        r["reflector"] = reflector
+    return r
+
+
+def reflector_roi(y0, y1, x0, x1):
+    """Reflector rectangle in pupil-crop coordinates (facemap/utils.py:656-661)."""
+    return {"yrange": np.arange(y0, y1), "xrange": np.arange(x0, x1), "ellipse": ellipse_mask(y1 - y0, x1 - x0)}
+
+
+def blink_roi(ivid, y0, y1, x0, x1, saturation):
+    return {"rind": 2, "rtype": "blink", "iROI": 0, "ivid": ivid, "color": (0, 0, 0),
+            "yrange": np.arange(y0, y1), "xrange": np.arange(x0, x1), "saturation": saturation,
+            "ellipse": ellipse_mask(y1 - y0, x1 - x0)}
+
+
+def running_roi(ivid, y0, y1, x0, x1):
+    return {"rind": 3, "rtype": "running", "iROI": 0, "ivid": ivid, "color": (0, 0, 0),
+            "yrange": np.arange(y0, y1), "xrange": np.arange(x0, x1), "saturation": 0}
+
+
+def fullres_case(name):
+    """-> (views, sbin, motSVD, movSVD, rois, fullSVD)"""
+    if name == "eye_all":            # every processor on one view, overlapping rectangles (paint order)
+        v = [eye_video(72, 96, 1150, seed=1)]
+        rois = [pupil_roi(0, 8, 44, 16, 64, 90.27), blink_roi(0, 4, 40, 40, 90, 140.25),
+                running_roi(0, 51, 72, 2, 94), motion_roi(0, 6, 60, 10, 80),
+                pupil_roi(0, 10, 40, 20, 60, 60.0, sigma=2.5)]
+        return v, 2, True, False, rois, True
+    if name == "eye_reflector":      # reflector fill-in, int saturation for blink (uint8 wrap), two views
+        v = [eye_video(64, 80, 700, seed=2, wheel=False), eye_video(48, 56, 700, seed=3)]
+        rois = [pupil_roi(0, 6, 42, 10, 58, 80.325, reflector=[reflector_roi(10, 18, 18, 27), reflector_roi(20, 24, 30, 36)]),
+                blink_roi(0, 2, 38, 6, 70, 200), running_roi(1, 34, 48, 0, 56), blink_roi(1, 0, 30, 3, 50, 120.7)]
+        return v, 1, True, True, rois, True
+    if name == "eye_only":           # no SVD at all: fullSVD off and no motion ROI
+        v = [eye_video(60, 70, 620, seed=4)]
+        rois = [pupil_roi(0, 5, 40, 8, 52, 100.47), running_roi(0, 42, 60, 0, 70)]
+        return v, 2, True, False, rois, False
+    raise KeyError(name)
+
+
+FULLRES_CASES = ("eye_all", "eye_reflector", "eye_only")
