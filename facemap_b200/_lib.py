@@ -66,6 +66,11 @@ SIGNATURES = {
     "fm_topk_components": (_I, [_P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P]),
     "fm_transpose": (_I, [_P, _L, _I, _I, _P, _L, _P]),
     "fm_gather_roi": (_I, [_P, _L, _I, _L, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "fm_paint": (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    "fm_blink": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "fm_running": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "fm_pupil_scratch_bytes": (_I, [_I, _I, _I, C.POINTER(C.c_size_t)]),
+    "fm_pupil": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, C.c_float, C.c_double, _P, _I, _P, _P]),
 }
 
 _lock = threading.Lock()

@@ -1,0 +1,95 @@
+// NumPy's pairwise float32 summation order, usable from device code and (for the CPU unit test that
+// pins it against numpy.sum, tests/test_numpy_sum.py) from plain C++.
+#pragma once
+#if defined(__CUDACC__)
+#define FM_HD __host__ __device__
+#else
+#define FM_HD
+#endif
+
+namespace fm {
+
+// one correctly rounded float32 addition that no compiler may fuse or reassociate
+FM_HD inline float fadd_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b;
+  return r;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// NumPy pairwise float32 sum (numpy/_core/src/umath/loops_utils.h.src, FLOAT_pairwise_sum), run by
+// ONE thread: the result depends on the association order, which is what is being reproduced.
+// ------------------------------------------------------------------------------------------------
+FM_HD inline float pairwise_leaf(const float* a, int n) {
+  if (n < 8) {
+    float r = -0.0f;
+    for (int i = 0; i < n; ++i) r = fadd_rn(r, a[i]);
+    return r;
+  }
+  float r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+  const int m = n - (n % 8);
+  for (int i = 8; i < m; i += 8) {
+    r0 = fadd_rn(r0, a[i + 0]);
+    r1 = fadd_rn(r1, a[i + 1]);
+    r2 = fadd_rn(r2, a[i + 2]);
+    r3 = fadd_rn(r3, a[i + 3]);
+    r4 = fadd_rn(r4, a[i + 4]);
+    r5 = fadd_rn(r5, a[i + 5]);
+    r6 = fadd_rn(r6, a[i + 6]);
+    r7 = fadd_rn(r7, a[i + 7]);
+  }
+  float res = fadd_rn(fadd_rn(fadd_rn(r0, r1), fadd_rn(r2, r3)),
+                        fadd_rn(fadd_rn(r4, r5), fadd_rn(r6, r7)));
+  for (int i = m; i < n; ++i) res = fadd_rn(res, a[i]);
+  return res;
+}
+
+FM_HD inline float pairwise_tree_f32(const float* a, int n) {
+  // post-order walk of the split tree with an explicit stack (depth <= log2(n / 128) + 1)
+  int lo_s[32], n_s[32];
+  float left_s[32];
+  unsigned char phase_s[32];
+  int sp = 0;
+  lo_s[0] = 0;
+  n_s[0] = n;
+  phase_s[0] = 0;
+  for (;;) {
+    if (n_s[sp] > 128) {                   // descend into the left half
+      int n2 = n_s[sp] / 2;
+      n2 -= n2 % 8;
+      phase_s[sp] = 1;
+      lo_s[sp + 1] = lo_s[sp];
+      n_s[sp + 1] = n2;
+      phase_s[sp + 1] = 0;
+      ++sp;
+      continue;
+    }
+    float val = pairwise_leaf(a + lo_s[sp], n_s[sp]);
+    // deliver `val` upwards until a node still waits for its right half
+    for (;;) {
+      if (sp == 0) return val;
+      --sp;
+      if (phase_s[sp] == 1) {              // left half done: remember it, descend right
+        left_s[sp] = val;
+        phase_s[sp] = 2;
+        int n2 = n_s[sp] / 2;
+        n2 -= n2 % 8;
+        lo_s[sp + 1] = lo_s[sp] + n2;
+        n_s[sp + 1] = n_s[sp] - n2;
+        phase_s[sp + 1] = 0;
+        ++sp;
+        break;
+      }
+      val = fadd_rn(left_s[sp], val);    // right half done: combine, keep delivering
+    }
+  }
+}
+
+// numpy.add.reduce starts from the identity 0 and adds the pairwise result to it (so an empty or all -0
+// input gives +0)
+FM_HD inline float pairwise_sum_f32(const float* a, int n) { return fadd_rn(0.0f, pairwise_tree_f32(a, n)); }
+
+}  // namespace fm

@@ -282,3 +282,87 @@ def gather_roi(X, rows, col0, Lxb, rect, out):
     y0, y1, x0, x1 = rect
     check(_lib.load().fm_gather_roi(ptr(X), X.stride(0), int(rows), int(col0), int(Lxb), int(y0), int(y1), int(x0),
                                     int(x1), ptr(out), out.stride(0), _stream()), "fm_gather_roi")
+
+
+# ---------------------------------------------------------------------------------------------
+# full-resolution ROI processors (include/facemap_b200.h: fm_paint, fm_blink, fm_running, fm_pupil)
+# ---------------------------------------------------------------------------------------------
+def _frames3(frames):
+    _need(frames, torch.uint8, "frames", 3)
+    if not frames.is_contiguous():
+        raise FacemapB200Error("frames must be contiguous [T, H, W]")
+    return frames.shape
+
+
+def paint(frames, ormask, out):
+    """out[t] = frames[t] | ormask (uint8 [H, W] of 0x00 / 0xFF)."""
+    T, H, W = _frames3(frames)
+    _need(ormask, torch.uint8, "ormask", 2)
+    _need(out, torch.uint8, "out", 3)
+    if tuple(ormask.shape) != (H, W) or out.shape[0] < T or tuple(out.shape[1:]) != (H, W) \
+            or not ormask.is_contiguous() or not out.is_contiguous():
+        raise FacemapB200Error("paint: shape mismatch")
+    check(_lib.load().fm_paint(ptr(frames), T, H, W, ptr(ormask), ptr(out), _stream()), "fm_paint")
+    return out[:T]
+
+
+def _crop_operand(t, rect, name, dtype=torch.uint8):
+    y0, y1, x0, x1 = rect
+    _need(t, dtype, name, 2)
+    if tuple(t.shape) != (y1 - y0, x1 - x0) or not t.is_contiguous():
+        raise FacemapB200Error(f"{name}: expected a contiguous [{y1 - y0}, {x1 - x0}] tensor, got {tuple(t.shape)}")
+
+
+def blink(frames, rect, mask, term, out):
+    """out[t] (float64) = sum over the painted ROI of term[pixel] (term: float64 [256])."""
+    T, H, W = _frames3(frames)
+    _crop_operand(mask, rect, "mask")
+    _need(term, torch.float64, "term", 1)
+    _need(out, torch.float64, "out", 1)
+    if term.numel() != 256 or out.numel() < T or not out.is_contiguous():
+        raise FacemapB200Error("blink: term must have 256 entries and out at least T")
+    y0, y1, x0, x1 = (int(v) for v in rect)
+    check(_lib.load().fm_blink(ptr(frames), T, H, W, y0, y1, x0, x1, ptr(mask), ptr(term), ptr(out), _stream()),
+          "fm_blink")
+
+
+def running(frames, rect, ormask, g2, means, out, prev_crop=None, prev_mean=None):
+    """out[t] = (dy, dx) int32 between frame t and its predecessor (row 0 needs prev_crop / prev_mean)."""
+    T, H, W = _frames3(frames)
+    _crop_operand(ormask, rect, "ormask")
+    _crop_operand(g2, rect, "g2", torch.float32)
+    _need(means, torch.float32, "means", 1)
+    _need(out, torch.int32, "out", 2)
+    if prev_crop is not None:
+        _crop_operand(prev_crop, rect, "prev_crop")
+        _need(prev_mean, torch.float32, "prev_mean", 1)
+    if means.numel() < T or out.shape[0] < T or out.shape[1] != 2 or not out.is_contiguous():
+        raise FacemapB200Error("running: means / out too small")
+    y0, y1, x0, x1 = (int(v) for v in rect)
+    check(_lib.load().fm_running(ptr(frames), T, H, W, y0, y1, x0, x1, ptr(ormask), ptr(prev_crop), ptr(prev_mean),
+                                 ptr(g2), ptr(means), ptr(out), _stream()), "fm_running")
+
+
+def pupil_scratch(rect, blocks, device):
+    y0, y1, x0, x1 = rect
+    n = C.c_size_t(0)
+    check(_lib.load().fm_pupil_scratch_bytes(int(y1 - y0), int(x1 - x0), int(blocks), C.byref(n)), "fm_pupil_scratch_bytes")
+    return torch.empty(int(n.value), dtype=torch.uint8, device=device)
+
+
+def pupil(frames, rect, mask, dark_offset, sigma, scratch, blocks, out, reflector=None):
+    """out[t] (float64 [T, 9]) = com(2), area, axdir(4), axlen(2) of the Gaussian pupil fit."""
+    T, H, W = _frames3(frames)
+    _crop_operand(mask, rect, "mask")
+    if reflector is not None:
+        _crop_operand(reflector, rect, "reflector")
+    _need(scratch, torch.uint8, "scratch", 1)
+    _need(out, torch.float64, "out", 2)
+    if out.shape[0] < T or out.shape[1] != 9 or not out.is_contiguous():
+        raise FacemapB200Error("pupil: out must be a contiguous [>=T, 9] float64 tensor")
+    y0, y1, x0, x1 = (int(v) for v in rect)
+    if scratch.numel() < blocks * (y1 - y0) * (x1 - x0) * 8:
+        raise FacemapB200Error("pupil: scratch too small for this ROI / block count")
+    check(_lib.load().fm_pupil(ptr(frames), T, H, W, y0, y1, x0, x1, ptr(mask), ptr(reflector),
+                               C.c_float(float(dark_offset)), C.c_double(float(sigma)), ptr(scratch), int(blocks),
+                               ptr(out), _stream()), "fm_pupil")

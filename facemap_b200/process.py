@@ -16,7 +16,7 @@ import time
 import numpy as np
 import torch
 
-from . import _lib, svd
+from . import _lib, fullres, svd
 from .frames import FrameSource, as_source
 from .utils import binned_inds, multivideo_reshape, roi_bin_ranges, video_placement
 
@@ -127,6 +127,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                 r["yrange_bin"], r["xrange_bin"] = roi_bin_ranges(r, sbin)   # mutated in place, like the reference
                 nroi += 1
     geo = svd.Geometry(Ly, Lx, sbin, rois)
+    has_fullres = any(r["rind"] in (fullres.PUPIL, fullres.BLINK, fullres.RUNNING) for r in (rois or []))
     mods = [m for m, on in (("mot", motSVD), ("mov", movSVD)) if on]
     timer = svd.StageTimer(enabled=timing is not None)
     wall0 = time.perf_counter()
@@ -157,12 +158,13 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     mark("stage1")
     # stage 3's bin phase depends on the averages only: start it underneath the stage-2 eigensolves
     s3 = None
+    fr = None
+    if dist is not None and dist.world > 1:
+        from .parallel import frame_ranges
+        fr = frame_ranges(N, dist.world)[dist.rank]
+    fres = fullres.FullRes(rois, Ly, Lx, N, dev, frame_range=fr) if has_fullres else None
     if mods and (fullSVD or nroi > 0):
-        fr = None
-        if dist is not None and dist.world > 1:
-            from .parallel import frame_ranges
-            fr = frame_ranges(N, dist.world)[dist.rank]
-        s3 = svd.Stage3(source, geo, avgframe, avgmotion, mods, fullSVD, ws, dev, timer, frame_range=fr)
+        s3 = svd.Stage3(source, geo, avgframe, avgmotion, mods, fullSVD, ws, dev, timer, frame_range=fr, fullres=fres)
         if overlap_stage3:
             s3.start_early()
     # ---- stage 2 ----
@@ -192,6 +194,17 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         if not single:
             V, E, E_roi = dist.gather_stage3(V, E, E_roi, N, mods, timer)
 
+    # ---- pupil / blink / running: rode on stage 3's sweep, or get their own when there is no SVD sweep ----
+    fres_out = ([], [], [])
+    if fres is not None:
+        if s3 is None:
+            with timer("fullres.sweep"):
+                fres.sweep(source)
+        fres_out = fres.device_outputs()
+        if dist is not None and dist.world > 1 and gather_outputs:
+            ranges = frame_ranges(N, dist.world)
+            fres_out = tuple([dist.gather_rows(a, ranges) for a in group] for group in fres_out)
+
     mark("stage3")
     # ---- assemble (device -> host) ----
     f0_out = 0
@@ -215,8 +228,8 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                                                            Lybin, Lxbin, iinds)),
         "rois": rois,
     }
-    if f0_out or (dist is not None and dist.world > 1 and not gather_outputs and s3 is not None):
-        proc["frame_range"] = (s3.f0, s3.f1)     # motSVD / movSVD / motion rows cover this range only
+    if dist is not None and dist.world > 1 and not gather_outputs and (s3 is not None or fres is not None):
+        proc["frame_range"] = tuple(fr)          # motSVD / movSVD / motion / ROI rows cover this range only
 
     def host(t):
         if keep_on_device:
@@ -293,7 +306,20 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                     avgmotion_l[v] = avgmotion_l[v].reshape(Lybin[v], Lxbin[v])
                 if movSVD:
                     avgframe_l[v] = avgframe_l[v].reshape(Lybin[v], Lxbin[v])
+    elif not fullSVD and nroi == 0:
+        # process.py:346-349: without any SVD the reference still returns these empty placeholders
+        for m in mods:
+            V_out[m].append(np.zeros((0, 1), np.float32))
+        M.append(np.zeros((0,), np.float32))
+    if keep_on_device:
+        pups, blinks, runs = fres_out
+    else:
+        with timer("assemble.d2h"):
+            raw = tuple([a.cpu().numpy() for a in group] for group in fres_out)
+        # only a whole video can be smoothed (a shard's traces are left raw)
+        pups, blinks, runs = fullres.assemble(*raw, smooth="frame_range" not in proc)
     proc.update({
+        "pupil": pups, "blink": blinks, "running": runs,
         "motion": M, "motSv": S_out["mot"], "movSv": S_out["mov"],
         "motMask": U_out["mot"], "movMask": U_out["mov"],
         "motMask_reshape": U_resh["mot"], "movMask_reshape": U_resh["mov"],
@@ -369,7 +395,7 @@ def run(filenames, sbin=1, motSVD=True, movSVD=False, GUIobject=None, parent=Non
         "motMask": out["motMask"], "movMask": out["movMask"],
         "motMask_reshape": out["motMask_reshape"], "movMask_reshape": out["movMask_reshape"],
         "motSVD": out["motSVD"], "movSVD": out["movSVD"],
-        "pupil": [], "running": [], "blink": [], "rois": rois, "sy": sy, "sx": sx,
+        "pupil": out["pupil"], "running": out["running"], "blink": out["blink"], "rois": rois, "sy": sy, "sx": sx,
     }
     savename = save(full, savepath)
     if parent is not None:

@@ -573,8 +573,9 @@ class Stage3:
     frame 0 stays zero).  The reference's row conventions (Q1/Q2) are applied by the caller."""
 
     def __init__(self, source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer, frame_range=None,
-                 fetch_frames=2368, kmax=NCOMPS):
+                 fetch_frames=2368, kmax=NCOMPS, fullres=None):
         self.source, self.geo, self.avgframe, self.avgmotion = source, geo, avgframe, avgmotion
+        self.fullres = fullres          # facemap_b200.fullres.FullRes: pupil / blink / running on the same sweep
         self.mods, self.fullSVD, self.ws, self.device, self.timer = mods, fullSVD, ws, device, timer
         N = source.nframes
         self.f0, self.f1 = (0, N) if frame_range is None else frame_range
@@ -611,6 +612,10 @@ class Stage3:
         if self.have0 and not self._halo_done:
             with self.timer("stage3.fetch"):
                 halo = self.source.fetch(self.f0 - 1, self.f0, self.device)
+            if self.fullres is not None:
+                with self.timer("stage3.fullres"):
+                    self.fullres.seed(halo)
+                    halo = self.fullres.painted(halo)
             for v, fr in enumerate(halo):
                 K.bin_motion(fr, self.geo.sbin, last_sum=self.carry[self.flip][v])
         self._halo_done = True
@@ -625,6 +630,11 @@ class Stage3:
                     nxt = self.flat[self.pos + 1]
                     self.source.prefetch(nxt[0], nxt[0] + nxt[1], self.device)
             self.pos += 1
+            if self.fullres is not None:
+                # full-resolution ROIs read the raw frames; binning reads the copy they painted (process.py:543)
+                with self.timer("stage3.fullres"):
+                    self.fullres.chunk(frames, t)
+                    frames = self.fullres.painted(frames)
             first_frame = t if have else t + 1
             with self.timer("stage3.bin"):
                 r = row0 + filled

@@ -193,6 +193,39 @@ int fm_transpose(const float* in, int64_t ldin, int rows, int cols, float* out, 
 int fm_gather_roi(const float* X, int64_t ldx, int rows, int64_t col0, int Lxb,
                   int y0, int y1, int x0, int x1, float* out, int64_t ldout, void* stream);
 
+/* ---- full-resolution ROI processors riding on the stage-3 frame sweep (facemap/process.py:410-425) ----
+ * ROI rectangles are [y0, y1) x [x0, x1) in frame pixels (the reference's yrange[0]..yrange[-1] inclusive,
+ * process.py:538-542).  `mask` / `ormask` are uint8 [ny, nx] (ROI crop) or [H, W] (fm_paint): non-zero =
+ * the pixel reads as 255 because an earlier ROI painted it (process.py:543, 567 write into the chunk). */
+
+/* out[t] = frames[t] | ormask   (ormask bytes 0x00 / 0xFF): the frames stage 3 bins after painting. */
+int fm_paint(const uint8_t* frames, int T, int H, int W, const uint8_t* ormask, uint8_t* out, void* stream);
+
+/* blink (process.py:557-572): out[t] = sum over the painted ROI of term[pixel value]; term = the reference's
+ * elementwise expression `maximum(0, 255 - v - (255 - saturation))` tabulated for v = 0..255 as float64. */
+int fm_blink(const uint8_t* frames, int T, int H, int W, int y0, int y1, int x0, int x1,
+             const uint8_t* mask, const double* term, double* out, void* stream);
+
+/* running (running.py:91-133 as executed — its fft2/ifft2 results are discarded): for frame t and its
+ * predecessor, the first argmax over the (2l+1)^2 corner window (l = min(floor(.4 ny), floor(.4 nx))) of
+ * sign(x_t - mean_t) * sign(x_{t-1} - mean_{t-1}) * g2, g2 = float32 square of the float32 Fourier-domain
+ * Gaussian [ny, nx].  out[t] = (dy, dx) int32; out[0] needs prev_crop (painted uint8 [ny, nx]) and
+ * prev_mean (float32 [1]) of the frame before the chunk, else it is left untouched.  means: float32 [T]
+ * (written: the NumPy-rounded ROI mean of every frame; means[T-1] is the next call's prev_mean). */
+int fm_running(const uint8_t* frames, int T, int H, int W, int y0, int y1, int x0, int x1,
+               const uint8_t* ormask, const uint8_t* prev_crop, const float* prev_mean, const float* g2,
+               float* means, int32_t* out, void* stream);
+
+/* pupil (pupil.py:8-132): Gaussian fit of darkness = max(0, (255 - v) - dark_offset) (float32; dark_offset =
+ * float32(255 - saturation)) over the painted ROI, 5 refinement rounds at `sigma`, optional reflector map
+ * (uint8 [ny, nx], non-zero = filled in from the median, utils.py:666-700).  out: float64 [T, 9] =
+ * com(2), area, axdir(2x2 row-major), axlen(2); a frame the reference leaves NaN is all NaN.
+ * scratch: fm_pupil_scratch_bytes(ny, nx, blocks) bytes; `blocks` persistent thread blocks share the frames. */
+int fm_pupil_scratch_bytes(int ny, int nx, int blocks, size_t* bytes);
+int fm_pupil(const uint8_t* frames, int T, int H, int W, int y0, int y1, int x0, int x1,
+             const uint8_t* mask, const uint8_t* reflector, float dark_offset, double sigma,
+             void* scratch, int blocks, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
