@@ -244,6 +244,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=2000)
+    ap.add_argument("--with-rois", action="store_true",
+                    help="side measurement (not the headline workload): add a pupil, a blink and a running ROI")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -298,11 +300,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def bench_rois():
+        """pupil + blink (100x140 ellipses) and a running band (120x400) on the one view: SURVEY.md §8f row 4"""
+        if not args.with_rois:
+            return None
+        import numpy as np
+
+        yy, xx = np.meshgrid(np.arange(100), np.arange(140), indexing="ij")
+        ell = ((yy - 50) ** 2 / 50 ** 2 + (xx - 70) ** 2 / 70 ** 2) <= 1
+        base = {"iROI": 0, "ivid": 0, "color": (0, 0, 0)}
+        return [dict(base, rind=0, rtype="Pupil", yrange=np.arange(100, 200), xrange=np.arange(180, 320),
+                     saturation=90.27, pupil_sigma=2.0, ellipse=ell),
+                dict(base, rind=2, rtype="blink", yrange=np.arange(60, 160), xrange=np.arange(400, 540),
+                     saturation=140.25, ellipse=ell),
+                dict(base, rind=3, rtype="running", yrange=np.arange(340, 460), xrange=np.arange(100, 500), saturation=0)]
+
     def one_step(src, timing=None, keep=True, overlap=True):
         # every rank keeps the projections of its own frame range (north_star: "each rank projects its own
         # frames with no further communication"); the gather for the file is process.run's business
         return process.process_source(src, sbin=SBIN, motSVD=True, movSVD=False, dist=shard, timing=timing,
-                                      keep_on_device=keep, overlap_stage3=overlap, gather_outputs=False)
+                                      keep_on_device=keep, overlap_stage3=overlap, gather_outputs=False,
+                                      rois=bench_rois())
 
     nwarm = max(args.warmup, 5)      # allocator pools, cuSOLVER workspaces and NCCL channels settle in ~4 passes
     clocks = ClockSampler(local)
@@ -444,7 +462,8 @@ def main():
             "dtype_detail": "u8 frames, integer block sums / energies, f32 operands as 3xTF32 tensor-core products with f64 chain reduction, f64 eigensolve",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_total": total_frames, "frame_bytes": H * W,
-                       "l2": "inputs (30.7 GB per GPU) exceed L2; no flush needed", "parallelism": f"frame-range x{world}"},
+                       "l2": "inputs (30.7 GB per GPU) exceed L2; no flush needed", "parallelism": f"frame-range x{world}",
+                       **({"rois": "pupil 100x140 + blink 100x140 + running 120x400 (side measurement)"} if args.with_rois else {})},
             "clocks": clk, "e2e": e2e if e2e is not None else ({"value": None, "skipped": e2e_skip} if e2e_skip else None),
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,

@@ -47,8 +47,10 @@ FM_HD inline float pairwise_leaf(const float* a, int n) {
   return res;
 }
 
-FM_HD inline float pairwise_tree_f32(const float* a, int n) {
-  // post-order walk of the split tree with an explicit stack (depth <= log2(n / 128) + 1)
+// Post-order walk of NumPy's split tree over [0, n) with an explicit stack (depth <= log2(n / 128) + 1).
+// `leaf(lo, len)` is called for every <=128-element leaf, left to right, and returns its sum.
+template <class Leaf>
+FM_HD inline float pairwise_walk(int n, Leaf leaf) {
   int lo_s[32], n_s[32];
   float left_s[32];
   unsigned char phase_s[32];
@@ -67,7 +69,7 @@ FM_HD inline float pairwise_tree_f32(const float* a, int n) {
       ++sp;
       continue;
     }
-    float val = pairwise_leaf(a + lo_s[sp], n_s[sp]);
+    float val = leaf(lo_s[sp], n_s[sp]);
     // deliver `val` upwards until a node still waits for its right half
     for (;;) {
       if (sp == 0) return val;
@@ -86,6 +88,94 @@ FM_HD inline float pairwise_tree_f32(const float* a, int n) {
       val = fadd_rn(left_s[sp], val);    // right half done: combine, keep delivering
     }
   }
+}
+
+struct PairwiseSerialLeaf {
+  const float* a;
+  FM_HD float operator()(int lo, int len) const { return pairwise_leaf(a + lo, len); }
+};
+
+FM_HD inline float pairwise_tree_f32(const float* a, int n) { return pairwise_walk(n, PairwiseSerialLeaf{a}); }
+
+// The same sum split for parallel evaluation: list the leaves, sum them anywhere (each with pairwise_leaf's
+// order), then fold the leaf sums along the tree.
+struct PairwiseListLeaf {
+  int* lo;
+  int* len;
+  int cap;
+  int* count;
+  FM_HD float operator()(int l, int n) const {
+    if (*count < cap) {
+      lo[*count] = l;
+      len[*count] = n;
+    }
+    ++*count;
+    return 0.f;
+  }
+};
+
+// returns the number of leaves (entries beyond `cap` are not stored: the caller falls back to the serial form)
+FM_HD inline int pairwise_list_leaves(int n, int* lo, int* len, int cap) {
+  int count = 0;
+  pairwise_walk(n, PairwiseListLeaf{lo, len, cap, &count});
+  return count;
+}
+
+struct PairwiseFoldLeaf {
+  const float* sums;
+  int* next;
+  FM_HD float operator()(int, int) const { return sums[(*next)++]; }
+};
+
+FM_HD inline float pairwise_fold_leaves(int n, const float* leaf_sums) {
+  int next = 0;
+  return pairwise_walk(n, PairwiseFoldLeaf{leaf_sums, &next});
+}
+
+// The same tree as a flat plan, for evaluation without a tree walk per sum: leaves left to right, and for
+// each leaf the number of pending left partial sums that get folded in right after it ("left + value",
+// repeated comb[l] times; a right child completes its parent, which may complete its own parent, ...).
+// `st` is caller-provided stack storage (3 x 32 ints) so that device code can keep it out of local memory.
+FM_HD inline int pairwise_plan(int n, int* lo, int* len, unsigned char* comb, int cap, int* st) {
+  int* st_lo = st;
+  int* st_n = st + 32;
+  int* st_c = st + 64;
+  int sp = 1, count = 0;
+  st_lo[0] = 0;
+  st_n[0] = n;
+  st_c[0] = 0;
+  while (sp > 0) {
+    --sp;
+    int l = st_lo[sp], m = st_n[sp], c = st_c[sp];
+    while (m > 128) {                  // push the right half, descend into the left one
+      int n2 = m / 2;
+      n2 -= n2 % 8;
+      st_lo[sp] = l + n2;
+      st_n[sp] = m - n2;
+      st_c[sp] = c + 1;
+      ++sp;
+      m = n2;
+      c = 0;
+    }
+    if (count < cap) {
+      lo[count] = l;
+      len[count] = m;
+      comb[count] = (unsigned char)c;
+    }
+    ++count;
+  }
+  return count;
+}
+
+// fold the leaf sums of a plan; `vstack` holds 32 floats
+FM_HD inline float pairwise_fold_plan(int count, const float* sums, const unsigned char* comb, float* vstack) {
+  int sp = 0;
+  for (int l = 0; l < count; ++l) {
+    float v = sums[l];
+    for (int k = 0; k < (int)comb[l]; ++k) v = fadd_rn(vstack[--sp], v);
+    vstack[sp++] = v;
+  }
+  return vstack[0];
 }
 
 // numpy.add.reduce starts from the identity 0 and adds the pairwise result to it (so an empty or all -0

@@ -26,7 +26,14 @@ from ._lib import FacemapB200Error
 
 PUPIL, BLINK, RUNNING = 0, 2, 3
 NOT_PAINTED = 255
-PUPIL_BLOCKS = 148 * 4          # persistent blocks of the pupil fit (one frame each at a time)
+PUPIL_BLOCKS = 148 * 4          # persistent blocks of the pupil fit (one frame per block at a time)
+PUPIL_SCRATCH_MAX = 1 << 30     # bytes of per-warp compaction scratch; fewer blocks for very large ROIs
+
+
+def pupil_blocks(rect):
+    y0, y1, x0, x1 = rect
+    per_block = K.pupil_scratch_bytes(rect, 1)
+    return int(max(8, min(PUPIL_BLOCKS, PUPIL_SCRATCH_MAX // per_block)))
 
 
 def roi_rect(r):
@@ -155,7 +162,8 @@ class FullRes:
                 refl = reflector_map(r) if "reflector" in r else None
                 entry["reflector"] = None if refl is None or not refl.any() else \
                     torch.from_numpy(np.ascontiguousarray(refl.astype(np.uint8))).to(device)
-                entry["scratch"] = K.pupil_scratch(pl["rect"], PUPIL_BLOCKS, device)
+                entry["blocks"] = pupil_blocks(pl["rect"])
+                entry["scratch"] = K.pupil_scratch(pl["rect"], entry["blocks"], device)
                 entry["out"] = torch.zeros((n_out, 9), dtype=torch.float64, device=device)
                 self.pupils.append(entry)
             else:
@@ -202,7 +210,7 @@ class FullRes:
         o = t - self.f0
         for e in self.pupils:
             fr = frames[e["view"]]
-            K.pupil(fr, e["rect"], e["mask"], e["dark_offset"], e["sigma"], e["scratch"], PUPIL_BLOCKS,
+            K.pupil(fr, e["rect"], e["mask"], e["dark_offset"], e["sigma"], e["scratch"], e["blocks"],
                     e["out"][o:o + fr.shape[0]], reflector=e["reflector"])
         for e in self.blinks:
             fr = frames[e["view"]]

@@ -343,11 +343,15 @@ def running(frames, rect, ormask, g2, means, out, prev_crop=None, prev_mean=None
                                  ptr(g2), ptr(means), ptr(out), _stream()), "fm_running")
 
 
-def pupil_scratch(rect, blocks, device):
+def pupil_scratch_bytes(rect, blocks):
     y0, y1, x0, x1 = rect
     n = C.c_size_t(0)
     check(_lib.load().fm_pupil_scratch_bytes(int(y1 - y0), int(x1 - x0), int(blocks), C.byref(n)), "fm_pupil_scratch_bytes")
-    return torch.empty(int(n.value), dtype=torch.uint8, device=device)
+    return int(n.value)
+
+
+def pupil_scratch(rect, blocks, device):
+    return torch.empty(pupil_scratch_bytes(rect, blocks), dtype=torch.uint8, device=device)
 
 
 def pupil(frames, rect, mask, dark_offset, sigma, scratch, blocks, out, reflector=None):
@@ -361,7 +365,7 @@ def pupil(frames, rect, mask, dark_offset, sigma, scratch, blocks, out, reflecto
     if out.shape[0] < T or out.shape[1] != 9 or not out.is_contiguous():
         raise FacemapB200Error("pupil: out must be a contiguous [>=T, 9] float64 tensor")
     y0, y1, x0, x1 = (int(v) for v in rect)
-    if scratch.numel() < blocks * (y1 - y0) * (x1 - x0) * 8:
+    if scratch.numel() < pupil_scratch_bytes(rect, blocks):
         raise FacemapB200Error("pupil: scratch too small for this ROI / block count")
     check(_lib.load().fm_pupil(ptr(frames), T, H, W, y0, y1, x0, x1, ptr(mask), ptr(reflector),
                                C.c_float(float(dark_offset)), C.c_double(float(sigma)), ptr(scratch), int(blocks),

@@ -220,7 +220,8 @@ int fm_running(const uint8_t* frames, int T, int H, int W, int y0, int y1, int x
  * float32(255 - saturation)) over the painted ROI, 5 refinement rounds at `sigma`, optional reflector map
  * (uint8 [ny, nx], non-zero = filled in from the median, utils.py:666-700).  out: float64 [T, 9] =
  * com(2), area, axdir(2x2 row-major), axlen(2); a frame the reference leaves NaN is all NaN.
- * scratch: fm_pupil_scratch_bytes(ny, nx, blocks) bytes; `blocks` persistent thread blocks share the frames. */
+ * scratch: fm_pupil_scratch_bytes(ny, nx, blocks) bytes; `blocks` persistent thread blocks share the
+ * frames, one frame per block at a time. */
 int fm_pupil_scratch_bytes(int ny, int nx, int blocks, size_t* bytes);
 int fm_pupil(const uint8_t* frames, int T, int H, int W, int y0, int y1, int x0, int x1,
              const uint8_t* mask, const uint8_t* reflector, float dark_offset, double sigma,

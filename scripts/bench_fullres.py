@@ -60,9 +60,12 @@ def main():
     out["blink_100x140"] = {"ms": ms, "us_per_frame": 1e3 * ms / T, "roi_GBps": T * 100 * 140 / ms / 1e6}
     # pupil 100x140 (disc of radius 30 -> ~2800 dark pixels)
     o9 = torch.zeros((T, 9), dtype=torch.float64, device=dev)
-    scratch = K.pupil_scratch(rect, fullres.PUPIL_BLOCKS, dev)
-    ms = timed(lambda: K.pupil(fr, rect, mask, np.float32(255.0 - 90.27), 2.0, scratch, fullres.PUPIL_BLOCKS, o9), a.reps)
-    out["pupil_100x140"] = {"ms": ms, "us_per_frame": 1e3 * ms / T, "nan_frames": int(torch.isnan(o9[:, 2]).sum())}
+    out["pupil_100x140"] = {}
+    for blocks in (296, 592, 1184):
+        scratch = K.pupil_scratch(rect, blocks, dev)
+        ms = timed(lambda: K.pupil(fr, rect, mask, np.float32(255.0 - 90.27), 2.0, scratch, blocks, o9), a.reps)
+        out["pupil_100x140"][f"blocks_{blocks}"] = {"ms": ms, "us_per_frame": 1e3 * ms / T,
+                                                    "nan_frames": int(torch.isnan(o9[:, 2]).sum())}
     # running 120x400
     rrect = (340, 460, 100, 500)
     ormask = torch.zeros((120, 400), dtype=torch.uint8, device=dev)

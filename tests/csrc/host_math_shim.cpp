@@ -4,6 +4,32 @@
 
 extern "C" float shim_pairwise_sum_f32(const float* a, int n) { return fm::pairwise_sum_f32(a, n); }
 
+// the split form the kernel uses: list leaves, sum each leaf, fold along the tree
+extern "C" float shim_pairwise_sum_split(const float* a, int n, int cap) {
+  static int lo[4096], len[4096];
+  static float sums[4096];
+  const int count = fm::pairwise_list_leaves(n, lo, len, cap);
+  if (count > cap) return fm::pairwise_sum_f32(a, n);
+  for (int i = 0; i < count; ++i) sums[i] = fm::pairwise_leaf(a + lo[i], len[i]);
+  return fm::fadd_rn(0.0f, fm::pairwise_fold_leaves(n, sums));
+}
+
+// the flat plan the kernel uses: leaves + fold counts, no tree walk per sum
+extern "C" float shim_pairwise_sum_plan(const float* a, int n, int cap) {
+  static int lo[4096], len[4096], st[96];
+  static unsigned char comb[4096];
+  static float sums[4096], vstack[32];
+  const int count = fm::pairwise_plan(n, lo, len, comb, cap, st);
+  if (count > cap) return fm::pairwise_sum_f32(a, n);
+  for (int i = 0; i < count; ++i) sums[i] = fm::pairwise_leaf(a + lo[i], len[i]);
+  return fm::fadd_rn(0.0f, fm::pairwise_fold_plan(count, sums, comb, vstack));
+}
+
+extern "C" int shim_pairwise_leaf_count(int n) {
+  static int lo[4096], len[4096];
+  return fm::pairwise_list_leaves(n, lo, len, 4096);
+}
+
 extern "C" void shim_inv2x2(double a, double b, double c, double* out) {
   fm::inv2x2(a, b, c, out[0], out[1], out[2], out[3]);
 }

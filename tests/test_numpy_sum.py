@@ -24,6 +24,11 @@ def shim(tmp_path_factory):
     lib = C.CDLL(str(out))
     lib.shim_pairwise_sum_f32.restype = C.c_float
     lib.shim_pairwise_sum_f32.argtypes = [C.c_void_p, C.c_int]
+    lib.shim_pairwise_sum_split.restype = C.c_float
+    lib.shim_pairwise_sum_split.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.shim_pairwise_leaf_count.argtypes = [C.c_int]
+    lib.shim_pairwise_sum_plan.restype = C.c_float
+    lib.shim_pairwise_sum_plan.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.shim_inv2x2.argtypes = [C.c_double] * 3 + [C.c_void_p]
     lib.shim_median_from_hist.restype = C.c_float
     lib.shim_median_from_hist.argtypes = [C.c_void_p, C.c_float]
@@ -43,6 +48,14 @@ def test_pairwise_sum_matches_numpy_bitwise(shim):
             got = shim.shim_pairwise_sum_f32(a.ctypes.data, n)
             want = a.sum()
             assert np.float32(got).tobytes() == np.float32(want).tobytes(), (n, scale, got, want)
+            # the leaf-list / fold split used for the block-parallel evaluation (cap 1024 leaves, serial beyond)
+            got = shim.shim_pairwise_sum_split(a.ctypes.data, n, 1024)
+            assert np.float32(got).tobytes() == np.float32(want).tobytes(), ("split", n, scale, got, want)
+            got = shim.shim_pairwise_sum_plan(a.ctypes.data, n, 512)          # flat plan (what the pupil kernel runs)
+            assert np.float32(got).tobytes() == np.float32(want).tobytes(), ("plan", n, scale, got, want)
+    # leaves hold 64..128 elements once the array is split at all: 1024 leaves cover >= 65536 elements
+    for n in (129, 1000, 32768, 65536):
+        assert shim.shim_pairwise_leaf_count(n) <= max(1, n // 64)
 
 
 def test_inv2x2_matches_numpy(shim):
