@@ -48,6 +48,8 @@ SIGNATURES = {
     "fm_host_register": (_I, [_P, C.c_size_t]),
     "fm_host_unregister": (_I, [_P]),
     "fm_bin_motion": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, C.POINTER(Rois), _P, _P, _P, _P, _P]),
+    "fm_bin_motion_painted": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, C.POINTER(Rois), _P, _P, _P, _P,
+                                   _P, _P]),
     "fm_mean_update": (_I, [_P, _P, _L, _I, _I, _I, _P]),
     "fm_gemm_tn": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _I, _P, _L, _I, _I, _P]),
     "fm_split_lo": (_I, [_P, _L, _I, _I, _P, _L, _P]),

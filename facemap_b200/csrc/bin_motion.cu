@@ -40,6 +40,7 @@ struct K1Params {
   int frame_off;  // frame index of row 0
   int slab;       // rows per slab
   fm_rois rois;
+  const uint8_t* ormask;  // optional [H, W] bytes OR-ed into every frame (0x00 / 0xFF: painted pixels read 255)
 };
 
 // streaming (read-once) loads of VB bytes as 32-bit words
@@ -53,6 +54,20 @@ __device__ __forceinline__ void ldg_stream(const uint8_t* p, unsigned (&w)[NW]) 
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p));
   } else {
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(w[0]) : "l"(p));
+  }
+}
+
+// mask words (read by every slab and frame: ordinary cached loads)
+template <int NW>
+__device__ __forceinline__ void ldg_mask(const uint8_t* p, unsigned (&w)[NW]) {
+  if constexpr (NW == 4) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  } else if constexpr (NW == 2) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    w[0] = v.x; w[1] = v.y;
+  } else {
+    w[0] = __ldg(reinterpret_cast<const unsigned*>(p));
   }
 }
 
@@ -97,7 +112,9 @@ __device__ __forceinline__ void store_row(float* dst, const float (&x)[PX], int 
 // ROI energies and the movie operand are compile-time options so the common motion-only
 // instantiation stays light on registers.
 // ---------------------------------------------------------------------------------------------
-template <int SBIN, bool ROI, bool MOV>
+// PAINT ORs a per-pixel byte mask into the frames as they are loaded (facemap/process.py:543, 567: pupil and
+// blink ROIs paint the chunk buffer that is binned afterwards) — no painted copy of the frames is made.
+template <int SBIN, bool ROI, bool MOV, bool PAINT>
 __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Params p) {
   constexpr int VB = (SBIN >= 4) ? 16 : 4 * SBIN;
   constexpr int NW = VB / 4;
@@ -146,6 +163,34 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Para
   const bool vec_ok = (PX >= 2) && ((p.col0 + pix0) % VALIGN == 0) && (p.ldx % VALIGN == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.x_mot) | reinterpret_cast<uintptr_t>(p.x_mov)) % 16 == 0);
 
+  // paint words of this thread's raw rows: registers for small sbin, re-read (L1) for sbin >= 8
+  constexpr bool PAINT_REGS = PAINT && SBIN <= 4;
+  unsigned pm[PAINT_REGS ? SBIN : 1][NW];
+  const uint8_t* mbase = PAINT ? p.ormask + (size_t)by * SBIN * p.W + (size_t)bx0 * SBIN : nullptr;
+  if constexpr (PAINT_REGS) {
+#pragma unroll
+    for (int r = 0; r < SBIN; ++r) {
+      if (active) ldg_mask<NW>(mbase + (size_t)r * p.W, pm[r]);
+      else
+#pragma unroll
+        for (int q = 0; q < NW; ++q) pm[r][q] = 0u;
+    }
+  }
+  auto painted = [&](const unsigned (&raw_row)[NW], int r, unsigned (&out)[NW]) {
+    if constexpr (PAINT_REGS) {
+#pragma unroll
+      for (int q = 0; q < NW; ++q) out[q] = raw_row[q] | pm[r][q];
+    } else if constexpr (PAINT) {
+      unsigned m[NW];
+      ldg_mask<NW>(mbase + (size_t)r * p.W, m);
+#pragma unroll
+      for (int q = 0; q < NW; ++q) out[q] = raw_row[q] | m[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < NW; ++q) out[q] = raw_row[q];
+    }
+  };
+
   // previous frame's block sums
   int prev[PX];
 #pragma unroll
@@ -159,9 +204,10 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Para
       const uint8_t* fp = base + (size_t)f_prev * frame_bytes;
 #pragma unroll
       for (int r = 0; r < SBIN; ++r) {
-        unsigned w[NW];
+        unsigned w[NW], wp[NW];
         ldg_stream<NW>(fp + (size_t)r * p.W, w);
-        accumulate_row<SBIN, PX, NW>(w, prev);
+        painted(w, r, wp);
+        accumulate_row<SBIN, PX, NW>(wp, prev);
       }
       if (r0 == 0) {  // halo frame of slab 0 is frame 0 of a carry-less call: part of the time sum
 #pragma unroll
@@ -194,7 +240,15 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Para
 #pragma unroll
         for (int j = 0; j < PX; ++j) cur[j] = 0;
 #pragma unroll
-        for (int r = 0; r < SBIN; ++r) accumulate_row<SBIN, PX, NW>(raw[f][r], cur);
+        for (int r = 0; r < SBIN; ++r) {
+          if constexpr (PAINT) {
+            unsigned wp[NW];
+            painted(raw[f][r], r, wp);
+            accumulate_row<SBIN, PX, NW>(wp, cur);
+          } else {
+            accumulate_row<SBIN, PX, NW>(raw[f][r], cur);
+          }
+        }
         float xm[PX], xf[MOV ? PX : 1];
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
@@ -268,11 +322,16 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Para
 // Generic path: any sbin / width / alignment.  One thread per binned pixel, byte loads,
 // float64 division (the reference's float64 means are reproduced to <= 1 ulp of float32).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int block_sum_bytes(const uint8_t* p, int sbin, int W) {
+__device__ __forceinline__ int block_sum_bytes(const uint8_t* p, int sbin, int W, const uint8_t* m) {
   int s = 0;
   for (int r = 0; r < sbin; ++r) {
     const uint8_t* q = p + (size_t)r * W;
-    for (int c = 0; c < sbin; ++c) s += (int)__ldg(q + c);
+    if (m) {
+      const uint8_t* mq = m + (size_t)r * W;
+      for (int c = 0; c < sbin; ++c) s += (int)(__ldg(q + c) | __ldg(mq + c));
+    } else {
+      for (int c = 0; c < sbin; ++c) s += (int)__ldg(q + c);
+    }
   }
   return s;
 }
@@ -292,6 +351,7 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_generic_kernel(const K1
   const int bx = active ? g - by * p.Lxb : 0;
   const size_t frame_bytes = (size_t)p.H * p.W;
   const uint8_t* base = p.frames + (size_t)by * p.sbin * p.W + (size_t)bx * p.sbin;
+  const uint8_t* mbase = p.ormask ? p.ormask + (size_t)by * p.sbin * p.W + (size_t)bx * p.sbin : nullptr;
   const double s2 = (double)p.sbin * (double)p.sbin;
   const double am = (active && p.avgmotion) ? (double)p.avgmotion[g] : 0.0;
   const double af = (active && p.avgframe) ? (double)p.avgframe[g] : 0.0;
@@ -305,7 +365,7 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_generic_kernel(const K1
   const int f_prev = r0 + p.frame_off - 1;
   if (active) {
     if (f_prev >= 0) {
-      prev = block_sum_bytes(base + (size_t)f_prev * frame_bytes, p.sbin, p.W);
+      prev = block_sum_bytes(base + (size_t)f_prev * frame_bytes, p.sbin, p.W, mbase);
       if (r0 == 0) tsb += prev;
     } else if (p.prev_sum) {
       prev = p.prev_sum[g];
@@ -314,7 +374,7 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_generic_kernel(const K1
   for (int row = r0; row < r1; ++row) {
     unsigned long long e = 0;
     if (active) {
-      const int cur = block_sum_bytes(base + (size_t)(row + p.frame_off) * frame_bytes, p.sbin, p.W);
+      const int cur = block_sum_bytes(base + (size_t)(row + p.frame_off) * frame_bytes, p.sbin, p.W, mbase);
       const int d = abs(cur - prev);
       if (p.x_mot) p.x_mot[(size_t)row * p.ldx + p.col0 + g] = (float)((double)d / s2 - am);
       if (p.x_mov) p.x_mov[(size_t)row * p.ldx + p.col0 + g] = (float)((double)cur / s2 - af);
@@ -363,12 +423,12 @@ __global__ void mean_update_kernel(float* acc, const long long* tsum, int64_t n,
 
 }  // namespace fm
 
-extern "C" int fm_bin_motion(const uint8_t* frames, int T, int H, int W, int sbin,
-                             const int32_t* prev_sum, const float* avgmotion, const float* avgframe,
-                             float* x_mot, float* x_mov, int64_t ldx, int64_t col0,
-                             unsigned long long* energy, const fm_rois* rois,
-                             unsigned long long* roi_energy, int32_t* last_sum, long long* tsum_bin,
-                             long long* tsum_adiff, void* stream) {
+static int bin_motion_impl(const uint8_t* frames, int T, int H, int W, int sbin,
+                           const int32_t* prev_sum, const float* avgmotion, const float* avgframe,
+                           float* x_mot, float* x_mov, int64_t ldx, int64_t col0,
+                           unsigned long long* energy, const fm_rois* rois,
+                           unsigned long long* roi_energy, int32_t* last_sum, long long* tsum_bin,
+                           long long* tsum_adiff, const uint8_t* ormask, void* stream) {
   using namespace fm;
   FM_REQUIRE(frames != nullptr && T >= 1 && H >= 1 && W >= 1 && sbin >= 1, "fm_bin_motion: bad shape");
   const int Lyb = H / sbin, Lxb = W / sbin;
@@ -386,6 +446,7 @@ extern "C" int fm_bin_motion(const uint8_t* frames, int T, int H, int W, int sbi
   p.rows = prev_sum ? T : T - 1;
   p.frame_off = prev_sum ? 0 : 1;
   if (rois && roi_energy) p.rois = *rois; else p.rois.n = 0;
+  p.ormask = ormask;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   if (p.rows == 0) {
@@ -395,7 +456,8 @@ extern "C" int fm_bin_motion(const uint8_t* frames, int T, int H, int W, int sbi
   }
   const int vb = sbin >= 4 ? 16 : 4 * sbin;
   const bool vec = (sbin == 1 || sbin == 2 || sbin == 4 || sbin == 8 || sbin == 16) && (W % vb == 0) &&
-                   ((reinterpret_cast<uintptr_t>(frames) % vb) == 0);
+                   ((reinterpret_cast<uintptr_t>(frames) % vb) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(ormask) % vb) == 0);
   const int px = vec ? vb / sbin : 1;
   const int64_t ngroups = vec ? (int64_t)Lyb * ((Lxb + px - 1) / px) : (int64_t)Lyb * Lxb;
   const int gx = (int)cdiv(ngroups, K1_THREADS);
@@ -408,12 +470,18 @@ extern "C" int fm_bin_motion(const uint8_t* frames, int T, int H, int W, int sbi
   dim3 grid(gx, gy);
   const bool roi = p.rois.n > 0;
   const bool mov = x_mov != nullptr;
+  const bool paint = ormask != nullptr;
+#define FM_K1_LAUNCH_P(S, PT)                                                                        \
+  do {                                                                                               \
+    if (roi && mov) bin_motion_vec_kernel<S, true, true, PT><<<grid, K1_THREADS, 0, st>>>(p);        \
+    else if (roi) bin_motion_vec_kernel<S, true, false, PT><<<grid, K1_THREADS, 0, st>>>(p);         \
+    else if (mov) bin_motion_vec_kernel<S, false, true, PT><<<grid, K1_THREADS, 0, st>>>(p);         \
+    else bin_motion_vec_kernel<S, false, false, PT><<<grid, K1_THREADS, 0, st>>>(p);                 \
+  } while (0)
 #define FM_K1_LAUNCH(S)                                                                              \
   do {                                                                                               \
-    if (roi && mov) bin_motion_vec_kernel<S, true, true><<<grid, K1_THREADS, 0, st>>>(p);            \
-    else if (roi) bin_motion_vec_kernel<S, true, false><<<grid, K1_THREADS, 0, st>>>(p);             \
-    else if (mov) bin_motion_vec_kernel<S, false, true><<<grid, K1_THREADS, 0, st>>>(p);             \
-    else bin_motion_vec_kernel<S, false, false><<<grid, K1_THREADS, 0, st>>>(p);                     \
+    if (paint) FM_K1_LAUNCH_P(S, true);                                                              \
+    else FM_K1_LAUNCH_P(S, false);                                                                   \
   } while (0)
   if (vec) {
     switch (sbin) {
@@ -427,8 +495,30 @@ extern "C" int fm_bin_motion(const uint8_t* frames, int T, int H, int W, int sbi
     bin_motion_generic_kernel<<<grid, K1_THREADS, 0, st>>>(p);
   }
 #undef FM_K1_LAUNCH
+#undef FM_K1_LAUNCH_P
   FM_LAUNCH_CHECK();
   return FM_OK;
+}
+
+extern "C" int fm_bin_motion(const uint8_t* frames, int T, int H, int W, int sbin,
+                             const int32_t* prev_sum, const float* avgmotion, const float* avgframe,
+                             float* x_mot, float* x_mov, int64_t ldx, int64_t col0,
+                             unsigned long long* energy, const fm_rois* rois,
+                             unsigned long long* roi_energy, int32_t* last_sum, long long* tsum_bin,
+                             long long* tsum_adiff, void* stream) {
+  return bin_motion_impl(frames, T, H, W, sbin, prev_sum, avgmotion, avgframe, x_mot, x_mov, ldx, col0, energy, rois,
+                         roi_energy, last_sum, tsum_bin, tsum_adiff, nullptr, stream);
+}
+
+extern "C" int fm_bin_motion_painted(const uint8_t* frames, int T, int H, int W, int sbin,
+                                     const int32_t* prev_sum, const float* avgmotion, const float* avgframe,
+                                     float* x_mot, float* x_mov, int64_t ldx, int64_t col0,
+                                     unsigned long long* energy, const fm_rois* rois,
+                                     unsigned long long* roi_energy, int32_t* last_sum, long long* tsum_bin,
+                                     long long* tsum_adiff, const uint8_t* ormask, void* stream) {
+  FM_REQUIRE(ormask != nullptr, "fm_bin_motion_painted: ormask is NULL (use fm_bin_motion)");
+  return bin_motion_impl(frames, T, H, W, sbin, prev_sum, avgmotion, avgframe, x_mot, x_mov, ldx, col0, energy, rois,
+                         roi_energy, last_sum, tsum_bin, tsum_adiff, ormask, stream);
 }
 
 extern "C" int fm_mean_update(float* acc, const long long* tsum, int64_t n, int sbin, int count,

@@ -49,8 +49,9 @@ def launch_count() -> int:
 
 def bin_motion(frames, sbin, *, prev_sum=None, avgmotion=None, avgframe=None, x_mot=None, x_mov=None,
                col0=0, energy=None, rois=None, roi_energy=None, last_sum=None, tsum_bin=None,
-               tsum_adiff=None):
-    """K1 on one view.  frames: uint8 [T,H,W] contiguous.  See fm_bin_motion in the header."""
+               tsum_adiff=None, ormask=None):
+    """K1 on one view.  frames: uint8 [T,H,W] contiguous.  See fm_bin_motion in the header.
+    ormask: optional uint8 [H, W] of 0x00 / 0xFF OR-ed into the frames on load (fm_bin_motion_painted)."""
     _need(frames, torch.uint8, "frames", 3)
     if not frames.is_contiguous():
         raise FacemapB200Error("frames must be contiguous [T, H, W]")
@@ -86,6 +87,15 @@ def bin_motion(frames, sbin, *, prev_sum=None, avgmotion=None, avgframe=None, x_
         if roi_energy.numel() < r.n * rows:
             raise FacemapB200Error("roi_energy too small")
     lib = _lib.load()
+    if ormask is not None:
+        _need(ormask, torch.uint8, "ormask", 2)
+        if tuple(ormask.shape) != (H, W) or not ormask.is_contiguous():
+            raise FacemapB200Error(f"ormask: expected a contiguous [{H}, {W}] uint8 tensor")
+        check(lib.fm_bin_motion_painted(ptr(frames), T, H, W, int(sbin), ptr(prev_sum), ptr(avgmotion), ptr(avgframe),
+                                        ptr(x_mot), ptr(x_mov), ldx, int(col0), ptr(energy),
+                                        C.byref(r) if r is not None else None, ptr(roi_energy), ptr(last_sum),
+                                        ptr(tsum_bin), ptr(tsum_adiff), ptr(ormask), _stream()), "fm_bin_motion_painted")
+        return rows
     check(lib.fm_bin_motion(ptr(frames), T, H, W, int(sbin), ptr(prev_sum), ptr(avgmotion), ptr(avgframe),
                             ptr(x_mot), ptr(x_mov), ldx, int(col0), ptr(energy),
                             C.byref(r) if r is not None else None, ptr(roi_energy), ptr(last_sum),

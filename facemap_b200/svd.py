@@ -437,8 +437,10 @@ def stage2_plan(N, ncomps=NCOMPS):
     return nt0, nsegs, nc, tf
 
 
-def _bin_chunk(frames, geo, avgframe, avgmotion, mods, X, prev=None, last=None, energy=None, roi_energy=None):
-    """K1 over every view of one fetched chunk into the modality matrices X[m] ([rows, p])."""
+def _bin_chunk(frames, geo, avgframe, avgmotion, mods, X, prev=None, last=None, energy=None, roi_energy=None,
+               ormask=None):
+    """K1 over every view of one fetched chunk into the modality matrices X[m] ([rows, p]).
+    ormask: per-view paint masks (fullres.FullRes.ormask) OR-ed into the frames on load, or None."""
     rows = None
     for v, fr in enumerate(frames):
         c0, n = geo.col0[v], geo.npix_v[v]
@@ -452,7 +454,8 @@ def _bin_chunk(frames, geo, avgframe, avgmotion, mods, X, prev=None, last=None, 
             energy=None if energy is None else energy[v],
             rois=Rois.from_rects(rects) if (roi_energy is not None and rects) else None,
             roi_energy=None if (roi_energy is None or not rects) else roi_energy[v],
-            last_sum=None if last is None else last[v])
+            last_sum=None if last is None else last[v],
+            ormask=None if ormask is None else ormask[v])
     return rows
 
 
@@ -615,9 +618,9 @@ class Stage3:
             if self.fullres is not None:
                 with self.timer("stage3.fullres"):
                     self.fullres.seed(halo)
-                    halo = self.fullres.painted(halo)
             for v, fr in enumerate(halo):
-                K.bin_motion(fr, self.geo.sbin, last_sum=self.carry[self.flip][v])
+                K.bin_motion(fr, self.geo.sbin, last_sum=self.carry[self.flip][v],
+                             ormask=None if self.fullres is None else self.fullres.ormask[v])
         self._halo_done = True
 
     def _bin_fetches(self, fetches, X, row0):
@@ -631,10 +634,9 @@ class Stage3:
                     self.source.prefetch(nxt[0], nxt[0] + nxt[1], self.device)
             self.pos += 1
             if self.fullres is not None:
-                # full-resolution ROIs read the raw frames; binning reads the copy they painted (process.py:543)
+                # full-resolution ROIs read the raw frames; K1 ORs their paint in as it loads (process.py:543)
                 with self.timer("stage3.fullres"):
                     self.fullres.chunk(frames, t)
-                    frames = self.fullres.painted(frames)
             first_frame = t if have else t + 1
             with self.timer("stage3.bin"):
                 r = row0 + filled
@@ -650,7 +652,8 @@ class Stage3:
                 _bin_chunk(frames, geo, self.avgframe, self.avgmotion, self.mods if rows > 0 else [], Xv,
                            prev=self.carry[self.flip] if have else None, last=self.carry[1 - self.flip],
                            energy=energy if rows > 0 else None,
-                           roi_energy=roi_e if (self.nroi and rows > 0) else None)
+                           roi_energy=roi_e if (self.nroi and rows > 0) else None,
+                           ormask=None if self.fullres is None else self.fullres.ormask)
                 if self.nroi and rows > 0:
                     for v in range(self.nv):
                         for q, j in enumerate(geo.rois_on_view[v]):

@@ -84,6 +84,18 @@ int fm_bin_motion(const uint8_t* frames, int T, int H, int W, int sbin,
                   int32_t* last_sum, long long* tsum_bin, long long* tsum_adiff, void* stream);
 
 /*
+ * The same on frames that pupil / blink ROIs have painted (facemap/process.py:543, 567 write 255 into the
+ * chunk buffer that stage 3 bins afterwards): every frame byte is OR-ed with `ormask` (uint8 [H, W], 0x00 or
+ * 0xFF) as it is loaded, so no painted copy of the frames is needed.  All other arguments as fm_bin_motion.
+ */
+int fm_bin_motion_painted(const uint8_t* frames, int T, int H, int W, int sbin,
+                          const int32_t* prev_sum, const float* avgmotion, const float* avgframe,
+                          float* x_mot, float* x_mov, int64_t ldx, int64_t col0,
+                          unsigned long long* energy, const fm_rois* rois, unsigned long long* roi_energy,
+                          int32_t* last_sum, long long* tsum_bin, long long* tsum_adiff,
+                          const uint8_t* ormask, void* stream);
+
+/*
  * Stage-1 accumulator update, bit-compatible with subsampled_mean (facemap/process.py:82-86,
  * 95-96): acc32 = f32( f64(acc32) + (f64(tsum) / sbin^2) / count ) for n pixels.
  * `finalize_div` > 0 additionally divides by that segment count in float32 (process.py:95-96).

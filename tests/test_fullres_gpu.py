@@ -220,3 +220,26 @@ def test_fullres_host_source_and_file(cuda_device, tmp_path):
     assert set(p["pupil"][0]) == {"area", "com", "axdir", "axlen", "area_smooth", "com_smooth"}
     assert np.allclose(p["pupil"][0]["area"], z["pupil0_area"], rtol=PUPIL_TOL, equal_nan=True)
     assert p["motion"][0].shape == (0,) and p["motSVD"][0].shape == (0, 1) and p["motMask"] == []
+
+
+def test_fullres_frame_range_shards_concatenate(cuda_device):
+    """what a rank of a multi-GPU run does: its own frame range with the one-frame halo seeding running's
+    predecessor; the shards put together are the single-range result bit for bit"""
+    from facemap_b200 import fullres
+    from facemap_b200.frames import DeviceArraySource
+
+    views, sbin, mot, mov, rois, fullSVD = fullres_case("eye_all")
+    N = views[0].shape[0]
+    src = DeviceArraySource([torch.from_numpy(v).to(cuda_device) for v in views])
+    Ly, Lx = [v.shape[1] for v in views], [v.shape[2] for v in views]
+    whole = fullres.FullRes(rois, Ly, Lx, N, cuda_device)
+    whole.sweep(src, fetch_frames=300)
+    parts = []
+    for rng in ((0, 500), (500, 501), (501, N)):
+        fr = fullres.FullRes(rois, Ly, Lx, N, cuda_device, frame_range=rng)
+        fr.sweep(src, fetch_frames=128)
+        parts.append(fr.device_outputs())
+    for kind in range(3):
+        for k, ref in enumerate(whole.device_outputs()[kind]):
+            got = torch.cat([p[kind][k] for p in parts], dim=0)
+            assert torch.equal(torch.nan_to_num(got.double(), nan=-1.0), torch.nan_to_num(ref.double(), nan=-1.0)), (kind, k)

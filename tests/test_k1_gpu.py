@@ -150,3 +150,45 @@ def test_stage1_mean_update_bit_exact(cuda_device):
         torch.cuda.synchronize()
         assert np.array_equal(acc_f.cpu().numpy(), ref_f), f"avgframe sbin={sbin}"
         assert np.array_equal(acc_m.cpu().numpy(), ref_m), f"avgmotion sbin={sbin}"
+
+
+@pytest.mark.parametrize("T,H,W,sbin", CASES)
+@pytest.mark.parametrize("with_carry,lean", [(False, False), (True, False), (True, True)])
+def test_k1_painted_equals_k1_on_painted_frames(cuda_device, T, H, W, sbin, with_carry, lean):
+    """fm_bin_motion_painted(frames, ormask) == fm_bin_motion(frames | ormask) bit for bit (every output),
+    i.e. the fused form of process.py:543, 567 painting the chunk buffer before it is binned."""
+    from facemap_b200 import kernels as K
+    from facemap_b200._lib import Rois
+
+    dev = cuda_device
+    frames = _video(T, H, W, seed=3 * T + sbin)
+    rng = np.random.RandomState(7)
+    m = np.zeros((H, W), np.uint8)
+    m[H // 5:H // 2, W // 6:2 * W // 3] = np.where(rng.rand(H // 2 - H // 5, 2 * W // 3 - W // 6) < 0.6, 255, 0)
+    Lyb, Lxb = H // sbin, W // sbin
+    p = Lyb * Lxb
+    avgmot = torch.from_numpy((rng.rand(p) * 3).astype(np.float32)).to(dev)
+    avgfrm = torch.from_numpy((rng.rand(p) * 200).astype(np.float32)).to(dev)
+    rects = [(1, max(2, Lyb // 2), 0, max(1, Lxb // 2))]
+    prev = torch.from_numpy(rng.randint(0, 255 * sbin * sbin, size=p).astype(np.int32)).to(dev) if with_carry else None
+    rows = T if with_carry else T - 1
+
+    def run(fr, ormask):
+        out = {"xm": K.alloc_matrix(rows, p, dev, zero=True), "xf": K.alloc_matrix(rows, p, dev, zero=True),
+               "e": torch.zeros(rows, dtype=torch.int64, device=dev),
+               "re": torch.zeros((1, rows), dtype=torch.int64, device=dev),
+               "last": torch.zeros(p, dtype=torch.int32, device=dev),
+               "tsb": torch.zeros(p, dtype=torch.int64, device=dev), "tsa": torch.zeros(p, dtype=torch.int64, device=dev)}
+        if lean:      # the motion-only instantiation (no movie operand, no ROI energies)
+            K.bin_motion(fr, sbin, prev_sum=prev, avgmotion=avgmot, x_mot=out["xm"], energy=out["e"],
+                         last_sum=out["last"], ormask=ormask)
+        else:
+            K.bin_motion(fr, sbin, prev_sum=prev, avgmotion=avgmot, avgframe=avgfrm, x_mot=out["xm"], x_mov=out["xf"],
+                         energy=out["e"], rois=Rois.from_rects(rects), roi_energy=out["re"], last_sum=out["last"],
+                         tsum_bin=out["tsb"], tsum_adiff=out["tsa"], ormask=ormask)
+        return out
+
+    a = run(torch.from_numpy(frames).to(dev), torch.from_numpy(m).to(dev))
+    b = run(torch.from_numpy(frames | m).to(dev), None)
+    for key in a:
+        assert torch.equal(a[key], b[key]), key
