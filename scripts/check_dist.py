@@ -35,6 +35,22 @@ for (H, W, N, sbin, mov, rois) in [(96, 128, 5300, 2, False, None), (64, 96, 310
             ok &= good
             print(f"N={N} {sk}: rel {rel:.2e} angle(10) {ang:.2e} trace {tr:.2e} -> {'ok' if good else 'FAIL'}")
     dist.barrier()
+# full-resolution ROI processors: sharded by frame range (running's predecessor comes from the one-frame halo),
+# gathered; pupil / blink / running and the painted motion energy must be bit-identical to the single-GPU run
+from tests.helpers import fullres_case
+views, sbin, mot, mov, rois, fullSVD = fullres_case("eye_all")
+vs = [torch.from_numpy(a).to(dev) for a in views]
+pd = process.process_source(DeviceArraySource(vs), sbin=sbin, motSVD=mot, movSVD=mov, rois=copy.deepcopy(rois), dist=sh)
+if rank == 0:
+    ps = process.process_source(DeviceArraySource(vs), sbin=sbin, motSVD=mot, movSVD=mov, rois=copy.deepcopy(rois))
+    checks = [("blink", pd["blink"], ps["blink"]), ("running", pd["running"], ps["running"]), ("motion", pd["motion"], ps["motion"])]
+    for key in ("com", "area", "axdir", "axlen", "area_smooth", "com_smooth"):
+        checks.append(("pupil." + key, [p[key] for p in pd["pupil"]], [p[key] for p in ps["pupil"]]))
+    for name, a, b in checks:
+        same = len(a) == len(b) and all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, b))
+        ok &= same
+        print(f"rois {name}: bit-identical {same}")
+dist.barrier()
 if rank == 0:
     print("DIST CHECK", "PASSED" if ok else "FAILED")
 dist.destroy_process_group()
