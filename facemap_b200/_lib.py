@@ -50,6 +50,9 @@ SIGNATURES = {
     "fm_bin_motion": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, C.POINTER(Rois), _P, _P, _P, _P, _P]),
     "fm_bin_motion_painted": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, C.POINTER(Rois), _P, _P, _P, _P,
                                    _P, _P]),
+    "fm_pairwise_plan": (_I, [_I, _I, _P, _P, _P]),
+    "fm_motion_ref_scratch_bytes": (_I, [_I, _I, _I, _I, _I, C.POINTER(C.c_size_t)]),
+    "fm_motion_ref": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P]),
     "fm_mean_update": (_I, [_P, _P, _L, _I, _I, _I, _P]),
     "fm_gemm_tn": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _I, _P, _L, _I, _I, _P]),
     "fm_split_lo": (_I, [_P, _L, _I, _I, _P, _L, _P]),

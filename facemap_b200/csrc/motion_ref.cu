@@ -1,0 +1,138 @@
+// fm_motion_ref — the motion energy `imbin_mot.sum(-1)` (facemap/process.py:460) evaluated with the
+// reference's own floating-point arithmetic, for the cases where the exact integer energy of K1 cannot decide
+// the reference's float32 result:
+//   * sbin not a power of two: the binned frames are float64 means of means (process.py:38-39: sum of a raw
+//     row segment / sbin, those summed row by row / sbin), their |differences| are summed over the pixels in
+//     NumPy's pairwise order, and the per-view sums are accumulated into a float32 array.  With two or more
+//     views ~3 % of the frames land exactly on a float32 rounding tie of the exact value, which the reference
+//     breaks by the sign of its 1e-13 float64 rounding error.
+//   * sbin == 1 with more than 65 793 pixels per view: the reference sums float32 values whose total exceeds
+//     2^24, so its pairwise float32 rounding differs from the correctly rounded integer sum.
+// One block per frame pair: |b_t - b_{t-1}| per binned pixel into a scratch row, leaf sums by 8-lane groups in
+// NumPy's accumulator order, fold by the (host-made, per view) pairwise plan.  Costs one more read of the frames.
+#include "common.cuh"
+#include "numpy_sum.cuh"
+
+namespace fm {
+
+constexpr int MR_THREADS = 256;
+
+template <class F>
+struct MotionRefParams {
+  const uint8_t* frames;
+  const uint8_t* prev_frame;   // frame preceding frames[0] or NULL
+  const uint8_t* ormask;       // [H, W] 0x00 / 0xFF or NULL
+  int T, H, W, sbin, Lyb, Lxb, rows, frame_off;
+  const int* leaf_lo;
+  const int* leaf_len;
+  const unsigned char* leaf_comb;
+  int nleaves;
+  F* scratch;                  // [grid, npix + nleaves]
+  double* out;                 // [rows]
+};
+
+// the reference's binned value of one pixel block (process.py:34-43)
+template <class F>
+__device__ __forceinline__ F binned_value(const uint8_t* fr, const uint8_t* mask, int W, int sbin, int by, int bx) {
+  const uint8_t* p = fr + (size_t)by * sbin * W + (size_t)bx * sbin;
+  const uint8_t* m = mask ? mask + (size_t)by * sbin * W + (size_t)bx * sbin : nullptr;
+  if constexpr (sizeof(F) == 4) {        // sbin == 1: imbin = im.astype(float32)
+    return (F)(unsigned)(m ? (p[0] | m[0]) : p[0]);
+  } else {
+    const double s = (double)sbin;
+    double acc = 0.0;
+    for (int r = 0; r < sbin; ++r) {
+      int rowsum = 0;
+      for (int c = 0; c < sbin; ++c) rowsum += (int)(m ? (p[(size_t)r * W + c] | m[(size_t)r * W + c]) : p[(size_t)r * W + c]);
+      const double mean_r = __ddiv_rn((double)rowsum, s);      // .mean(axis=-1)
+      acc = r == 0 ? mean_r : __dadd_rn(acc, mean_r);          // .mean(axis=-2) adds the rows in order
+    }
+    return __ddiv_rn(acc, s);
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(MR_THREADS) motion_ref_kernel(const MotionRefParams<F> p) {
+  const int npix = p.Lyb * p.Lxb;
+  F* d = p.scratch + (size_t)blockIdx.x * (npix + p.nleaves);
+  F* leaf_sum = d + npix;
+  const size_t hw = (size_t)p.H * p.W;
+  for (int row = blockIdx.x; row < p.rows; row += gridDim.x) {
+    const int f = row + p.frame_off;
+    const uint8_t* cur = p.frames + (size_t)f * hw;
+    const uint8_t* prv = f > 0 ? p.frames + (size_t)(f - 1) * hw : p.prev_frame;
+    for (int i = threadIdx.x; i < npix; i += MR_THREADS) {
+      const int by = i / p.Lxb, bx = i - by * p.Lxb;
+      const F a = binned_value<F>(cur, p.ormask, p.W, p.sbin, by, bx);
+      const F b = binned_value<F>(prv, p.ormask, p.W, p.sbin, by, bx);
+      d[i] = fabs(fadd_rn(a, -b));
+    }
+    __syncthreads();
+    const int group = threadIdx.x >> 3, j = threadIdx.x & 7;
+    for (int l0 = 0; l0 < p.nleaves; l0 += MR_THREADS / 8) {       // uniform trip count: the shuffles stay convergent
+      const int l = l0 + group;
+      const int len = l < p.nleaves ? p.leaf_len[l] : 0;
+      const F* a = d + (l < p.nleaves ? p.leaf_lo[l] : 0);
+      const int m = len >= 8 ? len - (len % 8) : 0;
+      F r = len >= 8 ? a[j] : (F)0;
+      for (int i = 8; i < m; i += 8) r = fadd_rn(r, a[i + j]);
+      __syncwarp();
+      F s1 = fadd_rn(r, __shfl_down_sync(0xffffffffu, r, 1, 8));       // r0+r1, r2+r3, r4+r5, r6+r7
+      s1 = fadd_rn(s1, __shfl_down_sync(0xffffffffu, s1, 2, 8));       // (r0+r1)+(r2+r3), (r4+r5)+(r6+r7)
+      s1 = fadd_rn(s1, __shfl_down_sync(0xffffffffu, s1, 4, 8));
+      if (j == 0 && l < p.nleaves) {
+        if (len < 8) s1 = (F)-0.0;
+        for (int i = m; i < len; ++i) s1 = fadd_rn(s1, a[i]);
+        leaf_sum[l] = s1;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      F vstack[32];
+      p.out[row] = (double)fadd_rn((F)0, pairwise_fold_plan<F>(p.nleaves, leaf_sum, p.leaf_comb, vstack));
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace fm
+
+// the leaf plan of numpy's pairwise sum over n elements (host arrays of capacity `cap`); returns the leaf count
+extern "C" int fm_pairwise_plan(int n, int cap, int32_t* lo, int32_t* len, uint8_t* comb) {
+  int st[96];
+  if (n < 0 || cap < 1 || !lo || !len || !comb) return -1;
+  return fm::pairwise_plan(n, lo, len, comb, cap, st);
+}
+
+extern "C" int fm_motion_ref_scratch_bytes(int H, int W, int sbin, int nleaves, int blocks, size_t* bytes) {
+  using namespace fm;
+  FM_REQUIRE(H >= 1 && W >= 1 && sbin >= 1 && nleaves >= 1 && blocks >= 1 && bytes, "fm_motion_ref_scratch_bytes: bad args");
+  *bytes = (size_t)blocks * ((size_t)(H / sbin) * (W / sbin) + nleaves) * (sbin == 1 ? 4 : 8);
+  return FM_OK;
+}
+
+extern "C" int fm_motion_ref(const uint8_t* frames, int T, int H, int W, int sbin, const uint8_t* prev_frame,
+                             const uint8_t* ormask, const int32_t* leaf_lo, const int32_t* leaf_len,
+                             const uint8_t* leaf_comb, int nleaves, void* scratch, int blocks, double* out,
+                             void* stream) {
+  using namespace fm;
+  FM_REQUIRE(frames && leaf_lo && leaf_len && leaf_comb && scratch && out && T >= 1 && H >= 1 && W >= 1 && sbin >= 1 &&
+                 nleaves >= 1 && blocks >= 1, "fm_motion_ref: bad args");
+  const int Lyb = H / sbin, Lxb = W / sbin;
+  FM_REQUIRE(Lyb >= 1 && Lxb >= 1, "fm_motion_ref: sbin %d larger than the %dx%d frame", sbin, H, W);
+  const int rows = prev_frame ? T : T - 1;
+  if (rows == 0) return FM_OK;
+  const int grid = rows < blocks ? rows : blocks;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (sbin == 1) {
+    MotionRefParams<float> p{frames, prev_frame, ormask, T, H, W, sbin, Lyb, Lxb, rows, prev_frame ? 0 : 1,
+                             leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<float*>(scratch), out};
+    motion_ref_kernel<float><<<grid, MR_THREADS, 0, st>>>(p);
+  } else {
+    MotionRefParams<double> p{frames, prev_frame, ormask, T, H, W, sbin, Lyb, Lxb, rows, prev_frame ? 0 : 1,
+                              leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<double*>(scratch), out};
+    motion_ref_kernel<double><<<grid, MR_THREADS, 0, st>>>(p);
+  }
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}

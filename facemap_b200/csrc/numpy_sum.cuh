@@ -19,17 +19,28 @@ FM_HD inline float fadd_rn(float a, float b) {
 #endif
 }
 
+FM_HD inline double fadd_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  volatile double r = a + b;
+  return r;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
-// NumPy pairwise float32 sum (numpy/_core/src/umath/loops_utils.h.src, FLOAT_pairwise_sum), run by
-// ONE thread: the result depends on the association order, which is what is being reproduced.
+// NumPy pairwise sum (numpy/_core/src/umath/loops_utils.h.src, FLOAT_/DOUBLE_pairwise_sum — the same
+// algorithm for both types), run by ONE thread: the result depends on the association order, which is what
+// is being reproduced.
 // ------------------------------------------------------------------------------------------------
-FM_HD inline float pairwise_leaf(const float* a, int n) {
+template <class F>
+FM_HD inline F pairwise_leaf(const F* a, int n) {
   if (n < 8) {
-    float r = -0.0f;
+    F r = (F)-0.0;
     for (int i = 0; i < n; ++i) r = fadd_rn(r, a[i]);
     return r;
   }
-  float r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+  F r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
   const int m = n - (n % 8);
   for (int i = 8; i < m; i += 8) {
     r0 = fadd_rn(r0, a[i + 0]);
@@ -41,8 +52,7 @@ FM_HD inline float pairwise_leaf(const float* a, int n) {
     r6 = fadd_rn(r6, a[i + 6]);
     r7 = fadd_rn(r7, a[i + 7]);
   }
-  float res = fadd_rn(fadd_rn(fadd_rn(r0, r1), fadd_rn(r2, r3)),
-                        fadd_rn(fadd_rn(r4, r5), fadd_rn(r6, r7)));
+  F res = fadd_rn(fadd_rn(fadd_rn(r0, r1), fadd_rn(r2, r3)), fadd_rn(fadd_rn(r4, r5), fadd_rn(r6, r7)));
   for (int i = m; i < n; ++i) res = fadd_rn(res, a[i]);
   return res;
 }
@@ -167,11 +177,12 @@ FM_HD inline int pairwise_plan(int n, int* lo, int* len, unsigned char* comb, in
   return count;
 }
 
-// fold the leaf sums of a plan; `vstack` holds 32 floats
-FM_HD inline float pairwise_fold_plan(int count, const float* sums, const unsigned char* comb, float* vstack) {
+// fold the leaf sums of a plan; `vstack` holds 32 values
+template <class F>
+FM_HD inline F pairwise_fold_plan(int count, const F* sums, const unsigned char* comb, F* vstack) {
   int sp = 0;
   for (int l = 0; l < count; ++l) {
-    float v = sums[l];
+    F v = sums[l];
     for (int k = 0; k < (int)comb[l]; ++k) v = fadd_rn(vstack[--sp], v);
     vstack[sp++] = v;
   }

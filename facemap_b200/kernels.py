@@ -380,3 +380,45 @@ def pupil(frames, rect, mask, dark_offset, sigma, scratch, blocks, out, reflecto
     check(_lib.load().fm_pupil(ptr(frames), T, H, W, y0, y1, x0, x1, ptr(mask), ptr(reflector),
                                C.c_float(float(dark_offset)), C.c_double(float(sigma)), ptr(scratch), int(blocks),
                                ptr(out), _stream()), "fm_pupil")
+
+
+# ---------------------------------------------------------------------------------------------
+# motion energy in the reference's floating-point arithmetic (fm_motion_ref)
+# ---------------------------------------------------------------------------------------------
+def pairwise_plan(n, device):
+    """(lo int32, len int32, comb uint8) device tensors: the leaves of NumPy's pairwise sum over n elements."""
+    import numpy as np
+
+    cap = max(1, n // 64 + 2)
+    lo, ln, comb = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.uint8)
+    count = int(_lib.load().fm_pairwise_plan(int(n), cap, C.c_void_p(lo.ctypes.data), C.c_void_p(ln.ctypes.data),
+                                             C.c_void_p(comb.ctypes.data)))
+    if count < 1 or count > cap:
+        raise FacemapB200Error(f"fm_pairwise_plan({n}) failed ({count})")
+    return tuple(torch.from_numpy(a[:count].copy()).to(device) for a in (lo, ln, comb))
+
+
+def motion_ref_scratch(H, W, sbin, nleaves, blocks, device):
+    n = C.c_size_t(0)
+    check(_lib.load().fm_motion_ref_scratch_bytes(int(H), int(W), int(sbin), int(nleaves), int(blocks), C.byref(n)),
+          "fm_motion_ref_scratch_bytes")
+    return torch.empty(int(n.value), dtype=torch.uint8, device=device)
+
+
+def motion_ref(frames, sbin, plan, scratch, blocks, out, prev_frame=None, ormask=None):
+    """out[r] (float64) = the reference's `imbin_mot.sum(-1)` of one view, bit for bit (rows as bin_motion)."""
+    T, H, W = _frames3(frames)
+    lo, ln, comb = plan
+    _need(out, torch.float64, "out", 1)
+    rows = T if prev_frame is not None else T - 1
+    if out.numel() < rows or not out.is_contiguous():
+        raise FacemapB200Error("motion_ref: out too small")
+    for t, name in ((prev_frame, "prev_frame"), (ormask, "ormask")):
+        if t is not None:
+            _need(t, torch.uint8, name, 2)
+            if tuple(t.shape) != (H, W) or not t.is_contiguous():
+                raise FacemapB200Error(f"{name}: expected a contiguous [{H}, {W}] uint8 tensor")
+    check(_lib.load().fm_motion_ref(ptr(frames), T, H, W, int(sbin), ptr(prev_frame), ptr(ormask), ptr(lo), ptr(ln),
+                                    ptr(comb), int(lo.numel()), ptr(scratch), int(blocks), ptr(out), _stream()),
+          "fm_motion_ref")
+    return rows

@@ -49,19 +49,22 @@ def save(proc, savepath=None):
     return savename
 
 
-def _motion_from_energy(E_views, sbin, N, f0=0):
+def _motion_from_energy(E_views, sbin, N, f0=0, ref_views=None):
     """Reference float semantics of `M[.] += imbin_mot.sum(-1)` per view (process.py:460) applied
     to exact integer energies, then the chunk-0 layout (quirk Q1): entries [0, nt1-1) hold the
     diffs of frames 1..nt1-1, entry nt1-1 stays 0.  E_views cover frames [f0, f0 + len) of an
-    N-frame video (a rank's shard when the outputs are not gathered)."""
+    N-frame video (a rank's shard when the outputs are not gathered).
+    ref_views[v]: optional float64 sums in the reference's own arithmetic (fm_motion_ref) for the views whose
+    float32 accumulation the integer energy cannot decide (svd.motion_needs_reference)."""
     s2 = float(sbin * sbin)
     n = len(E_views[0])
     acc = np.zeros(n, np.float32)
-    for e in E_views:
-        if sbin == 1:
-            acc = acc + e.astype(np.float32)                    # float32 sums in the reference
+    for v, e in enumerate(E_views):
+        ref = None if ref_views is None else ref_views[v]
+        if sbin == 1:                                           # float32 sums in the reference
+            acc = acc + (e.astype(np.float32) if ref is None else ref.astype(np.float32))
         else:
-            acc = (acc.astype(np.float64) + e.astype(np.float64) / s2).astype(np.float32)
+            acc = (acc.astype(np.float64) + (e.astype(np.float64) / s2 if ref is None else ref)).astype(np.float32)
     nt1 = min(500, N)
     out = acc.copy()
     if f0 < nt1:                                                # this range holds (part of) the first chunk
@@ -184,15 +187,18 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     # ---- stage 3 ----
     sink = None if keep_on_device else _HostSink(dev)
     pending_masks = {}
-    V, E, E_roi = {}, None, None
+    V, E, E_roi, Eref = {}, None, None, None
     if mods and masks:
         single = dist is None or dist.world == 1 or not gather_outputs
         if sink is not None:
             # masks and singular values leave while stage 3 runs; projections leave batch by batch
             pending_masks = {m: ([sink.to_host(u) for u in masks[m][1]], sink.to_host(masks[m][2])) for m in masks}
         V, E, E_roi = s3.project(masks, sink=sink if single else None)
+        Eref = s3.Eref
         if not single:
             V, E, E_roi = dist.gather_stage3(V, E, E_roi, N, mods, timer)
+            if Eref is not None:
+                Eref = dist.gather_rows(Eref.t().contiguous(), frame_ranges(N, dist.world)).t().contiguous()
 
     # ---- pupil / blink / running: rode on stage 3's sweep, or get their own when there is no SVD sweep ----
     fres_out = ([], [], [])
@@ -216,6 +222,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         avgmotion_h = avgmotion.cpu().numpy()
         E_h = E.cpu().numpy() if E is not None else None
         E_roi_h = E_roi.cpu().numpy() if E_roi is not None else None
+        Eref_h = Eref.cpu().numpy() if Eref is not None else None
     avgframe_l = [avgframe_h[ir].copy() for ir in iinds]
     avgmotion_l = [avgmotion_h[ir].copy() for ir in iinds]
     proc = {
@@ -292,7 +299,8 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                     v[0] = v[1]                         # quirk Q2: first projected row duplicated
                 V_out[m].append(v)
         if fullSVD:
-            M.append(_motion_from_energy([E_h[v] for v in range(len(Ly))], sbin, N, f0_out) if motSVD
+            refs = None if Eref_h is None else [Eref_h[v] if v in s3.ref_views else None for v in range(len(Ly))]
+            M.append(_motion_from_energy([E_h[v] for v in range(len(Ly))], sbin, N, f0_out, refs) if motSVD
                      else np.zeros(E_h.shape[1], np.float32))
         else:
             M.append(np.zeros((0,), np.float32))

@@ -560,6 +560,18 @@ def projection_rows_per_batch(p, k, budget_bytes=6 << 30):
     return int(min(rows, cap))
 
 
+MOTION_REF_BLOCKS = 148 * 4
+
+
+def motion_needs_reference(sbin, npix):
+    """True when `M += imbin_mot.sum(-1)` (process.py:460) is not decided by the exact integer energy: float64
+    means of means for a non-power-of-two sbin (float32 rounding ties across views), float32 sums beyond 2^24
+    for sbin == 1."""
+    if sbin & (sbin - 1):
+        return True
+    return sbin == 1 and npix * 255 >= (1 << 24)
+
+
 class Stage3:
     """Projection of every frame in [f0, f1) onto the masks (process.py:394-515), in two phases:
 
@@ -609,6 +621,16 @@ class Stage3:
         self.X_full = None
         self.early_done = None
         self._halo_done = False
+        # views whose float32 motion accumulator the exact integer energy cannot decide (fm_motion_ref)
+        self.Eref, self.ref_views = None, []
+        if fullSVD and "mot" in mods:
+            self.ref_views = [v for v in range(self.nv) if motion_needs_reference(geo.sbin, geo.npix_v[v])]
+        if self.ref_views:
+            self.Eref = torch.zeros((self.nv, self.n_out), dtype=torch.float64, device=device)
+            self.ref_plan = {v: K.pairwise_plan(geo.npix_v[v], device) for v in self.ref_views}
+            self.ref_scratch = {v: K.motion_ref_scratch(geo.Ly[v], geo.Lx[v], geo.sbin, self.ref_plan[v][0].numel(),
+                                                        MOTION_REF_BLOCKS, device) for v in self.ref_views}
+            self.ref_last = {v: None for v in self.ref_views}
 
     # ---- bin phase -------------------------------------------------------------------------------
     def _seed_halo(self):
@@ -621,6 +643,8 @@ class Stage3:
             for v, fr in enumerate(halo):
                 K.bin_motion(fr, self.geo.sbin, last_sum=self.carry[self.flip][v],
                              ormask=None if self.fullres is None else self.fullres.ormask[v])
+            for v in self.ref_views:
+                self.ref_last[v] = halo[v][-1].clone()
         self._halo_done = True
 
     def _bin_fetches(self, fetches, X, row0):
@@ -658,6 +682,12 @@ class Stage3:
                     for v in range(self.nv):
                         for q, j in enumerate(geo.rois_on_view[v]):
                             self.E_roi[j, o:o + rows] = roi_e[v][q, :rows]
+                for v in self.ref_views:
+                    if rows > 0:
+                        K.motion_ref(frames[v], geo.sbin, self.ref_plan[v], self.ref_scratch[v], MOTION_REF_BLOCKS,
+                                     self.Eref[v, o:o + rows], prev_frame=self.ref_last[v] if have else None,
+                                     ormask=None if self.fullres is None else self.fullres.ormask[v])
+                    self.ref_last[v] = frames[v][-1].clone()
             self.flip = 1 - self.flip
             filled += rows
         return filled

@@ -96,6 +96,21 @@ int fm_bin_motion_painted(const uint8_t* frames, int T, int H, int W, int sbin,
                           const uint8_t* ormask, void* stream);
 
 /*
+ * Motion energy in the reference's own floating-point arithmetic (facemap/process.py:34-43, 455-460): per row
+ * the sum over the view's binned pixels of |b_t - b_{t-1}|, b = float64 mean of means (sbin > 1) or float32
+ * pixel value (sbin == 1), summed in NumPy's pairwise order — bit-identical to `imbin_mot.sum(-1)`.  Needed
+ * where K1's exact integer energy cannot decide the reference's float32 accumulator: sbin not a power of two
+ * (float32 rounding ties between views) and sbin == 1 on views of more than 65 793 pixels (float32 sums
+ * beyond 2^24).  Row convention as fm_bin_motion: with prev_frame (uint8 [H, W], the frame before frames[0])
+ * rows = T, else rows = T - 1.  leaf_*: fm_pairwise_plan(Lyb*Lxb) uploaded to the device.  out: float64 [rows].
+ */
+int fm_pairwise_plan(int n, int cap, int32_t* lo, int32_t* len, uint8_t* comb);   /* host arrays; returns #leaves */
+int fm_motion_ref_scratch_bytes(int H, int W, int sbin, int nleaves, int blocks, size_t* bytes);
+int fm_motion_ref(const uint8_t* frames, int T, int H, int W, int sbin, const uint8_t* prev_frame,
+                  const uint8_t* ormask, const int32_t* leaf_lo, const int32_t* leaf_len,
+                  const uint8_t* leaf_comb, int nleaves, void* scratch, int blocks, double* out, void* stream);
+
+/*
  * Stage-1 accumulator update, bit-compatible with subsampled_mean (facemap/process.py:82-86,
  * 95-96): acc32 = f32( f64(acc32) + (f64(tsum) / sbin^2) / count ) for n pixels.
  * `finalize_div` > 0 additionally divides by that segment count in float32 (process.py:95-96).

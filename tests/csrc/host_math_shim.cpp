@@ -25,6 +25,16 @@ extern "C" float shim_pairwise_sum_plan(const float* a, int n, int cap) {
   return fm::fadd_rn(0.0f, fm::pairwise_fold_plan(count, sums, comb, vstack));
 }
 
+// float64 flavour (numpy's DOUBLE_pairwise_sum): what fm_motion_ref runs for sbin > 1
+extern "C" double shim_pairwise_sum_plan_f64(const double* a, int n) {
+  static int lo[1 << 16], len[1 << 16], st[96];
+  static unsigned char comb[1 << 16];
+  static double sums[1 << 16], vstack[32];
+  const int count = fm::pairwise_plan(n, lo, len, comb, 1 << 16, st);
+  for (int i = 0; i < count; ++i) sums[i] = fm::pairwise_leaf(a + lo[i], len[i]);
+  return fm::fadd_rn(0.0, fm::pairwise_fold_plan(count, sums, comb, vstack));
+}
+
 extern "C" int shim_pairwise_leaf_count(int n) {
   static int lo[4096], len[4096];
   return fm::pairwise_list_leaves(n, lo, len, 4096);

@@ -192,3 +192,34 @@ def test_k1_painted_equals_k1_on_painted_frames(cuda_device, T, H, W, sbin, with
     b = run(torch.from_numpy(frames | m).to(dev), None)
     for key in a:
         assert torch.equal(a[key], b[key]), key
+
+
+@pytest.mark.parametrize("T,H,W,sbin", [(9, 61, 67, 3), (7, 144, 192, 12), (12, 140, 196, 7), (6, 50, 70, 5),
+                                        (5, 300, 310, 1), (4, 24, 32, 1), (5, 96, 128, 4), (3, 400, 600, 1)])
+def test_motion_ref_matches_numpy_bitwise(cuda_device, T, H, W, sbin):
+    """fm_motion_ref == the reference's `np.abs(np.diff(spatial_bin(im))).sum(-1)` (process.py:34-43, 455-460),
+    bit for bit, with and without a carried previous frame and a paint mask"""
+    from facemap_b200 import kernels as K
+
+    dev = cuda_device
+    frames = _video(T + 1, H, W, seed=11 * T + sbin)
+    if H * W > 200000:        # white noise: float32 sums beyond 2^24, where the summation order shows
+        frames = np.random.RandomState(9).randint(0, 256, size=(T + 1, H, W)).astype(np.uint8)
+    m = np.where(np.random.RandomState(3).rand(H, W) < 0.2, 255, 0).astype(np.uint8)
+    Lyb, Lxb = H // sbin, W // sbin
+    plan = K.pairwise_plan(Lyb * Lxb, dev)
+    blocks = 3
+    scratch = K.motion_ref_scratch(H, W, sbin, plan[0].numel(), blocks, dev)
+    for mask in (None, m):
+        painted = frames if mask is None else (frames | mask)
+        b = orc.bin_frames(painted, sbin, Lyb, Lxb)
+        ref = np.abs(np.diff(b, axis=0)).sum(axis=-1)            # float64 (sbin > 1) or float32 (sbin == 1)
+        d_mask = None if mask is None else torch.from_numpy(mask).to(dev)
+        out = torch.zeros(T, dtype=torch.float64, device=dev)
+        rows = K.motion_ref(torch.from_numpy(frames).to(dev), sbin, plan, scratch, blocks, out, ormask=d_mask)
+        assert rows == T
+        assert np.array_equal(out.cpu().numpy(), ref.astype(np.float64))
+        out2 = torch.zeros(T, dtype=torch.float64, device=dev)
+        rows = K.motion_ref(torch.from_numpy(frames[1:]).to(dev), sbin, plan, scratch, blocks, out2,
+                            prev_frame=torch.from_numpy(frames[0]).to(dev), ormask=d_mask)
+        assert rows == T and np.array_equal(out2.cpu().numpy(), ref.astype(np.float64))

@@ -29,6 +29,8 @@ def shim(tmp_path_factory):
     lib.shim_pairwise_leaf_count.argtypes = [C.c_int]
     lib.shim_pairwise_sum_plan.restype = C.c_float
     lib.shim_pairwise_sum_plan.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.shim_pairwise_sum_plan_f64.restype = C.c_double
+    lib.shim_pairwise_sum_plan_f64.argtypes = [C.c_void_p, C.c_int]
     lib.shim_inv2x2.argtypes = [C.c_double] * 3 + [C.c_void_p]
     lib.shim_median_from_hist.restype = C.c_float
     lib.shim_median_from_hist.argtypes = [C.c_void_p, C.c_float]
@@ -56,6 +58,15 @@ def test_pairwise_sum_matches_numpy_bitwise(shim):
     # leaves hold 64..128 elements once the array is split at all: 1024 leaves cover >= 65536 elements
     for n in (129, 1000, 32768, 65536):
         assert shim.shim_pairwise_leaf_count(n) <= max(1, n // 64)
+
+
+def test_pairwise_sum_f64_matches_numpy_bitwise(shim):
+    rs = np.random.RandomState(5)
+    for n in [1, 7, 8, 9, 127, 128, 129, 332, 540, 1000, 4096, 19200, 34080, 100003, 1310720]:
+        a = rs.rand(n) * 3.0 + rs.rand(n) * 1e-9
+        got = shim.shim_pairwise_sum_plan_f64(a.ctypes.data, n)
+        want = a.sum()
+        assert np.float64(got).tobytes() == np.float64(want).tobytes(), (n, got, want)
 
 
 def test_inv2x2_matches_numpy(shim):
