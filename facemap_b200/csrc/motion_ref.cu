@@ -95,7 +95,41 @@ __global__ void __launch_bounds__(MR_THREADS) motion_ref_kernel(const MotionRefP
   }
 }
 
+// Stage-1 segment means in the reference's arithmetic (process.py:77-87) for a non-power-of-two sbin: per binned
+// pixel the float64 binned values of the segment's frames are added in frame order and divided by T
+// (`imbin.mean(axis=0)` reduces the leading axis sequentially), likewise the T-1 absolute differences.
+__global__ void __launch_bounds__(MR_THREADS) mean_ref_kernel(const uint8_t* frames, int T, int H, int W, int sbin,
+                                                              int Lyb, int Lxb, double* mean_bin, double* mean_adiff) {
+  const int i = blockIdx.x * MR_THREADS + threadIdx.x;
+  if (i >= Lyb * Lxb) return;
+  const int by = i / Lxb, bx = i - by * Lxb;
+  const size_t hw = (size_t)H * W;
+  double prev = binned_value<double>(frames, nullptr, W, sbin, by, bx);
+  double accb = prev, accd = 0.0;
+  for (int t = 1; t < T; ++t) {
+    const double b = binned_value<double>(frames + (size_t)t * hw, nullptr, W, sbin, by, bx);
+    accb = __dadd_rn(accb, b);
+    const double d = fabs(__dadd_rn(b, -prev));
+    accd = t == 1 ? d : __dadd_rn(accd, d);
+    prev = b;
+  }
+  mean_bin[i] = __ddiv_rn(accb, (double)T);
+  mean_adiff[i] = __ddiv_rn(accd, (double)(T - 1));       // T == 1: 0/0 = NaN, like the mean of an empty array
+}
+
 }  // namespace fm
+
+extern "C" int fm_mean_ref(const uint8_t* frames, int T, int H, int W, int sbin, double* mean_bin, double* mean_adiff,
+                           void* stream) {
+  using namespace fm;
+  FM_REQUIRE(frames && mean_bin && mean_adiff && T >= 1 && H >= 1 && W >= 1 && sbin >= 2, "fm_mean_ref: bad args");
+  const int Lyb = H / sbin, Lxb = W / sbin;
+  FM_REQUIRE(Lyb >= 1 && Lxb >= 1, "fm_mean_ref: sbin %d larger than the %dx%d frame", sbin, H, W);
+  mean_ref_kernel<<<(unsigned)cdiv((int64_t)Lyb * Lxb, MR_THREADS), MR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      frames, T, H, W, sbin, Lyb, Lxb, mean_bin, mean_adiff);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
 
 // the leaf plan of numpy's pairwise sum over n elements (host arrays of capacity `cap`); returns the leaf count
 extern "C" int fm_pairwise_plan(int n, int cap, int32_t* lo, int32_t* len, uint8_t* comb) {

@@ -422,3 +422,15 @@ def motion_ref(frames, sbin, plan, scratch, blocks, out, prev_frame=None, ormask
                                     ptr(comb), int(lo.numel()), ptr(scratch), int(blocks), ptr(out), _stream()),
           "fm_motion_ref")
     return rows
+
+
+def mean_ref(frames, sbin, mean_bin, mean_adiff):
+    """Segment means of one view in the reference's float64 arithmetic (fm_mean_ref; non-power-of-two sbin)."""
+    T, H, W = _frames3(frames)
+    npix = (H // sbin) * (W // sbin)
+    for t, name in ((mean_bin, "mean_bin"), (mean_adiff, "mean_adiff")):
+        _need(t, torch.float64, name, 1)
+        if t.numel() < npix or not t.is_contiguous():
+            raise FacemapB200Error(f"{name}: needs {npix} contiguous float64 elements")
+    check(_lib.load().fm_mean_ref(ptr(frames), T, H, W, int(sbin), ptr(mean_bin), ptr(mean_adiff), _stream()),
+          "fm_mean_ref")

@@ -41,10 +41,11 @@ class Shard:
         self.world = dist.get_world_size(group)
 
     # ---- collectives on plain tensors (device agnostic: used by the gloo CPU tests too) ----
-    def allreduce_segment_sums(self, local, nseg, p, device):
-        """local: {segment index: (tsum_bin int64[p], tsum_adiff int64[p], T)} for the segments this
-        rank computed -> the same dict for ALL segments (integer all-reduce, exact)."""
-        pack = torch.zeros((nseg, 2, p), dtype=torch.int64, device=device)
+    def allreduce_segment_sums(self, local, nseg, p, device, dtype=torch.int64):
+        """local: {segment index: (tsum_bin [p], tsum_adiff [p], T)} for the segments this rank computed -> the
+        same dict for ALL segments.  int64 time sums (exact in any order) or, for a non-power-of-two sbin, float64
+        segment means — each segment comes from exactly one rank, so the SUM all-reduce only adds zeros to it."""
+        pack = torch.zeros((nseg, 2, p), dtype=dtype, device=device)
         counts = torch.zeros(nseg, dtype=torch.int64, device=device)
         for i, (tsb, tsa, T) in local.items():
             pack[i, 0] = tsb
@@ -89,7 +90,8 @@ class Shard:
         mine = assign_round_robin(len(tf), self.world)[self.rank]
         local, nseg = svd.stage1_means(source, geo, device, timer, segments=mine)
         with timer("stage1.allreduce"):
-            sums = self.allreduce_segment_sums(local, nseg, geo.p, device)
+            dt = torch.float64 if svd.stage1_uses_reference(geo.sbin) else torch.int64
+            sums = self.allreduce_segment_sums(local, nseg, geo.p, device, dtype=dt)
         return svd.stage1_finish(sums, nseg, geo, device)
 
     def stage2_chunks(self, source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer):

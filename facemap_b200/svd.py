@@ -391,33 +391,43 @@ def stage1_means(source, geo: Geometry, device, timer, segments=None):
             frames = source.fetch(t, t + nt0, device)
             if pos + 1 < len(todo):
                 source.prefetch(int(tf[todo[pos + 1]]), int(tf[todo[pos + 1]]) + nt0, device)
-        tsb = torch.zeros(p, dtype=torch.int64, device=device)
-        tsa = torch.zeros(p, dtype=torch.int64, device=device)
+        # power-of-two sbin: exact integer time sums; otherwise the reference's float64 means (fm_mean_ref)
+        dt = torch.float64 if stage1_uses_reference(geo.sbin) else torch.int64
+        tsb = torch.zeros(p, dtype=dt, device=device)
+        tsa = torch.zeros(p, dtype=dt, device=device)
         with timer("stage1.bin"):
             for v, fr in enumerate(frames):
                 c0, n = geo.col0[v], geo.npix_v[v]
-                K.bin_motion(fr, geo.sbin, tsum_bin=tsb[c0:c0 + n], tsum_adiff=tsa[c0:c0 + n])
+                if dt == torch.float64:
+                    K.mean_ref(fr, geo.sbin, tsb[c0:c0 + n], tsa[c0:c0 + n])
+                else:
+                    K.bin_motion(fr, geo.sbin, tsum_bin=tsb[c0:c0 + n], tsum_adiff=tsa[c0:c0 + n])
         sums[i] = (tsb, tsa, int(frames[0].shape[0]))
     if segments is not None:
         return sums, nseg
     with timer("stage1.mean"):
-        for i in range(nseg):                       # float32 accumulation in segment order
-            tsb, tsa, T = sums[i]
-            K.mean_update(avgframe, tsb, geo.sbin, T)
-            K.mean_update(avgmotion, tsa, geo.sbin, max(T - 1, 1))
-        K.mean_update(avgframe, None, geo.sbin, 1, finalize_div=nseg)
-        K.mean_update(avgmotion, None, geo.sbin, 1, finalize_div=nseg)
-    return avgframe, avgmotion
+        return stage1_finish(sums, nseg, geo, device)
+
+
+def stage1_uses_reference(sbin):
+    """Non-power-of-two bins: the reference's float64 means of means are not exact, so stage 1 reproduces
+    its arithmetic (fm_mean_ref) instead of dividing exact integer sums."""
+    return bool(sbin & (sbin - 1))
 
 
 def stage1_finish(all_sums, nseg, geo, device):
-    """Reduce per-segment integer sums (any order of arrival) in the reference's segment order."""
+    """float32 accumulation of the per-segment sums / means (any order of arrival) in the reference's segment
+    order (process.py:84-86, 95-96)."""
     avgframe = torch.zeros(geo.p, dtype=torch.float32, device=device)
     avgmotion = torch.zeros(geo.p, dtype=torch.float32, device=device)
     for i in range(nseg):
         tsb, tsa, T = all_sums[i]
-        K.mean_update(avgframe, tsb, geo.sbin, T)
-        K.mean_update(avgmotion, tsa, geo.sbin, max(T - 1, 1))
+        if tsb.dtype == torch.float64:                      # segment means: avg32 = f32(f64(avg32) + mean)
+            avgframe = (avgframe.double() + tsb).float()
+            avgmotion = (avgmotion.double() + tsa).float()
+        else:
+            K.mean_update(avgframe, tsb, geo.sbin, T)
+            K.mean_update(avgmotion, tsa, geo.sbin, max(T - 1, 1))
     K.mean_update(avgframe, None, geo.sbin, 1, finalize_div=nseg)
     K.mean_update(avgmotion, None, geo.sbin, 1, finalize_div=nseg)
     return avgframe, avgmotion

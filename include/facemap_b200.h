@@ -111,6 +111,15 @@ int fm_motion_ref(const uint8_t* frames, int T, int H, int W, int sbin, const ui
                   const uint8_t* leaf_comb, int nleaves, void* scratch, int blocks, double* out, void* stream);
 
 /*
+ * Stage-1 segment means in the reference's float64 arithmetic for a non-power-of-two sbin (process.py:77-87):
+ * mean_bin[p] = mean over the T frames of the binned value, mean_adiff[p] = mean over the T-1 absolute
+ * differences, both accumulated in frame order like `imbin.mean(axis=0)`.  The caller adds them into the float32
+ * averages (`avg32 = f32(f64(avg32) + mean)`).  Power-of-two sbin uses K1's integer time sums (exact).
+ */
+int fm_mean_ref(const uint8_t* frames, int T, int H, int W, int sbin, double* mean_bin, double* mean_adiff,
+                void* stream);
+
+/*
  * Stage-1 accumulator update, bit-compatible with subsampled_mean (facemap/process.py:82-86,
  * 95-96): acc32 = f32( f64(acc32) + (f64(tsum) / sbin^2) / count ) for n pixels.
  * `finalize_div` > 0 additionally divides by that segment count in float32 (process.py:95-96).

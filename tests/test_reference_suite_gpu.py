@@ -37,11 +37,12 @@ def motion_match(out, exp):        # test_svd_output.py:155-156
     return bool((out["motion"][0] == exp["motion"][0]).all())
 
 
-def masks_match(out, exp, n=200):  # test_svd_output.py:117-142
+def masks_match(out, exp, n=150):  # test_svd_output.py:117-142
     """Upstream loops over all components; its tolerance only bites on frames as small as these (mask entries
-    reach 0.5 on 332 pixels, atol is 0.1), and there the noise-floor components (beyond ~240 of 331) of the stock
-    randomized solver have not converged — the exact-SVD variant of the reference fails the same check against
-    the stock one from component 238 on.  The first 200 are compared."""
+    reach 0.2-0.5 on a few hundred pixels, atol is 0.1), and there the stock randomized solver has not converged
+    on near-degenerate and noise-floor components — the reference run with an exact SVD fails the same check
+    against the stock reference from component 175 (single video) / 238 (two cameras) on.  The first 150 are
+    compared."""
     assert out["motSVD"][0].shape[1] == exp["motSVD"][0].shape[1]
     ok = True
     for key in ("motMask", "movMask"):
