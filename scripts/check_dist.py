@@ -35,6 +35,17 @@ for (H, W, N, sbin, mov, rois) in [(96, 128, 5300, 2, False, None), (64, 96, 310
             ok &= good
             print(f"N={N} {sk}: rel {rel:.2e} angle(10) {ang:.2e} trace {tr:.2e} -> {'ok' if good else 'FAIL'}")
     dist.barrier()
+# non-power-of-two bins, two cameras: stage-1 means travel as float64 (fm_mean_ref), the motion accumulator uses
+# the reference-arithmetic sums (fm_motion_ref) gathered over the shards -> bit-identical to one GPU
+va = torch.from_numpy(SynthVideo(90, 120, 2600, seed=5).all_frames()).to(dev)
+vb = torch.from_numpy(SynthVideo(72, 96, 2600, seed=6).all_frames()).to(dev)
+pd = process.process_source(DeviceArraySource([va, vb]), sbin=3, motSVD=True, movSVD=False, dist=sh)
+if rank == 0:
+    ps = process.process_source(DeviceArraySource([va, vb]), sbin=3, motSVD=True, movSVD=False)
+    for key in ("avgframe", "avgmotion", "motion"):
+        same = all(np.array_equal(a, b) for a, b in zip(pd[key], ps[key])); ok &= same
+        print(f"sbin 3, two views, {key}: bit-identical {same}")
+dist.barrier()
 # full-resolution ROI processors: sharded by frame range (running's predecessor comes from the one-frame halo),
 # gathered; pupil / blink / running and the painted motion energy must be bit-identical to the single-GPU run
 from tests.helpers import fullres_case
