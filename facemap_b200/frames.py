@@ -284,55 +284,193 @@ class HostArraySource(FrameSource):
             pass
 
 
+class _DecodeCache:
+    """Decode-once cache of a file source: every frame of `home` is decoded exactly once, by `workers` threads
+    with their own capture handles (OpenCV releases the GIL while decoding), into pinned staging buffers and
+    copied into HBM-resident views on a private stream.  Pieces touched by the SVD sample ranges are decoded
+    first, the rest in frame order — the order in which stages 1-3 consume them.  Readers block (host side)
+    until the pieces they need are decoded, then wait (device side) on the copy event."""
+
+    def __init__(self, src, priority, home, device, piece=256, workers=8):
+        import queue
+        import threading
+
+        self.src, self.device, self.piece = src, device, piece
+        self.lo, self.hi = home
+        n = self.hi - self.lo
+        self.bufs = [torch.empty((n, h, w), dtype=torch.uint8, device=device) for h, w in zip(src.Ly, src.Lx)]
+        self.npieces = -(-n // piece)
+        nv = len(src.Ly)
+        order, seen = [], set()
+        for a, b in priority:
+            a, b = max(a, self.lo), min(b, self.hi)
+            if a >= b:
+                continue
+            for pc in range((a - self.lo) // piece, (b - 1 - self.lo) // piece + 1):
+                if pc not in seen:
+                    seen.add(pc)
+                    order.append(pc)
+        order += [pc for pc in range(self.npieces) if pc not in seen]
+        self.ready = [[threading.Event() for _ in range(nv)] for _ in range(self.npieces)]
+        self.copied = [[None] * nv for _ in range(self.npieces)]
+        self.error = None
+        self.stop = False
+        self.stream = torch.cuda.Stream(device)
+        self.jobs = queue.Queue()
+        for pc in order:
+            for v in range(nv):
+                self.jobs.put((pc, v))
+        self.decoded_frames = 0
+        self._lock = threading.Lock()
+        self.threads = [threading.Thread(target=self._work, daemon=True) for _ in range(max(1, workers))]
+        for t in self.threads:
+            t.start()
+
+    def _work(self):
+        import queue
+
+        caps = None
+        try:
+            torch.cuda.set_device(self.device)
+            caps = self.src._open()
+            staging = {}
+            while not self.stop:
+                try:
+                    pc, v = self.jobs.get_nowait()
+                except queue.Empty:
+                    break
+                a = self.lo + pc * self.piece
+                b = min(self.hi, a + self.piece)
+                if v not in staging:
+                    staging[v] = torch.empty((self.piece, self.src.Ly[v], self.src.Lx[v]), dtype=torch.uint8,
+                                             pin_memory=True)
+                host = staging[v][:b - a]
+                self.src._read(v, a, b, out=host.numpy(), caps=caps)
+                with torch.cuda.stream(self.stream):
+                    self.bufs[v][a - self.lo:b - self.lo].copy_(host, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.stream)
+                self.copied[pc][v] = ev
+                self.ready[pc][v].set()
+                with self._lock:
+                    self.decoded_frames += b - a
+                ev.synchronize()                      # the staging buffer is free again
+        except Exception as e:                        # surface in the reader instead of hanging it
+            self.error = e
+            for row in self.ready:
+                for r in row:
+                    r.set()
+        finally:
+            if caps is not None:
+                self.src._release(caps)
+
+    def covers(self, a, b):
+        return a >= self.lo and b <= self.hi
+
+    def get(self, a, b):
+        cur = torch.cuda.current_stream()
+        for pc in range((a - self.lo) // self.piece, (b - 1 - self.lo) // self.piece + 1):
+            for v in range(len(self.bufs)):
+                self.ready[pc][v].wait()
+                if self.error is not None:
+                    raise self.error
+                cur.wait_event(self.copied[pc][v])
+        return [buf[a - self.lo:b - self.lo] for buf in self.bufs]
+
+    def close(self):
+        self.stop = True
+        for t in self.threads:
+            t.join()
+        self.bufs = None
+
+
 class VideoFileSource(FrameSource):
     """filenames: 2-D list [[view0, view1, ...] per sequential block] (facemap/process.py:652-654).
     Decoding stays on the host (OpenCV); decode failures repeat the previous frame like
-    utils.get_frames (facemap/utils.py:545-547).  Every view has its own decode thread (OpenCV
-    releases the GIL), decoding into pinned buffers; `prefetch` starts the next range while the GPU
-    works on the current one, and the H2D copy is asynchronous on a side stream."""
+    utils.get_frames (facemap/utils.py:545-547).
 
-    def __init__(self, filenames):
+    When the frames a pass needs fit in HBM (`plan_access`), every frame is decoded ONCE by a pool of decoder
+    threads straight into HBM-resident views (`_DecodeCache`); the reference decodes each frame up to three
+    times (stage-1 segments, stage-2 chunks, stage-3 sweep) on one thread.  Otherwise ranges are decoded on
+    demand: one decode thread per view into pinned buffers, `prefetch` starting the next range while the GPU
+    works on the current one, asynchronous H2D on a side stream."""
+
+    def __init__(self, filenames, decode_workers=None, cache_on_device=True, mem_fraction=0.55):
         import cv2
         from concurrent.futures import ThreadPoolExecutor
 
         self._cv2 = cv2
         self.filenames = filenames
-        self.caps = []
+        self.caps = self._open()
         cum = [0]
         self.Ly, self.Lx = [], []
-        for b, block in enumerate(filenames):
-            caps = []
-            for f in block:
-                cap = cv2.VideoCapture(f)
-                if not cap.isOpened():
-                    raise IOError(f"cannot open video {f}")
-                caps.append(cap)
-                if b == 0:
+        for b, caps in enumerate(self.caps):
+            if b == 0:
+                for cap in caps:
                     self.Ly.append(int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)))
                     self.Lx.append(int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)))
-            self.caps.append(caps)
             cum.append(cum[-1] + int(caps[0].get(cv2.CAP_PROP_FRAME_COUNT)))
         self.cumframes = np.array(cum).astype(int)
         self.nframes = int(cum[-1])
         self.block_frames = [int(x) for x in np.diff(self.cumframes)]
-        self._workers = [ThreadPoolExecutor(max_workers=1) for _ in self.Ly]   # one decoder per view
+        self._workers = [ThreadPoolExecutor(max_workers=1) for _ in self.Ly]   # on-demand path: one decoder per view
         self._jobs = {}
         self._pipe = _H2DPipe()
         self.h2d = 0
+        import os
+
+        self.decode_workers = decode_workers if decode_workers is not None else max(2, min(16, (os.cpu_count() or 4) // 2))
+        self.cache_on_device = cache_on_device
+        self.mem_fraction = mem_fraction
+        self._cache = None
+
+    def _open(self):
+        """a private set of capture handles [block][view] (a handle is not thread safe)"""
+        out = []
+        for block in self.filenames:
+            caps = []
+            for f in block:
+                cap = self._cv2.VideoCapture(f)
+                if not cap.isOpened():
+                    raise IOError(f"cannot open video {f}")
+                caps.append(cap)
+            out.append(caps)
+        return out
+
+    @staticmethod
+    def _release(caps):
+        for block in caps:
+            for c in block:
+                c.release()
 
     def h2d_bytes(self, nframes):
         return int(nframes) * sum(h * w for h, w in zip(self.Ly, self.Lx))
 
-    def _read(self, view, a, b, out=None):
+    def plan_access(self, priority, home, device):
+        if self._cache is not None:
+            self._cache.close()
+            self._cache = None
+        lo, hi = home
+        nbytes = self.h2d_bytes(hi - lo)
+        if not self.cache_on_device or hi <= lo:
+            return
+        free, _ = torch.cuda.mem_get_info(device)
+        if nbytes > self.mem_fraction * free:
+            return
+        self._cache = _DecodeCache(self, priority, (lo, hi), device, workers=self.decode_workers)
+        self.h2d += nbytes
+
+    def _read(self, view, a, b, out=None, caps=None):
         cv2 = self._cv2
+        caps = self.caps if caps is None else caps
         if out is None:
             out = np.zeros((b - a, self.Ly[view], self.Lx[view]), np.uint8)
         k = 0
-        for blk in range(len(self.caps)):
+        for blk in range(len(caps)):
             lo, hi = max(a, self.cumframes[blk]), min(b, self.cumframes[blk + 1])
             if lo >= hi:
                 continue
-            cap = self.caps[blk][view]
+            cap = caps[blk][view]
             first = int(lo - self.cumframes[blk])
             if int(cap.get(cv2.CAP_PROP_POS_FRAMES)) != first:
                 cap.set(cv2.CAP_PROP_POS_FRAMES, first)
@@ -358,10 +496,14 @@ class VideoFileSource(FrameSource):
 
     def prefetch(self, t0, t1, device):
         a, b = self.clamp(t0, t1)
+        if self._cache is not None and self._cache.covers(a, b):
+            return
         self._submit(a, b)
 
     def fetch(self, t0, t1, device):
         a, b = self.clamp(t0, t1)
+        if self._cache is not None and self._cache.covers(a, b):
+            return self._cache.get(a, b)
         self._submit(a, b)
         host = [f.result() for f in self._jobs.pop((a, b))]
         self.h2d += self.h2d_bytes(b - a)
@@ -369,11 +511,12 @@ class VideoFileSource(FrameSource):
         return self._pipe.take((a, b))
 
     def close(self):
+        if self._cache is not None:
+            self._cache.close()
+            self._cache = None
         for w in self._workers:
             w.shutdown(wait=True)
-        for caps in self.caps:
-            for c in caps:
-                c.release()
+        self._release(self.caps)
 
 
 def as_source(obj):

@@ -97,3 +97,38 @@ def test_run_on_video_files_matches_oracle(cuda_device, avi_files, tmp_path):
         assert (np.abs(nrm - nrm_r)[big] / nrm_r[big]).max() <= 1e-4, mk
         cos = np.abs((U[:, :4] * Ur[:, :4]).sum(axis=0)) / (nrm[:4] * nrm_r[:4])
         assert np.abs(cos - 1).max() < 1e-5, mk
+
+
+@pytest.mark.gpu
+def test_decode_cache_equals_on_demand_decoding(cuda_device, avi_files):
+    """the decode-once HBM cache (threaded decoders, priority pieces first) hands out the same frames as the
+    on-demand path, for ranges in any order, across a file boundary, and end to end"""
+    import torch
+
+    from facemap_b200 import process
+    from facemap_b200.frames import VideoFileSource
+
+    paths, arr = avi_files
+    whole = np.concatenate((arr["a"], arr["b"]))
+    src = VideoFileSource([[paths["a"]], [paths["b"]]], decode_workers=5)
+    try:
+        src.plan_access([(2000, 2100), (0, 100), (1250, 1350)], (0, src.nframes), cuda_device)
+        assert src._cache is not None
+        for a, b in ((1250, 1350), (0, 100), (2100, 2200), (255, 258), (1299, 1301), (0, 2200)):
+            got = src.fetch(a, b, cuda_device)[0]
+            torch.cuda.synchronize()
+            assert np.array_equal(got.cpu().numpy(), whole[a:b]), (a, b)
+        assert src._cache.decoded_frames == src.nframes            # every frame decoded exactly once
+    finally:
+        src.close()
+    outs = []
+    for cached in (True, False):
+        src = VideoFileSource([[paths["a"], paths["c"]]], cache_on_device=cached)
+        try:
+            outs.append(process.process_source(src, sbin=2, motSVD=True, movSVD=True))
+            assert (src._cache is not None) == cached
+        finally:
+            src.close()
+    for key in ("avgframe", "avgmotion", "motion", "motMask", "movMask", "motSVD", "movSVD"):
+        for x, y in zip(outs[0][key], outs[1][key]):
+            assert np.array_equal(x, y), key
