@@ -419,7 +419,14 @@ class VideoFileSource(FrameSource):
         self.h2d = 0
         import os
 
-        self.decode_workers = decode_workers if decode_workers is not None else max(2, min(16, (os.cpu_count() or 4) // 2))
+        # decoder threads of the decode-once cache: the host cores this process may use (its affinity mask),
+        # shared between the ranks of one box, two left for the main and copy threads
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 4
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        self.decode_workers = decode_workers if decode_workers is not None else max(2, min(32, (cores - 2) // ranks))
         self.cache_on_device = cache_on_device
         self.mem_fraction = mem_fraction
         self._cache = None
