@@ -15,7 +15,6 @@ rank-1 correction:  G = X X^T - p m m^T,  G = W L W^T,  U S = X^T W - 1 (m^T W).
 from __future__ import annotations
 
 import math
-import time
 
 import numpy as np
 import torch

@@ -59,7 +59,6 @@ def test_frame_count_boundaries(cuda_device, N):
 def test_odd_geometry_and_bin_factors(cuda_device, H, W, sbin):
     from facemap_b200 import process
     from facemap_b200.frames import DeviceArraySource
-    from tests.helpers import ulp_distance
 
     N = 2100
     v = _video(N, H, W, seed=H)

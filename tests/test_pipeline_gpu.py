@@ -14,8 +14,7 @@ import pytest
 import torch
 
 from oracle import facemap_oracle as orc
-from tests.helpers import (CASES, KEEP, case_rois, case_videos, frame_window, sign_align, subspace_sin,
-                           ulp_distance)
+from tests.helpers import CASES, KEEP, case_rois, case_videos, frame_window, sign_align, subspace_sin
 
 pytestmark = pytest.mark.gpu
 
