@@ -74,6 +74,22 @@ def main():
     o2 = torch.zeros((T, 2), dtype=torch.int32, device=dev)
     ms = timed(lambda: K.running(fr, rrect, ormask, g2, means, o2), a.reps)
     out["running_120x400"] = {"ms": ms, "us_per_frame": 1e3 * ms / T, "roi_GBps": T * 120 * 400 / ms / 1e6}
+    # the reference-arithmetic motion / mean kernels of the non-power-of-two bins (sbin 3 and 7) and K1 beside them
+    from facemap_b200 import svd
+    for sbin in (3, 7):
+        npix = (H // sbin) * (W // sbin)
+        plan = K.pairwise_plan(npix, dev)
+        scr = K.motion_ref_scratch(H, W, sbin, plan[0].numel(), svd.MOTION_REF_BLOCKS, dev)
+        o64 = torch.zeros(T, dtype=torch.float64, device=dev)
+        ms = timed(lambda: K.motion_ref(fr, sbin, plan, scr, svd.MOTION_REF_BLOCKS, o64), a.reps)
+        X = K.alloc_matrix(T - 1, npix, dev)
+        avg = torch.zeros(npix, dtype=torch.float32, device=dev)
+        e = torch.zeros(T - 1, dtype=torch.int64, device=dev)
+        ms_k1 = timed(lambda: K.bin_motion(fr, sbin, avgmotion=avg, x_mot=X, energy=e), a.reps)
+        mb, ma = torch.zeros(npix, dtype=torch.float64, device=dev), torch.zeros(npix, dtype=torch.float64, device=dev)
+        ms_mean = timed(lambda: K.mean_ref(fr[:100], sbin, mb, ma), a.reps)
+        out[f"sbin{sbin}"] = {"motion_ref_ms": ms, "motion_ref_GBps": T * H * W / ms / 1e6, "k1_generic_ms": ms_k1,
+                              "k1_generic_GBps": T * H * W / ms_k1 / 1e6, "mean_ref_100_frames_ms": ms_mean}
     print(json.dumps(out))
 
 

@@ -34,6 +34,8 @@ CASES = [
     # T, H, W, sbin   (vector path needs W % min(16, 4*sbin) == 0)
     (40, 64, 96, 4), (37, 60, 100, 4), (33, 48, 64, 2), (20, 24, 32, 1), (25, 64, 128, 8),
     (19, 64, 64, 16), (21, 50, 70, 3), (18, 61, 67, 4), (16, 30, 50, 5), (140, 32, 48, 4),
+    # non-power-of-two bins on 4-byte aligned rows: the generic kernel's masked word loads
+    (20, 60, 96, 3), (14, 70, 140, 7), (10, 96, 144, 12), (15, 60, 100, 5), (9, 66, 132, 6),
 ]
 
 
