@@ -131,7 +131,7 @@ def make_sources(rank, world, device, want_host):
             self.dcache = DeviceFrameCache()
             self.base = resident
             if on_host:
-                self.base = torch.empty(resident.shape, dtype=torch.uint8).pin_memory()
+                self.base = torch.empty(tuple(resident.shape), dtype=torch.uint8, pin_memory=True)
                 self.base.copy_(resident)
 
         def _range(self, a, b):
@@ -182,7 +182,9 @@ def make_sources(rank, world, device, want_host):
         def h2d_bytes(self, nframes):
             return int(nframes) * H * W if self.on_host else 0
 
-    return ShardSource(False), (ShardSource(True) if want_host else None)
+    # the pinned host copy is made lazily, AFTER the device-resident measurement: page-locking and filling
+    # 30.7 GB per rank keeps the host busy (and jittery) for a while
+    return ShardSource(False), ((lambda: ShardSource(True)) if want_host else None)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -291,7 +293,7 @@ def main():
         if avail < need:
             want_host = False
             e2e_skip = f"host memory: {avail / 2**30:.0f} GiB available < {need / 2**30:.0f} GiB needed to pin the frames of {world} ranks"
-    dev_src, host_src = make_sources(rank, world, device, want_host)
+    dev_src, host_factory = make_sources(rank, world, device, want_host)
     total_frames = world * FRAMES_PER_GPU
 
     def barrier():
@@ -409,6 +411,7 @@ def main():
     # ---- e2e: host-resident frames through the public API ----
     e2e = None
     if want_host:
+        host_src = host_factory()
         for _ in range(2):                                   # warm-up (host cache of sample chunks, pinned pools)
             one_step(host_src, timing={}, keep=False)
         barrier()
