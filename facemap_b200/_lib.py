@@ -109,9 +109,18 @@ def check(rc: int, what: str = "") -> None:
         raise FacemapB200Error(f"{what or 'facemap_b200'} failed (code {rc}): {msg}")
 
 
+_checked_devices = set()
+
+
 def require_device(dev: int = 0) -> None:
-    """Raise unless `dev` is a Blackwell part this library carries code for (no CPU fallback)."""
-    check(load().fm_check_device(int(dev)), "fm_check_device")
+    """Raise unless `dev` is a Blackwell part this library carries code for (no CPU fallback).
+    The answer is cached per device: fm_check_device calls cudaGetDeviceProperties, which takes a driver-wide
+    lock (tens of ms when something else, e.g. an NVML clock query, holds it) — not something to repeat per call."""
+    dev = int(dev)
+    if dev in _checked_devices:
+        return
+    check(load().fm_check_device(dev), "fm_check_device")
+    _checked_devices.add(dev)
 
 
 def ptr(t):

@@ -115,6 +115,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     overlap_stage3: run stage 3's bin/diff pass on a side stream underneath the stage-2 eigensolves
             when the frames are HBM-resident (svd.Stage3.start_early).
     dist:   optional facemap_b200.parallel.Shard (frame-range sharding across ranks)."""
+    t_enter = time.perf_counter()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     _lib.require_device(dev.index or 0)
     torch.cuda.set_device(dev)
@@ -338,6 +339,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         if marks:
             timing["wall_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks[:-1], marks[1:])}
         timing["host_marks_ms"] = {b[0]: round(1e3 * (b[1] - a[1]), 2) for a, b in zip(hmarks[:-1], hmarks[1:])}
+        timing["host_marks_ms"]["preamble"] = round(1e3 * (hmarks[0][1] - t_enter), 2)
         t_rep = time.perf_counter()
         torch.cuda.synchronize()
         timing["final_sync_ms"] = round(1e3 * (time.perf_counter() - t_rep), 2)
