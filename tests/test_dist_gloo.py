@@ -1,5 +1,6 @@
-"""Multi-rank host logic on CPU (gloo, world_size 2 and 3): work assignment, the integer all-reduce
-of stage 1, the chunk-block all-gather of stage 2 and the row gather of stage 3."""
+"""Multi-rank host logic on CPU (gloo, world_size 2 and 3): work assignment, the integer (and, for
+non-power-of-two bins, float64) all-reduce of stage 1, the chunk-block all-gather of stage 2 and the row gather of
+stage 3 and of the ROI-processor outputs."""
 import os
 import socket
 
@@ -61,7 +62,22 @@ def _worker(rank, world, port, out):
         ranges = parallel.frame_ranges(N, world)
         a, b = ranges[rank]
         ok3 = np.array_equal(sh.gather_rows(torch.from_numpy(rows[a:b]), ranges).numpy(), rows)
-        out[rank] = (ok1, ok2, ok3)
+        # stage 1 of a non-power-of-two sbin: float64 segment means, each from exactly one rank (x + 0 == x)
+        means_all = rng.rand(nseg, 2, p) * 255 + rng.rand(nseg, 2, p) * 1e-9
+        mine = parallel.assign_round_robin(nseg, world)[rank]
+        local = {i: (torch.from_numpy(means_all[i, 0]), torch.from_numpy(means_all[i, 1]), 100) for i in mine}
+        full = sh.allreduce_segment_sums(local, nseg, p, torch.device("cpu"), dtype=torch.float64)
+        ok4 = all(full[i][0].dtype == torch.float64 and np.array_equal(full[i][0].numpy(), means_all[i, 0])
+                  and np.array_equal(full[i][1].numpy(), means_all[i, 1]) for i in range(nseg))
+        # outputs of the ROI processors / fm_motion_ref: float64 [n, 9] (with NaN rows), int32 [n, 2], float64 [n]
+        pup = rng.rand(N, 9)
+        pup[rng.rand(N) < 0.05] = np.nan
+        run = rng.randint(-40, 41, size=(N, 2)).astype(np.int32)
+        eref = rng.rand(N) * 1e5
+        ok5 = (np.array_equal(sh.gather_rows(torch.from_numpy(pup[a:b]), ranges).numpy(), pup, equal_nan=True)
+               and np.array_equal(sh.gather_rows(torch.from_numpy(run[a:b]), ranges).numpy(), run)
+               and np.array_equal(sh.gather_rows(torch.from_numpy(eref[a:b]), ranges).numpy(), eref))
+        out[rank] = (ok1, ok2, ok3, ok4, ok5)
     finally:
         dist.destroy_process_group()
 

@@ -92,3 +92,79 @@ def test_gram_ksplit_and_batch_sizes():
     r = svd.projection_rows_per_batch(19200, 500)
     assert r % 128 == 0 and r * 19200 * 4 <= 6 << 30
     assert svd.projection_rows_per_batch(1310720, 500) % 128 == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# host side of the full-resolution ROI processors (facemap_b200/fullres.py) against oracle/roi_oracle.py
+# ---------------------------------------------------------------------------------------------
+def test_fullres_paint_plan_reproduces_in_place_painting():
+    """R1: every ROI's crop mask, the running masks and the per-view mask that stage 3 bins equal what the
+    reference's in-place writes (process.py:543, 567) leave behind, overlapping rectangles included"""
+    from facemap_b200 import fullres
+    from oracle import roi_oracle
+    from tests.helpers import fullres_case
+
+    for name in ("eye_all", "eye_reflector"):
+        views, sbin, mot, mov, rois, full = fullres_case(name)
+        views = [v[:3] for v in views]
+        Ly, Lx = [v.shape[1] for v in views], [v.shape[2] for v in views]
+        painters, runners, ormask = fullres.paint_plan(rois, Ly, Lx)
+        ims = [v.copy() for v in views]
+        pup, bl, run = roi_oracle.processing_order(rois)
+        assert [p["index"] for p in painters] == pup + bl and [r["index"] for r in runners] == run
+        for pl, i in zip(painters, pup + bl):
+            r = rois[i]
+            y0, y1, x0, x1 = roi_oracle.roi_rect(r)
+            assert pl["rect"] == (y0, y1, x0, x1)
+            crop = ims[r["ivid"]][:, y0:y1, x0:x1]
+            crop[:, ~r["ellipse"]] = 255                                     # the reference's write through a view
+            assert np.array_equal(np.where(pl["mask"] > 0, 255, views[r["ivid"]][:, y0:y1, x0:x1]), crop), (name, i)
+        for rn in runners:
+            y0, y1, x0, x1 = rn["rect"]
+            assert np.array_equal(views[rn["view"]][:, y0:y1, x0:x1] | rn["ormask"], ims[rn["view"]][:, y0:y1, x0:x1])
+        for v in range(len(views)):
+            assert np.array_equal(views[v] | (ormask[v] if ormask[v] is not None else 0), ims[v])
+
+
+def test_fullres_tables_match_oracle():
+    from facemap_b200 import fullres
+    from oracle import roi_oracle
+
+    for ny, nx in ((21, 30), (24, 92), (85, 97)):                                   # running: g^2 in float32
+        g = roi_oracle.running_filter(ny, nx).astype(np.complex64)
+        assert np.array_equal(np.real(g * g), fullres.gaussian_fourier_sq(ny, nx))
+    crop = np.arange(256).astype(np.uint8).reshape(1, 16, 16)                        # blink: R3 dtype rules
+    for sat in (100.5, 100, 0, 255, 254.9):
+        t = fullres.blink_terms(sat)
+        assert t.dtype == np.float64 and abs(roi_oracle.blink_chunk(crop, sat)[0] - t.sum()) <= 1e-9 * max(1.0, t.sum())
+    assert fullres.blink_terms(100)[200] == float((100 - 200) % 256)                 # uint8 wrap-around
+    assert fullres.blink_terms(100.0)[200] == 0.0                                    # float clamp
+
+
+def test_fullres_smooth_trace_matches_oracle_bitwise():
+    import warnings
+
+    from facemap_b200 import fullres
+    from oracle import roi_oracle
+
+    rs = np.random.RandomState(0)
+    for trial in range(30):
+        n = int(rs.choice([5, 29, 30, 31, 100, 700]))
+        x = rs.randn(n).cumsum() + 10
+        x[rs.rand(n) < 0.1] = np.nan
+        if trial % 5 == 0:
+            x[:] = np.nan
+        if trial % 7 == 0:
+            x[rs.randint(n)] = 1e3
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert np.array_equal(fullres.smooth_trace(x), roi_oracle.smooth_trace(x), equal_nan=True), (trial, n)
+
+
+def test_motion_needs_reference_rule():
+    from facemap_b200 import svd
+
+    assert not svd.motion_needs_reference(4, 19200) and not svd.motion_needs_reference(1, 24 * 32)
+    assert svd.motion_needs_reference(3, 100) and svd.motion_needs_reference(12, 332) and svd.motion_needs_reference(7, 560)
+    assert not svd.motion_needs_reference(1, 65793) and svd.motion_needs_reference(1, 65794)      # 255 * p >= 2^24
+    assert svd.stage1_uses_reference(7) and not svd.stage1_uses_reference(8) and not svd.stage1_uses_reference(1)
