@@ -43,10 +43,31 @@ struct K1Params {
   const uint8_t* ormask;  // optional [H, W] bytes OR-ed into every frame (0x00 / 0xFF: painted pixels read 255)
 };
 
-// streaming (read-once) loads of VB bytes as 32-bit words
+// Per-thread geometry of the vector kernel.  Power-of-two bins: 16 raw bytes per row (4 * sbin below sbin 4),
+// i.e. 4, 4, 4, 2, 1 binned pixels for sbin 1, 2, 4, 8, 16.  Other bins: PX binned pixels with PX * sbin a
+// multiple of 4, so a thread's row segment is PX * sbin / 4 aligned words (PX = 4, or 2 for large even bins).
+constexpr bool k1_pow2(int sbin) { return (sbin & (sbin - 1)) == 0; }
+constexpr int k1_px(int sbin) {
+  return k1_pow2(sbin) ? ((sbin >= 4 ? 16 : 4 * sbin) / sbin) : ((sbin >= 8 && sbin % 2 == 0) ? 2 : 4);
+}
+constexpr int k1_nw(int sbin) { return k1_px(sbin) * sbin / 4; }
+// bins the vector kernel is instantiated for
+inline bool k1_vector_bin(int sbin) {
+  return sbin == 1 || sbin == 2 || sbin == 4 || sbin == 8 || sbin == 16 || sbin == 3 || sbin == 5 || sbin == 6 ||
+         sbin == 7 || sbin == 10 || sbin == 12;
+}
+
+// streaming (read-once) loads of VB bytes as 32-bit words; word q is skipped (0) when it starts at or beyond
+// `nwords_left` (only the last pixel group of a row of a non-power-of-two bin can run past the row end)
 template <int NW>
-__device__ __forceinline__ void ldg_stream(const uint8_t* p, unsigned (&w)[NW]) {
-  if constexpr (NW == 4) {
+__device__ __forceinline__ void ldg_stream(const uint8_t* p, unsigned (&w)[NW], int nwords_left = NW) {
+  if constexpr (NW != 1 && NW != 2 && NW != 4) {
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+      w[q] = 0u;
+      if (q < nwords_left) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(w[q]) : "l"(p + 4 * q));
+    }
+  } else if constexpr (NW == 4) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
                  : "l"(p));
@@ -59,8 +80,11 @@ __device__ __forceinline__ void ldg_stream(const uint8_t* p, unsigned (&w)[NW]) 
 
 // mask words (read by every slab and frame: ordinary cached loads)
 template <int NW>
-__device__ __forceinline__ void ldg_mask(const uint8_t* p, unsigned (&w)[NW]) {
-  if constexpr (NW == 4) {
+__device__ __forceinline__ void ldg_mask(const uint8_t* p, unsigned (&w)[NW], int nwords_left = NW) {
+  if constexpr (NW != 1 && NW != 2 && NW != 4) {
+#pragma unroll
+    for (int q = 0; q < NW; ++q) w[q] = q < nwords_left ? __ldg(reinterpret_cast<const unsigned*>(p) + q) : 0u;
+  } else if constexpr (NW == 4) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
     w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
   } else if constexpr (NW == 2) {
@@ -74,7 +98,19 @@ __device__ __forceinline__ void ldg_mask(const uint8_t* p, unsigned (&w)[NW]) {
 // Add the bytes of one raw row segment (NW words) into the PX block sums.
 template <int SBIN, int PX, int NW>
 __device__ __forceinline__ void accumulate_row(const unsigned (&w)[NW], int (&s)[PX]) {
-  if constexpr (SBIN >= 4) {
+  if constexpr (!k1_pow2(SBIN)) {
+    // binned pixel j owns bytes [j*SBIN, (j+1)*SBIN) of the segment: one dp4a per (pixel, overlapping word)
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+#pragma unroll
+      for (int q = (j * SBIN) / 4; q <= ((j + 1) * SBIN - 1) / 4; ++q) {
+        const int lo = (j * SBIN > 4 * q ? j * SBIN : 4 * q) - 4 * q;
+        const int hi = ((j + 1) * SBIN < 4 * q + 4 ? (j + 1) * SBIN : 4 * q + 4) - 4 * q;
+        const unsigned ones = (0x01010101u >> (8 * (4 - hi))) & (0x01010101u << (8 * lo));
+        s[j] = (int)__dp4a(w[q], ones, (unsigned)s[j]);
+      }
+    }
+  } else if constexpr (SBIN >= 4) {
     constexpr int WPP = SBIN / 4;  // words per binned pixel
 #pragma unroll
     for (int j = 0; j < PX; ++j)
@@ -116,11 +152,14 @@ __device__ __forceinline__ void store_row(float* dst, const float (&x)[PX], int 
 // blink ROIs paint the chunk buffer that is binned afterwards) — no painted copy of the frames is made.
 template <int SBIN, bool ROI, bool MOV, bool PAINT>
 __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Params p) {
-  constexpr int VB = (SBIN >= 4) ? 16 : 4 * SBIN;
-  constexpr int NW = VB / 4;
-  constexpr int PX = VB / SBIN;
-  constexpr int FB = (SBIN >= 8) ? 1 : 8 / SBIN;  // frames fetched per batch (>= 8 loads in flight)
+  constexpr int PX = k1_px(SBIN);
+  constexpr int NW = k1_nw(SBIN);
+  constexpr bool POW2 = k1_pow2(SBIN);
+  // frames fetched per batch (>= 8 load instructions in flight: one vector load per raw row for power-of-two
+  // bins, NW scalar loads per raw row otherwise)
+  constexpr int FB = POW2 ? ((SBIN >= 8) ? 1 : 8 / SBIN) : 1;
   constexpr float INV_S2 = 1.0f / (float)(SBIN * SBIN);
+  constexpr double S2 = (double)(SBIN * SBIN);
   constexpr int NROI_SLOTS = ROI ? FM_MAX_ROIS : 0;
 
   __shared__ unsigned s_energy[(1 + NROI_SLOTS) * K1_MAX_SLAB];
@@ -163,14 +202,17 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Para
   const bool vec_ok = (PX >= 2) && ((p.col0 + pix0) % VALIGN == 0) && (p.ldx % VALIGN == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.x_mot) | reinterpret_cast<uintptr_t>(p.x_mov)) % 16 == 0);
 
+  // words of the raw row from this thread's first byte on (only non-power-of-two bins can run past the end)
+  const int wleft = POW2 ? NW : (p.W - bx0 * SBIN) / 4;
+
   // paint words of this thread's raw rows: registers for small sbin, re-read (L1) for sbin >= 8
-  constexpr bool PAINT_REGS = PAINT && SBIN <= 4;
+  constexpr bool PAINT_REGS = PAINT && SBIN * NW <= 16;
   unsigned pm[PAINT_REGS ? SBIN : 1][NW];
   const uint8_t* mbase = PAINT ? p.ormask + (size_t)by * SBIN * p.W + (size_t)bx0 * SBIN : nullptr;
   if constexpr (PAINT_REGS) {
 #pragma unroll
     for (int r = 0; r < SBIN; ++r) {
-      if (active) ldg_mask<NW>(mbase + (size_t)r * p.W, pm[r]);
+      if (active) ldg_mask<NW>(mbase + (size_t)r * p.W, pm[r], wleft);
       else
 #pragma unroll
         for (int q = 0; q < NW; ++q) pm[r][q] = 0u;
@@ -182,7 +224,7 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Para
       for (int q = 0; q < NW; ++q) out[q] = raw_row[q] | pm[r][q];
     } else if constexpr (PAINT) {
       unsigned m[NW];
-      ldg_mask<NW>(mbase + (size_t)r * p.W, m);
+      ldg_mask<NW>(mbase + (size_t)r * p.W, m, wleft);
 #pragma unroll
       for (int q = 0; q < NW; ++q) out[q] = raw_row[q] | m[q];
     } else {
@@ -205,7 +247,7 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Para
 #pragma unroll
       for (int r = 0; r < SBIN; ++r) {
         unsigned w[NW], wp[NW];
-        ldg_stream<NW>(fp + (size_t)r * p.W, w);
+        ldg_stream<NW>(fp + (size_t)r * p.W, w, wleft);
         painted(w, r, wp);
         accumulate_row<SBIN, PX, NW>(wp, prev);
       }
@@ -226,7 +268,7 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Para
       for (int f = 0; f < FB; ++f) {
         const uint8_t* fp = base + (size_t)(min(rb + f, r1 - 1) + p.frame_off) * frame_bytes;
 #pragma unroll
-        for (int r = 0; r < SBIN; ++r) ldg_stream<NW>(fp + (size_t)r * p.W, raw[f][r]);
+        for (int r = 0; r < SBIN; ++r) ldg_stream<NW>(fp + (size_t)r * p.W, raw[f][r], wleft);
       }
     }
 #pragma unroll
@@ -254,8 +296,13 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Para
         for (int j = 0; j < PX; ++j) {
           const int d = abs(cur[j] - prev[j]);
           dvals[j] = (j < nvalid) ? (unsigned)d : 0u;
-          xm[j] = __fmaf_rn((float)d, INV_S2, -am[j]);
-          if constexpr (MOV) xf[j] = __fmaf_rn((float)cur[j], INV_S2, -af[j]);
+          if constexpr (POW2) {       // exact: d / s^2 is a float, one rounding in the FMA
+            xm[j] = __fmaf_rn((float)d, INV_S2, -am[j]);
+            if constexpr (MOV) xf[j] = __fmaf_rn((float)cur[j], INV_S2, -af[j]);
+          } else {                    // the reference's float64 evaluation, as in the generic kernel
+            xm[j] = (float)((double)d / S2 - (double)am[j]);
+            if constexpr (MOV) xf[j] = (float)((double)cur[j] / S2 - (double)af[j]);
+          }
           if (j < nvalid) {
             esum += (unsigned)d;
             tsa[j] += d;
@@ -454,11 +501,11 @@ static int bin_motion_impl(const uint8_t* frames, int T, int H, int W, int sbin,
     if (last_sum == nullptr && tsum_bin == nullptr) return FM_OK;
     p.rows = 0;
   }
-  const int vb = sbin >= 4 ? 16 : 4 * sbin;
-  const bool vec = (sbin == 1 || sbin == 2 || sbin == 4 || sbin == 8 || sbin == 16) && (W % vb == 0) &&
-                   ((reinterpret_cast<uintptr_t>(frames) % vb) == 0) &&
+  // power-of-two bins: whole 16-byte (4*sbin below sbin 4) groups per row; other bins: 4-byte aligned rows
+  const int vb = k1_pow2(sbin) ? (sbin >= 4 ? 16 : 4 * sbin) : 4;
+  const bool vec = k1_vector_bin(sbin) && (W % vb == 0) && ((reinterpret_cast<uintptr_t>(frames) % vb) == 0) &&
                    ((reinterpret_cast<uintptr_t>(ormask) % vb) == 0);
-  const int px = vec ? vb / sbin : 1;
+  const int px = vec ? k1_px(sbin) : 1;
   const int64_t ngroups = vec ? (int64_t)Lyb * ((Lxb + px - 1) / px) : (int64_t)Lyb * Lxb;
   const int gx = (int)cdiv(ngroups, K1_THREADS);
   // slab length: long enough to amortise the halo frame, short enough to fill the machine
@@ -489,7 +536,13 @@ static int bin_motion_impl(const uint8_t* frames, int T, int H, int W, int sbin,
       case 2: FM_K1_LAUNCH(2); break;
       case 4: FM_K1_LAUNCH(4); break;
       case 8: FM_K1_LAUNCH(8); break;
-      default: FM_K1_LAUNCH(16); break;
+      case 16: FM_K1_LAUNCH(16); break;
+      case 3: FM_K1_LAUNCH(3); break;
+      case 5: FM_K1_LAUNCH(5); break;
+      case 6: FM_K1_LAUNCH(6); break;
+      case 7: FM_K1_LAUNCH(7); break;
+      case 10: FM_K1_LAUNCH(10); break;
+      default: FM_K1_LAUNCH(12); break;
     }
   } else {
     bin_motion_generic_kernel<<<grid, K1_THREADS, 0, st>>>(p);

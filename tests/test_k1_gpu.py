@@ -34,8 +34,10 @@ CASES = [
     # T, H, W, sbin   (vector path needs W % min(16, 4*sbin) == 0)
     (40, 64, 96, 4), (37, 60, 100, 4), (33, 48, 64, 2), (20, 24, 32, 1), (25, 64, 128, 8),
     (19, 64, 64, 16), (21, 50, 70, 3), (18, 61, 67, 4), (16, 30, 50, 5), (140, 32, 48, 4),
-    # non-power-of-two bins on 4-byte aligned rows: the generic kernel's masked word loads
+    # non-power-of-two bins on 4-byte aligned rows: vector kernel instantiations for sbin 3, 5, 6, 7, 10, 12
     (20, 60, 96, 3), (14, 70, 140, 7), (10, 96, 144, 12), (15, 60, 100, 5), (9, 66, 132, 6),
+    # ... with a cropped remainder / a partial last pixel group (the row-end guard of the vector kernel)
+    (6, 42, 640, 3), (6, 49, 648, 7), (5, 60, 104, 10), (7, 36, 76, 6),
 ]
 
 
