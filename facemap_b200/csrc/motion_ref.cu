@@ -27,7 +27,7 @@ struct MotionRefParams {
   const int* leaf_len;
   const unsigned char* leaf_comb;
   int nleaves;
-  F* scratch;                  // [grid, npix + nleaves]
+  F* scratch;                  // [grid, 2 * npix + nleaves]: |differences|, previous binned frame, leaf sums
   double* out;                 // [rows]
 };
 
@@ -51,21 +51,85 @@ __device__ __forceinline__ F binned_value(const uint8_t* fr, const uint8_t* mask
   }
 }
 
-template <class F>
+// The same for 4 horizontally adjacent binned pixels (bx0 a multiple of 4) of a 4-byte aligned frame: their
+// 4*sbin raw bytes per row are `sbin` aligned words, each word feeds at most two pixels (sbin >= 3) through
+// dp4a byte masks.  Words at or beyond the row end are skipped (pixels past Lxb come out as garbage: unused).
+__device__ __forceinline__ void binned_group4(const uint8_t* fr, const uint8_t* mask, int W, int sbin, int by, int bx0,
+                                              double (&out)[4]) {
+  const size_t off = (size_t)by * sbin * W + (size_t)bx0 * sbin;
+  const int wleft = (W - bx0 * sbin) / 4;
+  const int nw = sbin < wleft ? sbin : wleft;
+  const double s = (double)sbin;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int r = 0; r < sbin; ++r) {
+    const unsigned* w = reinterpret_cast<const unsigned*>(fr + off + (size_t)r * W);
+    const unsigned* mw = mask ? reinterpret_cast<const unsigned*>(mask + off + (size_t)r * W) : nullptr;
+    int rs[4] = {0, 0, 0, 0};
+    for (int q = 0; q < nw; ++q) {
+      unsigned word = __ldg(w + q);
+      if (mw) word |= __ldg(mw + q);
+      const int j0 = (4 * q) / sbin;                       // pixel of the word's first byte
+      const int c0 = min(4, (j0 + 1) * sbin - 4 * q);      // how many of its 4 bytes belong to that pixel
+      const unsigned lo_ones = 0x01010101u >> (8 * (4 - c0));
+      const int v0 = (int)__dp4a(word, lo_ones, 0u);
+      const int v1 = (int)__dp4a(word, 0x01010101u & ~lo_ones, 0u);     // the rest goes to the next pixel
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rs[j] += (j == j0 ? v0 : 0) + (j == j0 + 1 ? v1 : 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double mean_r = __ddiv_rn((double)rs[j], s);
+      acc[j] = r == 0 ? mean_r : __dadd_rn(acc[j], mean_r);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[j] = __ddiv_rn(acc[j], s);
+}
+
+// One block per run of consecutive rows: the binned values of a frame are kept (scratch `bprev`) for the next
+// row, so every frame is binned once per block run instead of twice per row.
+template <class F, bool VEC4>
 __global__ void __launch_bounds__(MR_THREADS) motion_ref_kernel(const MotionRefParams<F> p) {
   const int npix = p.Lyb * p.Lxb;
-  F* d = p.scratch + (size_t)blockIdx.x * (npix + p.nleaves);
-  F* leaf_sum = d + npix;
+  F* d = p.scratch + (size_t)blockIdx.x * (2 * (size_t)npix + p.nleaves);
+  F* bprev = d + npix;
+  F* leaf_sum = bprev + npix;
   const size_t hw = (size_t)p.H * p.W;
-  for (int row = blockIdx.x; row < p.rows; row += gridDim.x) {
+  const int per_block = (p.rows + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * per_block;
+  const int r_end = min(p.rows, r_begin + per_block);
+  for (int row = r_begin; row < r_end; ++row) {
     const int f = row + p.frame_off;
     const uint8_t* cur = p.frames + (size_t)f * hw;
     const uint8_t* prv = f > 0 ? p.frames + (size_t)(f - 1) * hw : p.prev_frame;
-    for (int i = threadIdx.x; i < npix; i += MR_THREADS) {
-      const int by = i / p.Lxb, bx = i - by * p.Lxb;
-      const F a = binned_value<F>(cur, p.ormask, p.W, p.sbin, by, bx);
-      const F b = binned_value<F>(prv, p.ormask, p.W, p.sbin, by, bx);
-      d[i] = fabs(fadd_rn(a, -b));
+    const bool first = row == r_begin;
+    // every thread owns the same pixels in every row of the run: bprev needs no synchronisation
+    if constexpr (VEC4) {
+      const int GX = (p.Lxb + 3) / 4;
+      for (int g = threadIdx.x; g < p.Lyb * GX; g += MR_THREADS) {
+        const int by = g / GX, bx0 = 4 * (g - by * GX);
+        const int nvalid = min(4, p.Lxb - bx0);
+        double a[4], b[4];
+        binned_group4(cur, p.ormask, p.W, p.sbin, by, bx0, a);
+        if (first) binned_group4(prv, p.ormask, p.W, p.sbin, by, bx0, b);
+        const int i = by * p.Lxb + bx0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nvalid) {
+            const double bj = first ? b[j] : (double)bprev[i + j];
+            d[i + j] = (F)fabs(fadd_rn(a[j], -bj));
+            bprev[i + j] = (F)a[j];
+          }
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < npix; i += MR_THREADS) {
+        const int by = i / p.Lxb, bx = i - by * p.Lxb;
+        const F a = binned_value<F>(cur, p.ormask, p.W, p.sbin, by, bx);
+        const F b = first ? binned_value<F>(prv, p.ormask, p.W, p.sbin, by, bx) : bprev[i];
+        d[i] = fabs(fadd_rn(a, -b));
+        bprev[i] = a;
+      }
     }
     __syncthreads();
     const int group = threadIdx.x >> 3, j = threadIdx.x & 7;
@@ -141,7 +205,7 @@ extern "C" int fm_pairwise_plan(int n, int cap, int32_t* lo, int32_t* len, uint8
 extern "C" int fm_motion_ref_scratch_bytes(int H, int W, int sbin, int nleaves, int blocks, size_t* bytes) {
   using namespace fm;
   FM_REQUIRE(H >= 1 && W >= 1 && sbin >= 1 && nleaves >= 1 && blocks >= 1 && bytes, "fm_motion_ref_scratch_bytes: bad args");
-  *bytes = (size_t)blocks * ((size_t)(H / sbin) * (W / sbin) + nleaves) * (sbin == 1 ? 4 : 8);
+  *bytes = (size_t)blocks * (2 * (size_t)(H / sbin) * (W / sbin) + nleaves) * (sbin == 1 ? 4 : 8);
   return FM_OK;
 }
 
@@ -161,11 +225,15 @@ extern "C" int fm_motion_ref(const uint8_t* frames, int T, int H, int W, int sbi
   if (sbin == 1) {
     MotionRefParams<float> p{frames, prev_frame, ormask, T, H, W, sbin, Lyb, Lxb, rows, prev_frame ? 0 : 1,
                              leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<float*>(scratch), out};
-    motion_ref_kernel<float><<<grid, MR_THREADS, 0, st>>>(p);
+    motion_ref_kernel<float, false><<<grid, MR_THREADS, 0, st>>>(p);
   } else {
     MotionRefParams<double> p{frames, prev_frame, ormask, T, H, W, sbin, Lyb, Lxb, rows, prev_frame ? 0 : 1,
                               leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<double*>(scratch), out};
-    motion_ref_kernel<double><<<grid, MR_THREADS, 0, st>>>(p);
+    const bool aligned = sbin >= 3 && W % 4 == 0 &&
+                         ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(prev_frame) |
+                           reinterpret_cast<uintptr_t>(ormask)) % 4 == 0);
+    if (aligned) motion_ref_kernel<double, true><<<grid, MR_THREADS, 0, st>>>(p);
+    else motion_ref_kernel<double, false><<<grid, MR_THREADS, 0, st>>>(p);
   }
   FM_LAUNCH_CHECK();
   return FM_OK;
