@@ -68,3 +68,16 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_header_is_plain_c():
+    """the boundary is a C ABI: the header must compile as C99 (no C++ types, `extern "C"` guarded)"""
+    import subprocess
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "hdr.c")
+        with open(src, "w") as f:
+            f.write('#include "facemap_b200.h"\nint main(void) { return fm_version(); }\n')
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                               "-I", os.path.join(ROOT, "include"), src])
