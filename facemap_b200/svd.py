@@ -570,6 +570,15 @@ def projection_rows_per_batch(p, k, budget_bytes=6 << 30):
 
 
 MOTION_REF_BLOCKS = 148 * 4
+MOTION_REF_SCRATCH_MAX = 1 << 30        # bytes of per-block scratch of fm_motion_ref per view
+
+
+def motion_ref_blocks(npix, nleaves, sbin):
+    """Persistent blocks of fm_motion_ref for one view: as many as fill the machine, fewer when the per-block
+    scratch (two rows of binned values + the leaf sums, fm_motion_ref_scratch_bytes) would pass the budget —
+    a 1280x1024 view at sbin 1 needs 10.5 MB per block."""
+    per_block = (2 * int(npix) + int(nleaves)) * (4 if sbin == 1 else 8)
+    return int(max(8, min(MOTION_REF_BLOCKS, MOTION_REF_SCRATCH_MAX // per_block)))
 
 
 def motion_needs_reference(sbin, npix):
@@ -637,8 +646,10 @@ class Stage3:
         if self.ref_views:
             self.Eref = torch.zeros((self.nv, self.n_out), dtype=torch.float64, device=device)
             self.ref_plan = {v: K.pairwise_plan(geo.npix_v[v], device) for v in self.ref_views}
+            self.ref_blocks = {v: motion_ref_blocks(geo.npix_v[v], self.ref_plan[v][0].numel(), geo.sbin)
+                               for v in self.ref_views}
             self.ref_scratch = {v: K.motion_ref_scratch(geo.Ly[v], geo.Lx[v], geo.sbin, self.ref_plan[v][0].numel(),
-                                                        MOTION_REF_BLOCKS, device) for v in self.ref_views}
+                                                        self.ref_blocks[v], device) for v in self.ref_views}
             self.ref_last = {v: None for v in self.ref_views}
 
     # ---- bin phase -------------------------------------------------------------------------------
@@ -693,7 +704,7 @@ class Stage3:
                             self.E_roi[j, o:o + rows] = roi_e[v][q, :rows]
                 for v in self.ref_views:
                     if rows > 0:
-                        K.motion_ref(frames[v], geo.sbin, self.ref_plan[v], self.ref_scratch[v], MOTION_REF_BLOCKS,
+                        K.motion_ref(frames[v], geo.sbin, self.ref_plan[v], self.ref_scratch[v], self.ref_blocks[v],
                                      self.Eref[v, o:o + rows], prev_frame=self.ref_last[v] if have else None,
                                      ormask=None if self.fullres is None else self.fullres.ormask[v])
                     self.ref_last[v] = frames[v][-1].clone()

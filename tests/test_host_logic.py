@@ -168,3 +168,12 @@ def test_motion_needs_reference_rule():
     assert svd.motion_needs_reference(3, 100) and svd.motion_needs_reference(12, 332) and svd.motion_needs_reference(7, 560)
     assert not svd.motion_needs_reference(1, 65793) and svd.motion_needs_reference(1, 65794)      # 255 * p >= 2^24
     assert svd.stage1_uses_reference(7) and not svd.stage1_uses_reference(8) and not svd.stage1_uses_reference(1)
+
+
+def test_motion_ref_block_count_respects_scratch_budget():
+    from facemap_b200 import svd
+
+    assert svd.motion_ref_blocks(34080, 400, 3) == svd.MOTION_REF_BLOCKS                  # 640x480 at sbin 3: 548 KB per block
+    big = svd.motion_ref_blocks(1280 * 1024, 13000, 1)                                    # C4 at sbin 1: 10.5 MB per block
+    assert 8 <= big < svd.MOTION_REF_BLOCKS and big * (2 * 1280 * 1024 + 13000) * 4 <= svd.MOTION_REF_SCRATCH_MAX
+    assert svd.motion_ref_blocks(10 ** 9, 10 ** 7, 7) == 8                                # never below 8 blocks
