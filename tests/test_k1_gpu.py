@@ -227,3 +227,22 @@ def test_motion_ref_matches_numpy_bitwise(cuda_device, T, H, W, sbin):
         rows = K.motion_ref(torch.from_numpy(frames[1:]).to(dev), sbin, plan, scratch, blocks, out2,
                             prev_frame=torch.from_numpy(frames[0]).to(dev), ormask=d_mask)
         assert rows == T and np.array_equal(out2.cpu().numpy(), ref.astype(np.float64))
+
+
+def test_motion_ref_full_resolution_view_with_budgeted_blocks(cuda_device):
+    """a 1280x1024 view at sbin 1 (BASELINE configs[3]) with the block count svd.motion_ref_blocks picks under its
+    1 GiB scratch budget: still the reference's float32 sums, bit for bit"""
+    from facemap_b200 import kernels as K, svd
+
+    dev = cuda_device
+    T, H, W = 4, 1024, 1280
+    frames = np.random.RandomState(5).randint(0, 256, size=(T + 1, H, W)).astype(np.uint8)
+    plan = K.pairwise_plan(H * W, dev)
+    blocks = svd.motion_ref_blocks(H * W, plan[0].numel(), 1)
+    assert 8 <= blocks < svd.MOTION_REF_BLOCKS
+    scratch = K.motion_ref_scratch(H, W, 1, plan[0].numel(), blocks, dev)
+    assert scratch.numel() <= svd.MOTION_REF_SCRATCH_MAX
+    ref = np.abs(np.diff(orc.bin_frames(frames, 1, H, W), axis=0)).sum(axis=-1)
+    out = torch.zeros(T, dtype=torch.float64, device=dev)
+    assert K.motion_ref(torch.from_numpy(frames).to(dev), 1, plan, scratch, blocks, out) == T
+    assert np.array_equal(out.cpu().numpy(), ref.astype(np.float64))
