@@ -386,8 +386,8 @@ class _DecodeCache:
 
 class VideoFileSource(FrameSource):
     """filenames: 2-D list [[view0, view1, ...] per sequential block] (facemap/process.py:652-654).
-    Decoding stays on the host (OpenCV); decode failures repeat the previous frame like
-    utils.get_frames (facemap/utils.py:545-547).
+    Decoding stays on the host (OpenCV); a decode failure repeats the previous frame once and leaves the rest
+    of that file's range zero like utils.get_frames (facemap/utils.py:541-548; see `_read`).
 
     When the frames a pass needs fit in HBM (`plan_access`), every frame is decoded ONCE by a pool of decoder
     threads straight into HBM-resident views (`_DecodeCache`); the reference decodes each frame up to three
@@ -481,14 +481,19 @@ class VideoFileSource(FrameSource):
             first = int(lo - self.cumframes[blk])
             if int(cap.get(cv2.CAP_PROP_POS_FRAMES)) != first:
                 cap.set(cv2.CAP_PROP_POS_FRAMES, first)
-            for _ in range(hi - lo):
+            end = k + (hi - lo)
+            while k < end:
                 ok, frame = cap.read()
-                if ok:
-                    out[k] = frame if frame.ndim == 2 else cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
-                elif k > 0:
-                    out[k] = out[k - 1]
-                else:
-                    out[k] = 0
+                if not ok:
+                    # utils.py:541-548: the frame that fails to decode repeats its predecessor (a zero frame when
+                    # it is the first of the request), reading of this file then stops and the rest of its range
+                    # keeps the zeros of the freshly allocated chunk buffer (process.py:46-50)
+                    print("img load failed, replacing with prev..")
+                    out[k] = out[k - 1] if k > 0 else 0
+                    out[k + 1:end] = 0
+                    k = end
+                    break
+                out[k] = frame if frame.ndim == 2 else cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
                 k += 1
         return out
 

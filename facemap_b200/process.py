@@ -1,8 +1,8 @@
 """Drop-in for `facemap.process.run` (reference: /root/reference/facemap/process.py:638-903) on the
 B200 kernels.  Same signature, same config precedence (parent > proc > kwargs, :676-708), same
 `*_proc.npy` dict (keys/dtypes/shapes of :859-892) and the same quirks, written by
-`save` (:605-635).  Only the SVD/motion outputs are produced; pupil / blink / running ROIs are
-outside this library's scope and come back empty.
+`save` (:605-635).  The pupil / blink / running ROIs of `rois` (rind 0, 2, 3) are processed on the same frame
+sweep (facemap_b200/fullres.py); keypoints and the GUI's own post-processing are not part of this path.
 
 Beyond the reference signature, `filenames` may also be a FrameSource or a list of uint8
 [T,H,W] arrays/tensors (one per simultaneous view), and `process_source` returns the dict without

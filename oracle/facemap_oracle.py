@@ -138,6 +138,43 @@ class ArrayVideo:
         return [v[a:b + 1] for v in self.views]
 
 
+def read_frames(containers, cumframes, shapes, t0, n):
+    """utils.get_frames (facemap/utils.py:522-553) on duck-typed captures `containers[block][view]`
+    (`.get(POS_FRAMES)`, `.set`, `.read`), into freshly zeroed chunk buffers like imall_init (process.py:46-50).
+
+    Restated behaviours: the request is clamped to the video and re-expanded to a contiguous range (:523-525);
+    sequential files are stitched in order (:527-535); a frame that fails to decode takes the previous slot of the
+    buffer — slot -1, i.e. the still-zero LAST slot, when it is the very first of the request — and reading of that
+    file stops there, so the rest of its range keeps the buffer's zeros (:541-548); the buffers are cut to the
+    frames that exist (:551-553).  Returns one uint8 (T', H, W) array per view."""
+    import cv2
+
+    cumframes = np.asarray(cumframes).astype(int)
+    N = int(cumframes[-1])
+    a = max(0, min(N - 1, int(t0)))
+    b = max(0, min(N - 1, int(t0) + int(n) - 1))
+    cframes = np.arange(a, b + 1).astype(int)
+    ivids = (cframes[np.newaxis, :] >= cumframes[1:, np.newaxis]).sum(axis=0)
+    bufs = [np.zeros((int(n), h, w), np.uint8) for (h, w) in shapes]
+    nk = 0
+    for ii in range(len(shapes)):
+        nk = 0
+        for blk in np.unique(ivids):
+            cfr = cframes[ivids == blk]
+            start, count = int(cfr[0] - cumframes[blk]), int(cfr.size)
+            cap = containers[blk][ii]
+            if int(cap.get(cv2.CAP_PROP_POS_FRAMES)) != start:
+                cap.set(cv2.CAP_PROP_POS_FRAMES, start)
+            for fc in range(count):
+                ok, frame = cap.read()
+                if not ok:
+                    bufs[ii][nk + fc] = bufs[ii][nk + fc - 1]
+                    break
+                bufs[ii][nk + fc] = frame if frame.ndim == 2 else cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
+            nk += count
+    return [buf[:nk].copy() for buf in bufs]
+
+
 # ------------------------------------------------------------------------------------------
 # stage 1
 # ------------------------------------------------------------------------------------------

@@ -132,3 +132,93 @@ def test_decode_cache_equals_on_demand_decoding(cuda_device, avi_files):
     for key in ("avgframe", "avgmotion", "motion", "motMask", "movMask", "motSVD", "movSVD"):
         for x, y in zip(outs[0][key], outs[1][key]):
             assert np.array_equal(x, y), key
+
+
+class _FlakyCapture:
+    """cv2.VideoCapture duck type over an array whose decoder fails from frame `fail_from` on (a truncated file:
+    the header promises more frames than can be decoded)."""
+
+    def __init__(self, arr, fail_from=None):
+        self.arr, self.pos, self.fail_from = arr, 0, arr.shape[0] if fail_from is None else fail_from
+
+    def isOpened(self):
+        return True
+
+    def get(self, prop):
+        return {cv2.CAP_PROP_POS_FRAMES: self.pos, cv2.CAP_PROP_FRAME_COUNT: self.arr.shape[0],
+                cv2.CAP_PROP_FRAME_HEIGHT: self.arr.shape[1], cv2.CAP_PROP_FRAME_WIDTH: self.arr.shape[2]}.get(prop, 0.0)
+
+    def set(self, prop, value):
+        if prop == cv2.CAP_PROP_POS_FRAMES:
+            self.pos = int(value)
+        return True
+
+    def read(self):
+        if self.pos >= self.fail_from:
+            return False, None
+        f = self.arr[self.pos]
+        self.pos += 1
+        return True, np.repeat(f[:, :, None], 3, axis=2)
+
+    def release(self):
+        pass
+
+
+def _flaky_blocks():
+    rs = np.random.RandomState(4)
+    a = rs.randint(1, 256, size=(60, 12, 16)).astype(np.uint8)         # no zero pixels: a zero frame is a hole
+    b = rs.randint(1, 256, size=(50, 12, 16)).astype(np.uint8)
+    return [(a, 37), (b, None)]                                        # block 0 stops decoding at frame 37 of 60
+
+
+_FLAKY_REQUESTS = [(0, 30), (20, 30), (36, 10), (37, 10), (45, 10), (30, 60), (55, 20), (100, 30), (-5, 20)]
+
+
+def test_decode_failure_semantics_match_get_frames():
+    """a frame that fails to decode repeats its predecessor once, the rest of that file's range stays zero, the next
+    sequential file is read normally (facemap/utils.py:536-553) — against the oracle's restatement of get_frames"""
+    from facemap_b200.frames import VideoFileSource
+
+    blocks = _flaky_blocks()
+
+    class Src(VideoFileSource):
+        def _open(self):
+            return [[_FlakyCapture(arr, ff)] for arr, ff in blocks]
+
+    src = Src([["a.avi"], ["b.avi"]])
+    try:
+        assert src.nframes == 110 and src.block_frames == [60, 50]
+        stage = np.full((64, 12, 16), 7, np.uint8)                      # a reused (dirty) staging buffer
+        for t0, n in _FLAKY_REQUESTS:
+            want = orc.read_frames([[_FlakyCapture(arr, ff)] for arr, ff in blocks], src.cumframes, [(12, 16)], t0, n)[0]
+            a, b = src.clamp(t0, t0 + n)
+            got = src._read(0, a, b)
+            assert got.shape == want.shape and np.array_equal(got, want), (t0, n)
+            got2 = src._read(0, a, b, out=stage[:b - a])
+            assert np.array_equal(got2, want), (t0, n)
+        whole = src._read(0, 0, 110)
+        assert np.array_equal(whole[:37], blocks[0][0][:37]) and np.array_equal(whole[37], blocks[0][0][36])
+        assert not whole[38:60].any() and np.array_equal(whole[60:], blocks[1][0])
+    finally:
+        src.close()
+
+
+def test_oracle_read_frames_is_the_reference_get_frames():
+    """pins oracle.read_frames to the unmodified utils.get_frames (only where /root/reference exists)"""
+    from oracle import ref_harness
+
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree not present on this machine")
+    _, ref_utils = ref_harness._import_reference()
+    blocks = _flaky_blocks()
+    cum = np.array([0, 60, 110])
+    import contextlib
+    import io
+
+    for t0, n in _FLAKY_REQUESTS:
+        imall = [np.zeros((n, 12, 16), np.uint8)]
+        caps = [[_FlakyCapture(arr, ff)] for arr, ff in blocks]
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref_utils.get_frames(imall, caps, np.arange(t0, t0 + n), cum)
+        want = orc.read_frames([[_FlakyCapture(arr, ff)] for arr, ff in blocks], cum, [(12, 16)], t0, n)[0]
+        assert imall[0].shape == want.shape and np.array_equal(imall[0], want), (t0, n)
