@@ -3,6 +3,7 @@
 // Reference seams: facemap/utils.py:751-776 (svdecon) -> sklearn/decomposition/_pca.py:733-758,
 // sklearn/utils/extmath.py:924-982 (svd_flip); facemap/process.py:218-222, 479-483 (ROI slices).
 #include "common.cuh"
+#include "slice_math.cuh"
 
 namespace fm {
 
@@ -314,6 +315,51 @@ extern "C" int fm_split_lo(const float* X, int64_t ldx, int rows, int cols, floa
   FM_REQUIRE(X && lo && rows >= 1 && cols >= 1 && ldx >= cols && ldlo >= cols, "fm_split_lo: bad args");
   dim3 grid((unsigned)cdiv(cdiv(cols, 4), 256), (unsigned)(rows < 65535 ? rows : 65535));
   split_lo_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, ldx, rows, cols, lo, ldlo);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+// ---- 8-bit row slices of a Gram operand (svd.sliced_gram) -----------------------------------------
+// One block per row: |max| of the row -> its slice grid -> three planes (slice_math.cuh).  The row is read twice
+// (the second time from L2); pad columns [ncols, lds) are zeroed so the planes are clean TMA operands.
+namespace fm {
+__global__ void __launch_bounds__(256) slice_rows_kernel(const float* __restrict__ X, int64_t ldx, int64_t ncols,
+                                                         float* __restrict__ S0, float* __restrict__ S1,
+                                                         float* __restrict__ S2, int64_t lds) {
+  __shared__ float sh[8];
+  __shared__ int s_ex;
+  const float* row = X + (size_t)blockIdx.x * ldx;
+  float amax = 0.0f;
+  for (int64_t i = threadIdx.x; i < ncols; i += 256) amax = fmaxf(amax, fabsf(row[i]));
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = sh[0];
+    for (int i = 1; i < 8; ++i) v = fmaxf(v, sh[i]);
+    s_ex = slice_exponent(v);
+  }
+  __syncthreads();
+  const SliceGrid g = slice_grid(s_ex);
+  float* o0 = S0 + (size_t)blockIdx.x * lds;
+  float* o1 = S1 + (size_t)blockIdx.x * lds;
+  float* o2 = S2 + (size_t)blockIdx.x * lds;
+  for (int64_t i = threadIdx.x; i < lds; i += 256) {
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+    if (i < ncols) slice3(row[i], g, a0, a1, a2);
+    o0[i] = a0;
+    o1[i] = a1;
+    o2[i] = a2;
+  }
+}
+}  // namespace fm
+
+extern "C" int fm_slice_rows(const float* X, int64_t ldx, int rows, int64_t ncols, float* S0, float* S1, float* S2,
+                             int64_t lds, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(X && S0 && S1 && S2 && rows >= 0 && ncols >= 1 && ldx >= ncols && lds >= ncols, "fm_slice_rows: bad args");
+  if (rows == 0) return FM_OK;
+  slice_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, ldx, ncols, S0, S1, S2, lds);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }

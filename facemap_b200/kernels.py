@@ -121,6 +121,24 @@ def split_lo(X, out=None):
     return lo
 
 
+def slice_rows(X, out=None):
+    """Three 8-bit row-scaled slices (S0, S1, S2) of X, S0 + S1 + S2 == X up to 2^-24 of each row's largest
+    magnitude (fm_slice_rows).  `out`: optional triple of [rows, cols] matrices sharing one row pitch."""
+    _need(X, torch.float32, "X", 2)
+    rows, cols = X.shape
+    planes = tuple(alloc_matrix(rows, cols, X.device) for _ in range(3)) if out is None else tuple(out)
+    lds = planes[0].stride(0)
+    for pl in planes:
+        _need(pl, torch.float32, "slice", 2)
+        if tuple(pl.shape) != (rows, cols) or pl.stride(1) != 1 or pl.stride(0) != lds:
+            raise FacemapB200Error("slice_rows: planes must have X's shape and one common row pitch")
+    if X.stride(1) != 1:
+        raise FacemapB200Error("slice_rows: X must be row-major")
+    check(_lib.load().fm_slice_rows(ptr(X), X.stride(0), rows, cols, ptr(planes[0]), ptr(planes[1]), ptr(planes[2]),
+                                    lds, _stream()), "fm_slice_rows")
+    return planes
+
+
 def gemm_tn(A, B, C_out=None, *, rscale=None, rbias=None, ksplit=1, workspace=None, upper_only=False, impl=0,
             B_lo=None, A_lo=None):
     """C[M,N] = rscale[m] * (A[M,K] @ B[N,K]^T) + rbias[m]; both operands K-contiguous float32.

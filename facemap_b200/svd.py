@@ -151,7 +151,7 @@ def get_solver(device):
 class SvdWorkspace:
     """Reusable device buffers for the Gram -> eigensolve -> left-vector sequence."""
 
-    def __init__(self, device, eig_fp32=False, gemm_impl=0, timer=None):
+    def __init__(self, device, eig_fp32=False, gemm_impl=0, timer=None, merge_gram=None):
         self.device = device
         self.timer = timer if timer is not None else StageTimer(enabled=False)
         self.solver = get_solver(device)
@@ -162,6 +162,12 @@ class SvdWorkspace:
         self.proj_impl = int(_os.environ.get("FM_PROJ_IMPL", gemm_impl))
         self.eig_fp32 = eig_fp32
         self.gemm_impl = gemm_impl
+        # merge Gram: "tf32x3" (one 3xTF32 GEMM, float64-reduced partials) or "sliced" (sliced_gram: 8-bit row
+        # slices, leading product exact; resolves the tail singular values to float64-Gram accuracy at ~4x the
+        # merge-Gram time)
+        self.merge_gram = _os.environ.get("FM_MERGE_GRAM", "tf32x3") if merge_gram is None else merge_gram
+        if self.merge_gram not in ("tf32x3", "sliced"):
+            raise FacemapB200Error(f"unknown merge_gram {self.merge_gram!r}")
         self._ws = None
         self._bufs = {}
 
@@ -228,12 +234,58 @@ def centred_gram(ws: SvdWorkspace, X, timer, label, out=None):
     return mean, G
 
 
+SLICE_KBLOCKS = 15     # k-blocks of 16 per exact partial of the top-slice product: 2^16 * 240 < 2^24
+
+
+def sliced_gram(ws: SvdWorkspace, X, timer, label, out=None):
+    """centred_gram with the rows of X cut into three 8-bit slices X = S0 + S1 + S2 (fm_slice_rows):
+
+        pass A   S0 S0^T                       K partials of <= 240: every product and every partial sum is an
+                                               integer (times a power of two) below 2^24, so the tensor cores'
+                                               truncating float32 accumulation never rounds — exact
+        pass B   S0 S1^T + S1 S0^T + S1 S1^T   2^-8 of A:  the 3xTF32 kernel with (lo, hi) = (S0, S1)
+        pass C   ... with (S0, S2)             2^-16 of A
+        pass D   ... with (S1, S2)             2^-24 of A  (S2 S2^T enters twice: 2^-32)
+
+    all into one stack of partials that fm_gram_assemble sums in float64.  What is left is the float32 rounding of
+    passes B-D (5e-8 of 2^-8 of an entry) and the 2^-25 representation error of the slices, instead of 5e-8 of the
+    entry itself: scripts/model_accuracy.py (`passesm`) puts the 500th singular value of the merge at 2e-5 of the
+    exact one where the one-GEMM Gram gives 1e-3.  Pass A runs on the same kernel with an all-zero lo plane."""
+    n, p = X.shape
+    with timer(label + ".colmean"):
+        mean = K.row_means(X)
+    with timer(label + ".gram.split"):
+        S0, S1, S2 = K.slice_rows(X, out=tuple(ws.matrix(f"gram.slice{d}", n, p) for d in range(3)))
+        Z = ws.matrix("gram.zero", n, p)
+        Z.zero_()
+    ks_a = max(1, math.ceil(math.ceil(p / 16) / SLICE_KBLOCKS))
+    mt, nt = math.ceil(n / 128), math.ceil(n / 256)
+    tiles = sum(1 for i in range(mt) for j in range(nt) if (j + 1) * 256 - 1 >= i * 128)
+    ks_f = _fill_ksplit(tiles, p)
+    part = ws.workspace(ks_a + 3 * ks_f, n)
+    with timer(label + ".gram.mma"):
+        at = 0
+        for hi, lo, ks in ((S0, Z, ks_a), (S1, S0, ks_f), (S2, S0, ks_f), (S2, S1, ks_f)):
+            if ks > 1:
+                K.gemm_tn(hi, hi, ksplit=ks, workspace=part[at:at + ks], upper_only=True, impl=0, B_lo=lo, A_lo=lo)
+            else:
+                K.gemm_tn(hi, hi, part[at], upper_only=True, impl=0, B_lo=lo, A_lo=lo)
+            at += ks
+    with timer(label + ".gram.assemble"):
+        G = K.gram_assemble(part, at, n, mean, p, True, out=out)
+    return mean, G
+
+
 def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
     """Centred Gram of the rows of X [n, p], eigensolve, top-k.  Returns (Wt [k, n], sval, rbias,
     rscale): the right singular vectors of X^T (sign-fixed), singular values, and the epilogue
     terms for the left-vector GEMM."""
     n, p = X.shape
-    mean, G = centred_gram(ws, X, timer, label)
+    # the sliced Gram needs the 128 x 256 chain kernel (K partition in 16-wide k-blocks): outputs wider than 128
+    if ws.merge_gram == "sliced" and n > 128 and ws.gram_impl == 0:
+        mean, G = sliced_gram(ws, X, timer, label)
+    else:
+        mean, G = centred_gram(ws, X, timer, label)
     with timer(label + ".syevd"):
         if ws.eig_fp32 or k == n:
             lam, nev = ws.solver.syevd(G, use_fp32=ws.eig_fp32), n

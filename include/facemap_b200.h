@@ -155,6 +155,18 @@ int fm_gemm_tn(const float* A, int64_t lda, const float* A_lo, int64_t lda_lo, c
 int fm_split_lo(const float* X, int64_t ldx, int rows, int cols, float* lo, int64_t ldlo, void* stream);
 
 /*
+ * Row-scaled 8-bit slices of a Gram operand: X[r,c] = S0 + S1 + S2 + rest, S_d = k_d * 2^(e_r - 8(d+1)) with k_d
+ * the nearest integer (signed digits, |k_0| <= 256, |k_1|, |k_2| <= 128), |rest| <= 2^(e_r - 25), 2^e_r bounding
+ * row r.  Slices are exact TF32 operands and products of two slices add up exactly in float32 over 240 terms, so
+ * fm_gemm_tn on (S0, S0) with K partials of <= 240 yields the leading part of X X^T without any rounding; the
+ * cross terms are 2^-8 and 2^-16 of it.  Used for the merge Gram of utils.svdecon (facemap/utils.py:751-776) when
+ * its small eigenvalues are wanted to float64 accuracy (svd.sliced_gram).
+ * All planes have row pitch lds >= ncols; pad columns are zeroed.
+ */
+int fm_slice_rows(const float* X, int64_t ldx, int rows, int64_t ncols, float* S0, float* S1, float* S2,
+                  int64_t lds, void* stream);
+
+/*
  * Reduction of split-K partials: C[m,n] = rscale[m] * sum_s part[s,m,n] + rbias[m], summed in
  * float64.  tcgen05 accumulates in float32 with truncation, so long contractions are cut into
  * short K chains (fm_gemm_tn with ksplit > 1) and reduced exactly here.

@@ -51,3 +51,19 @@ extern "C" float shim_median_from_hist(const unsigned* hist, float dark_offset) 
 extern "C" void shim_sym2x2_eig(double a, double b, double c, double* out) {
   fm::sym2x2_eig_lapack(a, b, c, out[0], out[1], out[2], out[3], out[4], out[5]);
 }
+
+// the row slicing of fm_slice_rows, run on the host exactly like one block of the kernel does
+#include "../../facemap_b200/csrc/slice_math.cuh"
+extern "C" void shim_slice_rows(const float* x, int rows, int cols, float* s0, float* s1, float* s2, int* ex_out) {
+  for (int r = 0; r < rows; ++r) {
+    float amax = 0.0f;
+    for (int c = 0; c < cols; ++c) amax = fmaxf(amax, fabsf(x[(size_t)r * cols + c]));
+    const int ex = fm::slice_exponent(amax);
+    ex_out[r] = ex;
+    const fm::SliceGrid g = fm::slice_grid(ex);
+    for (int c = 0; c < cols; ++c) {
+      const size_t i = (size_t)r * cols + c;
+      fm::slice3(x[i], g, s0[i], s1[i], s2[i]);
+    }
+  }
+}

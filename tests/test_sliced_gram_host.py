@@ -1,0 +1,147 @@
+"""svd.sliced_gram's orchestration (which planes go into which pass, K partition, the stack of partials) on the CPU,
+with NumPy stand-ins for the kernels that restate their contracts:
+
+  fm_slice_rows     the arithmetic of csrc/slice_math.cuh (pinned in tests/test_slice_math.py)
+  fm_gemm_tn        impl 0 with both lo planes: per K partial (16-wide k-blocks dealt as in the kernel) the float32
+                    value of  lo.hi^T + hi.lo^T + hi.hi^T  on the top 19 bits of every word; tiles entirely below the
+                    diagonal are left untouched (poisoned with NaN here)
+  fm_gram_assemble  float64 sum of the partials, upper triangle mirrored, minus p m m^T
+
+The stand-in REFUSES to round in pass A: it asserts that every partial of S0 S0^T is exactly representable in float32,
+which is the property the whole scheme rests on (a truncating accumulator never rounds an exact sum)."""
+import math
+import types
+
+import numpy as np
+import torch
+
+from facemap_b200 import svd
+
+
+def _trunc19(x):
+    return (np.ascontiguousarray(x, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+class FakeKernels:
+    def __init__(self):
+        self.calls = []
+
+    @staticmethod
+    def round_up(x, m):
+        return (int(x) + m - 1) // m * m
+
+    @staticmethod
+    def row_means(X):
+        return torch.from_numpy(X.numpy().astype(np.float64).mean(axis=1))
+
+    @staticmethod
+    def slice_rows(X, out):
+        A = X.numpy()
+        amax = np.abs(A).max(axis=1)
+        e = np.where(amax > 0, np.floor(np.log2(np.maximum(amax, 1e-300))) + 1, -100.0)
+        R = A.astype(np.float32)
+        for d, pl in enumerate(out):
+            q = np.exp2(e - 8 * (d + 1)).astype(np.float32)[:, None]
+            S = (np.rint(R / q) * q).astype(np.float32)
+            R = (R - S).astype(np.float32)
+            pl.copy_(torch.from_numpy(S))
+        return tuple(out)
+
+    def gemm_tn(self, A, B, C_out=None, *, ksplit=1, workspace=None, upper_only=False, impl=0, B_lo=None, A_lo=None,
+                rscale=None, rbias=None):
+        assert impl == 0 and A_lo is not None and B_lo is not None and upper_only and A is B and A_lo is B_lo
+        hi = _trunc19(A.numpy()).astype(np.float64)
+        lo = _trunc19(A_lo.numpy()).astype(np.float64)
+        n, K = hi.shape
+        assert n > 128, "the chain kernel serves outputs wider than 128 only"
+        KB = -(-K // 16)
+        ksplit = min(ksplit, -(-K // 32))
+        outs = [C_out] if ksplit == 1 else [workspace[z] for z in range(ksplit)]
+        if ksplit > 1:
+            assert workspace.shape[0] == ksplit and workspace.stride(0) == n * workspace.stride(1)
+        exact_pass = not lo.any()
+        for z, dst in enumerate(outs):
+            k0, k1 = 16 * ((z * KB) // ksplit), min(K, 16 * (((z + 1) * KB) // ksplit))
+            h, l = hi[:, k0:k1], lo[:, k0:k1]
+            P = l @ h.T + h @ l.T + h @ h.T
+            P32 = P.astype(np.float32)
+            if exact_pass:
+                assert k1 - k0 <= 240 and np.array_equal(P32.astype(np.float64), P), "pass A partial would round"
+            full = np.full((n, dst.shape[1]), np.nan, np.float32)
+            for i0 in range(0, n, 128):
+                for j0 in range(0, n, 256):
+                    if j0 + 255 >= i0:                                  # the kernel skips tiles below the diagonal
+                        full[i0:i0 + 128, j0:min(n, j0 + 256)] = P32[i0:i0 + 128, j0:min(n, j0 + 256)]
+            dst.copy_(torch.from_numpy(full))
+        self.calls.append((ksplit, exact_pass))
+
+    @staticmethod
+    def gram_assemble(part, ksplit, n, mean, ncols, upper_only, out=None):
+        P = part[:ksplit].numpy().astype(np.float64)[:, :, :n]
+        iu = np.triu_indices(n)
+        assert upper_only and np.isfinite(P[:, iu[0], iu[1]]).all(), "an upper-triangle entry was never written"
+        G = np.triu(P.sum(axis=0))
+        G = G + np.triu(G, 1).T
+        m = mean.numpy()
+        G -= ncols * np.outer(m, m)
+        G = torch.from_numpy(G)
+        if out is not None:
+            out.copy_(G)
+            return out
+        return G
+
+
+def _workspace():
+    ws = svd.SvdWorkspace.__new__(svd.SvdWorkspace)
+    ws.device, ws._ws, ws._bufs = torch.device("cpu"), None, {}
+    ws.timer = svd.StageTimer(enabled=False)
+    ws.gram_impl, ws.merge_gram = 0, "sliced"
+    return ws
+
+
+def test_sliced_gram_matches_float64_gram(monkeypatch):
+    fake = FakeKernels()
+    monkeypatch.setattr(svd, "K", fake)
+    rs = np.random.RandomState(0)
+    n, p = 300, 1000                                       # p not a multiple of 16 or 240: ragged last partial
+    base = rs.randn(40, p)
+    Y = (rs.randn(n, 40) @ base) * np.logspace(2, -3, n)[:, None] + 1e-4 * rs.randn(n, p)
+    Y = Y.astype(np.float32)
+    ws = _workspace()
+    X = ws.matrix("Y", n, p)
+    X.copy_(torch.from_numpy(Y))
+    mean, G = svd.sliced_gram(ws, X, ws.timer, "merge")
+    Y64 = Y.astype(np.float64)
+    m = Y64.mean(axis=1)
+    want = Y64 @ Y64.T - p * np.outer(m, m)
+    d = np.sqrt(np.diag(Y64 @ Y64.T))
+    err = np.abs(G.numpy() - want) / np.outer(d, d)
+    assert np.array_equal(mean.numpy(), m)
+    # what is left: the 2^-25 (of the row bound) representation error of the slices, unbiased, averaged over K = 1000
+    # (19 200 in the merge this serves), and the float32 rounding of passes B-D (2^-8 of an entry)
+    assert err.max() < 5e-8 and np.median(err) < 5e-9, (err.max(), np.median(err))
+    assert np.array_equal(G.numpy(), G.numpy().T)
+    ks_a = math.ceil(math.ceil(p / 16) / svd.SLICE_KBLOCKS)
+    assert [c[1] for c in fake.calls] == [True, False, False, False] and fake.calls[0][0] == ks_a
+    # the one-GEMM Gram of the product path, same stand-in arithmetic, for scale: ~1e-7
+    hi = _trunc19(Y).astype(np.float64)
+    lo = _trunc19(Y - _trunc19(Y)).astype(np.float64)
+    one = (lo @ hi.T + hi @ lo.T + hi @ hi.T).astype(np.float32).astype(np.float64) - p * np.outer(m, m)
+    err_one = np.abs(one - want) / np.outer(d, d)
+    print("sliced max/median", err.max(), np.median(err), "one GEMM max/median", err_one.max(), np.median(err_one))
+    assert np.median(err_one) > 3 * np.median(err)
+
+
+def test_gram_eig_routes_by_option(monkeypatch):
+    seen = []
+    monkeypatch.setattr(svd, "sliced_gram", lambda *a, **k: seen.append("sliced") or (_ for _ in ()).throw(StopIteration))
+    monkeypatch.setattr(svd, "centred_gram", lambda *a, **k: seen.append("plain") or (_ for _ in ()).throw(StopIteration))
+    ws = _workspace()
+    for merge_gram, n, impl, want in (("sliced", 3750, 0, "sliced"), ("sliced", 100, 0, "plain"),
+                                      ("sliced", 3750, 9, "plain"), ("tf32x3", 3750, 0, "plain")):
+        ws.merge_gram, ws.gram_impl = merge_gram, impl
+        try:
+            svd.gram_eig(ws, types.SimpleNamespace(shape=(n, 19200)), 500, ws.timer, True, "merge")
+        except StopIteration:
+            pass
+        assert seen[-1] == want, (merge_gram, n, impl)
