@@ -106,7 +106,7 @@ class _HostSink:
 
 def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD=True, device=None,
                    eig_fp32=False, gemm_impl=0, timing=None, dist=None, keep_on_device=False,
-                   overlap_stage3=True, gather_outputs=True, merge_gram=None):
+                   overlap_stage3=True, gather_outputs=True, gram_mode=None):
     """Run the three stages on a FrameSource and return the proc-dict entries this path owns.
 
     timing: optional dict that receives per-stage device times (ms) and wall times.
@@ -115,8 +115,8 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     overlap_stage3: run stage 3's bin/diff pass on a side stream underneath the stage-2 eigensolves
             when the frames are HBM-resident (svd.Stage3.start_early).
     dist:   optional facemap_b200.parallel.Shard (frame-range sharding across ranks).
-    merge_gram: "tf32x3" (default) or "sliced" — how the second-level Gram matrix is formed (svd.sliced_gram);
-            None reads the environment variable FM_MERGE_GRAM."""
+    gram_mode: "tf32x3" (default), "sliced_merge" or "sliced" — how the Gram matrices of the two SVD levels are
+            formed (svd.SvdWorkspace, svd.sliced_gram); None reads the environment variable FM_GRAM_MODE."""
     t_enter = time.perf_counter()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     _lib.require_device(dev.index or 0)
@@ -151,7 +151,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                 marks.append((name, time.perf_counter()))
 
     mark("start")
-    ws = svd.SvdWorkspace(dev, eig_fp32=eig_fp32, gemm_impl=gemm_impl, timer=timer, merge_gram=merge_gram)
+    ws = svd.SvdWorkspace(dev, eig_fp32=eig_fp32, gemm_impl=gemm_impl, timer=timer, gram_mode=gram_mode)
     source.plan_access(*svd.access_plan(source, dist), dev)
     mark("setup")
 

@@ -151,7 +151,7 @@ def get_solver(device):
 class SvdWorkspace:
     """Reusable device buffers for the Gram -> eigensolve -> left-vector sequence."""
 
-    def __init__(self, device, eig_fp32=False, gemm_impl=0, timer=None, merge_gram=None):
+    def __init__(self, device, eig_fp32=False, gemm_impl=0, timer=None, gram_mode=None):
         self.device = device
         self.timer = timer if timer is not None else StageTimer(enabled=False)
         self.solver = get_solver(device)
@@ -162,12 +162,13 @@ class SvdWorkspace:
         self.proj_impl = int(_os.environ.get("FM_PROJ_IMPL", gemm_impl))
         self.eig_fp32 = eig_fp32
         self.gemm_impl = gemm_impl
-        # merge Gram: "tf32x3" (one 3xTF32 GEMM, float64-reduced partials) or "sliced" (sliced_gram: 8-bit row
-        # slices, leading product exact; resolves the tail singular values to float64-Gram accuracy at ~4x the
-        # merge-Gram time)
-        self.merge_gram = _os.environ.get("FM_MERGE_GRAM", "tf32x3") if merge_gram is None else merge_gram
-        if self.merge_gram not in ("tf32x3", "sliced"):
-            raise FacemapB200Error(f"unknown merge_gram {self.merge_gram!r}")
+        # how the Gram matrices that feed the eigensolves are formed:
+        #   "tf32x3"        one 3xTF32 GEMM with float64-reduced K partials (centred_gram) — the measured default
+        #   "sliced_merge"  the second-level (merge) Gram from 8-bit row slices with an exact leading product
+        #   "sliced"        chunk Grams as well (sliced_gram; ~4x the Gram time, tail singular values to 1e-5)
+        self.gram_mode = _os.environ.get("FM_GRAM_MODE", "tf32x3") if gram_mode is None else gram_mode
+        if self.gram_mode not in ("tf32x3", "sliced_merge", "sliced"):
+            raise FacemapB200Error(f"unknown gram_mode {self.gram_mode!r}")
         self._ws = None
         self._bufs = {}
 
@@ -212,9 +213,19 @@ class SvdWorkspace:
         return buf[:need].view(max(rows, 1), ld)[:rows, :cols]
 
 
+def gram_is_sliced(ws: SvdWorkspace, label, n):
+    """sliced_gram serves the levels `ws.gram_mode` names; it needs the 128 x 256 chain kernel (K dealt in 16-wide
+    k-blocks), i.e. impl 0 and an output wider than 128."""
+    if ws.gram_mode == "tf32x3" or ws.gram_impl != 0 or n <= 128:
+        return False
+    return ws.gram_mode == "sliced" or label.endswith("merge")
+
+
 def centred_gram(ws: SvdWorkspace, X, timer, label, out=None):
     """mean over columns of every row of X [n, p] and the centred Gram  X X^T - p m m^T  (float64)."""
     n, p = X.shape
+    if gram_is_sliced(ws, label, n):
+        return sliced_gram(ws, X, timer, label, out=out)
     with timer(label + ".colmean"):
         mean = K.row_means(X)
     ksplit = _gram_ksplit(n, p)
@@ -249,8 +260,10 @@ def sliced_gram(ws: SvdWorkspace, X, timer, label, out=None):
 
     all into one stack of partials that fm_gram_assemble sums in float64.  What is left is the float32 rounding of
     passes B-D (5e-8 of 2^-8 of an entry) and the 2^-25 representation error of the slices, instead of 5e-8 of the
-    entry itself: scripts/model_accuracy.py (`passesm`) puts the 500th singular value of the merge at 2e-5 of the
-    exact one where the one-GEMM Gram gives 1e-3.  Pass A runs on the same kernel with an all-zero lo plane."""
+    entry itself.  scripts/model_accuracy.py (a NumPy model of this arithmetic, `passes` / `passesm`): with both
+    levels sliced every one of the 500 singular values lands within 1e-4 of the exact oracle's, motion and movie,
+    where the one-GEMM Gram leaves the tail at 1e-4 .. 4e-3.  Pass A runs on the same kernel with an all-zero lo
+    plane."""
     n, p = X.shape
     with timer(label + ".colmean"):
         mean = K.row_means(X)
@@ -281,11 +294,7 @@ def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
     rscale): the right singular vectors of X^T (sign-fixed), singular values, and the epilogue
     terms for the left-vector GEMM."""
     n, p = X.shape
-    # the sliced Gram needs the 128 x 256 chain kernel (K partition in 16-wide k-blocks): outputs wider than 128
-    if ws.merge_gram == "sliced" and n > 128 and ws.gram_impl == 0:
-        mean, G = sliced_gram(ws, X, timer, label)
-    else:
-        mean, G = centred_gram(ws, X, timer, label)
+    mean, G = centred_gram(ws, X, timer, label)
     with timer(label + ".syevd"):
         if ws.eig_fp32 or k == n:
             lam, nev = ws.solver.syevd(G, use_fp32=ws.eig_fp32), n

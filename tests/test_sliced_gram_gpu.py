@@ -83,8 +83,9 @@ def test_sliced_gram_against_float64(cuda_device):
     Y = _graded(rs, n, p)
     X = K.alloc_matrix(n, p, cuda_device)
     X.copy_(torch.from_numpy(Y))
-    ws = svd.SvdWorkspace(cuda_device, merge_gram="sliced")
+    ws = svd.SvdWorkspace(cuda_device, gram_mode="sliced")
     mean, G = svd.sliced_gram(ws, X, ws.timer, "merge")
+    ws.gram_mode = "tf32x3"
     mean1, G1 = svd.centred_gram(ws, X, ws.timer, "merge")
     Y64 = Y.astype(np.float64)
     m = Y64.mean(axis=1)
@@ -106,13 +107,15 @@ def test_pipeline_with_sliced_merge_gram_resolves_all_singular_values(cuda_devic
 
     H, W, N, sbin = 96, 128, 2600, 2
     v = SynthVideo(H, W, N, seed=5).all_frames()
-    o = orc.run_oracle([v], sbin=sbin, motSVD=True, movSVD=False, svd="exact")
+    o = orc.run_oracle([v], sbin=sbin, motSVD=True, movSVD=True, svd="exact")
     src = DeviceArraySource([torch.from_numpy(v).to(cuda_device)])
-    p = process.process_source(src, sbin=sbin, merge_gram="sliced")
-    p1 = process.process_source(src, sbin=sbin, merge_gram="tf32x3")
-    S_ref = o["motSv"].astype(np.float64)
-    rel = np.abs(p["motSv"].astype(np.float64) - S_ref) / S_ref
-    rel1 = np.abs(p1["motSv"].astype(np.float64) - S_ref) / S_ref
-    print("sliced", [float(rel[:k].max()) for k in (10, 100, 250, 500)], "one GEMM", [float(rel1[:k].max()) for k in (10, 100, 250, 500)])
-    assert rel.max() <= 1e-4
+    p = process.process_source(src, sbin=sbin, movSVD=True, gram_mode="sliced")
+    p1 = process.process_source(src, sbin=sbin, movSVD=True, gram_mode="tf32x3")
+    for sk in ("motSv", "movSv"):
+        S_ref = o[sk].astype(np.float64)
+        rel = np.abs(p[sk].astype(np.float64) - S_ref) / S_ref
+        rel1 = np.abs(p1[sk].astype(np.float64) - S_ref) / S_ref
+        print(sk, "sliced", [float(rel[:k].max()) for k in (10, 100, 250, 500)],
+              "one GEMM", [float(rel1[:k].max()) for k in (10, 100, 250, 500)])
+        assert rel.max() <= 1e-4, sk
     assert np.array_equal(p["motion"][0], o["motion"][0]) and np.array_equal(p["avgmotion"][0], o["avgmotion"][0])

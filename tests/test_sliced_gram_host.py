@@ -10,7 +10,6 @@ with NumPy stand-ins for the kernels that restate their contracts:
 The stand-in REFUSES to round in pass A: it asserts that every partial of S0 S0^T is exactly representable in float32,
 which is the property the whole scheme rests on (a truncating accumulator never rounds an exact sum)."""
 import math
-import types
 
 import numpy as np
 import torch
@@ -95,7 +94,7 @@ def _workspace():
     ws = svd.SvdWorkspace.__new__(svd.SvdWorkspace)
     ws.device, ws._ws, ws._bufs = torch.device("cpu"), None, {}
     ws.timer = svd.StageTimer(enabled=False)
-    ws.gram_impl, ws.merge_gram = 0, "sliced"
+    ws.gram_impl, ws.gram_mode = 0, "sliced"
     return ws
 
 
@@ -132,16 +131,27 @@ def test_sliced_gram_matches_float64_gram(monkeypatch):
     assert np.median(err_one) > 3 * np.median(err)
 
 
-def test_gram_eig_routes_by_option(monkeypatch):
-    seen = []
-    monkeypatch.setattr(svd, "sliced_gram", lambda *a, **k: seen.append("sliced") or (_ for _ in ()).throw(StopIteration))
-    monkeypatch.setattr(svd, "centred_gram", lambda *a, **k: seen.append("plain") or (_ for _ in ()).throw(StopIteration))
+def test_gram_routing_by_mode():
     ws = _workspace()
-    for merge_gram, n, impl, want in (("sliced", 3750, 0, "sliced"), ("sliced", 100, 0, "plain"),
-                                      ("sliced", 3750, 9, "plain"), ("tf32x3", 3750, 0, "plain")):
-        ws.merge_gram, ws.gram_impl = merge_gram, impl
-        try:
-            svd.gram_eig(ws, types.SimpleNamespace(shape=(n, 19200)), 500, ws.timer, True, "merge")
-        except StopIteration:
-            pass
-        assert seen[-1] == want, (merge_gram, n, impl)
+    for mode, label, n, impl, want in (("sliced", "stage2.merge", 3750, 0, True), ("sliced", "stage2.chunk", 999, 0, True),
+                                       ("sliced", "stage2.roi", 999, 0, True), ("sliced", "stage2.roi_merge", 100, 0, False),
+                                       ("sliced_merge", "stage2.merge", 3750, 0, True),
+                                       ("sliced_merge", "stage2.roi_merge", 500, 0, True),
+                                       ("sliced_merge", "stage2.chunk", 999, 0, False),
+                                       ("sliced", "stage2.merge", 3750, 9, False), ("tf32x3", "stage2.merge", 3750, 0, False)):
+        ws.gram_mode, ws.gram_impl = mode, impl
+        assert svd.gram_is_sliced(ws, label, n) is want, (mode, label, n, impl)
+
+
+def test_centred_gram_dispatches_to_sliced(monkeypatch):
+    fake = FakeKernels()
+    monkeypatch.setattr(svd, "K", fake)
+    ws = _workspace()
+    X = ws.matrix("Y", 200, 480)
+    X.copy_(torch.from_numpy(np.random.RandomState(3).randn(200, 480).astype(np.float32)))
+    out = torch.empty((200, 200), dtype=torch.float64)
+    mean, G = svd.centred_gram(ws, X, ws.timer, "stage2.chunk", out=out)
+    assert G is out and [c[1] for c in fake.calls] == [True, False, False, False]
+    x = X.numpy().astype(np.float64)
+    want = x @ x.T - 480 * np.outer(x.mean(axis=1), x.mean(axis=1))
+    assert np.abs(G.numpy() - want).max() < 1e-6 * np.abs(want).max()
