@@ -8,7 +8,8 @@
 //
 // Kernels in this file (fm_gemm_tn's `impl`):
 //   gemm_tf32x3_chain_kernel   impl 0, the product configuration: 128 x 256 tiles, two TMEM accumulators used
-//                              alternately in chains of 128 K, drained into float32 register accumulators
+//                              alternately in chains of 128 K, drained into float32 register accumulators;
+//                              impl 10 = the same kernel issuing ONE product per K step (exact-in-TF32 operands)
 //   gemm_tf32x3_kernel         one TMEM chain per launch (impl 9; also serves outputs <= 128 wide), tile variants 2..6
 //   gemm_tf32x3_pair_kernel    CTA pair, cta_group::2 (impl 7/8)
 //   gemm_fp32_ref_kernel       plain FFMA reference for the tests (impl 1)
@@ -339,7 +340,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // to CH*BK/8*3 = 48 accumulations caps that bias at ~2.6e-6 of an entry without any split-K workspace,
 // partial-sum traffic or reduction kernel.
 //   SPLIT_MODE 0: A and B split in the kernel; 1: B pre-split (TMA stages B_lo), A split in the kernel;
-//              2: both pre-split (no split work; the warps only drain).
+//              2: both pre-split (no split work; the warps only drain);
+//              3: single product — the operands are taken as they are (top 19 bits of every word), ONE MMA per
+//                 K step, no lo planes staged.  For operands that are exact in TF32 (the 8-bit slices of
+//                 fm_slice_rows, integer planes): with K partials short enough every sum is exact.
 // ---------------------------------------------------------------------------------------------
 template <int BK, int SPLIT_MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -405,12 +409,12 @@ gemm_tf32x3_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), (uint32_t)(Cfg::HI_BYTES + (SPLIT_MODE >= 1 ? BN * BK * 4 : 0) +
+        mbar_expect_tx(full_bar(s), (uint32_t)(Cfg::HI_BYTES + ((SPLIT_MODE == 1 || SPLIT_MODE == 2) ? BN * BK * 4 : 0) +
                                                (SPLIT_MODE == 2 ? BM * BK * 4 : 0)));
         tma_load_2d(stage, &tmA, full_bar(s), (kb0 + i) * BK, m0);
         tma_load_2d(stage + BM * BK * 4, &tmB, full_bar(s), (kb0 + i) * BK, n0);
         if constexpr (SPLIT_MODE == 2) tma_load_2d(stage + Cfg::HI_BYTES, &tmAlo, full_bar(s), (kb0 + i) * BK, m0);
-        if constexpr (SPLIT_MODE >= 1)
+        if constexpr (SPLIT_MODE == 1 || SPLIT_MODE == 2)
           tma_load_2d(stage + Cfg::HI_BYTES + BM * BK * 4, &tmBlo, full_bar(s), (kb0 + i) * BK, n0);
       }
     }
@@ -428,7 +432,7 @@ gemm_tf32x3_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int j = 0; j < len; ++j, ++i) {
           const int s = i % STAGES;
           const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-          mbar_wait(SPLIT_MODE == 2 ? full_bar(s) : split_bar(s), ph);
+          mbar_wait(SPLIT_MODE >= 2 ? full_bar(s) : split_bar(s), ph);
           tcgen05_fence_after();
           const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
           const uint64_t a_hi = make_desc_kmajor<BK>(stage);
@@ -438,9 +442,13 @@ gemm_tf32x3_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);
-            umma_tf32(acc, a_lo + adv, b_hi + adv, IDESC, (j > 0 || k > 0) ? 1u : 0u);
-            umma_tf32(acc, a_hi + adv, b_lo + adv, IDESC, 1u);
-            umma_tf32(acc, a_hi + adv, b_hi + adv, IDESC, 1u);
+            if constexpr (SPLIT_MODE == 3) {
+              umma_tf32(acc, a_hi + adv, b_hi + adv, IDESC, (j > 0 || k > 0) ? 1u : 0u);
+            } else {
+              umma_tf32(acc, a_lo + adv, b_hi + adv, IDESC, (j > 0 || k > 0) ? 1u : 0u);
+              umma_tf32(acc, a_hi + adv, b_lo + adv, IDESC, 1u);
+              umma_tf32(acc, a_hi + adv, b_hi + adv, IDESC, 1u);
+            }
           }
           tcgen05_commit(empty_bar(s));
         }
@@ -472,7 +480,7 @@ gemm_tf32x3_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(accempty_bar(buf));
     };
-    if constexpr (SPLIT_MODE == 2) {
+    if constexpr (SPLIT_MODE >= 2) {
       for (int c = 0; c < nchains; ++c) drain(c);
     } else {
       for (int i = 0; i < nkb; ++i) {
@@ -919,7 +927,7 @@ static int launch_chain(const float* A, int64_t lda, const float* B, int64_t ldb
   if ((rc = make_map(&tb, B, ldb, p.N, p.K, BN, BK)) != FM_OK) return rc;
   tblo = tb;
   talo = ta;
-  if (SPLIT_MODE >= 1 && (rc = make_map(&tblo, B_lo, ldb_lo, p.N, p.K, BN, BK)) != FM_OK) return rc;
+  if ((SPLIT_MODE == 1 || SPLIT_MODE == 2) && (rc = make_map(&tblo, B_lo, ldb_lo, p.N, p.K, BN, BK)) != FM_OK) return rc;
   if (SPLIT_MODE == 2 && (rc = make_map(&talo, A_lo, lda_lo, p.M, p.K, BM, BK)) != FM_OK) return rc;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -986,7 +994,7 @@ extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* A_lo, int64_
     FM_LAUNCH_CHECK();
     return FM_OK;
   }
-  FM_REQUIRE(impl == 0 || (impl >= 2 && impl <= 9), "fm_gemm_tn: unknown impl %d", impl);
+  FM_REQUIRE(impl == 0 || (impl >= 2 && impl <= 10), "fm_gemm_tn: unknown impl %d", impl);
   FM_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
              "fm_gemm_tn: TMA operands need 16-byte aligned bases and ld %% 4 == 0 (lda=%lld ldb=%lld)",
              (long long)lda, (long long)ldb);
@@ -1002,6 +1010,12 @@ extern "C" int fm_gemm_tn(const float* A, int64_t lda, const float* A_lo, int64_
     if (B_lo != nullptr && A_lo != nullptr) return launch_chain<16, 2>(A, lda, B, ldb, p, st, B_lo, ldb_lo, A_lo, lda_lo);
     if (B_lo != nullptr) return launch_chain<16, 1>(A, lda, B, ldb, p, st, B_lo, ldb_lo, nullptr, 0);
     return launch_chain<16, 0>(A, lda, B, ldb, p, st, nullptr, 0, nullptr, 0);
+  }
+  // 10: the chained kernel with ONE product per K step (operands exact in TF32: slices, integer planes)
+  if (impl == 10) {
+    FM_REQUIRE(N > 128 && A_lo == nullptr && B_lo == nullptr,
+               "fm_gemm_tn: impl 10 (single product) serves outputs wider than 128 and takes no lo planes");
+    return launch_chain<16, 3>(A, lda, B, ldb, p, st, nullptr, 0, nullptr, 0);
   }
   // 2..8: tile-shape / CTA-pair variants, 9: the single-accumulator kernel (one TMEM chain per launch);
   // kept for the tests and tuning runs

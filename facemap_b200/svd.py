@@ -169,6 +169,9 @@ class SvdWorkspace:
         self.gram_mode = _os.environ.get("FM_GRAM_MODE", "tf32x3") if gram_mode is None else gram_mode
         if self.gram_mode not in ("tf32x3", "sliced_merge", "sliced"):
             raise FacemapB200Error(f"unknown gram_mode {self.gram_mode!r}")
+        # pass A of sliced_gram on the one-product kernel (fm_gemm_tn impl 10) instead of the 3xTF32 kernel with a
+        # zero lo plane: a third of the MMAs, no zero plane to stage
+        self.sliced_single = _os.environ.get("FM_SLICED_SINGLE", "0") == "1"
         self._ws = None
         self._bufs = {}
 
@@ -263,14 +266,16 @@ def sliced_gram(ws: SvdWorkspace, X, timer, label, out=None):
     entry itself.  scripts/model_accuracy.py (a NumPy model of this arithmetic, `passes` / `passesm`): with both
     levels sliced every one of the 500 singular values lands within 1e-4 of the exact oracle's, motion and movie,
     where the one-GEMM Gram leaves the tail at 1e-4 .. 4e-3.  Pass A runs on the same kernel with an all-zero lo
-    plane."""
+    plane, or (ws.sliced_single) on its one-product instantiation, fm_gemm_tn impl 10."""
     n, p = X.shape
     with timer(label + ".colmean"):
         mean = K.row_means(X)
     with timer(label + ".gram.split"):
         S0, S1, S2 = K.slice_rows(X, out=tuple(ws.matrix(f"gram.slice{d}", n, p) for d in range(3)))
-        Z = ws.matrix("gram.zero", n, p)
-        Z.zero_()
+        Z = None
+        if not ws.sliced_single:
+            Z = ws.matrix("gram.zero", n, p)
+            Z.zero_()
     ks_a = max(1, math.ceil(math.ceil(p / 16) / SLICE_KBLOCKS))
     mt, nt = math.ceil(n / 128), math.ceil(n / 256)
     tiles = sum(1 for i in range(mt) for j in range(nt) if (j + 1) * 256 - 1 >= i * 128)
@@ -279,10 +284,11 @@ def sliced_gram(ws: SvdWorkspace, X, timer, label, out=None):
     with timer(label + ".gram.mma"):
         at = 0
         for hi, lo, ks in ((S0, Z, ks_a), (S1, S0, ks_f), (S2, S0, ks_f), (S2, S1, ks_f)):
+            impl = 0 if lo is not None else 10
             if ks > 1:
-                K.gemm_tn(hi, hi, ksplit=ks, workspace=part[at:at + ks], upper_only=True, impl=0, B_lo=lo, A_lo=lo)
+                K.gemm_tn(hi, hi, ksplit=ks, workspace=part[at:at + ks], upper_only=True, impl=impl, B_lo=lo, A_lo=lo)
             else:
-                K.gemm_tn(hi, hi, part[at], upper_only=True, impl=0, B_lo=lo, A_lo=lo)
+                K.gemm_tn(hi, hi, part[at], upper_only=True, impl=impl, B_lo=lo, A_lo=lo)
             at += ks
     with timer(label + ".gram.assemble"):
         G = K.gram_assemble(part, at, n, mean, p, True, out=out)

@@ -142,7 +142,8 @@ int fm_mean_update(float* acc, const long long* tsum, int64_t n, int sbin, int c
  *   upper_only != 0: tiles entirely below the diagonal are skipped (symmetric Gram).
  *   impl: 0 = tcgen05 3xTF32 (product path), 1 = plain FP32 FFMA reference kernel (validation);
  *         2..8 = tile-shape / CTA-pair (cta_group::2) variants of the tensor-core kernel kept for the
- *         tests and tuning runs (same results, see csrc/gemm_tf32x3.cu).
+ *         tests and tuning runs (same results, see csrc/gemm_tf32x3.cu); 10 = one product per K step on the
+ *         operands as they are (no split: for operands exact in TF32 such as fm_slice_rows planes; N > 128).
  *   ksplit > 1 with ldw: reduce with fm_splitk_reduce (general) or fm_gram_assemble (Gram).
  */
 int fm_gemm_tn(const float* A, int64_t lda, const float* A_lo, int64_t lda_lo, const float* B, int64_t ldb,

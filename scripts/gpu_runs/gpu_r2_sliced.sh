@@ -1,11 +1,14 @@
 #!/bin/bash
-# Round-2 opener: validate the sliced merge Gram (written without a GPU at the end of round 1) and time it.
+# Round-2 opener: validate the sliced Gram path (written without a GPU at the end of round 1) and time it.
 mkdir -p gpurun_out; cd "$(dirname "$0")/../.."
 FM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_sliced_gram_gpu.py -x -q -m gpu -s > gpurun_out/sliced_tests.log 2>&1; echo "sliced tests rc $?"
 tail -15 gpurun_out/sliced_tests.log
-FM_GRAM_MODE=sliced timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_sliced.json 2> gpurun_out/bench_sliced.err; echo "bench sliced rc $?"
-python - <<'PY'
-import json
-d = json.loads(open("gpurun_out/bench_sliced.json").read().strip().splitlines()[-1])
-print("sliced merge Gram: ms/step", d["ms_per_step"], {k: v for k, v in d["stage_ms"].items() if ".gram" in k})
+for mode in "tf32x3 0" "sliced_merge 0" "sliced 0" "sliced 1"; do
+  set -- $mode
+  FM_GRAM_MODE=$1 FM_SLICED_SINGLE=$2 timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_gram_$1_$2.json 2> gpurun_out/bench_gram_$1_$2.err; echo "bench $1 single=$2 rc $?"
+  python - "$1" "$2" <<'PY'
+import json, sys
+d = json.loads(open(f"gpurun_out/bench_gram_{sys.argv[1]}_{sys.argv[2]}.json").read().strip().splitlines()[-1])
+print(sys.argv[1], "single", sys.argv[2], "ms/step", round(d["ms_per_step"], 2), {k: round(v, 2) for k, v in d["stage_ms"].items() if ".gram" in k})
 PY
+done

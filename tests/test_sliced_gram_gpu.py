@@ -75,6 +75,30 @@ def test_top_slice_product_is_exact_on_the_tensor_cores(cuda_device):
         assert np.array_equal(got[z][:, :n][iu], want[iu]), z
 
 
+def test_single_product_kernel_equals_zero_lo_plane(cuda_device):
+    """fm_gemm_tn impl 10 (one MMA per K step) == impl 0 with all-zero lo planes, bit for bit, on slice operands"""
+    from facemap_b200 import kernels as K
+
+    rs = np.random.RandomState(4)
+    n, p = 520, 3000
+    X = K.alloc_matrix(n, p, cuda_device)
+    X.copy_(torch.from_numpy(_graded(rs, n, p)))
+    S0, S1, _ = K.slice_rows(X)
+    Z = K.alloc_matrix(n, p, cuda_device, zero=True)
+    for A, B, upper in ((S0, S0, True), (S0, S1, False)):
+        Zb = Z
+        a = torch.full((7, n, 544), float("nan"), dtype=torch.float32, device=cuda_device)
+        b = torch.full((7, n, 544), float("nan"), dtype=torch.float32, device=cuda_device)
+        K.gemm_tn(A, B, ksplit=7, workspace=a, upper_only=upper, impl=0, B_lo=Zb, A_lo=Z)
+        K.gemm_tn(A, B, ksplit=7, workspace=b, upper_only=upper, impl=10)
+        assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+        c = torch.empty((n, 544), dtype=torch.float32, device=cuda_device)
+        K.gemm_tn(A, B, c, impl=10)
+        want = A.cpu().numpy().astype(np.float64) @ B.cpu().numpy().astype(np.float64).T
+        got = c[:, :n].cpu().numpy().astype(np.float64)
+        assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+
+
 def test_sliced_gram_against_float64(cuda_device):
     from facemap_b200 import kernels as K, svd
 
@@ -96,6 +120,9 @@ def test_sliced_gram_against_float64(cuda_device):
     print("sliced max/median", err.max(), np.median(err), "one GEMM max/median", err1.max(), np.median(err1))
     assert err.max() < 3e-8 and np.median(err) < 3e-9
     assert np.median(err1) > 3 * np.median(err)
+    ws.gram_mode, ws.sliced_single = "sliced", True
+    _, G2 = svd.sliced_gram(ws, X, ws.timer, "merge")
+    assert torch.equal(G, G2)
 
 
 def test_pipeline_with_sliced_merge_gram_resolves_all_singular_values(cuda_device):

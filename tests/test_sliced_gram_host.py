@@ -48,9 +48,10 @@ class FakeKernels:
 
     def gemm_tn(self, A, B, C_out=None, *, ksplit=1, workspace=None, upper_only=False, impl=0, B_lo=None, A_lo=None,
                 rscale=None, rbias=None):
-        assert impl == 0 and A_lo is not None and B_lo is not None and upper_only and A is B and A_lo is B_lo
+        assert upper_only and A is B and A_lo is B_lo
+        assert (impl == 0 and A_lo is not None) or (impl == 10 and A_lo is None)
         hi = _trunc19(A.numpy()).astype(np.float64)
-        lo = _trunc19(A_lo.numpy()).astype(np.float64)
+        lo = _trunc19(A_lo.numpy()).astype(np.float64) if A_lo is not None else np.zeros_like(hi)
         n, K = hi.shape
         assert n > 128, "the chain kernel serves outputs wider than 128 only"
         KB = -(-K // 16)
@@ -94,7 +95,7 @@ def _workspace():
     ws = svd.SvdWorkspace.__new__(svd.SvdWorkspace)
     ws.device, ws._ws, ws._bufs = torch.device("cpu"), None, {}
     ws.timer = svd.StageTimer(enabled=False)
-    ws.gram_impl, ws.gram_mode = 0, "sliced"
+    ws.gram_impl, ws.gram_mode, ws.sliced_single = 0, "sliced", False
     return ws
 
 
@@ -129,6 +130,19 @@ def test_sliced_gram_matches_float64_gram(monkeypatch):
     err_one = np.abs(one - want) / np.outer(d, d)
     print("sliced max/median", err.max(), np.median(err), "one GEMM max/median", err_one.max(), np.median(err_one))
     assert np.median(err_one) > 3 * np.median(err)
+
+
+def test_sliced_gram_single_product_pass(monkeypatch):
+    fake = FakeKernels()
+    monkeypatch.setattr(svd, "K", fake)
+    ws = _workspace()
+    Y = np.random.RandomState(5).randn(200, 777).astype(np.float32)
+    X = ws.matrix("Y", 200, 777)
+    X.copy_(torch.from_numpy(Y))
+    _, G0 = svd.sliced_gram(ws, X, ws.timer, "merge")
+    ws.sliced_single = True
+    _, G1 = svd.sliced_gram(ws, X, ws.timer, "merge")
+    assert np.array_equal(G0.numpy(), G1.numpy()) and "gram.zero" in ws._bufs
 
 
 def test_gram_routing_by_mode():
