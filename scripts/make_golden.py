@@ -42,8 +42,17 @@ CASES = {
 }
 
 
+# BASELINE configs[0] at full size and configs[1] at the 20 000-frame size SURVEY.md §8(d) names for parity runs (the
+# reference needs ~12 min for the 100k-frame video and a prefix is not equivalent: chunk positions depend on N).
+# Generated only when named on the command line; replayed by opt-in tests (tests/test_large_golden_gpu.py).
+LARGE_CASES = {
+    "c1_s4": ([(256, 256, 0)], 2000, 4, True, False, None),
+    "c2_20k_s4": ([(480, 640, 0)], 20000, 4, True, False, None),
+}
+
+
 def case_videos(name):
-    views, N, *_ = CASES[name]
+    views, N, *_ = {**CASES, **LARGE_CASES}[name]
     return [SynthVideo(H, W, N, seed=seed).all_frames() for (H, W, seed) in views]
 
 
@@ -95,9 +104,8 @@ def main():
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
     only = sys.argv[1:]
-    for name, (views, N, sbin, mot, mov, rois) in CASES.items():
-        if only and name not in only:
-            continue
+    todo = dict(CASES) if not only else {k: v for k, v in {**CASES, **LARGE_CASES}.items() if k in only}
+    for name, (views, N, sbin, mot, mov, rois) in todo.items():
         vids = case_videos(name)
         out = {"case": np.array(name), "N": np.int64(N), "sbin": np.int64(sbin),
                "motSVD": np.bool_(mot), "movSVD": np.bool_(mov), "keep": np.int64(KEEP),

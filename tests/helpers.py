@@ -23,15 +23,23 @@ CASES = {
 }
 
 
+# BASELINE configs[0] at full size and configs[1] at SURVEY §8(d)'s 20 000-frame parity size: fixtures made by
+# `python scripts/make_golden.py c1_s4 c2_20k_s4`; not part of the default parametrisations (minutes of oracle time)
+LARGE_CASES = {
+    "c1_s4": ([(256, 256, 0)], 2000, 4, True, False, None),
+    "c2_20k_s4": ([(480, 640, 0)], 20000, 4, True, False, None),
+}
+
+
 def case_videos(name):
-    views, N = CASES[name][0], CASES[name][1]
+    views, N = {**CASES, **LARGE_CASES}[name][0], {**CASES, **LARGE_CASES}[name][1]
     return [SynthVideo(H, W, N, seed=seed).all_frames() for (H, W, seed) in views]
 
 
 def case_rois(name):
     import copy
 
-    return copy.deepcopy(CASES[name][5])
+    return copy.deepcopy({**CASES, **LARGE_CASES}[name][5])
 
 
 def frame_window(N):

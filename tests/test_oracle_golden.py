@@ -9,13 +9,13 @@ import numpy as np
 import pytest
 
 from oracle import facemap_oracle as orc
-from tests.helpers import CASES, KEEP, case_rois, case_videos, frame_window
+from tests.helpers import CASES, KEEP, LARGE_CASES, case_rois, case_videos, frame_window
 
 
 @pytest.mark.parametrize("mode", ["exact", "stock"])
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(CASES) + ["c1_s4"])          # c1_s4 = BASELINE configs[0] at full size
 def test_oracle_reproduces_reference(golden_dir, name, mode):
-    views, N, sbin, mot, mov, _ = CASES[name]
+    views, N, sbin, mot, mov, _ = {**CASES, **LARGE_CASES}[name]
     z = np.load(os.path.join(golden_dir, name + ".npz"))
     assert int(z["N"]) == N and int(z["sbin"]) == sbin
     o = orc.run_oracle(case_videos(name), sbin=sbin, motSVD=mot, movSVD=mov, rois=case_rois(name), svd=mode)
@@ -46,7 +46,7 @@ def test_oracle_reproduces_reference(golden_dir, name, mode):
             V, Vr = o[vk][i], z[f"{pre}{vk}_{i}"]
             if V.shape[0] == N:
                 assert np.abs(V[w][:, :lead] - Vr[:, :lead]).max() <= 2e-3 * np.abs(Vr[:, :lead]).max(), (vk, i)
-    if CASES[name][5] is not None:
+    if {**CASES, **LARGE_CASES}[name][5] is not None:
         k = 0
         for i, r in enumerate(o["rois"]):
             if r["rind"] == 1:
