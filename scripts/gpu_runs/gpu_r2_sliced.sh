@@ -3,6 +3,8 @@
 mkdir -p gpurun_out; cd "$(dirname "$0")/../.."
 FM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_sliced_gram_gpu.py -x -q -m gpu -s > gpurun_out/sliced_tests.log 2>&1; echo "sliced tests rc $?"
 tail -15 gpurun_out/sliced_tests.log
+FM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_large_golden_gpu.py -x -q -m gpu -s > gpurun_out/large_golden_tests.log 2>&1; echo "large golden tests rc $?"
+grep -E "S rel err|kres|passed|failed" gpurun_out/large_golden_tests.log | tail -8
 for mode in "tf32x3 0" "sliced_merge 0" "sliced 0" "sliced 1"; do
   set -- $mode
   FM_GRAM_MODE=$1 FM_SLICED_SINGLE=$2 timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_gram_$1_$2.json 2> gpurun_out/bench_gram_$1_$2.err; echo "bench $1 single=$2 rc $?"
