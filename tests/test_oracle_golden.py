@@ -65,3 +65,32 @@ def test_gram_backend_equals_exact_backend():
         assert np.allclose(s1, s2, rtol=1e-5)
         assert np.abs(np.abs(u1[:, :10]) - np.abs(u2[:, :10])).max() < 1e-4
         assert np.array_equal(np.sign(v1[np.arange(10), np.argmax(np.abs(v1[:10]), 1)]), np.ones(10))
+
+
+def test_stage1_means_at_the_c2_parity_size(golden_dir):
+    """BASELINE configs[1] at SURVEY §8(d)'s parity size (640x480, 20 000 frames, sbin 4): the oracle's avgframe /
+    avgmotion from the 1 000 sampled frames equal the unmodified reference's, bit for bit (the whole-run comparison
+    ran when the fixture was made, scripts/make_golden.py; replaying all of it takes minutes)."""
+    from facemap_b200.synth import SynthVideo
+
+    views, N, sbin, *_ = LARGE_CASES["c2_20k_s4"]
+    (H, W, seed), = views
+    z = np.load(os.path.join(golden_dir, "c2_20k_s4.npz"))
+    synth = SynthVideo(H, W, N, seed=seed)
+
+    def get(t0, n):
+        a = max(0, min(N - 1, t0))
+        b = max(0, min(N - 1, t0 + n - 1))
+        return [synth.frames(a, b + 1)]
+
+    import types
+
+    lazy = types.SimpleNamespace(N=N, Ly=[H], Lx=[W], block_frames=[N], get=get)
+    avgframe, avgmotion = orc.stage1_means(lazy, sbin)
+    assert np.array_equal(avgframe[0], z["stock/avgframe_0"]) and np.array_equal(avgmotion[0], z["stock/avgmotion_0"])
+    assert np.array_equal(z["stock/avgmotion_0"], z["exact/avgmotion_0"])
+    # what the reference itself resolves at this size: its randomized svdecon agrees with the exact one to 2e-5 on
+    # the first 100 singular values and is off by percents in the tail (SURVEY F3)
+    S1, S2 = z["stock/motSv"].astype(np.float64), z["exact/motSv"].astype(np.float64)
+    rel = np.abs(S1 - S2) / S2
+    assert rel[:100].max() < 5e-5 and rel[250:].max() > 1e-2
