@@ -176,6 +176,33 @@ def gemm_tn(A, B, C_out=None, *, rscale=None, rbias=None, ksplit=1, workspace=No
                                  _stream()), "fm_gemm_tn")
 
 
+def gemm_i8_tn(A, B, C_out=None, *, ksplit=1, workspace=None, upper_only=False):
+    """EXPERIMENTAL (fm_gemm_i8_tn): int32 C[M,N] = A[M,K] @ B[N,K]^T for uint8 / int8 operands, exact.
+    With ksplit > 1 the int32 partials go to `workspace` [ksplit, M, ldw]."""
+    for t, name in ((A, "A"), (B, "B")):
+        if t.dtype not in (torch.uint8, torch.int8) or t.dim() != 2 or t.stride(1) != 1 or not t.is_cuda:
+            raise FacemapB200Error(f"gemm_i8_tn: {name} must be a row-major CUDA uint8 / int8 matrix")
+    M, K = A.shape
+    N, K2 = B.shape
+    if K != K2:
+        raise FacemapB200Error("gemm_i8_tn: operands must be [M,K] and [N,K]")
+    ldc = ldw = 0
+    if ksplit > 1:
+        _need(workspace, torch.int32, "workspace", 3)
+        if workspace.shape[0] < ksplit or workspace.shape[1] != M or workspace.shape[2] < N or workspace.stride(2) != 1 \
+                or workspace.stride(0) != M * workspace.stride(1):
+            raise FacemapB200Error("gemm_i8_tn: workspace must be [ksplit, M, >=N] packed")
+        ldw = workspace.stride(1)
+    else:
+        _need(C_out, torch.int32, "C", 2)
+        if C_out.shape[0] < M or C_out.shape[1] < N or C_out.stride(1) != 1:
+            raise FacemapB200Error("gemm_i8_tn: C must be row-major [>=M, >=N] int32")
+        ldc = C_out.stride(0)
+    check(_lib.load().fm_gemm_i8_tn(ptr(A), A.stride(0), int(A.dtype == torch.int8), ptr(B), B.stride(0),
+                                    int(B.dtype == torch.int8), M, N, K, ptr(C_out), ldc, int(ksplit), ptr(workspace),
+                                    ldw, int(bool(upper_only)), _stream()), "fm_gemm_i8_tn")
+
+
 def splitk_reduce(workspace, ksplit, C_out, *, rscale=None, rbias=None):
     """C[m,n] = rscale[m] * sum_s workspace[s,m,n] + rbias[m], summed in float64."""
     _need(workspace, torch.float32, "workspace", 3)

@@ -151,6 +151,18 @@ int fm_gemm_tn(const float* A, int64_t lda, const float* A_lo, int64_t lda_lo, c
                const float* rscale, const float* rbias,
                int ksplit, float* workspace, int64_t ldw, int upper_only, int impl, void* stream);
 
+/*
+ * EXPERIMENTAL (compiles for sm_100a, not yet run on a GPU; nothing in the product path calls it):
+ * C[M,N] (int32) = A[M,K] . B[N,K]^T with 8-bit operands, K-contiguous, on tcgen05.mma kind::i8 with exact int32
+ * accumulation.  a_signed / b_signed: 0 = uint8, 1 = int8.  Row pitches in bytes, multiples of 16; 16-byte aligned
+ * bases.  ksplit > 1 writes raw int32 partials to workspace[ksplit, M, ldw] (sum them in int64); at most 32 768 K
+ * per partial (int32 range).  For the integer operands of this path — motion energies and block sums
+ * (facemap/process.py:34-43, 201-212) as u8 digit planes, masks as s8 slices — see DESIGN.md §7.2.
+ */
+int fm_gemm_i8_tn(const uint8_t* A, int64_t lda, int a_signed, const uint8_t* B, int64_t ldb, int b_signed,
+                  int M, int N, int K, int32_t* C, int64_t ldc, int ksplit, int32_t* workspace, int64_t ldw,
+                  int upper_only, void* stream);
+
 /* lo[r,c] = X[r,c] - tf32_trunc(X[r,c]): pre-computed second plane of a B operand that many GEMMs
  * reuse (pass it as B_lo above). */
 int fm_split_lo(const float* X, int64_t ldx, int rows, int cols, float* lo, int64_t ldlo, void* stream);

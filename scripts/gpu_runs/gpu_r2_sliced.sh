@@ -3,6 +3,8 @@
 mkdir -p gpurun_out; cd "$(dirname "$0")/../.."
 FM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_sliced_gram_gpu.py -x -q -m gpu -s > gpurun_out/sliced_tests.log 2>&1; echo "sliced tests rc $?"
 tail -15 gpurun_out/sliced_tests.log
+FM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gemm_i8_gpu.py -q -m gpu > gpurun_out/i8_tests.log 2>&1; echo "i8 gemm tests rc $?"
+tail -5 gpurun_out/i8_tests.log
 FM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_large_golden_gpu.py -x -q -m gpu -s > gpurun_out/large_golden_tests.log 2>&1; echo "large golden tests rc $?"
 grep -E "S rel err|kres|passed|failed" gpurun_out/large_golden_tests.log | tail -8
 for mode in "tf32x3 0" "sliced_merge 0" "sliced 0" "sliced 1"; do
