@@ -409,7 +409,8 @@ class VideoFileSource(FrameSource):
                 for cap in caps:
                     self.Ly.append(int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)))
                     self.Lx.append(int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)))
-            cum.append(cum[-1] + int(caps[0].get(cv2.CAP_PROP_FRAME_COUNT)))
+            # utils.py:583-590: the frame count of a block is the one its LAST view reports
+            cum.append(cum[-1] + int(caps[-1].get(cv2.CAP_PROP_FRAME_COUNT)))
         self.cumframes = np.array(cum).astype(int)
         self.nframes = int(cum[-1])
         self.block_frames = [int(x) for x in np.diff(self.cumframes)]
