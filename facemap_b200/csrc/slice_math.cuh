@@ -47,4 +47,25 @@ FM_HD inline void slice3(float a, const SliceGrid& g, float& s0, float& s1, floa
   s2 = rintf(r * g.i2) * g.q2;
 }
 
+// Integer digits for tcgen05 kind::i8 (fm_slice_rows_i8): with t = a * 2^(7 - ex), |t| < 128,
+//   a ~ 2^(ex - 7) * (q0 + q1 / 2^8 + q2 / 2^16),  q0 = floor(t) in [-128, 127] (s8),  q1 = floor of the next 8 bits
+//   in [0, 255] (u8),  q2 = the following 8 bits rounded to nearest in [0, 255] (u8), carries propagated upward.
+// 23 bits below the row bound, unbiased.  An entry within 2^-24 of the bound whose rounding would carry out of q0
+// saturates at 127 + 255/2^8 + 255/2^16.  Evaluated in double so that every step is exact (t - floor(t) of a small
+// negative float32 needs 25 bits).
+FM_HD inline void slice3_i8(float a, int ex, signed char& q0, unsigned char& q1, unsigned char& q2) {
+  const double t = (double)a * ldexp(1.0, 7 - ex);
+  double f0 = floor(t);
+  double r = (t - f0) * 256.0;                  // in [0, 256)
+  double f1 = floor(r);
+  r = (r - f1) * 256.0;                         // in [0, 256)
+  double f2 = rint(r);
+  if (f2 == 256.0) { f2 = 0.0; f1 += 1.0; }
+  if (f1 == 256.0) { f1 = 0.0; f0 += 1.0; }
+  if (f0 == 128.0) { f0 = 127.0; f1 = 255.0; f2 = 255.0; }
+  q0 = (signed char)(int)f0;
+  q1 = (unsigned char)(int)f1;
+  q2 = (unsigned char)(int)f2;
+}
+
 }  // namespace fm

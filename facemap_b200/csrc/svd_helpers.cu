@@ -364,6 +364,97 @@ extern "C" int fm_slice_rows(const float* X, int64_t ldx, int rows, int64_t ncol
   return FM_OK;
 }
 
+// ---- integer digit planes and their Gram assembly (EXPERIMENTAL, svd.i8_gram; see gemm_i8.cu) -------------
+namespace fm {
+// one block per row: |max| -> exponent -> s8 / u8 / u8 digit planes (slice_math.cuh:slice3_i8); pad bytes zeroed
+__global__ void __launch_bounds__(256) slice_rows_i8_kernel(const float* __restrict__ X, int64_t ldx, int64_t ncols,
+                                                            int8_t* __restrict__ Q0, uint8_t* __restrict__ Q1,
+                                                            uint8_t* __restrict__ Q2, int64_t ldq,
+                                                            int32_t* __restrict__ exps) {
+  __shared__ float sh[8];
+  __shared__ int s_ex;
+  const float* row = X + (size_t)blockIdx.x * ldx;
+  float amax = 0.0f;
+  for (int64_t i = threadIdx.x; i < ncols; i += 256) amax = fmaxf(amax, fabsf(row[i]));
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = sh[0];
+    for (int i = 1; i < 8; ++i) v = fmaxf(v, sh[i]);
+    s_ex = slice_exponent(v);
+    exps[blockIdx.x] = s_ex;
+  }
+  __syncthreads();
+  const int ex = s_ex;
+  int8_t* o0 = Q0 + (size_t)blockIdx.x * ldq;
+  uint8_t* o1 = Q1 + (size_t)blockIdx.x * ldq;
+  uint8_t* o2 = Q2 + (size_t)blockIdx.x * ldq;
+  for (int64_t i = threadIdx.x; i < ldq; i += 256) {
+    signed char a0 = 0;
+    unsigned char a1 = 0, a2 = 0;
+    if (i < ncols) slice3_i8(row[i], ex, a0, a1, a2);
+    o0[i] = a0;
+    o1[i] = a1;
+    o2[i] = a2;
+  }
+}
+
+// P: int32 [6][ksplit][n][ldp] products of the digit planes in the order 00, 11, 22 (upper triangles), 01, 02, 12
+// (full), P_de[i,j] = sum_k Q_d[i,k] Q_e[j,k].  With y ~ 2^(e-7) (q0 + q1/2^8 + q2/2^16):
+//   G[i,j] = 2^(e_i+e_j-14) [ P00 + (P01[i,j] + P01[j,i]) / 2^8 + (P11 + P02[i,j] + P02[j,i]) / 2^16
+//                             + (P12[i,j] + P12[j,i]) / 2^24 + P22 / 2^32 ] - ncols m_i m_j        (j >= i, mirrored)
+// Everything inside the bracket is an exact integer combination evaluated in float64.
+__global__ void gram_assemble_i8_kernel(const int32_t* __restrict__ P, int ksplit, int n, int64_t ldp,
+                                        const int32_t* __restrict__ exps, const double* __restrict__ mean,
+                                        double ncols, double* __restrict__ G) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n || j >= n || j < i) return;
+  const size_t plane = (size_t)n * ldp;
+  const size_t prod = (size_t)ksplit * plane;
+  const size_t ij = (size_t)i * ldp + j, ji = (size_t)j * ldp + i;
+  long long s00 = 0, s11 = 0, s22 = 0, s01 = 0, s02 = 0, s12 = 0;
+  for (int s = 0; s < ksplit; ++s) {
+    const int32_t* base = P + (size_t)s * plane;
+    s00 += base[ij];
+    s11 += base[prod + ij];
+    s22 += base[2 * prod + ij];
+    s01 += (long long)base[3 * prod + ij] + base[3 * prod + ji];
+    s02 += (long long)base[4 * prod + ij] + base[4 * prod + ji];
+    s12 += (long long)base[5 * prod + ij] + base[5 * prod + ji];
+  }
+  double v = (double)s00 + (double)s01 * (1.0 / 256.0) + ((double)s11 + (double)s02) * (1.0 / 65536.0) +
+             (double)s12 * (1.0 / 16777216.0) + (double)s22 * (1.0 / 4294967296.0);
+  v = ldexp(v, exps[i] + exps[j] - 14);
+  if (mean) v -= ncols * (mean[i] * mean[j]);
+  G[(size_t)i * n + j] = v;
+  if (j != i) G[(size_t)j * n + i] = v;
+}
+}  // namespace fm
+
+extern "C" int fm_slice_rows_i8(const float* X, int64_t ldx, int rows, int64_t ncols, int8_t* Q0, uint8_t* Q1,
+                                uint8_t* Q2, int64_t ldq, int32_t* exps, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(X && Q0 && Q1 && Q2 && exps && rows >= 0 && ncols >= 1 && ldx >= ncols && ldq >= ncols,
+             "fm_slice_rows_i8: bad args");
+  if (rows == 0) return FM_OK;
+  slice_rows_i8_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, ldx, ncols, Q0, Q1, Q2, ldq, exps);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+extern "C" int fm_gram_assemble_i8(const int32_t* P, int ksplit, int n, int64_t ldp, const int32_t* exps,
+                                   const double* mean, int64_t ncols, double* G, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(P && exps && G && ksplit >= 1 && n >= 1 && ldp >= n, "fm_gram_assemble_i8: bad args");
+  dim3 block(32, 8), grid((unsigned)cdiv(n, 32), (unsigned)cdiv(n, 8));
+  gram_assemble_i8_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, ksplit, n, ldp, exps, mean,
+                                                                                      (double)ncols, G);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
 // ---- row-side Gram for wide matrices (merge of an ROI: p pixels < c stacked components) -------
 // svdecon(Y [p, c]) with PCA column centring Yc = Y - 1 mu^T:
 //   Yc Yc^T = Y Y^T - q 1^T - 1 q^T + (mu.mu) 1 1^T,   q = Y mu

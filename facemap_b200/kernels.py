@@ -203,6 +203,42 @@ def gemm_i8_tn(A, B, C_out=None, *, ksplit=1, workspace=None, upper_only=False):
                                     ldw, int(bool(upper_only)), _stream()), "fm_gemm_i8_tn")
 
 
+def slice_rows_i8(X, out=None):
+    """EXPERIMENTAL (fm_slice_rows_i8): (Q0 int8, Q1 uint8, Q2 uint8, exps int32) digit planes of the rows of X, row
+    pitch a multiple of 16 bytes.  `out`: optional (Q0, Q1, Q2) [rows, cols] views sharing one pitch."""
+    _need(X, torch.float32, "X", 2)
+    rows, cols = X.shape
+    if X.stride(1) != 1:
+        raise FacemapB200Error("slice_rows_i8: X must be row-major")
+    if out is None:
+        ld = round_up(cols, 16)
+        out = tuple(torch.empty((max(rows, 1), ld), dtype=dt, device=X.device)[:rows, :cols]
+                    for dt in (torch.int8, torch.uint8, torch.uint8))
+    Q0, Q1, Q2 = out
+    ldq = Q0.stride(0)
+    for q, dt in ((Q0, torch.int8), (Q1, torch.uint8), (Q2, torch.uint8)):
+        if q.dtype != dt or tuple(q.shape) != (rows, cols) or q.stride(1) != 1 or q.stride(0) != ldq or ldq % 16:
+            raise FacemapB200Error("slice_rows_i8: planes must be int8 / uint8 / uint8 [rows, cols] with one 16-byte pitch")
+    exps = torch.empty(max(rows, 1), dtype=torch.int32, device=X.device)[:rows]
+    check(_lib.load().fm_slice_rows_i8(ptr(X), X.stride(0), rows, cols, ptr(Q0), ptr(Q1), ptr(Q2), ldq, ptr(exps),
+                                       _stream()), "fm_slice_rows_i8")
+    return Q0, Q1, Q2, exps
+
+
+def gram_assemble_i8(P, ksplit, n, exps, mean, ncols, out=None):
+    """EXPERIMENTAL (fm_gram_assemble_i8): P int32 [6, ksplit, n, ldp] plane products -> float64 centred Gram."""
+    _need(P, torch.int32, "P", 4)
+    if P.shape[0] != 6 or P.shape[1] < ksplit or P.shape[2] != n or P.shape[3] < n or not P.is_contiguous():
+        raise FacemapB200Error("gram_assemble_i8: P must be a contiguous int32 [6, ksplit, n, >=n] stack")
+    _need(exps, torch.int32, "exps", 1)
+    _need(mean, torch.float64, "mean")
+    if out is None:
+        out = torch.empty((n, n), dtype=torch.float64, device=P.device)
+    check(_lib.load().fm_gram_assemble_i8(ptr(P), int(ksplit), int(n), P.stride(2), ptr(exps), ptr(mean), int(ncols),
+                                          ptr(out), _stream()), "fm_gram_assemble_i8")
+    return out
+
+
 def splitk_reduce(workspace, ksplit, C_out, *, rscale=None, rbias=None):
     """C[m,n] = rscale[m] * sum_s workspace[s,m,n] + rbias[m], summed in float64."""
     _need(workspace, torch.float32, "workspace", 3)

@@ -115,8 +115,9 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     overlap_stage3: run stage 3's bin/diff pass on a side stream underneath the stage-2 eigensolves
             when the frames are HBM-resident (svd.Stage3.start_early).
     dist:   optional facemap_b200.parallel.Shard (frame-range sharding across ranks).
-    gram_mode: "tf32x3" (default), "sliced_merge" or "sliced" — how the Gram matrices of the two SVD levels are
-            formed (svd.SvdWorkspace, svd.sliced_gram); None reads the environment variable FM_GRAM_MODE."""
+    gram_mode: "tf32x3" (default), "sliced_merge", "sliced", "i8_merge" or "i8" — how the Gram matrices of the two
+            SVD levels are formed (svd.SvdWorkspace, svd.sliced_gram, svd.i8_gram); None reads the environment
+            variable FM_GRAM_MODE."""
     t_enter = time.perf_counter()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     _lib.require_device(dev.index or 0)

@@ -167,7 +167,9 @@ class SvdWorkspace:
         #   "sliced_merge"  the second-level (merge) Gram from 8-bit row slices with an exact leading product
         #   "sliced"        chunk Grams as well (sliced_gram; ~4x the Gram time, tail singular values to 1e-5)
         self.gram_mode = _os.environ.get("FM_GRAM_MODE", "tf32x3") if gram_mode is None else gram_mode
-        if self.gram_mode not in ("tf32x3", "sliced_merge", "sliced"):
+        #   "i8_merge" / "i8"  EXPERIMENTAL: s8/u8/u8 digit planes and exact integer products on tcgen05 kind::i8
+        #                   (i8_gram); same accuracy as exact Grams in the CPU model, fewer bytes than "tf32x3"
+        if self.gram_mode not in ("tf32x3", "sliced_merge", "sliced", "i8_merge", "i8"):
             raise FacemapB200Error(f"unknown gram_mode {self.gram_mode!r}")
         # pass A of sliced_gram on the one-product kernel (fm_gemm_tn impl 10) instead of the 3xTF32 kernel with a
         # zero lo plane: a third of the MMAs, no zero plane to stage
@@ -206,6 +208,14 @@ class SvdWorkspace:
             self._ws = torch.empty(need, dtype=torch.float32, device=self.device)
         return self._ws[:need].view(ksplit, n, ld)
 
+    def raw(self, tag, numel, dtype):
+        """reusable flat buffer of `numel` elements of `dtype` (byte planes, int32 partials)"""
+        buf = self._bufs.get(tag)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = torch.empty(max(int(numel), 1), dtype=dtype, device=self.device)
+            self._bufs[tag] = buf
+        return buf[:numel]
+
     def matrix(self, tag, rows, cols):
         ld = max(32, K.round_up(cols, 32))
         need = max(rows, 1) * ld
@@ -216,10 +226,14 @@ class SvdWorkspace:
         return buf[:need].view(max(rows, 1), ld)[:rows, :cols]
 
 
+def gram_is_i8(ws: SvdWorkspace, label):
+    return ws.gram_mode == "i8" or (ws.gram_mode == "i8_merge" and label.endswith("merge"))
+
+
 def gram_is_sliced(ws: SvdWorkspace, label, n):
     """sliced_gram serves the levels `ws.gram_mode` names; it needs the 128 x 256 chain kernel (K dealt in 16-wide
     k-blocks), i.e. impl 0 and an output wider than 128."""
-    if ws.gram_mode == "tf32x3" or ws.gram_impl != 0 or n <= 128:
+    if ws.gram_mode not in ("sliced", "sliced_merge") or ws.gram_impl != 0 or n <= 128:
         return False
     return ws.gram_mode == "sliced" or label.endswith("merge")
 
@@ -227,6 +241,8 @@ def gram_is_sliced(ws: SvdWorkspace, label, n):
 def centred_gram(ws: SvdWorkspace, X, timer, label, out=None):
     """mean over columns of every row of X [n, p] and the centred Gram  X X^T - p m m^T  (float64)."""
     n, p = X.shape
+    if gram_is_i8(ws, label):
+        return i8_gram(ws, X, timer, label, out=out)
     if gram_is_sliced(ws, label, n):
         return sliced_gram(ws, X, timer, label, out=out)
     with timer(label + ".colmean"):
@@ -292,6 +308,37 @@ def sliced_gram(ws: SvdWorkspace, X, timer, label, out=None):
             at += ks
     with timer(label + ".gram.assemble"):
         G = K.gram_assemble(part, at, n, mean, p, True, out=out)
+    return mean, G
+
+
+I8_KMAX = 32768        # K per int32 partial of fm_gemm_i8_tn (255^2 * 32768 < 2^31)
+
+
+def i8_gram(ws: SvdWorkspace, X, timer, label, out=None):
+    """EXPERIMENTAL — centred_gram on the integer tensor cores: the rows of X become s8 / u8 / u8 digit planes
+    (fm_slice_rows_i8: 23 bits below each row's bound, unbiased), the six plane products are formed by fm_gemm_i8_tn
+    with exact int32 accumulation, fm_gram_assemble_i8 weighs and sums them in float64.  No rounding anywhere but the
+    2^-24 digit representation: scripts/model_accuracy.py (`i8`) puts all 500 singular values within 4e-6 of the
+    exact oracle's.  3 bytes per element are staged per product instead of the 8 (hi + lo planes) of the 3xTF32 Gram."""
+    n, p = X.shape
+    with timer(label + ".colmean"):
+        mean = K.row_means(X)
+    with timer(label + ".gram.split"):
+        ldq = K.round_up(p, 16)
+        raw = ws.raw("gram.i8", 3 * n * ldq, torch.uint8).view(3, n, ldq)
+        Q0, Q1, Q2, exps = K.slice_rows_i8(X, out=(raw[0].view(torch.int8)[:, :p], raw[1][:, :p], raw[2][:, :p]))
+    ks = max(1, math.ceil(math.ceil(p / 64) / (I8_KMAX // 64)))
+    ldp = K.round_up(n, 4)
+    P = ws.raw("gram.i8.P", 6 * ks * n * ldp, torch.int32).view(6, ks, n, ldp)
+    with timer(label + ".gram.mma"):
+        for d, (A, B, upper) in enumerate(((Q0, Q0, True), (Q1, Q1, True), (Q2, Q2, True),
+                                           (Q0, Q1, False), (Q0, Q2, False), (Q1, Q2, False))):
+            if ks > 1:
+                K.gemm_i8_tn(A, B, ksplit=ks, workspace=P[d], upper_only=upper)
+            else:
+                K.gemm_i8_tn(A, B, P[d, 0], upper_only=upper)
+    with timer(label + ".gram.assemble"):
+        G = K.gram_assemble_i8(P, ks, n, exps, mean, p, out=out)
     return mean, G
 
 

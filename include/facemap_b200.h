@@ -163,6 +163,20 @@ int fm_gemm_i8_tn(const uint8_t* A, int64_t lda, int a_signed, const uint8_t* B,
                   int M, int N, int K, int32_t* C, int64_t ldc, int ksplit, int32_t* workspace, int64_t ldw,
                   int upper_only, void* stream);
 
+/*
+ * EXPERIMENTAL companions of fm_gemm_i8_tn (svd.i8_gram; not yet run on a GPU):
+ * fm_slice_rows_i8: X[r,c] ~ 2^(exps[r] - 7) * (Q0 + Q1 / 2^8 + Q2 / 2^16), Q0 int8 (floor), Q1 uint8 (floor), Q2 uint8
+ *   (nearest, carries propagated), 2^exps[r] bounding row r: 23 bits below the row bound, unbiased.  Plane row pitch
+ *   ldq in bytes (a multiple of 16 for the GEMM); pad bytes zeroed.
+ * fm_gram_assemble_i8: P = int32 [6][ksplit][n][ldp], the plane products 00, 11, 22 (upper triangles), 01, 02, 12
+ *   (full) from fm_gemm_i8_tn  ->  G = X X^T - ncols * mean mean^T in float64 (mean may be NULL), exact up to the
+ *   2^-24 representation error of the digits.  The Gram form of utils.svdecon (facemap/utils.py:751-776).
+ */
+int fm_slice_rows_i8(const float* X, int64_t ldx, int rows, int64_t ncols, int8_t* Q0, uint8_t* Q1, uint8_t* Q2,
+                     int64_t ldq, int32_t* exps, void* stream);
+int fm_gram_assemble_i8(const int32_t* P, int ksplit, int n, int64_t ldp, const int32_t* exps, const double* mean,
+                        int64_t ncols, double* G, void* stream);
+
 /* lo[r,c] = X[r,c] - tf32_trunc(X[r,c]): pre-computed second plane of a B operand that many GEMMs
  * reuse (pass it as B_lo above). */
 int fm_split_lo(const float* X, int64_t ldx, int rows, int cols, float* lo, int64_t ldlo, void* stream);

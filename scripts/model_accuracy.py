@@ -22,6 +22,7 @@ Variants (which GEMMs are modelled as tensor-core arithmetic, which as exact flo
     grams_exact   chunk and merge Gram exact, left vectors emulated
     all_exact     every GEMM exact; only the float32 storage of W, Y and U remains
     ozaki3[_o]    Grams from three 8-bit row slices, every pair product with d + e <= o exact (default all)
+    i8 / i8m      Grams from s8/u8/u8 floor digits with exact integer products (the kind::i8 plan), both levels / merge
     passes / passesm   the four-pass scheme that fits the existing kernels (see Model.gemm), both levels / merge only
     sliced2       both Grams as  top-8-bit row slice (exact, one MMA per K step)  +  one 3-MMA pass on the remainder
     sliced3       the same with a second remainder pass;  sliced2m / sliced3m: merge Gram only
@@ -99,7 +100,7 @@ def slice_rows(A, bits=8):
     R = A - A0 exactly (float32).  The arithmetic of facemap_b200/csrc/slice_math.cuh."""
     A = np.ascontiguousarray(A, np.float32)
     amax = np.abs(A).max(axis=1)
-    e = np.where(amax > 0, np.floor(np.log2(np.maximum(amax, 1e-300))) + 1, 0.0)        # |a| < 2^e
+    e = np.where(amax > 0, np.floor(np.log2(np.maximum(amax.astype(np.float64), 1e-300))) + 1, 0.0)        # |a| < 2^e
     q = np.exp2(e - bits).astype(np.float32)[:, None]
     A0 = (np.rint(A / q) * q).astype(np.float32)
     R = (A - A0).astype(np.float32)
@@ -110,10 +111,36 @@ def slice_rows(A, bits=8):
 def slice_rows_like(R, A, bits):
     """next slice of the remainder R on the row grid of A: multiples of 2^(e_row(A) - bits)"""
     amax = np.abs(np.ascontiguousarray(A, np.float32)).max(axis=1)
-    e = np.where(amax > 0, np.floor(np.log2(np.maximum(amax, 1e-300))) + 1, 0.0)
+    e = np.where(amax > 0, np.floor(np.log2(np.maximum(amax.astype(np.float64), 1e-300))) + 1, 0.0)
     q = np.exp2(e - bits).astype(np.float32)[:, None]
     S = (np.rint(R / q) * q).astype(np.float32)
     return S, (R - S).astype(np.float32)
+
+
+def slice_rows_i8(A):
+    """A [n, K] float32 -> ([Q0, Q1, Q2] float64 integer planes, scale [n]): A ~ scale * (Q0 + Q1/2^8 + Q2/2^16) with
+    scale = 2^(e_row - 7), |A| < 2^e_row; Q0 = floor in [-128, 127], Q1 = floor in [0, 255], Q2 to nearest in [0, 255]
+    with carries (23 bits below the row bound, unbiased).  The arithmetic of csrc/slice_math.cuh:slice3_i8."""
+    A = np.ascontiguousarray(A, np.float32)
+    amax = np.abs(A).max(axis=1)
+    e = np.where(amax > 0, np.floor(np.log2(np.maximum(amax.astype(np.float64), 1e-300))) + 1, -100.0)
+    scale = np.exp2(e - 7)
+    t = A.astype(np.float64) / scale[:, None]                # exact: power-of-two scaling, |t| < 128
+    q0 = np.floor(t)
+    r = (t - q0) * 256.0
+    q1 = np.floor(r)
+    r = (r - q1) * 256.0
+    q2 = np.rint(r)                                          # last digit to nearest (unbiased), carries propagated
+    c = q2 == 256
+    q2[c] = 0
+    q1[c] += 1
+    c = q1 == 256
+    q1[c] = 0
+    q0[c] += 1
+    c = q0 == 128                                            # only for |a| within 2^-24 of the row bound: saturate
+    q0[c], q1[c], q2[c] = 127, 255, 255
+    assert q0.min() >= -128 and q0.max() <= 127 and q1.min() >= 0 and q1.max() <= 255 and 0 <= q2.min() and q2.max() <= 255
+    return [q0, q1, q2], scale
 
 
 def sliced_gram(A, passes, bits=8):
@@ -160,6 +187,16 @@ class Model:
             for lo, hi in ((Y0, Y1), (Y0, Y2), (Y1, Y2)):
                 G += emu_products([(lo, hi), (hi, lo), (hi, hi)], 4096)
             return G
+        if self.variant.startswith("i8") and role.endswith(".gram") and \
+                (role == "merge.gram" or not self.variant.endswith("m")):
+            # integer digits for tcgen05 kind::i8 (fm_slice_rows_i8 + fm_gemm_i8_tn, exact int32 accumulation):
+            # y ~ 2^(e-7) (q0 + q1 2^-8 + q2 2^-16), q0 = floor in [-128, 127] (s8), q1, q2 in [0, 255] (u8)
+            Q, scale = slice_rows_i8(A)
+            G = np.zeros((A.shape[0], A.shape[0]))
+            for d in range(3):
+                for e in range(3):
+                    G += (Q[d] @ Q[e].T) * 2.0 ** (-8 * (d + e))
+            return G * np.outer(scale, scale)
         if self.variant.startswith("ozaki") and role.endswith(".gram"):
             # ozaki3 / ozaki4: every pair product of 3 (4) 8-bit row slices exact = the exact Gram of the rows cut to
             # 24 (32) bits below their row maximum

@@ -67,3 +67,17 @@ extern "C" void shim_slice_rows(const float* x, int rows, int cols, float* s0, f
     }
   }
 }
+
+extern "C" void shim_slice_rows_i8(const float* x, int rows, int cols, signed char* q0, unsigned char* q1,
+                                   unsigned char* q2, int* ex_out) {
+  for (int r = 0; r < rows; ++r) {
+    float amax = 0.0f;
+    for (int c = 0; c < cols; ++c) amax = fmaxf(amax, fabsf(x[(size_t)r * cols + c]));
+    const int ex = fm::slice_exponent(amax);
+    ex_out[r] = ex;
+    for (int c = 0; c < cols; ++c) {
+      const size_t i = (size_t)r * cols + c;
+      fm::slice3_i8(x[i], ex, q0[i], q1[i], q2[i]);
+    }
+  }
+}

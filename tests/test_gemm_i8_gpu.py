@@ -62,3 +62,74 @@ def test_gemm_i8_upper_only_and_int32_range(cuda_device):
     with pytest.raises(Exception):
         K_.gemm_i8_tn(torch.zeros((128, 40000), dtype=torch.uint8, device=cuda_device),
                       torch.zeros((256, 40000), dtype=torch.uint8, device=cuda_device), C)   # would overflow int32
+
+
+def _graded(rs, n, p):
+    base = rs.randn(40, p)
+    Y = (rs.randn(n, 40) @ base) * np.logspace(2, -3, n)[:, None] + 1e-4 * rs.randn(n, p) + 0.3
+    return Y.astype(np.float32)
+
+
+def _model_digits(Y):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from model_accuracy import slice_rows_i8
+
+    return slice_rows_i8(Y)
+
+
+def test_slice_rows_i8_matches_model(cuda_device):
+    from facemap_b200 import kernels as K_
+
+    rs = np.random.RandomState(0)
+    for n, p in ((7, 33), (300, 1000), (64, 19200)):
+        Y = _graded(rs, n, p)
+        X = K_.alloc_matrix(n, p, cuda_device)
+        X.copy_(torch.from_numpy(Y))
+        Q0, Q1, Q2, exps = K_.slice_rows_i8(X)
+        (m0, m1, m2), scale = _model_digits(Y)
+        assert np.array_equal(Q0.cpu().numpy(), m0.astype(np.int8))
+        assert np.array_equal(Q1.cpu().numpy(), m1.astype(np.uint8)) and np.array_equal(Q2.cpu().numpy(), m2.astype(np.uint8))
+        assert np.array_equal(exps.cpu().numpy(), (np.log2(scale) + 7).astype(np.int32))
+
+
+def test_i8_gram_against_float64(cuda_device):
+    from facemap_b200 import kernels as K_, svd
+
+    rs = np.random.RandomState(2)
+    n, p = 700, 5000
+    Y = _graded(rs, n, p)
+    X = K_.alloc_matrix(n, p, cuda_device)
+    X.copy_(torch.from_numpy(Y))
+    ws = svd.SvdWorkspace(cuda_device, gram_mode="i8")
+    mean, G = svd.centred_gram(ws, X, ws.timer, "stage2.merge")
+    Y64 = Y.astype(np.float64)
+    m = Y64.mean(axis=1)
+    want = Y64 @ Y64.T - p * np.outer(m, m)
+    d = np.sqrt(np.diag(Y64 @ Y64.T))
+    err = np.abs(G.cpu().numpy() - want) / np.outer(d, d)
+    print("i8 gram max/median rel err", err.max(), np.median(err))
+    assert err.max() < 3e-8 and np.median(err) < 3e-9
+    # against the digits' own exact Gram: nothing but float64 rounding
+    (q0, q1, q2), scale = _model_digits(Y)
+    T = scale[:, None] * (q0 + q1 / 256.0 + q2 / 65536.0)
+    exact = T @ T.T - p * np.outer(m, m)
+    assert np.abs(G.cpu().numpy() - exact).max() <= 1e-12 * d.max() ** 2
+
+
+def test_pipeline_with_i8_grams_resolves_all_singular_values(cuda_device):
+    from facemap_b200 import process
+    from facemap_b200.frames import DeviceArraySource
+    from facemap_b200.synth import SynthVideo
+    from oracle import facemap_oracle as orc
+
+    H, W, N, sbin = 96, 128, 2600, 2
+    v = SynthVideo(H, W, N, seed=5).all_frames()
+    o = orc.run_oracle([v], sbin=sbin, motSVD=True, movSVD=True, svd="exact")
+    p = process.process_source(DeviceArraySource([torch.from_numpy(v).to(cuda_device)]), sbin=sbin, movSVD=True,
+                               gram_mode="i8")
+    for sk in ("motSv", "movSv"):
+        S_ref = o[sk].astype(np.float64)
+        rel = np.abs(p[sk].astype(np.float64) - S_ref) / S_ref
+        print(sk, "i8", [float(rel[:k].max()) for k in (10, 100, 250, 500)])
+        assert rel.max() <= 1e-4, sk

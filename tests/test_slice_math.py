@@ -107,3 +107,45 @@ def test_gram_from_slice_pair_products(shim):
     full = X.astype(np.float64) @ X.astype(np.float64).T
     # representation error: 2^-25 of the row bound per entry, unbiased -> averages down with sqrt(K)
     assert np.abs((G - full) / np.outer(d, d)).max() < 2e-8
+
+
+def test_i8_digits(shim):
+    """slice3_i8: s8 / u8 / u8 digits, 23 bits below the row bound, last digit to nearest with carries, saturation
+    instead of a carry out of the leading digit"""
+    shim.shim_slice_rows_i8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rs = np.random.RandomState(3)
+    X = graded_rows(rs, 40, 3000)
+    X[2] = 0
+    X[3, :] = np.float32(1.0)                              # row bound 2, t = 64 exactly
+    X[4, :5] = [np.nextafter(np.float32(4.0), np.float32(0)), -np.nextafter(np.float32(4.0), np.float32(0)),
+                np.float32(-4.0 + 2.0 ** -20), np.float32(2.0 ** -30), np.float32(-(2.0 ** -30))]
+    X[4, 5:] = 0
+    rows, cols = X.shape
+    q0 = np.empty((rows, cols), np.int8)
+    q1 = np.empty((rows, cols), np.uint8)
+    q2 = np.empty((rows, cols), np.uint8)
+    ex = np.empty(rows, np.int32)
+    shim.shim_slice_rows_i8(X.ctypes.data, rows, cols, q0.ctypes.data, q1.ctypes.data, q2.ctypes.data, ex.ctypes.data)
+    scale = np.exp2(ex.astype(np.float64) - 7)[:, None]
+    rec = scale * (q0.astype(np.float64) + q1 / 256.0 + q2 / 65536.0)
+    X64 = X.astype(np.float64)
+    err = (X64 - rec) / scale                              # in units of q0
+    sat = (q0 == 127) & (q1 == 255) & (q2 == 255)
+    assert np.abs(err[~sat]).max() <= 2.0 ** -17 + 1e-12   # half a unit of the last digit
+    assert np.abs(err[sat]).max() <= 2.0 ** -16            # saturated entries lose at most one unit
+    assert abs(err[np.abs(X64) > 0].mean()) < 2.0 ** -20   # unbiased
+    assert not q0[2].any() and not q1[2].any() and not q2[2].any()
+    assert (q0[3] == 64).all() and not q1[3].any()
+    # the entry just below the bound 4 = 2^2 rounds up into a carry chain: saturated, not wrapped to -128
+    assert (q0[4, 0], q1[4, 0], q2[4, 0]) == (127, 255, 255)
+    assert q0[4, 1] == -128 and q1[4, 1] == 0 and q2[4, 1] == 0          # -3.9999998 rounds to -4 = -128 units: representable
+    assert q0[4, 3] == 0 and q0[4, 4] in (-1, 0)           # tiny values: 0 or -1 + 255/256 + ... (floor digits)
+    # reference implementation in NumPy (scripts/model_accuracy.py:slice_rows_i8), digit for digit
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "scripts"))
+    from model_accuracy import slice_rows_i8
+
+    (m0, m1, m2), mscale = slice_rows_i8(X)
+    nz = np.abs(X).max(axis=1) > 0
+    assert np.array_equal(m0[nz], q0[nz]) and np.array_equal(m1[nz], q1[nz]) and np.array_equal(m2[nz], q2[nz])
+    assert np.array_equal(mscale[nz], scale[nz, 0])

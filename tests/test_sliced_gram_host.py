@@ -91,6 +91,88 @@ class FakeKernels:
         return G
 
 
+class FakeI8Kernels(FakeKernels):
+    """stand-ins for fm_slice_rows_i8 / fm_gemm_i8_tn / fm_gram_assemble_i8 (contracts in include/facemap_b200.h)"""
+
+    @staticmethod
+    def slice_rows_i8(X, out):
+        import os
+        import sys
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+        from model_accuracy import slice_rows_i8
+
+        (q0, q1, q2), scale = slice_rows_i8(X.numpy())
+        out[0].copy_(torch.from_numpy(q0.astype(np.int8)))
+        out[1].copy_(torch.from_numpy(q1.astype(np.uint8)))
+        out[2].copy_(torch.from_numpy(q2.astype(np.uint8)))
+        assert out[0].stride(0) % 16 == 0 and out[0].stride(0) == out[1].stride(0) == out[2].stride(0)
+        return out[0], out[1], out[2], torch.from_numpy((np.log2(scale) + 7).astype(np.int32))
+
+    def gemm_i8_tn(self, A, B, C_out=None, *, ksplit=1, workspace=None, upper_only=False):
+        a, b = A.numpy().astype(np.int64), B.numpy().astype(np.int64)
+        n, K = a.shape
+        KB = -(-K // 64)
+        ksplit = min(ksplit, KB)
+        assert -(-KB // ksplit) * 64 <= 32768, "int32 accumulator would overflow"
+        outs = [C_out] if ksplit == 1 else [workspace[z] for z in range(ksplit)]
+        for z, dst in enumerate(outs):
+            k0, k1 = 64 * ((z * KB) // ksplit), min(K, 64 * (((z + 1) * KB) // ksplit))
+            Pz = a[:, k0:k1] @ b[:, k0:k1].T
+            assert np.abs(Pz).max() < 2 ** 31
+            full = np.full((n, dst.shape[1]), -(2 ** 31), np.int64)          # poison: never-written entries
+            for i0 in range(0, n, 128):
+                for j0 in range(0, b.shape[0], 256):
+                    if not upper_only or j0 + 255 >= i0:
+                        full[i0:i0 + 128, j0:min(b.shape[0], j0 + 256)] = Pz[i0:i0 + 128, j0:min(b.shape[0], j0 + 256)]
+            dst.copy_(torch.from_numpy(full.astype(np.int32)))
+        self.calls.append(("i8", ksplit, upper_only, str(A.dtype), str(B.dtype)))
+
+    @staticmethod
+    def gram_assemble_i8(P, ksplit, n, exps, mean, ncols, out=None):
+        S = P[:, :ksplit].numpy().astype(np.int64).sum(axis=1)[:, :, :n]     # [6, n, n]
+        iu = np.triu_indices(n)
+        poison = -(2 ** 31) * ksplit
+        assert (S[:3][:, iu[0], iu[1]] != poison).all() and (S[3:] != poison).all()
+        br = (S[0] + (S[3] + S[3].T) / 2.0 ** 8 + (S[1] + S[4] + S[4].T) / 2.0 ** 16 + (S[5] + S[5].T) / 2.0 ** 24
+              + S[2] / 2.0 ** 32)
+        e = exps.numpy().astype(np.float64)
+        G = np.triu(br * np.exp2(e[:, None] + e[None, :] - 14))
+        G = G + np.triu(G, 1).T
+        m = mean.numpy()
+        G = torch.from_numpy(G - ncols * np.outer(m, m))
+        if out is not None:
+            out.copy_(G)
+            return out
+        return G
+
+
+def test_i8_gram_matches_float64_gram(monkeypatch):
+    rs = np.random.RandomState(1)
+    n, p = 300, 1000
+    base = rs.randn(40, p)
+    Y = ((rs.randn(n, 40) @ base) * np.logspace(2, -3, n)[:, None] + 1e-4 * rs.randn(n, p) + 0.3).astype(np.float32)
+    Y64 = Y.astype(np.float64)
+    m = Y64.mean(axis=1)
+    want = Y64 @ Y64.T - p * np.outer(m, m)
+    d = np.sqrt(np.diag(Y64 @ Y64.T))
+    for kmax, ks_want in ((32768, 1), (256, 4)):                        # one partial; forced split-K
+        fake = FakeI8Kernels()
+        monkeypatch.setattr(svd, "K", fake)
+        monkeypatch.setattr(svd, "I8_KMAX", kmax)
+        ws = _workspace()
+        ws.gram_mode = "i8"
+        X = ws.matrix("Y", n, p)
+        X.copy_(torch.from_numpy(Y))
+        mean, G = svd.centred_gram(ws, X, ws.timer, "stage2.chunk")
+        err = np.abs(G.numpy() - want) / np.outer(d, d)
+        # 2^-24 of the row bound per entry, unbiased, averaged over K = 1000
+        assert err.max() < 5e-8 and np.median(err) < 5e-9, (err.max(), np.median(err))
+        assert np.array_equal(G.numpy(), G.numpy().T) and np.array_equal(mean.numpy(), m)
+        assert [c[1] for c in fake.calls] == [ks_want] * 6
+        assert [c[2] for c in fake.calls] == [True, True, True, False, False, False]
+        assert [c[3:] for c in fake.calls][3] == ("torch.int8", "torch.uint8")
+
+
 def _workspace():
     ws = svd.SvdWorkspace.__new__(svd.SvdWorkspace)
     ws.device, ws._ws, ws._bufs = torch.device("cpu"), None, {}
@@ -152,9 +234,14 @@ def test_gram_routing_by_mode():
                                        ("sliced_merge", "stage2.merge", 3750, 0, True),
                                        ("sliced_merge", "stage2.roi_merge", 500, 0, True),
                                        ("sliced_merge", "stage2.chunk", 999, 0, False),
-                                       ("sliced", "stage2.merge", 3750, 9, False), ("tf32x3", "stage2.merge", 3750, 0, False)):
+                                       ("sliced", "stage2.merge", 3750, 9, False), ("tf32x3", "stage2.merge", 3750, 0, False),
+                                       ("i8", "stage2.merge", 3750, 0, False)):
         ws.gram_mode, ws.gram_impl = mode, impl
         assert svd.gram_is_sliced(ws, label, n) is want, (mode, label, n, impl)
+    for mode, label, want in (("i8", "stage2.chunk", True), ("i8", "stage2.roi_merge", True), ("i8_merge", "stage2.chunk", False),
+                              ("i8_merge", "stage2.merge", True), ("sliced", "stage2.merge", False), ("tf32x3", "stage2.merge", False)):
+        ws.gram_mode = mode
+        assert svd.gram_is_i8(ws, label) is want, (mode, label)
 
 
 def test_centred_gram_dispatches_to_sliced(monkeypatch):
