@@ -327,7 +327,8 @@ def i8_gram(ws: SvdWorkspace, X, timer, label, out=None):
         ldq = K.round_up(p, 16)
         raw = ws.raw("gram.i8", 3 * n * ldq, torch.uint8).view(3, n, ldq)
         Q0, Q1, Q2, exps = K.slice_rows_i8(X, out=(raw[0].view(torch.int8)[:, :p], raw[1][:, :p], raw[2][:, :p]))
-    ks = max(1, math.ceil(math.ceil(p / 64) / (I8_KMAX // 64)))
+    # split K where the int32 accumulator demands it, and where the tile count alone cannot fill the machine
+    ks = max(1, math.ceil(math.ceil(p / 64) / (I8_KMAX // 64)), _fill_ksplit(math.ceil(n / 128) * math.ceil(n / 256), p))
     ldp = K.round_up(n, 4)
     P = ws.raw("gram.i8.P", 6 * ks * n * ldp, torch.int32).view(6, ks, n, ldp)
     with timer(label + ".gram.mma"):
