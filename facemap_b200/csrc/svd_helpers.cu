@@ -390,13 +390,32 @@ __global__ void __launch_bounds__(256) slice_rows_i8_kernel(const float* __restr
   int8_t* o0 = Q0 + (size_t)blockIdx.x * ldq;
   uint8_t* o1 = Q1 + (size_t)blockIdx.x * ldq;
   uint8_t* o2 = Q2 + (size_t)blockIdx.x * ldq;
-  for (int64_t i = threadIdx.x; i < ldq; i += 256) {
-    signed char a0 = 0;
-    unsigned char a1 = 0, a2 = 0;
-    if (i < ncols) slice3_i8(row[i], ex, a0, a1, a2);
-    o0[i] = a0;
-    o1[i] = a1;
-    o2[i] = a2;
+  // four elements per thread: one packed 32-bit store per plane (ldq is a multiple of 4 and the planes are 4-byte
+  // aligned, checked by the caller), float4 loads where the source row allows
+  const bool v4 = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  for (int64_t i = (int64_t)threadIdx.x * 4; i < ldq; i += 1024) {
+    float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (v4 && i + 4 <= ncols) {
+      const float4 v = *reinterpret_cast<const float4*>(row + i);
+      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (i + t < ncols) x[t] = row[i + t];
+    }
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      signed char a0 = 0;
+      unsigned char a1 = 0, a2 = 0;
+      if (i + t < ncols) slice3_i8(x[t], ex, a0, a1, a2);
+      w0 |= (uint32_t)(unsigned char)a0 << (8 * t);
+      w1 |= (uint32_t)a1 << (8 * t);
+      w2 |= (uint32_t)a2 << (8 * t);
+    }
+    *reinterpret_cast<uint32_t*>(o0 + i) = w0;
+    *reinterpret_cast<uint32_t*>(o1 + i) = w1;
+    *reinterpret_cast<uint32_t*>(o2 + i) = w2;
   }
 }
 
@@ -438,6 +457,9 @@ extern "C" int fm_slice_rows_i8(const float* X, int64_t ldx, int rows, int64_t n
   using namespace fm;
   FM_REQUIRE(X && Q0 && Q1 && Q2 && exps && rows >= 0 && ncols >= 1 && ldx >= ncols && ldq >= ncols,
              "fm_slice_rows_i8: bad args");
+  FM_REQUIRE(ldq % 4 == 0 && ((reinterpret_cast<uintptr_t>(Q0) | reinterpret_cast<uintptr_t>(Q1) |
+                               reinterpret_cast<uintptr_t>(Q2)) & 3) == 0,
+             "fm_slice_rows_i8: planes need 4-byte aligned bases and a row pitch that is a multiple of 4");
   if (rows == 0) return FM_OK;
   slice_rows_i8_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, ldx, ncols, Q0, Q1, Q2, ldq, exps);
   FM_LAUNCH_CHECK();
