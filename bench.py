@@ -466,6 +466,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_total": total_frames, "frame_bytes": H * W,
                        "l2": "inputs (30.7 GB per GPU) exceed L2; no flush needed", "parallelism": f"frame-range x{world}",
+                       **({"gram_mode": os.environ["FM_GRAM_MODE"]} if os.environ.get("FM_GRAM_MODE") else {}),
                        **({"rois": "pupil 100x140 + blink 100x140 + running 120x400 (side measurement)"} if args.with_rois else {})},
             "clocks": clk, "e2e": e2e if e2e is not None else ({"value": None, "skipped": e2e_skip} if e2e_skip else None),
             "gpu_launches": int(launches),
