@@ -48,7 +48,13 @@ CASES = {
 LARGE_CASES = {
     "c1_s4": ([(256, 256, 0)], 2000, 4, True, False, None),
     "c2_20k_s4": ([(480, 640, 0)], 20000, 4, True, False, None),
+    # configs[2] at its 4 000-frame parity size: two cameras, motion + movie SVD, the three motion ROIs of SURVEY §8(d)
+    "c3_4k_s4": ([(480, 640, 0), (480, 640, 1)], 4000, 4, True, True,
+                 [motion_roi(0, 40, 200, 80, 320), motion_roi(1, 32, 160, 64, 300), motion_roi(0, 240, 440, 400, 600)]),
+    # configs[3] on a 256-pixel-wide crop: full resolution (sbin 1, float32 path of the reference), 262 144 pixels
+    "c4_crop_s1": ([(1024, 256, 0)], 2000, 1, True, False, None),
 }
+LARGE_KEEP = {"c3_4k_s4": 8, "c4_crop_s1": 2}          # leading components stored (fixture size)
 
 
 def case_videos(name):
@@ -62,7 +68,7 @@ def frame_window(N):
     return np.unique(idx)
 
 
-def reduce_proc(p, N, prefix, out):
+def reduce_proc(p, N, prefix, out, keep=KEEP):
     w = frame_window(N)
     out[prefix + "frame_window"] = w
     for key in ("Lybin", "Lxbin", "sybin", "sxbin"):
@@ -82,15 +88,27 @@ def reduce_proc(p, N, prefix, out):
         out[f"{prefix}{mk}_n"] = np.int64(len(p[mk]))
         for i, a in enumerate(p[mk]):
             out[f"{prefix}{mk}_{i}_shape"] = np.array(a.shape)
-            out[f"{prefix}{mk}_{i}"] = a[:, :KEEP].copy()
+            out[f"{prefix}{mk}_{i}"] = a[:, :keep].copy()
         for i, a in enumerate(p[vk]):
             out[f"{prefix}{vk}_{i}_shape"] = np.array(a.shape)
-            out[f"{prefix}{vk}_{i}"] = a[w][:, :KEEP].copy() if a.shape[0] == N else a
+            out[f"{prefix}{vk}_{i}"] = a[w][:, :keep].copy() if a.shape[0] == N else a
     if p["rois"] is not None:
         for i, r in enumerate(p["rois"]):
             if r["rind"] == 1:
                 out[f"{prefix}roi{i}_yrange_bin"] = r["yrange_bin"]
                 out[f"{prefix}roi{i}_xrange_bin"] = r["xrange_bin"]
+
+
+def slim(out):
+    """large fixtures: the integer-stage outputs are identical in both modes (checked above against the oracle) and the
+    canvases repeat the vectors — keep the stock copy of the vectors only, and of the stock SVD only the spectrum"""
+    import re
+
+    drop = [k for k in out if k.endswith("_reshape") or (k.startswith("exact/") and k.split("/")[1].split("_")[0] in
+                                                          ("avgframe", "avgmotion", "motion"))]
+    # masks and traces of the stock run: only its singular values are compared at these sizes
+    drop += [k for k in out if re.fullmatch(r"stock/(motMask|movMask|motSVD|movSVD)_\d+", k)]
+    return {k: v for k, v in out.items() if k not in drop}
 
 
 def same(a, b):
@@ -107,8 +125,9 @@ def main():
     todo = dict(CASES) if not only else {k: v for k, v in {**CASES, **LARGE_CASES}.items() if k in only}
     for name, (views, N, sbin, mot, mov, rois) in todo.items():
         vids = case_videos(name)
+        keep = LARGE_KEEP.get(name, KEEP)
         out = {"case": np.array(name), "N": np.int64(N), "sbin": np.int64(sbin),
-               "motSVD": np.bool_(mot), "movSVD": np.bool_(mov), "keep": np.int64(KEEP),
+               "motSVD": np.bool_(mot), "movSVD": np.bool_(mov), "keep": np.int64(keep),
                "views": np.array(views)}
         for mode, exact in (("stock", False), ("exact", True)):
             t = time.time()
@@ -123,7 +142,9 @@ def main():
                                "motSVD", "movSVD") if not same(p[k], o[k])]
             print(f"{name:14s} {mode:5s} reference {tr:6.1f}s oracle {to:6.1f}s  "
                   f"oracle==reference bit-for-bit: {'YES' if not bad else 'NO ' + str(bad)}")
-            reduce_proc(p, N, mode + "/", out)
+            reduce_proc(p, N, mode + "/", out, keep)
+        if name in LARGE_KEEP:
+            out = slim(out)
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **out)
         print("  wrote", name + ".npz", os.path.getsize(os.path.join(outdir, name + ".npz")) // 1024, "KiB")
 

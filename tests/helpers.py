@@ -28,6 +28,11 @@ CASES = {
 LARGE_CASES = {
     "c1_s4": ([(256, 256, 0)], 2000, 4, True, False, None),
     "c2_20k_s4": ([(480, 640, 0)], 20000, 4, True, False, None),
+    # configs[2] at its 4 000-frame parity size (two cameras, motion + movie SVD, SURVEY §8(d)'s three motion ROIs)
+    "c3_4k_s4": ([(480, 640, 0), (480, 640, 1)], 4000, 4, True, True,
+                 [motion_roi(0, 40, 200, 80, 320), motion_roi(1, 32, 160, 64, 300), motion_roi(0, 240, 440, 400, 600)]),
+    # configs[3] on a 256-pixel-wide crop (sbin 1: the reference's float32 path, 262 144 pixels)
+    "c4_crop_s1": ([(1024, 256, 0)], 2000, 1, True, False, None),
 }
 
 

@@ -94,3 +94,13 @@ def test_stage1_means_at_the_c2_parity_size(golden_dir):
     S1, S2 = z["stock/motSv"].astype(np.float64), z["exact/motSv"].astype(np.float64)
     rel = np.abs(S1 - S2) / S2
     assert rel[:100].max() < 5e-5 and rel[250:].max() > 1e-2
+
+
+def test_large_fixture_comparison_on_the_oracle(golden_dir):
+    """the comparison the opt-in GPU test applies to the large fixtures (tests/test_large_golden_gpu.py), run here on
+    the oracle's Gram back-end for BASELINE configs[0]: keeps that code path exercised on every CPU run"""
+    from tests.test_large_golden_gpu import compare_with_fixture
+
+    views, N, sbin, mot, mov, _ = LARGE_CASES["c1_s4"]
+    o = orc.run_oracle(case_videos("c1_s4"), sbin=sbin, motSVD=mot, movSVD=mov, svd="gram")
+    compare_with_fixture(o, np.load(os.path.join(golden_dir, "c1_s4.npz")), "c1_s4")
