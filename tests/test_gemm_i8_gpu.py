@@ -32,7 +32,7 @@ def test_gemm_i8_exact(cuda_device, M, N, K, a_signed, b_signed):
     rs = np.random.RandomState(M + 7 * N + K)
     a, A = _operand(rs, M, K, a_signed, cuda_device)
     b, B = _operand(rs, N, K, b_signed, cuda_device)
-    want = a @ b.T
+    want = (a.astype(np.float64) @ b.astype(np.float64).T).astype(np.int64)      # exact: |sums| < 2^53, BLAS speed
     ldc = -(-N // 4) * 4
     C = torch.full((M, ldc), -77, dtype=torch.int32, device=cuda_device)
     K_.gemm_i8_tn(A, B, C)
@@ -55,7 +55,7 @@ def test_gemm_i8_upper_only_and_int32_range(cuda_device):
     C = torch.full((n, 704), -1, dtype=torch.int32, device=cuda_device)
     K_.gemm_i8_tn(A, A, C, upper_only=True)
     got = C[:, :n].cpu().numpy().astype(np.int64)
-    want = a @ a.T
+    want = (a.astype(np.float64) @ a.astype(np.float64).T).astype(np.int64)
     iu = np.triu_indices(n)
     assert np.array_equal(got[iu], want[iu]) and got[5, 6] == 255 * 255 * K
     assert (got[256:, :256] == -1).all()                    # the tile below the diagonal was skipped
