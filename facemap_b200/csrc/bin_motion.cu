@@ -40,7 +40,13 @@ struct K1Params {
   int frame_off;  // frame index of row 0
   int slab;       // rows per slab
   fm_rois rois;
-  const uint8_t* ormask;  // optional [H, W] bytes OR-ed into every frame (0x00 / 0xFF: painted pixels read 255)
+  const uint8_t* ormask;  // optional [H, W] bytes OR-ed into every frame (0x00 / 0xFF: painted pixels read 255)  // optional integer operands for fm_project_i8: the motion energy |S_t - S_(t-1)| (mot) and the block sum S_t (mov)
+  // as u8 planes value = 256 * hi + lo, rows like x_mot / x_mov, pitch ldq bytes (hi may be NULL when sbin == 1)
+  uint8_t* q_mot_hi;
+  uint8_t* q_mot_lo;
+  uint8_t* q_mov_hi;
+  uint8_t* q_mov_lo;
+  int64_t ldq;
 };
 
 // Per-thread geometry of the vector kernel.  Power-of-two bins: 16 raw bytes per row (4 * sbin below sbin 4),
@@ -142,6 +148,34 @@ __device__ __forceinline__ void store_row(float* dst, const float (&x)[PX], int 
     if (j < nvalid) dst[j] = x[j];
 }
 
+// PX integer values (< 65 536) as two byte planes; one packed store per plane when the destination allows
+template <int PX>
+__device__ __forceinline__ void store_planes(uint8_t* hi, uint8_t* lo, size_t off, const unsigned (&v)[PX], int nvalid,
+                                             bool pack_ok) {
+  if (pack_ok && nvalid == PX && PX >= 2) {
+    unsigned wl = 0, wh = 0;
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+      wl |= (v[j] & 0xffu) << (8 * j);
+      wh |= ((v[j] >> 8) & 0xffu) << (8 * j);
+    }
+    if constexpr (PX == 4) {
+      *reinterpret_cast<unsigned*>(lo + off) = wl;
+      if (hi) *reinterpret_cast<unsigned*>(hi + off) = wh;
+    } else {
+      *reinterpret_cast<unsigned short*>(lo + off) = (unsigned short)wl;
+      if (hi) *reinterpret_cast<unsigned short*>(hi + off) = (unsigned short)wh;
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < PX; ++j)
+    if (j < nvalid) {
+      lo[off + j] = (uint8_t)(v[j] & 0xffu);
+      if (hi) hi[off + j] = (uint8_t)(v[j] >> 8);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Vector path: sbin in {1,2,4,8,16}; a thread reads VB = min(16, 4*sbin) bytes per raw row
 // (PX = VB/sbin <= 4 binned pixels).  Needs W % VB == 0 and VB-aligned frames.
@@ -150,7 +184,7 @@ __device__ __forceinline__ void store_row(float* dst, const float (&x)[PX], int 
 // ---------------------------------------------------------------------------------------------
 // PAINT ORs a per-pixel byte mask into the frames as they are loaded (facemap/process.py:543, 567: pupil and
 // blink ROIs paint the chunk buffer that is binned afterwards) — no painted copy of the frames is made.
-template <int SBIN, bool ROI, bool MOV, bool PAINT>
+template <int SBIN, bool ROI, bool MOV, bool PAINT, bool PLANES = false>
 __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Params p) {
   constexpr int PX = k1_px(SBIN);
   constexpr int NW = k1_nw(SBIN);
@@ -313,6 +347,18 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Para
         if (p.x_mot) store_row<PX>(p.x_mot + (size_t)row * p.ldx + p.col0 + pix0, xm, nvalid, vec_ok);
         if constexpr (MOV)
           if (p.x_mov) store_row<PX>(p.x_mov + (size_t)row * p.ldx + p.col0 + pix0, xf, nvalid, vec_ok);
+        if constexpr (PLANES) {                 // integer operands of the kind::i8 projection (own instantiations:
+                                                // the default kernels' code is untouched)
+          const size_t qoff = (size_t)row * p.ldq + p.col0 + pix0;
+          const bool pack_ok = ((p.col0 + pix0) % PX == 0) && (p.ldq % 4 == 0);
+          if (p.q_mot_lo) store_planes<PX>(p.q_mot_hi, p.q_mot_lo, qoff, dvals, nvalid, pack_ok);
+          if (p.q_mov_lo) {
+            unsigned cv[PX];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) cv[j] = (unsigned)prev[j];     // prev == cur after the loop above
+            store_planes<PX>(p.q_mov_hi, p.q_mov_lo, qoff, cv, nvalid, pack_ok);
+          }
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < PX; ++j) dvals[j] = 0u;
@@ -425,6 +471,14 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_generic_kernel(const K1
       const int d = abs(cur - prev);
       if (p.x_mot) p.x_mot[(size_t)row * p.ldx + p.col0 + g] = (float)((double)d / s2 - am);
       if (p.x_mov) p.x_mov[(size_t)row * p.ldx + p.col0 + g] = (float)((double)cur / s2 - af);
+      if (p.q_mot_lo) {
+        p.q_mot_lo[(size_t)row * p.ldq + p.col0 + g] = (uint8_t)(d & 0xff);
+        if (p.q_mot_hi) p.q_mot_hi[(size_t)row * p.ldq + p.col0 + g] = (uint8_t)(d >> 8);
+      }
+      if (p.q_mov_lo) {
+        p.q_mov_lo[(size_t)row * p.ldq + p.col0 + g] = (uint8_t)(cur & 0xff);
+        if (p.q_mov_hi) p.q_mov_hi[(size_t)row * p.ldq + p.col0 + g] = (uint8_t)(cur >> 8);
+      }
       e = (unsigned long long)d;
       tsa += d;
       tsb += cur;
@@ -475,9 +529,17 @@ static int bin_motion_impl(const uint8_t* frames, int T, int H, int W, int sbin,
                            float* x_mot, float* x_mov, int64_t ldx, int64_t col0,
                            unsigned long long* energy, const fm_rois* rois,
                            unsigned long long* roi_energy, int32_t* last_sum, long long* tsum_bin,
-                           long long* tsum_adiff, const uint8_t* ormask, void* stream) {
+                           long long* tsum_adiff, const uint8_t* ormask, void* stream,
+                           uint8_t* q_mot_hi = nullptr, uint8_t* q_mot_lo = nullptr, uint8_t* q_mov_hi = nullptr,
+                           uint8_t* q_mov_lo = nullptr, int64_t ldq = 0) {
   using namespace fm;
   FM_REQUIRE(frames != nullptr && T >= 1 && H >= 1 && W >= 1 && sbin >= 1, "fm_bin_motion: bad shape");
+  if (q_mot_lo || q_mov_lo) {
+    FM_REQUIRE(sbin <= 16, "fm_bin_motion_planes: two byte planes hold block sums up to sbin 16, got %d", sbin);
+    FM_REQUIRE(sbin == 1 || ((q_mot_lo == nullptr || q_mot_hi) && (q_mov_lo == nullptr || q_mov_hi)),
+               "fm_bin_motion_planes: sbin > 1 needs the high planes");
+    FM_REQUIRE(ldq >= col0 + (int64_t)(H / sbin) * (W / sbin), "fm_bin_motion_planes: ldq too small");
+  }
   const int Lyb = H / sbin, Lxb = W / sbin;
   FM_REQUIRE(Lyb >= 1 && Lxb >= 1, "fm_bin_motion: sbin %d larger than the %dx%d frame", sbin, H, W);
   FM_REQUIRE((int64_t)sbin * sbin * 255 * K1_MAX_SLAB < (1ll << 31), "fm_bin_motion: sbin too large");
@@ -494,6 +556,7 @@ static int bin_motion_impl(const uint8_t* frames, int T, int H, int W, int sbin,
   p.frame_off = prev_sum ? 0 : 1;
   if (rois && roi_energy) p.rois = *rois; else p.rois.n = 0;
   p.ormask = ormask;
+  p.q_mot_hi = q_mot_hi; p.q_mot_lo = q_mot_lo; p.q_mov_hi = q_mov_hi; p.q_mov_lo = q_mov_lo; p.ldq = ldq;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   if (p.rows == 0) {
@@ -518,9 +581,12 @@ static int bin_motion_impl(const uint8_t* frames, int T, int H, int W, int sbin,
   const bool roi = p.rois.n > 0;
   const bool mov = x_mov != nullptr;
   const bool paint = ormask != nullptr;
+  const bool planes = q_mot_lo != nullptr || q_mov_lo != nullptr;     // float operands are not written then
 #define FM_K1_LAUNCH_P(S, PT)                                                                        \
   do {                                                                                               \
-    if (roi && mov) bin_motion_vec_kernel<S, true, true, PT><<<grid, K1_THREADS, 0, st>>>(p);        \
+    if (planes && roi) bin_motion_vec_kernel<S, true, false, PT, true><<<grid, K1_THREADS, 0, st>>>(p); \
+    else if (planes) bin_motion_vec_kernel<S, false, false, PT, true><<<grid, K1_THREADS, 0, st>>>(p); \
+    else if (roi && mov) bin_motion_vec_kernel<S, true, true, PT><<<grid, K1_THREADS, 0, st>>>(p);   \
     else if (roi) bin_motion_vec_kernel<S, true, false, PT><<<grid, K1_THREADS, 0, st>>>(p);         \
     else if (mov) bin_motion_vec_kernel<S, false, true, PT><<<grid, K1_THREADS, 0, st>>>(p);         \
     else bin_motion_vec_kernel<S, false, false, PT><<<grid, K1_THREADS, 0, st>>>(p);                 \
@@ -572,6 +638,17 @@ extern "C" int fm_bin_motion_painted(const uint8_t* frames, int T, int H, int W,
   FM_REQUIRE(ormask != nullptr, "fm_bin_motion_painted: ormask is NULL (use fm_bin_motion)");
   return bin_motion_impl(frames, T, H, W, sbin, prev_sum, avgmotion, avgframe, x_mot, x_mov, ldx, col0, energy, rois,
                          roi_energy, last_sum, tsum_bin, tsum_adiff, ormask, stream);
+}
+
+extern "C" int fm_bin_motion_planes(const uint8_t* frames, int T, int H, int W, int sbin, const int32_t* prev_sum,
+                                    uint8_t* q_mot_hi, uint8_t* q_mot_lo, uint8_t* q_mov_hi, uint8_t* q_mov_lo,
+                                    int64_t ldq, int64_t col0, unsigned long long* energy, const fm_rois* rois,
+                                    unsigned long long* roi_energy, int32_t* last_sum, const uint8_t* ormask,
+                                    void* stream) {
+  FM_REQUIRE(q_mot_lo != nullptr || q_mov_lo != nullptr, "fm_bin_motion_planes: no plane to write (use fm_bin_motion)");
+  return bin_motion_impl(frames, T, H, W, sbin, prev_sum, nullptr, nullptr, nullptr, nullptr, 0, col0, energy, rois,
+                         roi_energy, last_sum, nullptr, nullptr, ormask, stream, q_mot_hi, q_mot_lo, q_mov_hi, q_mov_lo,
+                         ldq);
 }
 
 extern "C" int fm_mean_update(float* acc, const long long* tsum, int64_t n, int sbin, int count,

@@ -1,0 +1,279 @@
+// Integer tensor-core projection: V[t,c] = alpha * sum_p D[t,p] * U[c,p] - bias[c], the projection of every frame's
+// motion energy (or binned frame) onto the masks (facemap/process.py:485, 495, 503, 510) with the frame operand as
+// the INTEGERS it is: D = |S_t - S_{t-1}| (or S_t), a sum of sbin^2 bytes, held as one (D < 256) or two u8 planes
+// D = 256 D_hi + D_lo, and every mask row as the s8 / u8 / u8 digits of fm_slice_rows_i8,
+//   U[c,p] ~ 2^(exps[c] - 7) * (Q0 + Q1 / 2^8 + Q2 / 2^16).
+// The ND x 3 plane products run on tcgen05.mma kind::i8 with exact int32 accumulation, one TMEM accumulator per weight
+// class 256^(ND-1-j), j = d + e (products of equal weight share an accumulator): 3 or 4 accumulators of 128 columns.
+// The subtraction of the average (avgmotion / avgframe) is the rank-one term bias[c] = sum_p avg[p] U[c,p], formed once
+// in float64 (fm_row_dot).  Nothing rounds but the 2^-24 digit representation of the masks and the final float32 store.
+//
+// EXPERIMENTAL — written at the end of round 1 without GPU time left (like gemm_i8.cu, whose pipeline this shares):
+// it compiles for sm_100a but has not run yet; nothing in the default path calls it; its GPU test is opt-in
+// (tests/test_project_i8_gpu.py).  Why: the 3xTF32 projection issues 12 TF32 MMAs per 32 K; this one issues 6 (ND = 2)
+// or 3 (ND = 1) kind::i8 MMAs at four times the per-instruction K rate and stages 5 (4) bytes per K element and tile
+// row instead of 16 — DESIGN.md §7.2(a).
+//
+// One CTA per 128 frames x 128 components, the whole K range:
+//   warp 0      TMA producer: ND frame planes (128 x 64 B) and 3 digit planes (128 x 64 B) per stage
+//   warp 1      TMEM allocation (512 columns) and the MMA thread: 2 x ND x 3 instructions per stage; K is cut into
+//               chains of <= 16 384 (2 * 255^2 * 16 384 < 2^31: two u8 x u8 products per accumulator stay exact)
+//   warps 2..9  after each chain: tcgen05.ld of the class accumulators, Horner-combined into one int64 per element
+//               kept in registers (64 columns per thread); at the end  V = alpha * 2^(ex - 23) * acc - bias  in float64
+#include "i8_mma.cuh"
+
+namespace fm {
+namespace pi8 {
+
+using namespace fm::i8;
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int NE = 3;                    // digits per mask entry
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int COLS_PER_THREAD = BN / 2;  // two epilogue warps share a TMEM lane quarter, half the columns each
+constexpr int BAR_BYTES = 256;
+constexpr int KCHAIN = 16384;
+constexpr int TMEM_COLS = 512;
+
+template <int ND>
+struct Cfg {
+  static constexpr int NC = ND + NE - 1;                       // weight classes = TMEM accumulators
+  static constexpr int STAGE_BYTES = (ND * BM + NE * BN) * BKB;
+  static constexpr int STAGES = ND == 1 ? 6 : 5;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static_assert(NC * BN <= TMEM_COLS, "accumulators exceed TMEM");
+  static_assert(SMEM_BYTES <= 232448, "stage ring exceeds shared memory");
+};
+
+struct Params {
+  int M, N, K;
+  float* V;
+  int64_t ldv;
+  const int32_t* exps;
+  const double* bias;
+  double alpha;
+  uint32_t idesc_s8, idesc_u8;           // B operand signed (digit 0) / unsigned (digits 1, 2)
+};
+
+#define FM_I8_TMEM_LD_X8(taddr, r)                                                                       \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"           \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) \
+               : "r"(taddr)                                                                              \
+               : "memory")
+
+template <int ND>
+__global__ void __launch_bounds__(THREADS, 1)
+project_i8_kernel(const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1,
+                  const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
+                  const __grid_constant__ CUtensorMap tmQ2, const Params p) {
+  using C = Cfg<ND>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int NC = C::NC;
+  const int n0 = blockIdx.x * BN;        // the component tiles of one frame tile are neighbours: D is shared through L2
+  const int m0 = blockIdx.y * BM;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t accfull_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t accempty_bar = bar_base + 8u * (2 * STAGES + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + 8 * (2 * STAGES + 2));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nkb = (p.K + BKB - 1) / BKB;
+  constexpr int CHAIN_KB = KCHAIN / BKB;
+  const int nchains = (nkb + CHAIN_KB - 1) / CHAIN_KB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accfull_bar, 1);
+    mbar_init(accempty_bar, NUM_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t stage = smem_base + s * C::STAGE_BYTES;
+        const uint32_t qbase = stage + ND * BM * BKB;
+        mbar_expect_tx(full_bar(s), (uint32_t)C::STAGE_BYTES);
+        tma_load_2d(stage, &tmD0, full_bar(s), i * BKB, m0);
+        if constexpr (ND == 2) tma_load_2d(stage + BM * BKB, &tmD1, full_bar(s), i * BKB, m0);
+        tma_load_2d(qbase, &tmQ0, full_bar(s), i * BKB, n0);
+        tma_load_2d(qbase + BN * BKB, &tmQ1, full_bar(s), i * BKB, n0);
+        tma_load_2d(qbase + 2 * BN * BKB, &tmQ2, full_bar(s), i * BKB, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int i = 0;
+      for (int c = 0; c < nchains; ++c) {
+        if (c > 0) {                                       // the epilogue has drained the previous chain
+          mbar_wait(accempty_bar, (uint32_t)(c - 1) & 1u);
+          tcgen05_fence_after();
+        }
+        const int len = min(CHAIN_KB, nkb - c * CHAIN_KB);
+        for (int j = 0; j < len; ++j, ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tcgen05_fence_after();
+          const uint32_t stage = smem_base + s * C::STAGE_BYTES;
+          const uint32_t qbase = stage + ND * BM * BKB;
+#pragma unroll
+          for (int k = 0; k < BKB / 32; ++k) {             // K = 32 per instruction = 32 bytes = 2 descriptor units
+            const uint64_t adv = (uint64_t)(k * 2);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+              const uint64_t dd = make_desc(stage + d * BM * BKB) + adv;
+#pragma unroll
+              for (int e = 0; e < NE; ++e) {
+                const uint64_t dq = make_desc(qbase + e * BN * BKB) + adv;
+                // issue order (d outer, e inner): class d + e is first written by (0, e) or by (d, NE - 1)
+                const bool opens = (d == 0 || e == NE - 1);
+                umma_i8(tmem_acc + (uint32_t)((d + e) * BN), dd, dq, e == 0 ? p.idesc_s8 : p.idesc_u8,
+                        (opens && j == 0 && k == 0) ? 0u : 1u);
+              }
+            }
+          }
+          tcgen05_commit(empty_bar(s));
+        }
+        tcgen05_commit(accfull_bar);
+      }
+    }
+  } else {
+    const int q = warp & 3;                                // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;                      // which 64 of the 128 columns of every class
+    long long acc[COLS_PER_THREAD];
+#pragma unroll
+    for (int t = 0; t < COLS_PER_THREAD; ++t) acc[t] = 0;
+    for (int c = 0; c < nchains; ++c) {
+      mbar_wait(accfull_bar, (uint32_t)c & 1u);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < COLS_PER_THREAD; cc += 8) {
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_THREAD + cc);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {                     // class j carries the weight 256^(NC-1-j)
+          uint32_t r[8];
+          FM_I8_TMEM_LD_X8(taddr + (uint32_t)(j * BN), r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc[cc + t] += (long long)(int32_t)r[t] * (1ll << (8 * (NC - 1 - j)));
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accempty_bar);
+    }
+    // V = alpha * 2^(ex - 7) * 256^-(NE-1) * acc - bias
+    const int m = m0 + q * 32 + lane;
+    if (m < p.M) {
+      float* dst_row = p.V + (size_t)m * p.ldv;
+      const bool vec_ok = (p.ldv % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.V) & 15) == 0);
+      const int nbase = n0 + half * COLS_PER_THREAD;
+#pragma unroll
+      for (int t = 0; t < COLS_PER_THREAD; t += 4) {
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = nbase + t + u;
+          double v = 0.0;
+          if (n < p.N) {
+            // 2^(ex - 23) built from its exponent field (|ex| <= 126 by fm::slice_exponent: always normal)
+            v = (double)acc[t + u] * (p.alpha * __hiloint2double((1023 + p.exps[n] - 7 - 8 * (NE - 1)) << 20, 0));
+            if (p.bias) v -= p.bias[n];
+          }
+          o[u] = (float)v;
+        }
+        const int n = nbase + t;
+        if (vec_ok && n + 4 <= p.N) {
+          *reinterpret_cast<float4*>(dst_row + n) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (n + u < p.N) dst_row[n + u] = o[u];
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int ND>
+static int launch(const uint8_t* D_hi, const uint8_t* D_lo, int64_t ldd, const int8_t* Q0, const uint8_t* Q1,
+                  const uint8_t* Q2, int64_t ldq, const Params& p, cudaStream_t st) {
+  using C = Cfg<ND>;
+  CUtensorMap td0, td1, tq0, tq1, tq2;
+  int rc;
+  // plane 0 is the most significant one
+  if ((rc = make_map_u8(&td0, ND == 2 ? D_hi : D_lo, ldd, p.M, p.K, BM)) != FM_OK) return rc;
+  td1 = td0;
+  if (ND == 2 && (rc = make_map_u8(&td1, D_lo, ldd, p.M, p.K, BM)) != FM_OK) return rc;
+  if ((rc = make_map_u8(&tq0, reinterpret_cast<const uint8_t*>(Q0), ldq, p.N, p.K, BN)) != FM_OK) return rc;
+  if ((rc = make_map_u8(&tq1, Q1, ldq, p.N, p.K, BN)) != FM_OK) return rc;
+  if ((rc = make_map_u8(&tq2, Q2, ldq, p.N, p.K, BN)) != FM_OK) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(project_i8_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  });
+  FM_CUDA_TRY(attr_err);
+  dim3 grid((unsigned)cdiv(p.N, BN), (unsigned)cdiv(p.M, BM), 1);
+  project_i8_kernel<ND><<<grid, THREADS, C::SMEM_BYTES, st>>>(td0, td1, tq0, tq1, tq2, p);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+}  // namespace pi8
+}  // namespace fm
+
+extern "C" int fm_project_i8(const uint8_t* D_hi, const uint8_t* D_lo, int64_t ldd, const int8_t* Q0, const uint8_t* Q1,
+                             const uint8_t* Q2, int64_t ldq, const int32_t* exps, int M, int N, int K, double alpha,
+                             const double* bias, float* V, int64_t ldv, void* stream) {
+  using namespace fm;
+  using namespace fm::pi8;
+  FM_REQUIRE(D_lo && Q0 && Q1 && Q2 && exps && V && M >= 1 && N >= 1 && K >= 1 && ldv >= N,
+             "fm_project_i8: bad args M=%d N=%d K=%d", M, N, K);
+  FM_REQUIRE(ldd >= K && ldq >= K && ldd % 16 == 0 && ldq % 16 == 0 &&
+                 ((reinterpret_cast<uintptr_t>(D_hi) | reinterpret_cast<uintptr_t>(D_lo) |
+                   reinterpret_cast<uintptr_t>(Q0) | reinterpret_cast<uintptr_t>(Q1) | reinterpret_cast<uintptr_t>(Q2)) & 15) == 0,
+             "fm_project_i8: TMA operands need 16-byte aligned bases and row pitches (ldd=%lld ldq=%lld)",
+             (long long)ldd, (long long)ldq);
+  FM_REQUIRE(cdiv(M, BM) <= 65535, "fm_project_i8: more than 65535 frame tiles; project in batches");
+  FM_REQUIRE(K <= (1 << 22), "fm_project_i8: K = %d exceeds 2^22 (int64 accumulation over 256 chains)", K);
+  // instruction descriptor (cute/arch/mma_sm100_desc.hpp layout): c_format S32 = 2 at bit 4, a/b format (0 = u8,
+  // 1 = s8) at bits 7 / 10, K-major operands, N >> 3 at bit 17, M >> 4 at bit 24
+  const uint32_t idesc_u8 = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  Params p{M, N, K, V, ldv, exps, bias, alpha, idesc_u8 | (1u << 10), idesc_u8};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return D_hi ? launch<2>(D_hi, D_lo, ldd, Q0, Q1, Q2, ldq, p, st) : launch<1>(nullptr, D_lo, ldd, Q0, Q1, Q2, ldq, p, st);
+}

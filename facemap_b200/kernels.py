@@ -239,6 +239,79 @@ def gram_assemble_i8(P, ksplit, n, exps, mean, ncols, out=None):
     return out
 
 
+def bin_motion_planes(frames, sbin, *, prev_sum=None, q_mot=None, q_mov=None, col0=0, energy=None, rois=None,
+                      roi_energy=None, last_sum=None, ormask=None):
+    """EXPERIMENTAL (fm_bin_motion_planes): K1 writing its integer results as byte planes.  q_mot / q_mov: (hi, lo)
+    pairs of uint8 [rows, >= col0 + npix] matrices sharing one row pitch (hi may be None when sbin == 1); they receive
+    |S_t - S_(t-1)| and S_t as 256 * hi + lo — the frame operands of `project_i8`."""
+    _need(frames, torch.uint8, "frames", 3)
+    if not frames.is_contiguous():
+        raise FacemapB200Error("frames must be contiguous [T, H, W]")
+    T, H, W = frames.shape
+    npix = (H // sbin) * (W // sbin)
+    rows = T if prev_sum is not None else T - 1
+    _need(prev_sum, torch.int32, "prev_sum")
+    _need(energy, torch.int64, "energy")
+    _need(roi_energy, torch.int64, "roi_energy")
+    _need(last_sum, torch.int32, "last_sum")
+    if q_mot is None and q_mov is None:
+        raise FacemapB200Error("bin_motion_planes: no planes to write")
+    ldq, ptrs = 0, []
+    for pair, name in ((q_mot, "q_mot"), (q_mov, "q_mov")):
+        hi, lo = (None, None) if pair is None else pair
+        if pair is not None and (lo is None or (hi is None and sbin > 1)):
+            raise FacemapB200Error(f"bin_motion_planes: {name} needs (hi, lo) planes (hi optional only for sbin 1)")
+        for q in (hi, lo):
+            if q is not None:
+                _need(q, torch.uint8, name, 2)
+                if q.stride(1) != 1 or q.shape[0] < rows or col0 + npix > q.shape[1] or (ldq and q.stride(0) != ldq):
+                    raise FacemapB200Error(f"bin_motion_planes: {name} planes must be row-major [>= {rows}, >= "
+                                           f"{col0 + npix}] with one shared pitch")
+                ldq = q.stride(0)
+        ptrs += [ptr(hi), ptr(lo)]
+    for v, n, name in ((prev_sum, npix, "prev_sum"), (last_sum, npix, "last_sum"), (energy, rows, "energy")):
+        if v is not None and (v.numel() < n or not v.is_contiguous()):
+            raise FacemapB200Error(f"{name}: needs {n} contiguous elements, has {v.numel()}")
+    r = None
+    if roi_energy is not None:
+        r = rois if isinstance(rois, Rois) else Rois.from_rects(rois or [])
+        if roi_energy.numel() < r.n * rows:
+            raise FacemapB200Error("roi_energy too small")
+    if ormask is not None:
+        _need(ormask, torch.uint8, "ormask", 2)
+        if tuple(ormask.shape) != (H, W) or not ormask.is_contiguous():
+            raise FacemapB200Error(f"ormask: expected a contiguous [{H}, {W}] uint8 tensor")
+    check(_lib.load().fm_bin_motion_planes(ptr(frames), T, H, W, int(sbin), ptr(prev_sum), *ptrs, ldq, int(col0),
+                                           ptr(energy), C.byref(r) if r is not None else None, ptr(roi_energy),
+                                           ptr(last_sum), ptr(ormask), _stream()), "fm_bin_motion_planes")
+    return rows
+
+
+def project_i8(D, Q, exps, alpha, bias, V):
+    """EXPERIMENTAL (fm_project_i8): V[t, c] = alpha * sum_p D[t, p] U[c, p] - bias[c] on tcgen05 kind::i8, exactly.
+    D: (hi, lo) uint8 [M, K] planes of one pitch (hi None for operands < 256); Q: the (Q0 int8, Q1, Q2 uint8) [N, K]
+    digit planes and `exps` of `slice_rows_i8(U)`; bias: float64 [N] or None; V: float32 [M, >= N] row-major."""
+    hi, lo = D
+    Q0, Q1, Q2 = Q
+    _need(lo, torch.uint8, "D_lo", 2)
+    _need(hi, torch.uint8, "D_hi", 2)
+    M, Kd = lo.shape
+    N = Q0.shape[0]
+    if lo.stride(1) != 1 or (hi is not None and (tuple(hi.shape) != (M, Kd) or hi.stride(1) != 1 or hi.stride(0) != lo.stride(0))):
+        raise FacemapB200Error("project_i8: D planes must be row-major [M, K] with one shared pitch")
+    for q, dt in ((Q0, torch.int8), (Q1, torch.uint8), (Q2, torch.uint8)):
+        if q.dtype != dt or not q.is_cuda or tuple(q.shape) != (N, Kd) or q.stride(1) != 1 or q.stride(0) != Q0.stride(0):
+            raise FacemapB200Error("project_i8: Q must be int8 / uint8 / uint8 [N, K] planes with one shared pitch")
+    _need(exps, torch.int32, "exps", 1)
+    _need(bias, torch.float64, "bias", 1)
+    _need(V, torch.float32, "V", 2)
+    if exps.numel() < N or (bias is not None and bias.numel() < N) or V.shape[0] < M or V.shape[1] < N or V.stride(1) != 1:
+        raise FacemapB200Error("project_i8: exps / bias need N entries and V must be row-major [>= M, >= N]")
+    check(_lib.load().fm_project_i8(ptr(hi), ptr(lo), lo.stride(0), ptr(Q0), ptr(Q1), ptr(Q2), Q0.stride(0), ptr(exps),
+                                    M, N, Kd, float(alpha), ptr(bias), ptr(V), V.stride(0), _stream()), "fm_project_i8")
+    return V
+
+
 def splitk_reduce(workspace, ksplit, C_out, *, rscale=None, rbias=None):
     """C[m,n] = rscale[m] * sum_s workspace[s,m,n] + rbias[m], summed in float64."""
     _need(workspace, torch.float32, "workspace", 3)

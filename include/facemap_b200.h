@@ -96,6 +96,19 @@ int fm_bin_motion_painted(const uint8_t* frames, int T, int H, int W, int sbin,
                           const uint8_t* ormask, void* stream);
 
 /*
+ * EXPERIMENTAL (not yet run on a GPU): K1 writing its integer results instead of the float32 operands — the motion
+ * energy |S_t - S_(t-1)| (q_mot_*) and / or the block sum S_t (q_mov_*) of every binned pixel (facemap/process.py:34-43,
+ * 455-461 before the division and the subtraction of the average) as two uint8 planes, value = 256 * hi + lo, rows and
+ * columns like x_mot / x_mov of fm_bin_motion, row pitch ldq bytes.  These are the frame operands of fm_project_i8.
+ * sbin <= 16; the high planes may be NULL for sbin == 1; either pair may be NULL; ormask may be NULL.  energy,
+ * roi_energy, last_sum as in fm_bin_motion.
+ */
+int fm_bin_motion_planes(const uint8_t* frames, int T, int H, int W, int sbin, const int32_t* prev_sum,
+                         uint8_t* q_mot_hi, uint8_t* q_mot_lo, uint8_t* q_mov_hi, uint8_t* q_mov_lo, int64_t ldq,
+                         int64_t col0, unsigned long long* energy, const fm_rois* rois,
+                         unsigned long long* roi_energy, int32_t* last_sum, const uint8_t* ormask, void* stream);
+
+/*
  * Motion energy in the reference's own floating-point arithmetic (facemap/process.py:34-43, 455-460): per row
  * the sum over the view's binned pixels of |b_t - b_{t-1}|, b = float64 mean of means (sbin > 1) or float32
  * pixel value (sbin == 1), summed in NumPy's pairwise order — bit-identical to `imbin_mot.sum(-1)`.  Needed
@@ -176,6 +189,20 @@ int fm_slice_rows_i8(const float* X, int64_t ldx, int rows, int64_t ncols, int8_
                      int64_t ldq, int32_t* exps, void* stream);
 int fm_gram_assemble_i8(const int32_t* P, int ksplit, int n, int64_t ldp, const int32_t* exps, const double* mean,
                         int64_t ncols, double* G, void* stream);
+
+/*
+ * EXPERIMENTAL (not yet run on a GPU): the projection of process_ROIs (facemap/process.py:485, 495, 503, 510) on the
+ * integer tensor cores.  V[t,c] (float32) = alpha * sum_p D[t,p] U[c,p] - bias[c] with the frame operand as integers
+ * D = 256 * D_hi + D_lo (u8 planes [M, ldd]; D_hi may be NULL for operands below 256: sbin 1) — the motion energy
+ * |S_t - S_(t-1)| or the block sum S_t that fm_bin_motion forms, alpha = 1 / sbin^2 — and the masks as the digit planes
+ * of fm_slice_rows_i8 (Q0 int8, Q1 / Q2 uint8 [N, ldq], exps[N]).  bias[c] = sum_p avg[p] U[c,p] (float64, fm_row_dot;
+ * may be NULL) carries the subtraction of avgmotion / avgframe.  Exact int32 accumulation in chains of 16 384 K,
+ * int64 across chains, one float64 scaling and one rounding to float32 per output.  Pitches in bytes, multiples of 16;
+ * 16-byte aligned plane bases; K <= 2^22.  DESIGN.md section 7.2(a).
+ */
+int fm_project_i8(const uint8_t* D_hi, const uint8_t* D_lo, int64_t ldd, const int8_t* Q0, const uint8_t* Q1,
+                  const uint8_t* Q2, int64_t ldq, const int32_t* exps, int M, int N, int K, double alpha,
+                  const double* bias, float* V, int64_t ldv, void* stream);
 
 /* lo[r,c] = X[r,c] - tf32_trunc(X[r,c]): pre-computed second plane of a B operand that many GEMMs
  * reuse (pass it as B_lo above). */
