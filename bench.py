@@ -395,11 +395,22 @@ def main():
     if mm["achieved"]:
         mm["frac"] = mm["achieved"] / tc_peak
         mm["issued_tf32_tflops"] = 3 * mm["achieved"]
+    proj_i8 = os.environ.get("FM_PROJ_MODE") == "i8"
+    if proj_i8:     # experimental integer projection: byte planes out of K1, kind::i8 products (6 per 32 K at sbin 4)
+        k1.update({"kernel": "bin_motion_vec_kernel<4, planes> (stage 3)", "algorithmic_bytes_per_frame": H * W + 2 * p})
+        if k1_ms:
+            k1["achieved"] = rows3 * (H * W + 2 * p) / (k1_ms * 1e-3) / 1e9
+            k1["frac"] = k1["achieved"] / hbm_peak
+        mm.update({"kernel": "project_i8_kernel<2> (stage 3 projection)",
+                   "note": "peak = measured dense bf16; kind::i8 runs at twice the bf16 rate and 6 plane products form "
+                           "one algorithmic product (2 frame planes x 3 mask digits), so frac <= 1/3 by construction"})
+        mm.pop("issued_tf32_tflops", None)
     dominant, other = (mm, k1) if mma_ms >= k1_ms else (k1, mm)
     traffic = None
     try:    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = tj["gemm_tf32x3_projection" if dominant is mm else "bin_motion_vec_kernel"]["bytes_per_launch"]
+        traffic = None if proj_i8 else traffic               # no ncu capture of the experimental kernels yet
     except Exception:
         pass
     mm["algorithmic_bytes_per_launch"] = 4 * (18944 * p + NCOMP * p + 18944 * NCOMP)
@@ -467,6 +478,7 @@ def main():
             "config": {"workload": WORKLOAD, "frames_total": total_frames, "frame_bytes": H * W,
                        "l2": "inputs (30.7 GB per GPU) exceed L2; no flush needed", "parallelism": f"frame-range x{world}",
                        **({"gram_mode": os.environ["FM_GRAM_MODE"]} if os.environ.get("FM_GRAM_MODE") else {}),
+                       **({"proj_mode": os.environ["FM_PROJ_MODE"]} if os.environ.get("FM_PROJ_MODE") else {}),
                        **({"rois": "pupil 100x140 + blink 100x140 + running 120x400 (side measurement)"} if args.with_rois else {})},
             "clocks": clk, "e2e": e2e if e2e is not None else ({"value": None, "skipped": e2e_skip} if e2e_skip else None),
             "gpu_launches": int(launches),

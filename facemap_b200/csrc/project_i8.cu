@@ -203,9 +203,11 @@ project_i8_kernel(const __grid_constant__ CUtensorMap tmD0, const __grid_constan
           const int n = nbase + t + u;
           double v = 0.0;
           if (n < p.N) {
-            // 2^(ex - 23) built from its exponent field (|ex| <= 126 by fm::slice_exponent: always normal)
-            v = (double)acc[t + u] * (p.alpha * __hiloint2double((1023 + p.exps[n] - 7 - 8 * (NE - 1)) << 20, 0));
-            if (p.bias) v -= p.bias[n];
+            // 2^(ex - 23) built from its exponent field (|ex| <= 126 by fm::slice_exponent: always normal); separately
+            // rounded multiply and subtract (no FMA contraction) so that a host model reproduces every bit
+            const double sc = __dmul_rn(p.alpha, __hiloint2double((1023 + p.exps[n] - 7 - 8 * (NE - 1)) << 20, 0));
+            v = __dmul_rn((double)acc[t + u], sc);
+            if (p.bias) v = __dsub_rn(v, p.bias[n]);
           }
           o[u] = (float)v;
         }

@@ -174,6 +174,13 @@ class SvdWorkspace:
         # pass A of sliced_gram on the one-product kernel (fm_gemm_tn impl 10) instead of the 3xTF32 kernel with a
         # zero lo plane: a third of the MMAs, no zero plane to stage
         self.sliced_single = _os.environ.get("FM_SLICED_SINGLE", "0") == "1"
+        # how stage 3 projects the frames onto the masks:
+        #   "tf32x3"  K1 writes float32 operands, one 3xTF32 GEMM per batch — the measured default
+        #   "i8"      EXPERIMENTAL: K1 writes the integer energies / block sums as byte planes, the masks become s8/u8/u8
+        #             digits and fm_project_i8 forms the products exactly on tcgen05 kind::i8 (Stage3)
+        self.proj_mode = _os.environ.get("FM_PROJ_MODE", "tf32x3")
+        if self.proj_mode not in ("tf32x3", "i8"):
+            raise FacemapB200Error(f"unknown FM_PROJ_MODE {self.proj_mode!r}")
         self._ws = None
         self._bufs = {}
 
@@ -562,13 +569,22 @@ def stage2_plan(N, ncomps=NCOMPS):
 
 
 def _bin_chunk(frames, geo, avgframe, avgmotion, mods, X, prev=None, last=None, energy=None, roi_energy=None,
-               ormask=None):
+               ormask=None, planes=False):
     """K1 over every view of one fetched chunk into the modality matrices X[m] ([rows, p]).
-    ormask: per-view paint masks (fullres.FullRes.ormask) OR-ed into the frames on load, or None."""
+    ormask: per-view paint masks (fullres.FullRes.ormask) OR-ed into the frames on load, or None.
+    planes: X[m] are (hi, lo) uint8 plane pairs that receive the integer results (fm_bin_motion_planes)."""
     rows = None
     for v, fr in enumerate(frames):
         c0, n = geo.col0[v], geo.npix_v[v]
         rects = [geo.mot_rois[j][1:] for j in geo.rois_on_view[v]]
+        if planes and mods:
+            rows = K.bin_motion_planes(
+                fr, geo.sbin, prev_sum=None if prev is None else prev[v], q_mot=X.get("mot"), q_mov=X.get("mov"),
+                col0=c0, energy=None if energy is None else energy[v],
+                rois=Rois.from_rects(rects) if (roi_energy is not None and rects) else None,
+                roi_energy=None if (roi_energy is None or not rects) else roi_energy[v],
+                last_sum=None if last is None else last[v], ormask=None if ormask is None else ormask[v])
+            continue
         rows = K.bin_motion(
             fr, geo.sbin,
             prev_sum=None if prev is None else prev[v],
@@ -753,6 +769,12 @@ class Stage3:
         self.rows_total = max(0, self.f1 - self.first_row_frame)
         self.X_full = None
         self.early_done = None
+        # integer-plane operands for fm_project_i8 (ws.proj_mode == "i8"); asked for but not servable is an error, not
+        # a silent change of path
+        self.i8 = ws.proj_mode == "i8" and bool(mods)
+        if self.i8 and (not fullSVD or geo.mot_rois or geo.sbin > 16):
+            raise FacemapB200Error("FM_PROJ_MODE=i8 serves full-frame projections without motion ROIs at sbin <= 16")
+        self.ldq = K.round_up(geo.p, 16)
         self._halo_done = False
         # views whose float32 motion accumulator the exact integer energy cannot decide (fm_motion_ref)
         self.Eref, self.ref_views = None, []
@@ -766,6 +788,21 @@ class Stage3:
             self.ref_scratch = {v: K.motion_ref_scratch(geo.Ly[v], geo.Lx[v], geo.sbin, self.ref_plan[v][0].numel(),
                                                         self.ref_blocks[v], device) for v in self.ref_views}
             self.ref_last = {v: None for v in self.ref_views}
+
+    def _operands(self, tag, rows):
+        """per-modality stage-3 operands for `rows` difference rows: float32 [rows, p], or (hi, lo) byte planes"""
+        if not self.i8:
+            return {m: self.ws.matrix(tag + m, rows, self.geo.p) for m in self.mods}
+        out = {}
+        for m in self.mods:
+            buf = self.ws.raw(tag + "q." + m, 2 * max(rows, 1) * self.ldq, torch.uint8).view(2, max(rows, 1), self.ldq)
+            out[m] = (buf[0, :rows, :self.geo.p] if self.geo.sbin > 1 else None, buf[1, :rows, :self.geo.p])
+        return out
+
+    def _rows_of(self, X, r0, r1):
+        if not self.i8:
+            return {m: X[m][r0:r1] for m in self.mods}
+        return {m: (None if X[m][0] is None else X[m][0][r0:r1], X[m][1][r0:r1]) for m in self.mods}
 
     # ---- bin phase -------------------------------------------------------------------------------
     def _seed_halo(self):
@@ -799,7 +836,7 @@ class Stage3:
             first_frame = t if have else t + 1
             with self.timer("stage3.bin"):
                 r = row0 + filled
-                Xv = {m: X[m][r:r + rows] for m in self.mods} if rows > 0 else {m: None for m in self.mods}
+                Xv = self._rows_of(X, r, r + rows) if rows > 0 else {m: None for m in self.mods}
                 o = first_frame - self.f0
                 energy = [self.E[v, o:o + rows] for v in range(self.nv)]
                 roi_e = []
@@ -812,7 +849,7 @@ class Stage3:
                            prev=self.carry[self.flip] if have else None, last=self.carry[1 - self.flip],
                            energy=energy if rows > 0 else None,
                            roi_energy=roi_e if (self.nroi and rows > 0) else None,
-                           ormask=None if self.fullres is None else self.fullres.ormask)
+                           ormask=None if self.fullres is None else self.fullres.ormask, planes=self.i8)
                 if self.nroi and rows > 0:
                     for v in range(self.nv):
                         for q, j in enumerate(geo.rois_on_view[v]):
@@ -831,11 +868,11 @@ class Stage3:
         """Enqueue the whole bin phase on a side stream (see class docstring).  Returns True if taken."""
         if self.rows_total == 0 or not self.mods or not self.source.resident(self.f0, self.f1):
             return False
-        need = len(self.mods) * self.rows_total * max(32, K.round_up(self.geo.p, 32)) * 4
+        need = len(self.mods) * self.rows_total * (2 * self.ldq if self.i8 else max(32, K.round_up(self.geo.p, 32)) * 4)
         free, _ = torch.cuda.mem_get_info(self.device)
         if need > budget_bytes or need > 0.5 * free:
             return False
-        self.X_full = {m: self.ws.matrix("X3full." + m, self.rows_total, self.geo.p) for m in self.mods}
+        self.X_full = self._operands("X3full.", self.rows_total)
         main = torch.cuda.current_stream()
         side = torch.cuda.Stream(self.device)
         side.wait_stream(main)
@@ -865,12 +902,19 @@ class Stage3:
                         h[:self.first_row_frame - self.f0].zero_()      # frame 0 has no difference row
         # the masks are the B operand of every projection GEMM: split them once (lo plane), TMA stages both
         with timer("stage3.split_masks"):
-            Ut_lo = {m: [None if Ut is None else K.split_lo(Ut) for Ut in masks[m][0]] for m in mods}
+            if self.i8:
+                # digits of the masks and the rank-one term of the subtracted average, once per run
+                avg = {"mot": self.avgmotion, "mov": self.avgframe}
+                Ut_q = {m: K.slice_rows_i8(masks[m][0][0]) for m in mods}
+                Ut_bias = {m: K.row_dot(masks[m][0][0], avg[m].double()) for m in mods}
+                Ut_lo = None
+            else:
+                Ut_lo = {m: [None if Ut is None else K.split_lo(Ut) for Ut in masks[m][0]] for m in mods}
         if self.X_full is not None:
             torch.cuda.current_stream().wait_event(self.early_done)
             X = self.X_full
         else:
-            X = {m: ws.matrix("X3." + m, self.rows_batch, geo.p) for m in mods}
+            X = self._operands("X3.", self.rows_batch)
             self._seed_halo()
         row0 = 0
         for fetches, filled in self.batches:
@@ -884,6 +928,13 @@ class Stage3:
             o = self.first_row_frame + row0 - self.f0
             for m in mods:
                 Uts = masks[m][0]
+                if self.i8:
+                    with timer("stage3.project.mma"):
+                        K.project_i8(self._rows_of(X, base, base + filled)[m], Ut_q[m][:3], Ut_q[m][3],
+                                     1.0 / (geo.sbin * geo.sbin), Ut_bias[m], V[m][0][o:o + filled])
+                    if sink is not None:
+                        sink.copy(V[m][0][o:o + filled], V_host[m][0][o:o + filled])
+                    continue
                 Xm = X[m][base:base + filled]
                 if self.fullSVD and Uts[0] is not None:
                     ws.gemm(Xm, Uts[0], V[m][0][o:o + filled], label="stage3.project", B_lo=Ut_lo[m][0], impl=ws.proj_impl,
