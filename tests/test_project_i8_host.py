@@ -171,3 +171,101 @@ def test_stage3_i8_refuses_what_it_cannot_serve():
     src = ArraySource([np.zeros((5, 32, 32), np.uint8)])
     with pytest.raises(svd.FacemapB200Error):
         svd.Stage3(src, geo, None, None, ["mot"], True, ws, torch.device("cpu"), svd.StageTimer(enabled=False))
+
+
+class FloatFakeKernels:
+    """contracts of the kernels Stage3 calls on its DEFAULT path (float32 operands, fm_gemm_tn), on CPU tensors"""
+
+    round_up = staticmethod(FakeKernels.round_up)
+
+    def __init__(self):
+        self.gemms = []
+
+    @staticmethod
+    def bin_motion(frames, sbin, *, prev_sum=None, avgmotion=None, avgframe=None, x_mot=None, x_mov=None, col0=0,
+                   energy=None, rois=None, roi_energy=None, last_sum=None, tsum_bin=None, tsum_adiff=None, ormask=None):
+        S = M8.block_sums(frames.numpy(), sbin)
+        npix = S.shape[1]
+        prev = S[:1] if prev_sum is None else prev_sum.numpy().astype(np.int64)[None, :]
+        cur = S[1:] if prev_sum is None else S
+        d = np.abs(np.diff(np.concatenate([prev, cur]), axis=0))
+        rows = d.shape[0]
+        if x_mot is not None:
+            x_mot[:rows, col0:col0 + npix] = torch.from_numpy((d / sbin ** 2 - avgmotion.numpy().astype(np.float64)).astype(np.float32))
+        if x_mov is not None:
+            x_mov[:rows, col0:col0 + npix] = torch.from_numpy((cur / sbin ** 2 - avgframe.numpy().astype(np.float64)).astype(np.float32))
+        if energy is not None:
+            energy[:rows] = torch.from_numpy(d.sum(axis=1))
+        if roi_energy is not None and rois is not None:
+            Lxb = frames.shape[2] // sbin
+            img = d.reshape(rows, -1, Lxb)
+            for q in range(rois.n):
+                roi_energy.view(rois.n, -1)[q, :rows] = torch.from_numpy(
+                    img[:, rois.y0[q]:rois.y1[q], rois.x0[q]:rois.x1[q]].sum(axis=(1, 2)))
+        if last_sum is not None:
+            last_sum.copy_(torch.from_numpy(S[-1].astype(np.int32)))
+        return rows
+
+    @staticmethod
+    def split_lo(X, out=None):
+        return torch.zeros_like(X)
+
+    @staticmethod
+    def gather_roi(X, rows, col0, Lxb, rect, out):
+        y0, y1, x0, x1 = rect
+        cols = [col0 + y * Lxb + x for y in range(y0, y1) for x in range(x0, x1)]
+        out[:rows] = X[:rows, cols]
+
+    def gemm_tn(self, A, B, C_out=None, *, rscale=None, rbias=None, ksplit=1, workspace=None, upper_only=False, impl=0,
+                B_lo=None, A_lo=None):
+        assert rscale is None and rbias is None
+        P = torch.from_numpy((A.numpy().astype(np.float64) @ B.numpy().astype(np.float64).T).astype(np.float32))
+        if ksplit > 1:                                      # narrow outputs: K partials, summed by splitk_reduce
+            workspace[:ksplit].zero_()
+            workspace[0, :A.shape[0], :B.shape[0]] = P
+        else:
+            C_out[:A.shape[0], :B.shape[0]] = P
+        self.gemms.append((A.shape[0], B.shape[0], A.shape[1]))
+
+    @staticmethod
+    def splitk_reduce(workspace, ksplit, C_out, *, rscale=None, rbias=None):
+        C_out.copy_(workspace[:ksplit].sum(dim=0)[:C_out.shape[0], :C_out.shape[1]])
+
+
+@pytest.mark.parametrize("fetch_frames", [17, 1000])
+def test_stage3_default_float_orchestration(monkeypatch, fetch_frames):
+    """the default path through Stage3 (the one measured on the B200) with stand-in kernels: two views, motion and
+    movie operands, one motion ROI — guards the operand bookkeeping shared with the plane mode"""
+    rs = np.random.RandomState(77)
+    N, k, sbin = 61, 12, 2
+    views = [rs.randint(0, 256, size=(N, 24, 36)).astype(np.uint8), rs.randint(0, 256, size=(N, 16, 20)).astype(np.uint8)]
+    roi = {"rind": 1, "ivid": 1, "yrange_bin": np.arange(2, 6), "xrange_bin": np.arange(3, 9)}
+    geo = svd.Geometry([24, 16], [36, 20], sbin, [roi])
+    S = np.concatenate([M8.block_sums(v, sbin) for v in views], axis=1)
+    d = np.abs(np.diff(S, axis=0))
+    avgmotion = (d.mean(axis=0) / sbin ** 2).astype(np.float32)
+    avgframe = (S.mean(axis=0) / sbin ** 2).astype(np.float32)
+    mods = ["mot", "mov"]
+    U = {m: _masks(rs, k, geo.p) for m in mods}
+    Ur = {m: _masks(rs, 5, geo.roi_npix[0]) for m in mods}
+    fake = FloatFakeKernels()
+    monkeypatch.setattr(svd, "K", fake)
+    ws = object.__new__(svd.SvdWorkspace)
+    ws.device, ws._bufs, ws._ws = torch.device("cpu"), {}, None
+    ws.proj_mode, ws.proj_impl, ws.gemm_impl = "tf32x3", 0, 0
+    ws.timer = svd.StageTimer(enabled=False)
+    st = svd.Stage3(ArraySource(views), geo, torch.from_numpy(avgframe), torch.from_numpy(avgmotion), mods, True, ws,
+                    torch.device("cpu"), ws.timer, fetch_frames=fetch_frames)
+    assert not st.i8
+    masks = {m: ([torch.from_numpy(U[m]), torch.from_numpy(Ur[m])], None) for m in mods}
+    V, E, E_roi = st.project(masks)
+    assert np.array_equal(E.numpy()[:, 1:].sum(axis=0), d.sum(axis=1))
+    c0, Lxb = geo.col0[1], int(geo.Lxb[1])
+    cols = [c0 + y * Lxb + x for y in range(2, 6) for x in range(3, 9)]
+    assert np.array_equal(E_roi.numpy()[0, 1:], d[:, cols].sum(axis=1))
+    X = {"mot": d / sbin ** 2 - avgmotion.astype(np.float64), "mov": S[1:] / sbin ** 2 - avgframe.astype(np.float64)}
+    for m in mods:
+        want = X[m] @ U[m].astype(np.float64).T
+        assert np.abs(V[m][0].numpy()[1:] - want).max() <= 2e-6 * np.abs(want).max() and not V[m][0].numpy()[0].any()
+        want_r = X[m][:, cols] @ Ur[m].astype(np.float64).T
+        assert np.abs(V[m][1].numpy()[1:] - want_r).max() <= 2e-6 * np.abs(want_r).max()
