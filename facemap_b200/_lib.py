@@ -78,6 +78,7 @@ SIGNATURES = {
     "fm_topk_components": (_I, [_P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P]),
     "fm_transpose": (_I, [_P, _L, _I, _I, _P, _L, _P]),
     "fm_gather_roi": (_I, [_P, _L, _I, _L, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "fm_gather_roi_u8": (_I, [_P, _L, _I, _L, _I, _I, _I, _I, _I, _P, _L, _P]),
     "fm_paint": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "fm_blink": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "fm_running": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),

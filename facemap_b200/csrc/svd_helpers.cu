@@ -166,6 +166,16 @@ __global__ void gather_roi_kernel(const float* __restrict__ X, int64_t ldx, int 
   out[(size_t)r * ldout + q] = X[(size_t)r * ldx + col0 + (size_t)(y0 + y) * Lxb + (x0 + x)];
 }
 
+// the same gather on a byte plane (the integer operands of fm_project_i8)
+__global__ void gather_roi_u8_kernel(const uint8_t* __restrict__ X, int64_t ldx, int rows, int64_t col0, int Lxb,
+                                     int y0, int x0, int ny, int nx, uint8_t* __restrict__ out, int64_t ldout) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (q >= ny * nx) return;
+  const int y = q / nx, x = q - y * nx;
+  out[(size_t)r * ldout + q] = X[(size_t)r * ldx + col0 + (size_t)(y0 + y) * Lxb + (x0 + x)];
+}
+
 }  // namespace fm
 
 extern "C" int fm_row_means(const float* X, int64_t ldx, int rows, int64_t ncols, double* mean, void* stream) {
@@ -229,6 +239,21 @@ extern "C" int fm_gather_roi(const float* X, int64_t ldx, int rows, int64_t col0
   dim3 grid((unsigned)cdiv((int64_t)ny * nx, 256), (unsigned)rows);
   gather_roi_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, ldx, rows, col0, Lxb, y0, x0, ny,
                                                                              nx, out, ldout);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+extern "C" int fm_gather_roi_u8(const uint8_t* X, int64_t ldx, int rows, int64_t col0, int Lxb, int y0, int y1,
+                                int x0, int x1, uint8_t* out, int64_t ldout, void* stream) {
+  using namespace fm;
+  const int ny = y1 - y0, nx = x1 - x0;
+  FM_REQUIRE(X && out && rows >= 0 && ny >= 1 && nx >= 1 && x1 <= Lxb && ldout >= (int64_t)ny * nx,
+             "fm_gather_roi_u8: bad args");
+  if (rows == 0) return FM_OK;
+  FM_REQUIRE(rows <= 65535, "fm_gather_roi_u8: too many rows per call (%d)", rows);
+  dim3 grid((unsigned)cdiv((int64_t)ny * nx, 256), (unsigned)rows);
+  gather_roi_u8_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, ldx, rows, col0, Lxb, y0, x0, ny,
+                                                                                nx, out, ldout);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }

@@ -442,6 +442,15 @@ def transpose(src, dst):
           "fm_transpose")
 
 
+def gather_roi_u8(X, rows, col0, Lxb, rect, out):
+    """EXPERIMENTAL (fm_gather_roi_u8): ROI columns of one uint8 plane."""
+    _need(X, torch.uint8, "X", 2)
+    _need(out, torch.uint8, "out", 2)
+    y0, y1, x0, x1 = rect
+    check(_lib.load().fm_gather_roi_u8(ptr(X), X.stride(0), int(rows), int(col0), int(Lxb), int(y0), int(y1), int(x0),
+                                       int(x1), ptr(out), out.stride(0), _stream()), "fm_gather_roi_u8")
+
+
 def gather_roi(X, rows, col0, Lxb, rect, out):
     y0, y1, x0, x1 = rect
     check(_lib.load().fm_gather_roi(ptr(X), X.stride(0), int(rows), int(col0), int(Lxb), int(y0), int(y1), int(x0),

@@ -772,8 +772,8 @@ class Stage3:
         # integer-plane operands for fm_project_i8 (ws.proj_mode == "i8"); asked for but not servable is an error, not
         # a silent change of path
         self.i8 = ws.proj_mode == "i8" and bool(mods)
-        if self.i8 and (not fullSVD or geo.mot_rois or geo.sbin > 16):
-            raise FacemapB200Error("FM_PROJ_MODE=i8 serves full-frame projections without motion ROIs at sbin <= 16")
+        if self.i8 and geo.sbin > 16:
+            raise FacemapB200Error("FM_PROJ_MODE=i8: two byte planes hold block sums up to sbin 16")
         self.ldq = K.round_up(geo.p, 16)
         self._halo_done = False
         # views whose float32 motion accumulator the exact integer energy cannot decide (fm_motion_ref)
@@ -904,9 +904,15 @@ class Stage3:
         with timer("stage3.split_masks"):
             if self.i8:
                 # digits of the masks and the rank-one term of the subtracted average, once per run
-                avg = {"mot": self.avgmotion, "mov": self.avgframe}
-                Ut_q = {m: K.slice_rows_i8(masks[m][0][0]) for m in mods}
-                Ut_bias = {m: K.row_dot(masks[m][0][0], avg[m].double()) for m in mods}
+                # (targets: 0 = full frame, 1 + j = motion ROI j with the ROI's columns of the average)
+                avg = {"mot": self.avgmotion.double(), "mov": self.avgframe.double()}
+                roi_cols = []
+                for (v, y0, y1, x0, x1) in geo.mot_rois:
+                    yy = torch.arange(y0, y1, device=device)[:, None] * int(geo.Lxb[v])
+                    roi_cols.append((int(geo.col0[v]) + yy + torch.arange(x0, x1, device=device)[None, :]).reshape(-1))
+                Ut_q = {m: [None if Ut is None else K.slice_rows_i8(Ut) for Ut in masks[m][0]] for m in mods}
+                Ut_bias = {m: [None if Ut is None else K.row_dot(Ut, avg[m] if i == 0 else avg[m][roi_cols[i - 1]].contiguous())
+                               for i, Ut in enumerate(masks[m][0])] for m in mods}
                 Ut_lo = None
             else:
                 Ut_lo = {m: [None if Ut is None else K.split_lo(Ut) for Ut in masks[m][0]] for m in mods}
@@ -929,11 +935,28 @@ class Stage3:
             for m in mods:
                 Uts = masks[m][0]
                 if self.i8:
-                    with timer("stage3.project.mma"):
-                        K.project_i8(self._rows_of(X, base, base + filled)[m], Ut_q[m][:3], Ut_q[m][3],
-                                     1.0 / (geo.sbin * geo.sbin), Ut_bias[m], V[m][0][o:o + filled])
-                    if sink is not None:
-                        sink.copy(V[m][0][o:o + filled], V_host[m][0][o:o + filled])
+                    alpha = 1.0 / (geo.sbin * geo.sbin)
+                    hi, lo = self._rows_of(X, base, base + filled)[m]
+                    if self.fullSVD and Uts[0] is not None:
+                        with timer("stage3.project.mma"):
+                            K.project_i8((hi, lo), Ut_q[m][0][:3], Ut_q[m][0][3], alpha, Ut_bias[m][0], V[m][0][o:o + filled])
+                        if sink is not None:
+                            sink.copy(V[m][0][o:o + filled], V_host[m][0][o:o + filled])
+                    for j, (v, y0, y1, x0, x1) in enumerate(geo.mot_rois):
+                        ldr = K.round_up(geo.roi_npix[j], 16)
+                        for r0 in range(0, filled, 32768):
+                            r1 = min(filled, r0 + 32768)
+                            buf = ws.raw("X3roi.q", 2 * (r1 - r0) * ldr, torch.uint8).view(2, r1 - r0, ldr)
+                            with timer("stage3.roi_gather"):
+                                for src, dst in ((hi, buf[0]), (lo, buf[1])):
+                                    if src is not None:
+                                        K.gather_roi_u8(src[r0:r1], r1 - r0, geo.col0[v], int(geo.Lxb[v]), (y0, y1, x0, x1), dst)
+                            with timer("stage3.roi_project.mma"):
+                                K.project_i8((None if hi is None else buf[0][:, :geo.roi_npix[j]], buf[1][:, :geo.roi_npix[j]]),
+                                             Ut_q[m][1 + j][:3], Ut_q[m][1 + j][3], alpha, Ut_bias[m][1 + j],
+                                             V[m][1 + j][o + r0:o + r1])
+                            if sink is not None:
+                                sink.copy(V[m][1 + j][o + r0:o + r1], V_host[m][1 + j][o + r0:o + r1])
                     continue
                 Xm = X[m][base:base + filled]
                 if self.fullSVD and Uts[0] is not None:

@@ -294,6 +294,9 @@ int fm_transpose(const float* in, int64_t ldin, int rows, int cols, float* out, 
  * X[r, col0 + y*Lxb + x] for the binned rectangle. */
 int fm_gather_roi(const float* X, int64_t ldx, int rows, int64_t col0, int Lxb,
                   int y0, int y1, int x0, int x1, float* out, int64_t ldout, void* stream);
+/* EXPERIMENTAL (not yet run on a GPU): the same gather on one byte plane of fm_bin_motion_planes (pitches in bytes). */
+int fm_gather_roi_u8(const uint8_t* X, int64_t ldx, int rows, int64_t col0, int Lxb,
+                     int y0, int y1, int x0, int x1, uint8_t* out, int64_t ldout, void* stream);
 
 /* ---- full-resolution ROI processors riding on the stage-3 frame sweep (facemap/process.py:410-425) ----
  * ROI rectangles are [y0, y1) x [x0, x1) in frame pixels (the reference's yrange[0]..yrange[-1] inclusive,

@@ -131,3 +131,29 @@ def test_pipeline_in_i8_projection_mode(cuda_device, monkeypatch):
         rel = np.abs(a - b).max(axis=0) / np.abs(a).max(axis=0)
         print(key, "max relative trace difference, first 16 / all:", rel[:16].max(), rel.max())
         assert rel[:16].max() < 1e-4 and rel.max() < 1e-3
+
+
+def test_pipeline_in_i8_projection_mode_with_motion_rois(cuda_device, monkeypatch):
+    """two cameras, motion + movie SVD, two motion ROIs (tests/helpers.py:multi_roi_s4): the ROI projections come from
+    gathered byte planes (fm_gather_roi_u8) and must agree with the default path like the full-frame ones"""
+    from facemap_b200 import process
+    from facemap_b200.frames import DeviceArraySource
+
+    from .helpers import CASES, case_rois, case_videos
+
+    name = "multi_roi_s4"
+    vids = case_videos(name)
+    src = DeviceArraySource([torch.from_numpy(v).to(cuda_device) for v in vids])
+    sbin = CASES[name][2]
+    p0 = process.process_source(src, sbin=sbin, motSVD=True, movSVD=True, rois=case_rois(name))
+    monkeypatch.setenv("FM_PROJ_MODE", "i8")
+    p1 = process.process_source(src, sbin=sbin, motSVD=True, movSVD=True, rois=case_rois(name))
+    for key in ("motSVD", "movSVD"):
+        assert len(p0[key]) == len(p1[key]) == 3
+        for a, b in zip(p0[key], p1[key]):
+            a, b = a.astype(np.float64), b.astype(np.float64)
+            rel = np.abs(a - b).max(axis=0) / np.abs(a).max(axis=0)
+            print(key, a.shape, "max relative trace difference, first 16 / all:", rel[:16].max(), rel.max())
+            assert rel[:16].max() < 1e-4 and rel.max() < 1e-3
+    for a, b in zip(p0["motion"], p1["motion"]):
+        assert np.array_equal(a, b)

@@ -70,7 +70,7 @@ class FakeKernels:
 
     def bin_motion_planes(self, frames, sbin, *, prev_sum=None, q_mot=None, q_mov=None, col0=0, energy=None, rois=None,
                           roi_energy=None, last_sum=None, ormask=None):
-        assert ormask is None and roi_energy is None
+        assert ormask is None
         S = M8.block_sums(frames.numpy(), sbin)
         npix = S.shape[1]
         prev = S[:1] if prev_sum is None else prev_sum.numpy().astype(np.int64)[None, :]
@@ -89,10 +89,22 @@ class FakeKernels:
                     assert not h.any()
         if energy is not None:
             energy[:rows] = torch.from_numpy(d.sum(axis=1))
+        if roi_energy is not None and rois is not None:
+            img = d.reshape(rows, -1, frames.shape[2] // sbin)
+            for q in range(rois.n):
+                roi_energy.view(rois.n, -1)[q, :rows] = torch.from_numpy(
+                    img[:, rois.y0[q]:rois.y1[q], rois.x0[q]:rois.x1[q]].sum(axis=(1, 2)))
         if last_sum is not None:
             last_sum.copy_(torch.from_numpy(S[-1].astype(np.int32)))
         self.log.append(("bin", rows))
         return rows
+
+    @staticmethod
+    def gather_roi_u8(X, rows, col0, Lxb, rect, out):
+        assert X.dtype == torch.uint8 and out.dtype == torch.uint8
+        y0, y1, x0, x1 = rect
+        cols = [col0 + y * Lxb + x for y in range(y0, y1) for x in range(x0, x1)]
+        out[:rows, :len(cols)] = X[:rows, cols]
 
     @staticmethod
     def slice_rows_i8(X, out=None):
@@ -137,12 +149,16 @@ def test_stage3_i8_orchestration(monkeypatch, sbin, mods):
     rs = np.random.RandomState(10 + sbin)
     N, k = 61, 12
     views = [rs.randint(0, 256, size=(N, 24, 36)).astype(np.uint8), rs.randint(0, 256, size=(N, 16, 20)).astype(np.uint8)]
-    geo = svd.Geometry([24, 16], [36, 20], sbin, None)
+    ry, rx = (np.arange(1, 3), np.arange(2, 5)) if sbin == 4 else (np.arange(2, 6), np.arange(3, 9))
+    roi = {"rind": 1, "ivid": 1, "yrange_bin": ry, "xrange_bin": rx}
+    geo = svd.Geometry([24, 16], [36, 20], sbin, [roi])
     S = np.concatenate([M8.block_sums(v, sbin) for v in views], axis=1)
     d = np.abs(np.diff(S, axis=0))
     avgmotion = (d.mean(axis=0) / sbin ** 2).astype(np.float32)
     avgframe = (S.mean(axis=0) / sbin ** 2).astype(np.float32)
     U = {m: _masks(rs, k, geo.p) for m in mods}
+    Ur = {m: _masks(rs, 5, geo.roi_npix[0]) for m in mods}
+    cols = [geo.col0[1] + y * int(geo.Lxb[1]) + x for y in ry for x in rx]
     fake = FakeKernels()
     monkeypatch.setattr(svd, "K", fake)
     ws = object.__new__(svd.SvdWorkspace)
@@ -152,15 +168,18 @@ def test_stage3_i8_orchestration(monkeypatch, sbin, mods):
     st = svd.Stage3(ArraySource(views), geo, torch.from_numpy(avgframe), torch.from_numpy(avgmotion), mods, True, ws,
                     torch.device("cpu"), timer, fetch_frames=17)
     assert st.i8
-    masks = {m: ([torch.from_numpy(U[m])], None) for m in mods}
-    V, E, _ = st.project(masks)
+    masks = {m: ([torch.from_numpy(U[m]), torch.from_numpy(Ur[m])], None) for m in mods}
+    V, E, E_roi = st.project(masks)
     assert np.array_equal(E.numpy()[:, 1:].sum(axis=0), d.sum(axis=1)) and not E.numpy()[:, 0].any()
+    assert np.array_equal(E_roi.numpy()[0, 1:], d[:, cols].sum(axis=1))
     X = {"mot": d / sbin ** 2 - avgmotion.astype(np.float64), "mov": S[1:] / sbin ** 2 - avgframe.astype(np.float64)}
     for m in mods:
         got = V[m][0].numpy().astype(np.float64)
         want = X[m] @ U[m].astype(np.float64).T
         assert not got[0].any()                                 # frame 0 has no difference row
         assert np.abs(got[1:] - want).max() <= 2e-6 * np.abs(want).max()
+        want_r = X[m][:, cols] @ Ur[m].astype(np.float64).T     # the motion ROI: gathered planes, its own masks
+        assert np.abs(V[m][1].numpy()[1:] - want_r).max() <= 2e-6 * np.abs(want_r).max()
     assert [r for op, r in fake.log if op == "bin"][:2] == [16, 16]       # per view: 17 frames, no predecessor -> 16 rows
 
 
