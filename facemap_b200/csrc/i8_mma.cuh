@@ -92,16 +92,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-#define FM_I8_TMEM_LD_X16(taddr, r)                                                                      \
-  asm volatile(                                                                                          \
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                          \
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                   \
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),   \
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),         \
-        "=r"(r[15])                                                                                      \
-      : "r"(taddr)                                                                                       \
-      : "memory")
-
 static PFN_cuTensorMapEncodeTiled_v12000 encoder() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
