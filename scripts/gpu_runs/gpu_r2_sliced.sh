@@ -21,3 +21,9 @@ d = json.loads(open(f"gpurun_out/bench_gram_{sys.argv[1]}_{sys.argv[2]}.json").r
 print(sys.argv[1], "single", sys.argv[2], "ms/step", round(d["ms_per_step"], 2), {k: round(v, 2) for k, v in d["stage_ms"].items() if ".gram" in k})
 PY
 done
+# ncu evidence for the integer projection, only once its tests have passed without a profiler attached
+if grep -q " passed" gpurun_out/project_i8_tests.log && ! grep -q "failed" gpurun_out/project_i8_tests.log; then
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:project_i8_kernel -s 1 -c 1 -f -o gpurun_out/prof_project_i8 python scripts/probe_project_i8.py > gpurun_out/ncu_project_i8.log 2>&1; echo "ncu project_i8 rc $?"
+  ncu -i gpurun_out/prof_project_i8.ncu-rep --page raw --csv > gpurun_out/prof_project_i8_raw.csv 2>/dev/null
+  grep -E "sm__inst_executed_pipe_tensor|sm__pipe_tensor|dram__bytes_(read|write).sum\"|gpu__time_duration.sum|l1tex__data_bank_conflicts|smsp__warp_issue_stalled" gpurun_out/prof_project_i8_raw.csv | head -20
+fi
