@@ -479,6 +479,7 @@ def main():
                        "l2": "inputs (30.7 GB per GPU) exceed L2; no flush needed", "parallelism": f"frame-range x{world}",
                        **({"gram_mode": os.environ["FM_GRAM_MODE"]} if os.environ.get("FM_GRAM_MODE") else {}),
                        **({"proj_mode": os.environ["FM_PROJ_MODE"]} if os.environ.get("FM_PROJ_MODE") else {}),
+                       **({"proj_i8_impl": os.environ["FM_PROJ_I8_IMPL"]} if os.environ.get("FM_PROJ_I8_IMPL") else {}),
                        **({"rois": "pupil 100x140 + blink 100x140 + running 120x400 (side measurement)"} if args.with_rois else {})},
             "clocks": clk, "e2e": e2e if e2e is not None else ({"value": None, "skipped": e2e_skip} if e2e_skip else None),
             "gpu_launches": int(launches),

@@ -63,6 +63,55 @@ struct Params {
                : "r"(taddr)                                                                              \
                : "memory")
 
+// one chain's class accumulators -> the thread's int64 sums (Horner weights 256^(NC-1-j))
+template <int NC>
+__device__ __forceinline__ void drain_classes(uint32_t tmem_acc, int q, int half, long long (&acc)[COLS_PER_THREAD]) {
+#pragma unroll
+  for (int cc = 0; cc < COLS_PER_THREAD; cc += 8) {
+    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_THREAD + cc);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      uint32_t r[8];
+      FM_I8_TMEM_LD_X8(taddr + (uint32_t)(j * BN), r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[cc + t] += (long long)(int32_t)r[t] * (1ll << (8 * (NC - 1 - j)));
+    }
+  }
+}
+
+// V = alpha * 2^(ex - 7) * 256^-(NE-1) * acc - bias for the thread's row m and its 64 columns from nbase on
+__device__ __forceinline__ void store_row(const long long (&acc)[COLS_PER_THREAD], int m, int nbase, const Params& p) {
+  if (m >= p.M) return;
+  float* dst_row = p.V + (size_t)m * p.ldv;
+  const bool vec_ok = (p.ldv % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.V) & 15) == 0);
+#pragma unroll
+  for (int t = 0; t < COLS_PER_THREAD; t += 4) {
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int n = nbase + t + u;
+      double v = 0.0;
+      if (n < p.N) {
+        // 2^(ex - 23) built from its exponent field (|ex| <= 126 by fm::slice_exponent: always normal); separately
+        // rounded multiply and subtract (no FMA contraction) so that a host model reproduces every bit
+        const double sc = __dmul_rn(p.alpha, __hiloint2double((1023 + p.exps[n] - 7 - 8 * (NE - 1)) << 20, 0));
+        v = __dmul_rn((double)acc[t + u], sc);
+        if (p.bias) v = __dsub_rn(v, p.bias[n]);
+      }
+      o[u] = (float)v;
+    }
+    const int n = nbase + t;
+    if (vec_ok && n + 4 <= p.N) {
+      *reinterpret_cast<float4*>(dst_row + n) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (n + u < p.N) dst_row[n + u] = o[u];
+    }
+  }
+}
+
 template <int ND>
 __global__ void __launch_bounds__(THREADS, 1)
 project_i8_kernel(const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1,
@@ -173,54 +222,12 @@ project_i8_kernel(const __grid_constant__ CUtensorMap tmD0, const __grid_constan
     for (int c = 0; c < nchains; ++c) {
       mbar_wait(accfull_bar, (uint32_t)c & 1u);
       tcgen05_fence_after();
-#pragma unroll
-      for (int cc = 0; cc < COLS_PER_THREAD; cc += 8) {
-        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_THREAD + cc);
-#pragma unroll
-        for (int j = 0; j < NC; ++j) {                     // class j carries the weight 256^(NC-1-j)
-          uint32_t r[8];
-          FM_I8_TMEM_LD_X8(taddr + (uint32_t)(j * BN), r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int t = 0; t < 8; ++t) acc[cc + t] += (long long)(int32_t)r[t] * (1ll << (8 * (NC - 1 - j)));
-        }
-      }
+      drain_classes<NC>(tmem_acc, q, half, acc);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(accempty_bar);
     }
-    // V = alpha * 2^(ex - 7) * 256^-(NE-1) * acc - bias
-    const int m = m0 + q * 32 + lane;
-    if (m < p.M) {
-      float* dst_row = p.V + (size_t)m * p.ldv;
-      const bool vec_ok = (p.ldv % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.V) & 15) == 0);
-      const int nbase = n0 + half * COLS_PER_THREAD;
-#pragma unroll
-      for (int t = 0; t < COLS_PER_THREAD; t += 4) {
-        float o[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int n = nbase + t + u;
-          double v = 0.0;
-          if (n < p.N) {
-            // 2^(ex - 23) built from its exponent field (|ex| <= 126 by fm::slice_exponent: always normal); separately
-            // rounded multiply and subtract (no FMA contraction) so that a host model reproduces every bit
-            const double sc = __dmul_rn(p.alpha, __hiloint2double((1023 + p.exps[n] - 7 - 8 * (NE - 1)) << 20, 0));
-            v = __dmul_rn((double)acc[t + u], sc);
-            if (p.bias) v = __dsub_rn(v, p.bias[n]);
-          }
-          o[u] = (float)v;
-        }
-        const int n = nbase + t;
-        if (vec_ok && n + 4 <= p.N) {
-          *reinterpret_cast<float4*>(dst_row + n) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (n + u < p.N) dst_row[n + u] = o[u];
-        }
-      }
-    }
+    store_row(acc, m0 + q * 32 + lane, n0 + half * COLS_PER_THREAD, p);
   }
 
   tcgen05_fence_before();
@@ -230,27 +237,203 @@ project_i8_kernel(const __grid_constant__ CUtensorMap tmD0, const __grid_constan
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (impl 1, cta_group::2): two CTAs of a cluster project 256 frames x 128 components.  Each CTA stages
+// its own 128 frame rows and HALF of every digit plane (64 component rows), so per SM the TMA fill drops from 40 to
+// 28 KB per stage and the tensor core reads 6 instead of 8 KB of shared memory per instruction — the two limits a
+// 128 x 128 kind::i8 tile sits on.  The protocol is gemm_tf32x3_pair_kernel's, which has run
+// on B200: the leader's MMA thread issues for both tensor cores; a relay warp in each CTA forwards "my stage has
+// landed" to the LEADER's barrier (where that kernel's splitter warps arrived); tcgen05.commit multicasts "stage
+// free" and "chain complete" to both CTAs; between chains both CTAs' epilogue warps arrive on the leader's barrier.
+// ---------------------------------------------------------------------------------------------
+constexpr int PAIR_THREADS = 32 * (3 + NUM_EPI_WARPS);     // TMA, MMA, relay, 8 epilogue warps
+
+template <int ND>
+struct PairCfg {
+  static constexpr int NC = ND + NE - 1;
+  static constexpr int STAGE_BYTES = (ND * BM + NE * (BN / 2)) * BKB;
+  static constexpr int STAGES = ND == 1 ? 8 : 7;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static_assert(SMEM_BYTES <= 232448, "stage ring exceeds shared memory");
+  static_assert(8 * (3 * STAGES + 3) <= BAR_BYTES, "barrier block too small");
+};
+
+template <int ND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+project_i8_pair_kernel(const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1,
+                       const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
+                       const __grid_constant__ CUtensorMap tmQ2, const Params p) {
+  using C = PairCfg<ND>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int NC = C::NC;
+  constexpr int QROWS = BN / 2;                            // digit-plane rows staged by each CTA
+  const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the MMAs)
+  const int m0 = (int)(blockIdx.x >> 1) * (2 * BM) + (int)rank * BM;   // the pair = 2 consecutive CTAs along x
+  const int n0 = blockIdx.y * BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                  // local: TMA landed
+  auto ready_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };      // leader's: both CTAs' stages landed
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };  // local: MMAs done with the stage
+  const uint32_t accfull_bar = bar_base + 8u * (3 * STAGES);                 // local: chain complete (multicast)
+  const uint32_t accempty_bar = bar_base + 8u * (3 * STAGES + 1);            // leader's: both CTAs drained
+  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 2);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + 8 * (3 * STAGES + 2));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nkb = (p.K + BKB - 1) / BKB;
+  constexpr int CHAIN_KB = KCHAIN / BKB;
+  const int nchains = (nkb + CHAIN_KB - 1) / CHAIN_KB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(ready_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accfull_bar, 1);
+    mbar_init(accempty_bar, 2 * NUM_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // peer barriers initialised, TMEM allocated
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t stage = smem_base + s * C::STAGE_BYTES;
+        const uint32_t qbase = stage + ND * BM * BKB;
+        const int nq = n0 + (int)rank * QROWS;
+        mbar_expect_tx(full_bar(s), (uint32_t)C::STAGE_BYTES);
+        tma_load_2d(stage, &tmD0, full_bar(s), i * BKB, m0);
+        if constexpr (ND == 2) tma_load_2d(stage + BM * BKB, &tmD1, full_bar(s), i * BKB, m0);
+        tma_load_2d(qbase, &tmQ0, full_bar(s), i * BKB, nq);
+        tma_load_2d(qbase + QROWS * BKB, &tmQ1, full_bar(s), i * BKB, nq);
+        tma_load_2d(qbase + 2 * QROWS * BKB, &tmQ2, full_bar(s), i * BKB, nq);
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      int i = 0;
+      for (int c = 0; c < nchains; ++c) {
+        if (c > 0) {                                       // both CTAs have drained the previous chain
+          mbar_wait_cluster(accempty_bar, (uint32_t)(c - 1) & 1u);
+          tcgen05_fence_after();
+        }
+        const int len = min(CHAIN_KB, nkb - c * CHAIN_KB);
+        for (int j = 0; j < len; ++j, ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+          mbar_wait_cluster(ready_bar(s), ph);
+          tcgen05_fence_after();
+          const uint32_t stage = smem_base + s * C::STAGE_BYTES;
+          const uint32_t qbase = stage + ND * BM * BKB;
+#pragma unroll
+          for (int k = 0; k < BKB / 32; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+              const uint64_t dd = make_desc(stage + d * BM * BKB) + adv;
+#pragma unroll
+              for (int e = 0; e < NE; ++e) {
+                const uint64_t dq = make_desc(qbase + e * QROWS * BKB) + adv;
+                const bool opens = (d == 0 || e == NE - 1);
+                umma_i8_pair(tmem_acc + (uint32_t)((d + e) * BN), dd, dq, e == 0 ? p.idesc_s8 : p.idesc_u8,
+                             (opens && j == 0 && k == 0) ? 0u : 1u);
+              }
+            }
+          }
+          tcgen05_commit_pair(empty_bar(s));
+        }
+        tcgen05_commit_pair(accfull_bar);
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {                                       // relay: my stage has landed -> the leader's barrier
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        mbar_arrive_cluster(ready_bar(s), 0);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 3) >> 2;
+    long long acc[COLS_PER_THREAD];
+#pragma unroll
+    for (int t = 0; t < COLS_PER_THREAD; ++t) acc[t] = 0;
+    for (int c = 0; c < nchains; ++c) {
+      mbar_wait(accfull_bar, (uint32_t)c & 1u);
+      tcgen05_fence_after();
+      drain_classes<NC>(tmem_acc, q, half, acc);           // every CTA drains its own 128 TMEM lanes
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(accempty_bar, 0);
+    }
+    store_row(acc, m0 + q * 32 + lane, n0 + half * COLS_PER_THREAD, p);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // the peer's tensor core may still be reading this CTA's shared memory / TMEM
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 template <int ND>
 static int launch(const uint8_t* D_hi, const uint8_t* D_lo, int64_t ldd, const int8_t* Q0, const uint8_t* Q1,
-                  const uint8_t* Q2, int64_t ldq, const Params& p, cudaStream_t st) {
-  using C = Cfg<ND>;
+                  const uint8_t* Q2, int64_t ldq, Params p, int impl, cudaStream_t st) {
+  const bool pair = impl == 1;
   CUtensorMap td0, td1, tq0, tq1, tq2;
   int rc;
-  // plane 0 is the most significant one
+  // plane 0 is the most significant one; a pair CTA stages half of every digit tile
+  const int qrows = pair ? BN / 2 : BN;
   if ((rc = make_map_u8(&td0, ND == 2 ? D_hi : D_lo, ldd, p.M, p.K, BM)) != FM_OK) return rc;
   td1 = td0;
   if (ND == 2 && (rc = make_map_u8(&td1, D_lo, ldd, p.M, p.K, BM)) != FM_OK) return rc;
-  if ((rc = make_map_u8(&tq0, reinterpret_cast<const uint8_t*>(Q0), ldq, p.N, p.K, BN)) != FM_OK) return rc;
-  if ((rc = make_map_u8(&tq1, Q1, ldq, p.N, p.K, BN)) != FM_OK) return rc;
-  if ((rc = make_map_u8(&tq2, Q2, ldq, p.N, p.K, BN)) != FM_OK) return rc;
+  if ((rc = make_map_u8(&tq0, reinterpret_cast<const uint8_t*>(Q0), ldq, p.N, p.K, qrows)) != FM_OK) return rc;
+  if ((rc = make_map_u8(&tq1, Q1, ldq, p.N, p.K, qrows)) != FM_OK) return rc;
+  if ((rc = make_map_u8(&tq2, Q2, ldq, p.N, p.K, qrows)) != FM_OK) return rc;
   static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
+  static cudaError_t attr_err = cudaSuccess, attr_err_pair = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(project_i8_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(project_i8_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg<ND>::SMEM_BYTES);
+    attr_err_pair = cudaFuncSetAttribute(project_i8_pair_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         PairCfg<ND>::SMEM_BYTES);
   });
-  FM_CUDA_TRY(attr_err);
-  dim3 grid((unsigned)cdiv(p.N, BN), (unsigned)cdiv(p.M, BM), 1);
-  project_i8_kernel<ND><<<grid, THREADS, C::SMEM_BYTES, st>>>(td0, td1, tq0, tq1, tq2, p);
+  if (pair) {
+    FM_CUDA_TRY(attr_err_pair);
+    // instruction M spans both CTAs
+    const uint32_t m256 = ((uint32_t)((2 * BM) >> 4) << 24), mmask = ~(0x1Fu << 24);
+    p.idesc_s8 = (p.idesc_s8 & mmask) | m256;
+    p.idesc_u8 = (p.idesc_u8 & mmask) | m256;
+    dim3 grid((unsigned)(2 * cdiv(p.M, 2 * BM)), (unsigned)cdiv(p.N, BN), 1);
+    project_i8_pair_kernel<ND><<<grid, PAIR_THREADS, PairCfg<ND>::SMEM_BYTES, st>>>(td0, td1, tq0, tq1, tq2, p);
+  } else {
+    FM_CUDA_TRY(attr_err);
+    dim3 grid((unsigned)cdiv(p.N, BN), (unsigned)cdiv(p.M, BM), 1);
+    project_i8_kernel<ND><<<grid, THREADS, Cfg<ND>::SMEM_BYTES, st>>>(td0, td1, tq0, tq1, tq2, p);
+  }
   FM_LAUNCH_CHECK();
   return FM_OK;
 }
@@ -260,7 +443,7 @@ static int launch(const uint8_t* D_hi, const uint8_t* D_lo, int64_t ldd, const i
 
 extern "C" int fm_project_i8(const uint8_t* D_hi, const uint8_t* D_lo, int64_t ldd, const int8_t* Q0, const uint8_t* Q1,
                              const uint8_t* Q2, int64_t ldq, const int32_t* exps, int M, int N, int K, double alpha,
-                             const double* bias, float* V, int64_t ldv, void* stream) {
+                             const double* bias, float* V, int64_t ldv, int impl, void* stream) {
   using namespace fm;
   using namespace fm::pi8;
   FM_REQUIRE(D_lo && Q0 && Q1 && Q2 && exps && V && M >= 1 && N >= 1 && K >= 1 && ldv >= N,
@@ -271,11 +454,13 @@ extern "C" int fm_project_i8(const uint8_t* D_hi, const uint8_t* D_lo, int64_t l
              "fm_project_i8: TMA operands need 16-byte aligned bases and row pitches (ldd=%lld ldq=%lld)",
              (long long)ldd, (long long)ldq);
   FM_REQUIRE(cdiv(M, BM) <= 65535, "fm_project_i8: more than 65535 frame tiles; project in batches");
+  FM_REQUIRE(impl == 0 || impl == 1, "fm_project_i8: unknown impl %d (0 = one CTA per tile, 1 = CTA pairs)", impl);
   FM_REQUIRE(K <= (1 << 22), "fm_project_i8: K = %d exceeds 2^22 (int64 accumulation over 256 chains)", K);
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp layout): c_format S32 = 2 at bit 4, a/b format (0 = u8,
   // 1 = s8) at bits 7 / 10, K-major operands, N >> 3 at bit 17, M >> 4 at bit 24
   const uint32_t idesc_u8 = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   Params p{M, N, K, V, ldv, exps, bias, alpha, idesc_u8 | (1u << 10), idesc_u8};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return D_hi ? launch<2>(D_hi, D_lo, ldd, Q0, Q1, Q2, ldq, p, st) : launch<1>(nullptr, D_lo, ldd, Q0, Q1, Q2, ldq, p, st);
+  return D_hi ? launch<2>(D_hi, D_lo, ldd, Q0, Q1, Q2, ldq, p, impl, st)
+              : launch<1>(nullptr, D_lo, ldd, Q0, Q1, Q2, ldq, p, impl, st);
 }

@@ -287,10 +287,11 @@ def bin_motion_planes(frames, sbin, *, prev_sum=None, q_mot=None, q_mov=None, co
     return rows
 
 
-def project_i8(D, Q, exps, alpha, bias, V):
+def project_i8(D, Q, exps, alpha, bias, V, impl=0):
     """EXPERIMENTAL (fm_project_i8): V[t, c] = alpha * sum_p D[t, p] U[c, p] - bias[c] on tcgen05 kind::i8, exactly.
     D: (hi, lo) uint8 [M, K] planes of one pitch (hi None for operands < 256); Q: the (Q0 int8, Q1, Q2 uint8) [N, K]
-    digit planes and `exps` of `slice_rows_i8(U)`; bias: float64 [N] or None; V: float32 [M, >= N] row-major."""
+    digit planes and `exps` of `slice_rows_i8(U)`; bias: float64 [N] or None; V: float32 [M, >= N] row-major;
+    impl: 0 = one CTA per tile, 1 = CTA pairs (cta_group::2)."""
     hi, lo = D
     Q0, Q1, Q2 = Q
     _need(lo, torch.uint8, "D_lo", 2)
@@ -308,7 +309,7 @@ def project_i8(D, Q, exps, alpha, bias, V):
     if exps.numel() < N or (bias is not None and bias.numel() < N) or V.shape[0] < M or V.shape[1] < N or V.stride(1) != 1:
         raise FacemapB200Error("project_i8: exps / bias need N entries and V must be row-major [>= M, >= N]")
     check(_lib.load().fm_project_i8(ptr(hi), ptr(lo), lo.stride(0), ptr(Q0), ptr(Q1), ptr(Q2), Q0.stride(0), ptr(exps),
-                                    M, N, Kd, float(alpha), ptr(bias), ptr(V), V.stride(0), _stream()), "fm_project_i8")
+                                    M, N, Kd, float(alpha), ptr(bias), ptr(V), V.stride(0), int(impl), _stream()), "fm_project_i8")
     return V
 
 

@@ -181,6 +181,7 @@ class SvdWorkspace:
         self.proj_mode = _os.environ.get("FM_PROJ_MODE", "tf32x3")
         if self.proj_mode not in ("tf32x3", "i8"):
             raise FacemapB200Error(f"unknown FM_PROJ_MODE {self.proj_mode!r}")
+        self.proj_i8_impl = int(_os.environ.get("FM_PROJ_I8_IMPL", "0"))      # 1 = CTA pairs (fm_project_i8 impl)
         self._ws = None
         self._bufs = {}
 
@@ -939,7 +940,8 @@ class Stage3:
                     hi, lo = self._rows_of(X, base, base + filled)[m]
                     if self.fullSVD and Uts[0] is not None:
                         with timer("stage3.project.mma"):
-                            K.project_i8((hi, lo), Ut_q[m][0][:3], Ut_q[m][0][3], alpha, Ut_bias[m][0], V[m][0][o:o + filled])
+                            K.project_i8((hi, lo), Ut_q[m][0][:3], Ut_q[m][0][3], alpha, Ut_bias[m][0], V[m][0][o:o + filled],
+                                         impl=ws.proj_i8_impl)
                         if sink is not None:
                             sink.copy(V[m][0][o:o + filled], V_host[m][0][o:o + filled])
                     for j, (v, y0, y1, x0, x1) in enumerate(geo.mot_rois):
@@ -954,7 +956,7 @@ class Stage3:
                             with timer("stage3.roi_project.mma"):
                                 K.project_i8((None if hi is None else buf[0][:, :geo.roi_npix[j]], buf[1][:, :geo.roi_npix[j]]),
                                              Ut_q[m][1 + j][:3], Ut_q[m][1 + j][3], alpha, Ut_bias[m][1 + j],
-                                             V[m][1 + j][o + r0:o + r1])
+                                             V[m][1 + j][o + r0:o + r1], impl=ws.proj_i8_impl)
                             if sink is not None:
                                 sink.copy(V[m][1 + j][o + r0:o + r1], V_host[m][1 + j][o + r0:o + r1])
                     continue

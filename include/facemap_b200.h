@@ -198,11 +198,12 @@ int fm_gram_assemble_i8(const int32_t* P, int ksplit, int n, int64_t ldp, const 
  * of fm_slice_rows_i8 (Q0 int8, Q1 / Q2 uint8 [N, ldq], exps[N]).  bias[c] = sum_p avg[p] U[c,p] (float64, fm_row_dot;
  * may be NULL) carries the subtraction of avgmotion / avgframe.  Exact int32 accumulation in chains of 16 384 K,
  * int64 across chains, one float64 scaling and one rounding to float32 per output.  Pitches in bytes, multiples of 16;
- * 16-byte aligned plane bases; K <= 2^22.  DESIGN.md section 7.2(a).
+ * 16-byte aligned plane bases; K <= 2^22.  impl: 0 = one CTA per 128 x 128 tile, 1 = CTA pairs (cta_group::2, 256 x 128
+ * per pair, half of every digit tile staged per CTA); same results.  DESIGN.md section 7.2(a).
  */
 int fm_project_i8(const uint8_t* D_hi, const uint8_t* D_lo, int64_t ldd, const int8_t* Q0, const uint8_t* Q1,
                   const uint8_t* Q2, int64_t ldq, const int32_t* exps, int M, int N, int K, double alpha,
-                  const double* bias, float* V, int64_t ldv, void* stream);
+                  const double* bias, float* V, int64_t ldv, int impl, void* stream);
 
 /* lo[r,c] = X[r,c] - tf32_trunc(X[r,c]): pre-computed second plane of a B operand that many GEMMs
  * reuse (pass it as B_lo above). */

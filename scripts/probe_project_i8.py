@@ -37,14 +37,18 @@ def main():
         bias = K.row_dot(U, torch.rand(p, device=dev, generator=g, dtype=torch.float64))
         V = torch.empty((T, k), dtype=torch.float32, device=dev)
         ms_i8 = timed(lambda: K.project_i8((hi, lo), (Q0, Q1, Q2), exps, 1.0 / sbin ** 2, bias, V))
+        Vp = torch.empty((T, k), dtype=torch.float32, device=dev)
+        ms_pair = timed(lambda: K.project_i8((hi, lo), (Q0, Q1, Q2), exps, 1.0 / sbin ** 2, bias, Vp, impl=1))
+        same = bool(torch.equal(V, Vp))
         X = K.alloc_matrix(T, p, dev)
         X.copy_(lo.float() + (0 if hi is None else 256 * hi.float()))
         Ulo = K.split_lo(U)
         V2 = torch.empty((T, k), dtype=torch.float32, device=dev)
         ms_tf = timed(lambda: K.gemm_tn(X, U, V2, B_lo=Ulo, impl=0))
         flop = 2.0 * T * p * k
-        print(json.dumps({"T": T, "p": p, "k": k, "sbin": sbin, "ms_i8": ms_i8, "ms_tf32x3": ms_tf,
-                          "algorithmic_tflops_i8": flop / ms_i8 / 1e9, "algorithmic_tflops_tf32x3": flop / ms_tf / 1e9,
+        print(json.dumps({"T": T, "p": p, "k": k, "sbin": sbin, "ms_i8": ms_i8, "ms_i8_pair": ms_pair, "pair_equals_single": same,
+                          "ms_tf32x3": ms_tf,
+                          "algorithmic_tflops_i8": flop / ms_i8 / 1e9, "algorithmic_tflops_i8_pair": flop / ms_pair / 1e9, "algorithmic_tflops_tf32x3": flop / ms_tf / 1e9,
                           "operand_bytes_i8": T * p * (1 if hi is None else 2) + 3 * k * p,
                           "operand_bytes_tf32x3": 4 * T * p + 8 * k * p}), flush=True)
 

@@ -30,7 +30,8 @@ def _masks(rs, k, p):
 
 @pytest.mark.parametrize("M,N,K,sbin", [(128, 128, 64, 4), (300, 500, 19200, 4), (77, 130, 1000, 1), (1000, 500, 40000, 4),
                                         (5, 7, 33, 16), (260, 250, 16384 + 64, 2)])
-def test_project_i8_bit_exact_against_model(cuda_device, M, N, K, sbin):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_project_i8_bit_exact_against_model(cuda_device, M, N, K, sbin, impl):
     from facemap_b200 import kernels as K_
 
     rs = np.random.RandomState(M + N + K)
@@ -51,18 +52,19 @@ def test_project_i8_bit_exact_against_model(cuda_device, M, N, K, sbin):
     bias = K_.row_dot(Ug, torch.from_numpy(avg).to(cuda_device).double())
     assert np.allclose(bias.cpu().numpy(), M8.bias_of(U, avg), rtol=1e-12, atol=1e-14)
     V = torch.full((M, -(-N // 4) * 4), float("nan"), dtype=torch.float32, device=cuda_device)
-    K_.project_i8(Dg, (Q0, Q1, Q2), exps, alpha, bias, V)
+    K_.project_i8(Dg, (Q0, Q1, Q2), exps, alpha, bias, V, impl=impl)
     want = M8.project_i8_model(D, U, alpha, bias=bias.cpu().numpy())
     got = V[:, :N].cpu().numpy()
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     # and without a bias, into an unaligned output
     V2 = torch.full((M, N + 1), float("nan"), dtype=torch.float32, device=cuda_device)
-    K_.project_i8(Dg, (Q0, Q1, Q2), exps, alpha, None, V2[:, 1:])
+    K_.project_i8(Dg, (Q0, Q1, Q2), exps, alpha, None, V2[:, 1:], impl=impl)
     assert np.array_equal(V2[:, 1:].cpu().numpy().view(np.uint32), M8.project_i8_model(D, U, alpha).view(np.uint32))
     assert torch.isnan(V2[:, 0]).all()
 
 
-def test_project_i8_extreme_digits_fill_the_int32_chain(cuda_device):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_project_i8_extreme_digits_fill_the_int32_chain(cuda_device, impl):
     from facemap_b200 import kernels as K_
 
     M, N, K = 130, 129, 3 * 16384                            # three full chains at the largest digits
@@ -72,7 +74,7 @@ def test_project_i8_extreme_digits_fill_the_int32_chain(cuda_device):
     Q1 = _pitched(np.full((N, K), 255, np.uint8), cuda_device)
     exps = torch.zeros(N, dtype=torch.int32, device=cuda_device)
     V = torch.zeros((M, 132), dtype=torch.float32, device=cuda_device)
-    K_.project_i8(Dg, (Q0, Q1, Q1), exps, 1.0, None, V)
+    K_.project_i8(Dg, (Q0, Q1, Q1), exps, 1.0, None, V, impl=impl)
     acc = K * 65535 * ((-128 << 16) + (255 << 8) + 255)
     want = np.float32(np.float64(acc) * 2.0 ** -23)
     assert (V[:, :N].cpu().numpy() == want).all()
@@ -113,7 +115,8 @@ def test_bin_motion_planes_exact(cuda_device, sbin, H, W):
         assert np.array_equal(last.cpu().numpy(), S[-1])
 
 
-def test_pipeline_in_i8_projection_mode(cuda_device, monkeypatch):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_pipeline_in_i8_projection_mode(cuda_device, monkeypatch, impl):
     from facemap_b200 import process
     from facemap_b200.frames import DeviceArraySource
     from facemap_b200.synth import SynthVideo
@@ -123,6 +126,7 @@ def test_pipeline_in_i8_projection_mode(cuda_device, monkeypatch):
     src = DeviceArraySource([torch.from_numpy(v).to(cuda_device)])
     p0 = process.process_source(src, sbin=sbin, movSVD=True)
     monkeypatch.setenv("FM_PROJ_MODE", "i8")
+    monkeypatch.setenv("FM_PROJ_I8_IMPL", str(impl))
     p1 = process.process_source(src, sbin=sbin, movSVD=True)
     assert np.array_equal(p0["motion"][0], p1["motion"][0])
     for key, sk in (("motSVD", "motSv"), ("movSVD", "movSv")):

@@ -116,7 +116,7 @@ class FakeKernels:
         assert w.dtype == torch.float64
         return torch.from_numpy(Y.numpy().astype(np.float64) @ w.numpy())
 
-    def project_i8(self, D, Q, exps, alpha, bias, V):
+    def project_i8(self, D, Q, exps, alpha, bias, V, impl=0):
         hi, lo = D
         Dv = lo.numpy().astype(np.int64) + (0 if hi is None else 256 * hi.numpy().astype(np.int64))
         planes = [lo.numpy()] if hi is None else [hi.numpy(), lo.numpy()]
@@ -163,7 +163,7 @@ def test_stage3_i8_orchestration(monkeypatch, sbin, mods):
     monkeypatch.setattr(svd, "K", fake)
     ws = object.__new__(svd.SvdWorkspace)
     ws.device, ws._bufs, ws._ws = torch.device("cpu"), {}, None
-    ws.proj_mode, ws.proj_impl = "i8", 0
+    ws.proj_mode, ws.proj_impl, ws.proj_i8_impl = "i8", 0, 0
     timer = svd.StageTimer(enabled=False)
     st = svd.Stage3(ArraySource(views), geo, torch.from_numpy(avgframe), torch.from_numpy(avgmotion), mods, True, ws,
                     torch.device("cpu"), timer, fetch_frames=17)
@@ -186,7 +186,7 @@ def test_stage3_i8_orchestration(monkeypatch, sbin, mods):
 def test_stage3_i8_refuses_what_it_cannot_serve():
     geo = svd.Geometry([32], [32], 32, None)
     ws = object.__new__(svd.SvdWorkspace)
-    ws.device, ws._bufs, ws._ws, ws.proj_mode, ws.proj_impl = torch.device("cpu"), {}, None, "i8", 0
+    ws.device, ws._bufs, ws._ws, ws.proj_mode, ws.proj_impl, ws.proj_i8_impl = torch.device("cpu"), {}, None, "i8", 0, 0
     src = ArraySource([np.zeros((5, 32, 32), np.uint8)])
     with pytest.raises(svd.FacemapB200Error):
         svd.Stage3(src, geo, None, None, ["mot"], True, ws, torch.device("cpu"), svd.StageTimer(enabled=False))
