@@ -350,7 +350,9 @@ __global__ void __launch_bounds__(K1_THREADS) bin_motion_vec_kernel(const K1Para
         if constexpr (PLANES) {                 // integer operands of the kind::i8 projection (own instantiations:
                                                 // the default kernels' code is untouched)
           const size_t qoff = (size_t)row * p.ldq + p.col0 + pix0;
-          const bool pack_ok = ((p.col0 + pix0) % PX == 0) && (p.ldq % 4 == 0);
+          const bool pack_ok = ((p.col0 + pix0) % PX == 0) && (p.ldq % 4 == 0) &&
+                               ((reinterpret_cast<uintptr_t>(p.q_mot_hi) | reinterpret_cast<uintptr_t>(p.q_mot_lo) |
+                                 reinterpret_cast<uintptr_t>(p.q_mov_hi) | reinterpret_cast<uintptr_t>(p.q_mov_lo)) % 4 == 0);
           if (p.q_mot_lo) store_planes<PX>(p.q_mot_hi, p.q_mot_lo, qoff, dvals, nvalid, pack_ok);
           if (p.q_mov_lo) {
             unsigned cv[PX];
