@@ -106,7 +106,7 @@ class _HostSink:
 
 def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD=True, device=None,
                    eig_fp32=False, gemm_impl=0, timing=None, dist=None, keep_on_device=False,
-                   overlap_stage3=True, gather_outputs=True, gram_mode=None):
+                   overlap_stage3=True, gather_outputs=True, gram_mode=None, proj_mode=None):
     """Run the three stages on a FrameSource and return the proc-dict entries this path owns.
 
     timing: optional dict that receives per-stage device times (ms) and wall times.
@@ -117,7 +117,9 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     dist:   optional facemap_b200.parallel.Shard (frame-range sharding across ranks).
     gram_mode: "tf32x3" (default), "sliced_merge", "sliced", "i8_merge" or "i8" — how the Gram matrices of the two
             SVD levels are formed (svd.SvdWorkspace, svd.sliced_gram, svd.i8_gram); None reads the environment
-            variable FM_GRAM_MODE."""
+            variable FM_GRAM_MODE.
+    proj_mode: "tf32x3" (default) or "i8" (EXPERIMENTAL: stage 3 on byte planes and tcgen05 kind::i8, svd.Stage3);
+            None reads FM_PROJ_MODE."""
     t_enter = time.perf_counter()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     _lib.require_device(dev.index or 0)
@@ -152,7 +154,8 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                 marks.append((name, time.perf_counter()))
 
     mark("start")
-    ws = svd.SvdWorkspace(dev, eig_fp32=eig_fp32, gemm_impl=gemm_impl, timer=timer, gram_mode=gram_mode)
+    ws = svd.SvdWorkspace(dev, eig_fp32=eig_fp32, gemm_impl=gemm_impl, timer=timer, gram_mode=gram_mode,
+                          proj_mode=proj_mode)
     source.plan_access(*svd.access_plan(source, dist), dev)
     mark("setup")
 

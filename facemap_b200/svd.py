@@ -151,7 +151,7 @@ def get_solver(device):
 class SvdWorkspace:
     """Reusable device buffers for the Gram -> eigensolve -> left-vector sequence."""
 
-    def __init__(self, device, eig_fp32=False, gemm_impl=0, timer=None, gram_mode=None):
+    def __init__(self, device, eig_fp32=False, gemm_impl=0, timer=None, gram_mode=None, proj_mode=None):
         self.device = device
         self.timer = timer if timer is not None else StageTimer(enabled=False)
         self.solver = get_solver(device)
@@ -178,9 +178,9 @@ class SvdWorkspace:
         #   "tf32x3"  K1 writes float32 operands, one 3xTF32 GEMM per batch — the measured default
         #   "i8"      EXPERIMENTAL: K1 writes the integer energies / block sums as byte planes, the masks become s8/u8/u8
         #             digits and fm_project_i8 forms the products exactly on tcgen05 kind::i8 (Stage3)
-        self.proj_mode = _os.environ.get("FM_PROJ_MODE", "tf32x3")
+        self.proj_mode = _os.environ.get("FM_PROJ_MODE", "tf32x3") if proj_mode is None else proj_mode
         if self.proj_mode not in ("tf32x3", "i8"):
-            raise FacemapB200Error(f"unknown FM_PROJ_MODE {self.proj_mode!r}")
+            raise FacemapB200Error(f"unknown proj_mode {self.proj_mode!r}")
         self.proj_i8_impl = int(_os.environ.get("FM_PROJ_I8_IMPL", "0"))      # 1 = CTA pairs (fm_project_i8 impl)
         self._ws = None
         self._bufs = {}
