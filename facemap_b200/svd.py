@@ -691,13 +691,13 @@ def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS):
 # ---------------------------------------------------------------------------------------------
 # stage 3
 # ---------------------------------------------------------------------------------------------
-def projection_rows_per_batch(p, k, budget_bytes=6 << 30):
+def projection_rows_per_batch(p, k, budget_bytes=6 << 30, elem_bytes=4):
     """Rows per projection GEMM: whole waves of 128-row tiles over the 148 SMs, bounded by the
-    X-buffer budget."""
+    X-buffer budget (elem_bytes per binned pixel: 4 for the float32 operand, 1 or 2 for byte planes)."""
     ntn = max(1, math.ceil(k / 256))
     rows_wave = max(1, NUM_SMS // ntn) * 128
     rows = 2 * rows_wave
-    cap = max(128, (budget_bytes // (4 * max(p, 1))) // 128 * 128)
+    cap = max(128, (budget_bytes // (elem_bytes * max(p, 1))) // 128 * 128)
     return int(min(rows, cap))
 
 
@@ -750,7 +750,13 @@ class Stage3:
         self.E_roi = torch.zeros((max(self.nroi, 1), self.n_out), dtype=torch.int64, device=device)
         self.carry = [[torch.zeros(n, dtype=torch.int32, device=device) for n in geo.npix_v] for _ in range(2)]
         self.flip = 0
-        self.rows_batch = projection_rows_per_batch(geo.p, kmax)
+        # integer-plane operands for fm_project_i8 (ws.proj_mode == "i8"); asked for but not servable is an error, not
+        # a silent change of path
+        self.i8 = ws.proj_mode == "i8" and bool(mods)
+        if self.i8 and geo.sbin > 16:
+            raise FacemapB200Error("FM_PROJ_MODE=i8: two byte planes hold block sums up to sbin 16")
+        self.ldq = K.round_up(geo.p, 16)
+        self.rows_batch = projection_rows_per_batch(geo.p, kmax, elem_bytes=(1 if geo.sbin == 1 else 2) if self.i8 else 4)
         # fetch plan: GEMM batches of <= rows_batch rows, each filled by several fetches
         self.have0 = self.f0 > 0                         # a shard starting mid-video carries a 1-frame halo
         self.batches, t, have = [], self.f0, self.have0
@@ -770,12 +776,6 @@ class Stage3:
         self.rows_total = max(0, self.f1 - self.first_row_frame)
         self.X_full = None
         self.early_done = None
-        # integer-plane operands for fm_project_i8 (ws.proj_mode == "i8"); asked for but not servable is an error, not
-        # a silent change of path
-        self.i8 = ws.proj_mode == "i8" and bool(mods)
-        if self.i8 and geo.sbin > 16:
-            raise FacemapB200Error("FM_PROJ_MODE=i8: two byte planes hold block sums up to sbin 16")
-        self.ldq = K.round_up(geo.p, 16)
         self._halo_done = False
         # views whose float32 motion accumulator the exact integer energy cannot decide (fm_motion_ref)
         self.Eref, self.ref_views = None, []
