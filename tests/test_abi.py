@@ -81,3 +81,49 @@ def test_header_is_plain_c():
             f.write('#include "facemap_b200.h"\nint main(void) { return fm_version(); }\n')
         subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
                                "-I", os.path.join(ROOT, "include"), src])
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """ctypes does not check a prototype against the library: compare `_lib.SIGNATURES` with the header argument by
+    argument (count, and pointer / integer / floating-point class), so that a C-ABI change cannot silently shift the
+    arguments of a Python call"""
+    import ctypes as C
+    import re
+
+    from facemap_b200 import _lib
+
+    text = open(os.path.join(ROOT, "include", "facemap_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    protos = {m.group(2): m.group(3) for m in re.finditer(r"\b([A-Za-z_][\w\s\*]*?)\b(fm_\w+)\s*\(([^;{]*?)\)\s*;", text)}
+
+    def kind_of_c(arg):
+        arg = arg.strip()
+        if "*" in arg:
+            return "ptr"
+        base = arg.rsplit(None, 1)[0] if " " in arg else arg
+        if base in ("double", "float"):
+            return base
+        if "64" in base or base in ("size_t", "long long", "unsigned long long"):
+            return "int64"
+        return "int32"
+
+    def kind_of_ctypes(t):
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        if t is C.c_double:
+            return "double"
+        if t is C.c_float:
+            return "float"
+        return "int64" if C.sizeof(t) == 8 else "int32"
+
+    checked = 0
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert name in protos, f"{name} is in SIGNATURES but not declared in the header"
+        raw = protos[name].strip()
+        cargs = [] if raw in ("", "void") else [a for a in raw.split(",")]
+        assert len(cargs) == len(argtypes), f"{name}: header has {len(cargs)} arguments, SIGNATURES {len(argtypes)}"
+        for i, (ca, ct) in enumerate(zip(cargs, argtypes)):
+            assert kind_of_c(ca) == kind_of_ctypes(ct), f"{name} argument {i}: header `{ca.strip()}` vs ctypes {ct}"
+        checked += 1
+    assert checked >= 40
