@@ -127,3 +127,16 @@ def test_ctypes_signatures_match_header_prototypes():
             assert kind_of_c(ca) == kind_of_ctypes(ct), f"{name} argument {i}: header `{ca.strip()}` vs ctypes {ct}"
         checked += 1
     assert checked >= 40
+
+
+def test_integration_doc_bindings_match_the_abi():
+    """the ctypes stubs INTEGRATION.md shows a maintainer must have the argument counts of the real entry points"""
+    from facemap_b200 import _lib
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    found = re.findall(r"lib\.(fm_\w+)\.argtypes\s*=\s*\[([^\]]*)\]", text)
+    assert len(found) >= 10
+    for name, args in found:
+        n = len([a for a in args.split(",") if a.strip()])
+        assert name in _lib.SIGNATURES, name
+        assert n == len(_lib.SIGNATURES[name][1]), f"INTEGRATION.md: {name} has {n} argtypes, the ABI {len(_lib.SIGNATURES[name][1])}"
