@@ -288,3 +288,39 @@ def test_stage3_default_float_orchestration(monkeypatch, fetch_frames):
         assert np.abs(V[m][0].numpy()[1:] - want).max() <= 2e-6 * np.abs(want).max() and not V[m][0].numpy()[0].any()
         want_r = X[m][:, cols] @ Ur[m].astype(np.float64).T
         assert np.abs(V[m][1].numpy()[1:] - want_r).max() <= 2e-6 * np.abs(want_r).max()
+
+
+def test_dry_run_of_the_opt_in_gpu_tests(monkeypatch):
+    """the bodies of tests/test_project_i8_gpu.py on the CPU with stand-in kernels: their shapes, dtypes, pitches and
+    expected values are consistent with the model, so a GPU minute is never spent on a bug of the test itself"""
+    import facemap_b200.kernels as Kreal
+
+    from . import test_project_i8_gpu as T
+
+    fake = FakeKernels()
+
+    def alloc_matrix(rows, cols, device, zero=False):
+        return torch.zeros((rows, -(-cols // 32) * 32), dtype=torch.float32)[:, :cols]
+
+    def project_i8(D, Q, exps, alpha, bias, V, impl=0):
+        hi, lo = D
+        planes = [lo.numpy()] if hi is None else [hi.numpy(), lo.numpy()]
+        cls = M8.class_sums(planes, tuple(q.numpy() for q in Q))
+        nc = cls.shape[1]
+        acc = sum(cls[c, j] * (1 << (8 * (nc - 1 - j))) for c in range(cls.shape[0]) for j in range(nc))
+        v = acc.astype(np.float64) * (np.float64(alpha) * np.exp2(exps.numpy().astype(np.float64) - 23))[None, :]
+        if bias is not None:
+            v = v - bias.numpy()[None, :]
+        V[:lo.shape[0], :v.shape[1]] = torch.from_numpy(v.astype(np.float32))
+
+    monkeypatch.setattr(Kreal, "alloc_matrix", alloc_matrix)
+    monkeypatch.setattr(Kreal, "slice_rows_i8", FakeKernels.slice_rows_i8)
+    monkeypatch.setattr(Kreal, "row_dot", FakeKernels.row_dot)
+    monkeypatch.setattr(Kreal, "project_i8", project_i8)
+    monkeypatch.setattr(Kreal, "bin_motion_planes", fake.bin_motion_planes)
+    cpu = torch.device("cpu")
+    for (M, N, K, sbin) in [(128, 128, 64, 4), (77, 130, 1000, 1), (5, 7, 33, 16), (260, 250, 16384 + 64, 2)]:
+        T.test_project_i8_bit_exact_against_model(cpu, M, N, K, sbin, 1)
+    T.test_project_i8_extreme_digits_fill_the_int32_chain(cpu, 0)
+    for (sbin, H, W) in [(1, 40, 64), (4, 64, 96), (3, 45, 60), (4, 37, 53)]:
+        T.test_bin_motion_planes_exact(cpu, sbin, H, W)
