@@ -7,7 +7,9 @@ FM_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gemm_i8_gpu.py -q -m g
 tail -5 gpurun_out/i8_tests.log
 FM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_large_golden_gpu.py -x -q -m gpu -s > gpurun_out/large_golden_tests.log 2>&1; echo "large golden tests rc $?"
 grep -E "S rel err|kres|passed|failed" gpurun_out/large_golden_tests.log | tail -8
-FM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_project_i8_gpu.py -q -m gpu -s > gpurun_out/project_i8_tests.log 2>&1; echo "i8 projection tests rc $?"
+FM_EXPERIMENTAL=1 FM_TEST_I8_IMPLS=0 timeout 600 python -m pytest tests/test_project_i8_gpu.py -q -m gpu -s > gpurun_out/project_i8_tests.log 2>&1; echo "i8 projection tests (one CTA per tile) rc $?"
+FM_EXPERIMENTAL=1 FM_TEST_I8_IMPLS=1 timeout 600 python -m pytest tests/test_project_i8_gpu.py -q -m gpu -s -k "not planes_exact and not motion_rois" > gpurun_out/project_i8_pair_tests.log 2>&1; echo "i8 projection tests (CTA pairs) rc $?"
+grep -E "passed|failed|Error|timeout" gpurun_out/project_i8_pair_tests.log | tail -4
 grep -E "trace difference|passed|failed|Error|timeout" gpurun_out/project_i8_tests.log | tail -12
 timeout 300 python scripts/probe_project_i8.py > gpurun_out/probe_project_i8.log 2>&1; echo "probe i8 projection rc $?"; tail -4 gpurun_out/probe_project_i8.log
 FM_PROJ_MODE=i8 timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_proj_i8.json 2> gpurun_out/bench_proj_i8.err; echo "bench FM_PROJ_MODE=i8 rc $?"; tail -c 1500 gpurun_out/bench_proj_i8.json
