@@ -119,6 +119,14 @@ def test_bin_motion_planes_exact(cuda_device, sbin, H, W):
         assert (P[1][:, :col0] == 0xEE).all() and (P[1][:, col0 + npix:] == 0xEE).all()      # nothing outside the view
         assert np.array_equal(energy.cpu().numpy(), d.sum(axis=1))
         assert np.array_equal(last.cpu().numpy(), S[-1])
+    # painted frames (pupil / blink ROIs write 255 into the frames stage 3 bins, facemap/process.py:543, 567)
+    mask = np.where(rs.rand(H, W) < 0.2, 255, 0).astype(np.uint8)
+    Sp = M8.block_sums(fr | mask[None], sbin)
+    planes = torch.zeros((2, T - 1, ldq), dtype=torch.uint8, device=cuda_device)
+    K_.bin_motion_planes(frames, sbin, q_mot=(planes[0] if sbin > 1 else None, planes[1]), col0=col0,
+                         ormask=torch.from_numpy(mask).to(cuda_device))
+    P = planes.cpu().numpy().astype(np.int64)
+    assert np.array_equal(P[1][:, col0:col0 + npix] + 256 * P[0][:, col0:col0 + npix], np.abs(np.diff(Sp, axis=0)))
 
 
 @pytest.mark.parametrize("impl", IMPLS)

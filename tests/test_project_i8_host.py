@@ -70,8 +70,8 @@ class FakeKernels:
 
     def bin_motion_planes(self, frames, sbin, *, prev_sum=None, q_mot=None, q_mov=None, col0=0, energy=None, rois=None,
                           roi_energy=None, last_sum=None, ormask=None):
-        assert ormask is None
-        S = M8.block_sums(frames.numpy(), sbin)
+        fr = frames.numpy() if ormask is None else frames.numpy() | ormask.numpy()[None]
+        S = M8.block_sums(fr, sbin)
         npix = S.shape[1]
         prev = S[:1] if prev_sum is None else prev_sum.numpy().astype(np.int64)[None, :]
         cur = S[1:] if prev_sum is None else S
