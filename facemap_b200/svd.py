@@ -661,7 +661,7 @@ def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, t
     return Yt, ks, nsegs
 
 
-def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS):
+def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS, nc=None):
     """Second-level SVD (process.py:264-295).  Returns per modality lists Ut, U, and Sv (the
     singular values of the LAST target processed, quirk Q3)."""
     out = {}
@@ -680,8 +680,13 @@ def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS):
                 sv = s
             else:                               # quirk Q6: single chunk -> U S as is, Sv stays zero
                 Ut = Y
-                U = torch.empty((p_idx, Y.shape[0]), dtype=torch.float32, device=ws.device)
-                K.transpose(Y, U)
+                # the reference's full-frame buffer is nsegs * nc wide and only cut to its filled columns inside
+                # the merge (process.py:146-151, 267): fewer binned pixels than nc leave zero components behind
+                if idx == 0 and nc is not None and Y.shape[0] < nsegs * nc:
+                    Ut = K.alloc_matrix(nsegs * nc, p_idx, ws.device, zero=True)
+                    Ut[:Y.shape[0]].copy_(Y)
+                U = torch.empty((p_idx, Ut.shape[0]), dtype=torch.float32, device=ws.device)
+                K.transpose(Ut, U)
             Uts.append(Ut)
             Us.append(U)
         out[m] = (Uts, Us, sv)

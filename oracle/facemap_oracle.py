@@ -344,7 +344,13 @@ def stage2_masks(video, sbin, avgframe, avgmotion, motSVD=True, movSVD=False, ro
                 out_U[m].append(u)
                 out_S[m] = s                           # quirk Q3: last one wins
             else:
-                out_U[m].append(Y)                     # quirk Q6
+                # quirk Q6: a single chunk is never merged — U S of that chunk as is, singular values stay zero.
+                # The full-frame buffer was preallocated nsegs * nc wide (process.py:146-151) and is only cut to
+                # the filled columns inside the merge (process.py:267): with fewer binned pixels than nc the
+                # trailing columns stay zero.  ROI buffers are allocated to size (process.py:163-178).
+                if idx == 0 and Y.shape[1] < nsegs * nc:
+                    Y = np.ascontiguousarray(np.pad(Y, ((0, 0), (0, nsegs * nc - Y.shape[1]))))
+                out_U[m].append(Y)
     # quirk Q7: ROI placeholders exist for a modality that is off
     for m in ("mot", "mov"):
         if m not in mods:

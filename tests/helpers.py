@@ -20,6 +20,9 @@ CASES = {
     "onechunk_s1": ([(24, 32, 2)], 1300, 1, True, False, None),
     "crop_s3": ([(50, 70, 3)], 2100, 3, True, False, None),
     "short_s2": ([(40, 56, 4)], 700, 2, True, True, None),
+    # fewer binned pixels (384) than chunk components (500) in the single-chunk regime: the reference leaves the
+    # unfilled columns of its preallocated mask buffer zero (process.py:146-151, 246-259; never cut: :264-267)
+    "tiny_onechunk_s2": ([(32, 48, 5)], 1200, 2, True, True, None),
 }
 
 

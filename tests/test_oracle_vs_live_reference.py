@@ -1,0 +1,54 @@
+"""The oracle against the UNMODIFIED reference run live (oracle/ref_harness.py) on configurations the committed golden
+fixtures do not hold: odd frame sizes, sequential blocks, a non-power-of-two bin, frame counts around the chunk
+boundaries.  Integer stages bit for bit with the stock reference; the whole proc dict (singular values, masks,
+projections) bit for bit with the reference whose `utils.svdecon` is the exact float64 one — the same two oracles as
+SURVEY §8(c).  Runs where /root/reference exists (the build container); each case takes a few seconds."""
+import numpy as np
+import pytest
+
+from facemap_b200.synth import SynthVideo
+from oracle import facemap_oracle as orc
+from oracle import ref_harness
+
+pytestmark = pytest.mark.skipif(not ref_harness.reference_available(), reason="needs /root/reference (build container)")
+
+# (views [(H, W, seed)], frames per sequential block, sbin, motSVD, movSVD)
+CASES = {
+    "odd_size_s2": ([(46, 70, 21)], [1203], 2, True, True),
+    "two_blocks_s3": ([(45, 63, 22)], [700, 650], 3, True, False),
+    "two_views_s5": ([(50, 60, 23), (40, 75, 24)], [1100], 5, True, True),
+    "below_one_chunk_s1": ([(20, 28, 25)], [640], 1, True, False),
+}
+
+
+def _videos(views, blocks):
+    total = int(sum(blocks))
+    full = [SynthVideo(H, W, total, seed=seed).all_frames() for (H, W, seed) in views]
+    edges = np.concatenate([[0], np.cumsum(blocks)])
+    return full, [[v[edges[b]:edges[b + 1]] for v in full] for b in range(len(blocks))]
+
+
+def _equal(a, b, key):
+    if isinstance(a, (list, tuple)):
+        assert len(a) == len(b), key
+        for i, (x, y) in enumerate(zip(a, b)):
+            _equal(x, y, f"{key}[{i}]")
+    else:
+        a, b = np.asarray(a), np.asarray(b)
+        assert a.shape == b.shape and a.dtype == b.dtype, (key, a.shape, b.shape, a.dtype, b.dtype)
+        assert np.array_equal(a, b), key
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_the_live_reference(name):
+    views, blocks, sbin, mot, mov = CASES[name]
+    full, per_block = _videos(views, blocks)
+    stock = ref_harness.run_reference(per_block, sbin=sbin, motSVD=mot, movSVD=mov)
+    exact = ref_harness.run_reference(per_block, sbin=sbin, motSVD=mot, movSVD=mov, exact=True)
+    got = orc.run_oracle(full, sbin=sbin, motSVD=mot, movSVD=mov, svd="exact", block_frames=blocks)
+    for key in ("avgframe", "avgmotion", "motion", "avgframe_reshape", "avgmotion_reshape"):
+        _equal(got[key], stock[key], key)                     # integer-derived stages: stock reference, bit for bit
+    for key in ("motSv", "movSv", "motMask", "movMask", "motMask_reshape", "movMask_reshape", "motSVD", "movSVD"):
+        _equal(got[key], exact[key], key)                     # SVD outputs: reference with the exact svdecon
+    for key in ("Ly", "Lx", "Lybin", "Lxbin", "sybin", "sxbin", "LYbin", "LXbin"):
+        assert np.array_equal(np.asarray(got[key]), np.asarray(stock[key])), key
