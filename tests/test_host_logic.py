@@ -177,3 +177,36 @@ def test_motion_ref_block_count_respects_scratch_budget():
     big = svd.motion_ref_blocks(1280 * 1024, 13000, 1)                                    # C4 at sbin 1: 10.5 MB per block
     assert 8 <= big < svd.MOTION_REF_BLOCKS and big * (2 * 1280 * 1024 + 13000) * 4 <= svd.MOTION_REF_SCRATCH_MAX
     assert svd.motion_ref_blocks(10 ** 9, 10 ** 7, 7) == 8                                # never below 8 blocks
+
+
+def test_single_chunk_masks_keep_the_references_zero_columns(monkeypatch):
+    """svd.stage2_merge, nsegs == 1: the chunk's U S as is (quirk Q6), zero-padded to nsegs * nc components when the
+    view has fewer binned pixels than that (facemap/process.py:146-151, 264-267); ROI targets are not padded"""
+    import torch
+
+    from facemap_b200 import kernels, svd
+
+    class FakeK:
+        alloc_matrix = staticmethod(kernels.alloc_matrix)
+
+        @staticmethod
+        def transpose(src, dst):
+            dst.copy_(src.t())
+
+    monkeypatch.setattr(svd, "K", FakeK)
+    ws = object.__new__(svd.SvdWorkspace)
+    ws.device = torch.device("cpu")
+    g = torch.Generator().manual_seed(0)
+    Y0, Y1 = torch.randn(384, 384, generator=g), torch.randn(60, 60, generator=g)
+    out = svd.stage2_merge({"mot": [Y0, Y1]}, None, 1, None, ["mot"], True, ws, svd.StageTimer(enabled=False), nc=500)
+    Uts, Us, sv = out["mot"]
+    assert tuple(Uts[0].shape) == (500, 384) and tuple(Us[0].shape) == (384, 500)
+    assert torch.equal(Uts[0][:384], Y0) and not Uts[0][384:].any()
+    assert torch.equal(Us[0][:, :384], Y0.t()) and not Us[0][:, 384:].any()
+    assert Uts[0].stride(1) == 1 and Uts[0].stride(0) % 4 == 0          # still a legal GEMM operand
+    assert tuple(Uts[1].shape) == (60, 60) and tuple(Us[1].shape) == (60, 60) and torch.equal(Us[1], Y1.t())
+    assert tuple(sv.shape) == (500,) and not sv.any()
+    # enough pixels: nothing changes
+    Y2 = torch.randn(500, 560, generator=g)
+    Uts, Us, _ = svd.stage2_merge({"mot": [Y2]}, None, 1, None, ["mot"], True, ws, svd.StageTimer(enabled=False), nc=500)["mot"]
+    assert Uts[0] is Y2 and tuple(Us[0].shape) == (560, 500)
