@@ -18,6 +18,8 @@ CASES = {
     "two_blocks_s3": ([(45, 63, 22)], [700, 650], 3, True, False),
     "two_views_s5": ([(50, 60, 23), (40, 75, 24)], [1100], 5, True, True),
     "below_one_chunk_s1": ([(20, 28, 25)], [640], 1, True, False),
+    "tiny_two_chunks_s4": ([(40, 40, 26)], [2100], 4, True, True),          # 100 binned pixels < 250 chunk components
+    "tiny_three_views_s2": ([(16, 20, 27), (12, 30, 28), (20, 14, 29)], [1500], 2, True, False),
 }
 
 
