@@ -185,7 +185,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         else:
             Yt, ks, nsegs = dist.stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, dev, timer)
         mark("stage2.chunks")
-        masks = svd.stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, nc=svd.stage2_plan(N)[2])
+        masks = svd.stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, nc=svd.stage2_plan(N)[2], mot_on=bool(motSVD))
         del Yt
         mark("stage2.merge")
     nsegs_plan = svd.stage2_plan(N)[1]

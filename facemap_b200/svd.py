@@ -661,7 +661,7 @@ def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, t
     return Yt, ks, nsegs
 
 
-def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS, nc=None):
+def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS, nc=None, mot_on=True):
     """Second-level SVD (process.py:264-295).  Returns per modality lists Ut, U, and Sv (the
     singular values of the LAST target processed, quirk Q3)."""
     out = {}
@@ -674,11 +674,15 @@ def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS, nc
                 Us.append(torch.zeros((0, 1), dtype=torch.float32, device=ws.device))
                 continue
             p_idx = Y.shape[1]
-            if nsegs > 1:
+            # quirk Q8: the reference's merge loop runs over range(len(U_mot)) and indexes both lists with it
+            # (process.py:264-295); with the motion SVD off, U_mot holds only the ROI placeholders, so the movie targets
+            # from that position on (all of them without ROIs, the last ROI otherwise) keep their stacked chunk blocks
+            merged = idx < (1 if mot_on else 0) + (len(Yt[m]) - 1)
+            if nsegs > 1 and merged:
                 k = min(ncomps, p_idx - 1)
                 Ut, U, s = merge_components(ws, Y, k, timer, "stage2.merge" if idx == 0 else "stage2.roi_merge")
                 sv = s
-            else:                               # quirk Q6: single chunk -> U S as is, Sv stays zero
+            else:                               # quirk Q6 / Q8: not merged -> the chunks' U S as they are, Sv stays zero
                 Ut = Y
                 # the reference's full-frame buffer is nsegs * nc wide and only cut to its filled columns inside
                 # the merge (process.py:146-151, 267): fewer binned pixels than nc leave zero components behind

@@ -339,7 +339,12 @@ def stage2_masks(video, sbin, avgframe, avgmotion, motSVD=True, movSVD=False, ro
             # C-ordered like the reference's preallocated U buffer (process.py:146-151):
             # BLAS results depend on the operand layout, and 'stock' is held bit-for-bit
             Y = np.ascontiguousarray(np.concatenate(blocks[m][idx], axis=1))
-            if nsegs > 1:                              # process.py:264-295
+            # quirk Q8: the merge loop runs over range(len(U_mot)) (process.py:264) and indexes BOTH lists with it.
+            # With the motion SVD switched off U_mot holds only the ROI placeholders (process.py:146-178), so the
+            # movie targets from position len(U_mot) on — everything when there is no ROI, the last ROI otherwise —
+            # are never merged and stay the stacked U S blocks of their chunks.
+            merged = idx < (1 if motSVD else 0) + len(mot_rois)
+            if nsegs > 1 and merged:                   # process.py:264-295
                 u, s, _ = svd_centered(Y, min(ncomps, Y.shape[0] - 1), svd)
                 out_U[m].append(u)
                 out_S[m] = s                           # quirk Q3: last one wins

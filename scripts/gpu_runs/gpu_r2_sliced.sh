@@ -14,6 +14,7 @@ grep -E "trace difference|passed|failed|Error|timeout" gpurun_out/project_i8_tes
 timeout 300 python scripts/probe_project_i8.py > gpurun_out/probe_project_i8.log 2>&1; echo "probe i8 projection rc $?"; tail -4 gpurun_out/probe_project_i8.log
 FM_PROJ_MODE=i8 timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_proj_i8.json 2> gpurun_out/bench_proj_i8.err; echo "bench FM_PROJ_MODE=i8 rc $?"; tail -c 1500 gpurun_out/bench_proj_i8.json
 FM_PROJ_MODE=i8 FM_PROJ_I8_IMPL=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_proj_i8_pair.json 2> gpurun_out/bench_proj_i8_pair.err; echo "bench FM_PROJ_MODE=i8 pair rc $?"; tail -c 1500 gpurun_out/bench_proj_i8_pair.json
+FM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_edge_cases_gpu.py -q -m gpu -k "movie_svd_without_motion or frame_count_boundaries" > gpurun_out/edge_q8_tests.log 2>&1; echo "edge tests (Q6 padding, Q8 movie-only) rc $?"; tail -3 gpurun_out/edge_q8_tests.log
 # structured operands that say HOW a kernel is wrong (one process per kernel: a trap poisons the context)
 for part in gemm 0 1; do timeout 200 python scripts/triage_i8.py $part > gpurun_out/triage_i8_$part.log 2>&1; echo "triage $part rc $?: $(grep -c "^ok" gpurun_out/triage_i8_$part.log) ok, $(grep -c "^FAIL\|^ERROR" gpurun_out/triage_i8_$part.log) bad"; grep "^FAIL\|^ERROR" gpurun_out/triage_i8_$part.log | head -6; done
 timeout 200 python scripts/probe_gemm_i8.py > gpurun_out/probe_gemm_i8.log 2>&1; echo "probe i8 rc $?"; cat gpurun_out/probe_gemm_i8.log | tail -20

@@ -116,3 +116,27 @@ def test_fullsvd_off_with_roi(cuda_device):
     assert S.shape == Sr.shape and (np.abs(S - Sr)[big] / Sr[big]).max() <= 1e-4
     U, Ur = p["motMask"][1][:, :3].astype(np.float64), o["motMask"][1][:, :3].astype(np.float64)
     assert np.abs(np.abs((U * Ur).sum(axis=0)) - 1).max() < 1e-5
+
+
+@pytest.mark.skipif(__import__("os").environ.get("FM_EXPERIMENTAL") != "1",
+                    reason="written without a GPU (round 1 had spent its budget): opt-in until validated on a B200")
+@pytest.mark.parametrize("with_rois", [False, True])
+def test_movie_svd_without_motion_svd(cuda_device, with_rois):
+    """motSVD off, movSVD on: the reference's merge loop runs over len(U_mot) (process.py:264), so the movie targets
+    beyond it are never merged — all of them without ROIs, the last ROI with ROIs (quirk Q8, pinned against the live
+    reference in tests/test_oracle_vs_live_reference.py)"""
+    from facemap_b200 import process
+    from facemap_b200.frames import DeviceArraySource
+
+    from .helpers import motion_roi
+
+    v = _video(2100, 36, 44, seed=5)
+    rois = [motion_roi(0, 4, 16, 4, 20), motion_roi(0, 20, 34, 10, 40)] if with_rois else None
+    o = orc.run_oracle([v], sbin=2, motSVD=False, movSVD=True, rois=rois, svd="exact")
+    p = process.process_source(DeviceArraySource([torch.from_numpy(v).to(cuda_device)]), sbin=2, motSVD=False,
+                               movSVD=True, rois=rois)
+    _compare(p, o, False, True)
+    shapes = [tuple(u.shape) for u in p["movMask"]]
+    # full frame merged (395 = npix - 1), first ROI merged (40 pixels -> 39), last ROI left as 2 x 90 stacked chunk components
+    assert shapes == ([(396, 500)] if not with_rois else [(396, 395), (40, 39), (90, 180)]), shapes
+    assert [tuple(u.shape) for u in p["motMask"]] == [tuple(u.shape) for u in o["motMask"]]

@@ -210,3 +210,43 @@ def test_single_chunk_masks_keep_the_references_zero_columns(monkeypatch):
     Y2 = torch.randn(500, 560, generator=g)
     Uts, Us, _ = svd.stage2_merge({"mot": [Y2]}, None, 1, None, ["mot"], True, ws, svd.StageTimer(enabled=False), nc=500)["mot"]
     assert Uts[0] is Y2 and tuple(Us[0].shape) == (560, 500)
+
+
+def test_merge_loop_follows_the_references_len_u_mot_quirk(monkeypatch):
+    """svd.stage2_merge with the motion SVD off: targets at positions >= number of ROIs stay unmerged (quirk Q8)"""
+    import torch
+
+    from facemap_b200 import kernels, svd
+
+    merged_calls = []
+
+    class FakeK:
+        alloc_matrix = staticmethod(kernels.alloc_matrix)
+
+        @staticmethod
+        def transpose(src, dst):
+            dst.copy_(src.t())
+
+    def fake_merge(ws, Y, k, timer, label):
+        merged_calls.append((label, tuple(Y.shape), k))
+        return Y[:k], Y[:k].t().contiguous(), torch.ones(k)
+
+    monkeypatch.setattr(svd, "K", FakeK)
+    monkeypatch.setattr(svd, "merge_components", fake_merge)
+    ws = object.__new__(svd.SvdWorkspace)
+    ws.device = torch.device("cpu")
+    t = svd.StageTimer(enabled=False)
+    full, r0, r1 = torch.randn(500, 396), torch.randn(80, 40), torch.randn(180, 90)
+    # movie only, two ROIs: full frame and first ROI merged, last ROI kept as stacked chunk blocks
+    Uts, Us, sv = svd.stage2_merge({"mov": [full, r0, r1]}, None, 2, None, ["mov"], True, ws, t, nc=250, mot_on=False)["mov"]
+    assert [c[0] for c in merged_calls] == ["stage2.merge", "stage2.roi_merge"]
+    assert tuple(Us[0].shape) == (396, 395) and tuple(Us[1].shape) == (40, 39) and tuple(Us[2].shape) == (90, 180)
+    assert torch.equal(Us[2], r1.t()) and sv.numel() == 39
+    # movie only, no ROI: nothing merged, singular values stay zero
+    merged_calls.clear()
+    Uts, Us, sv = svd.stage2_merge({"mov": [full]}, None, 2, None, ["mov"], True, ws, t, nc=250, mot_on=False)["mov"]
+    assert not merged_calls and tuple(Us[0].shape) == (396, 500) and not sv.any()
+    # motion SVD on: everything merged, for both modalities
+    merged_calls.clear()
+    svd.stage2_merge({"mot": [full, r0], "mov": [full, r0]}, None, 2, None, ["mot", "mov"], True, ws, t, nc=250, mot_on=True)
+    assert len(merged_calls) == 4

@@ -10,9 +10,11 @@ from facemap_b200.synth import SynthVideo
 from oracle import facemap_oracle as orc
 from oracle import ref_harness
 
+from .helpers import motion_roi
+
 pytestmark = pytest.mark.skipif(not ref_harness.reference_available(), reason="needs /root/reference (build container)")
 
-# (views [(H, W, seed)], frames per sequential block, sbin, motSVD, movSVD)
+# (views [(H, W, seed)], frames per sequential block, sbin, motSVD, movSVD[, motion ROIs, fullSVD])
 CASES = {
     "odd_size_s2": ([(46, 70, 21)], [1203], 2, True, True),
     "two_blocks_s3": ([(45, 63, 22)], [700, 650], 3, True, False),
@@ -20,6 +22,12 @@ CASES = {
     "below_one_chunk_s1": ([(20, 28, 25)], [640], 1, True, False),
     "tiny_two_chunks_s4": ([(40, 40, 26)], [2100], 4, True, True),          # 100 binned pixels < 250 chunk components
     "tiny_three_views_s2": ([(16, 20, 27), (12, 30, 28), (20, 14, 29)], [1500], 2, True, False),
+    # movie SVD without the motion SVD: the reference's merge loop runs over len(U_mot) (process.py:264), so the movie
+    # targets beyond it are never merged — all of them without ROIs, the last ROI with ROIs
+    "mov_only_s2": ([(36, 44, 4)], [2200], 2, False, True),
+    "mov_only_two_rois_s2": ([(36, 44, 5)], [2100], 2, False, True, [motion_roi(0, 4, 16, 4, 20), motion_roi(0, 20, 34, 10, 40)], True),
+    "mov_only_rois_no_fullsvd_s2": ([(36, 44, 6)], [2100], 2, False, True, [motion_roi(0, 4, 16, 4, 20), motion_roi(0, 20, 34, 10, 40)], False),
+    "roi_single_chunk_s2": ([(40, 56, 1)], [1100], 2, True, True, [motion_roi(0, 4, 20, 6, 30)], True),
 }
 
 
@@ -43,11 +51,13 @@ def _equal(a, b, key):
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_oracle_reproduces_the_live_reference(name):
-    views, blocks, sbin, mot, mov = CASES[name]
+    views, blocks, sbin, mot, mov, *rest = CASES[name]
+    rois, fullSVD = rest if rest else (None, True)
     full, per_block = _videos(views, blocks)
-    stock = ref_harness.run_reference(per_block, sbin=sbin, motSVD=mot, movSVD=mov)
-    exact = ref_harness.run_reference(per_block, sbin=sbin, motSVD=mot, movSVD=mov, exact=True)
-    got = orc.run_oracle(full, sbin=sbin, motSVD=mot, movSVD=mov, svd="exact", block_frames=blocks)
+    kw = dict(sbin=sbin, motSVD=mot, movSVD=mov, rois=rois, fullSVD=fullSVD)
+    stock = ref_harness.run_reference(per_block, **kw)
+    exact = ref_harness.run_reference(per_block, exact=True, **kw)
+    got = orc.run_oracle(full, svd="exact", block_frames=blocks, **kw)
     for key in ("avgframe", "avgmotion", "motion", "avgframe_reshape", "avgmotion_reshape"):
         _equal(got[key], stock[key], key)                     # integer-derived stages: stock reference, bit for bit
     for key in ("motSv", "movSv", "motMask", "movMask", "motMask_reshape", "movMask_reshape", "motSVD", "movSVD"):
