@@ -28,6 +28,11 @@ CASES = {
     "mov_only_two_rois_s2": ([(36, 44, 5)], [2100], 2, False, True, [motion_roi(0, 4, 16, 4, 20), motion_roi(0, 20, 34, 10, 40)], True),
     "mov_only_rois_no_fullsvd_s2": ([(36, 44, 6)], [2100], 2, False, True, [motion_roi(0, 4, 16, 4, 20), motion_roi(0, 20, 34, 10, 40)], False),
     "roi_single_chunk_s2": ([(40, 56, 1)], [1100], 2, True, True, [motion_roi(0, 4, 20, 6, 30)], True),
+    "sixty_frames_s2": ([(30, 40, 6)], [60], 2, True, True),
+    "three_frames_s2": ([(30, 40, 8)], [3], 2, True, False),
+    "both_svds_off_roi_s2": ([(30, 40, 11)], [1200], 2, False, False, [motion_roi(0, 2, 20, 4, 30)], True),
+    "mov_only_single_chunk_roi_s2": ([(30, 40, 10)], [1500], 2, False, True, [motion_roi(0, 2, 20, 4, 30)], True),
+    "roi_s6_blocks": ([(48, 60, 14)], [1100, 1000], 6, True, True, [motion_roi(0, 5, 40, 7, 50)], True),
 }
 
 
