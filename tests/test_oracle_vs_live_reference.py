@@ -69,3 +69,48 @@ def test_oracle_reproduces_the_live_reference(name):
         _equal(got[key], exact[key], key)                     # SVD outputs: reference with the exact svdecon
     for key in ("Ly", "Lx", "Lybin", "Lxbin", "sybin", "sxbin", "LYbin", "LXbin"):
         assert np.array_equal(np.asarray(got[key]), np.asarray(stock[key])), key
+
+
+def _same_tree(a, b, path=""):
+    if isinstance(a, dict):
+        assert sorted(a) == sorted(b), path
+        for k in a:
+            _same_tree(a[k], b[k], f"{path}/{k}")
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _same_tree(x, y, f"{path}[{i}]")
+    else:
+        a, b = np.asarray(a), np.asarray(b)
+        assert a.shape == b.shape and a.dtype == b.dtype, (path, a.shape, b.shape, a.dtype, b.dtype)
+        assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f"), path
+
+
+def _fullres_cases():
+    from .helpers import blink_roi, eye_video, pupil_roi, running_roi
+
+    return {
+        # ROIs touching the frame border; 640 frames cross one 500-frame seam of process_ROIs
+        "border_rois": ([eye_video(50, 64, 640, seed=7)], 2, True, False,
+                        [pupil_roi(0, 0, 30, 0, 40, 75.5), blink_roi(0, 20, 50, 30, 64, 150.0), running_roi(0, 36, 50, 0, 64)]),
+        # no SVD at all, blink before pupil (paint order), integer blink saturation
+        "no_svd_sweep": ([eye_video(48, 60, 530, seed=8)], 1, False, False,
+                         [blink_roi(0, 4, 30, 6, 50, 99), pupil_roi(0, 5, 35, 8, 50, 110.2, sigma=3.0)]),
+        # two views, processors on different views next to a motion ROI, motion + movie SVD
+        "two_views_mixed": ([eye_video(48, 60, 1010, seed=9), eye_video(40, 52, 1010, seed=10, wheel=False)], 2, True, True,
+                            [running_roi(0, 34, 48, 2, 58), pupil_roi(1, 4, 34, 6, 46, 85.0), motion_roi(1, 2, 30, 4, 40)]),
+    }
+
+
+@pytest.mark.parametrize("name", ["border_rois", "no_svd_sweep", "two_views_mixed"])
+@pytest.mark.filterwarnings("ignore:Mean of empty slice", "ignore:invalid value encountered")
+def test_roi_processor_oracle_reproduces_the_live_reference(name):
+    """pupil / blink / running (oracle/roi_oracle.py) beyond the three committed fixtures, bit for bit — including what
+    the painted frames do to the motion energy and the projections of the same sweep"""
+    import copy
+
+    views, sbin, mot, mov, rois = _fullres_cases()[name]
+    ref = ref_harness.run_reference([views], sbin=sbin, motSVD=mot, movSVD=mov, rois=copy.deepcopy(rois), exact=True)
+    got = orc.run_oracle(views, sbin=sbin, motSVD=mot, movSVD=mov, rois=copy.deepcopy(rois), svd="exact")
+    for key in ("pupil", "blink", "running", "motion", "avgframe", "avgmotion", "motSVD", "movSVD", "motMask", "movMask"):
+        _same_tree(got[key], ref[key], key)
