@@ -61,6 +61,7 @@ SIGNATURES = {
     "fm_bin_motion_planes": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, C.POINTER(Rois), _P, _P, _P, _P]),
     "fm_slice_rows_i8": (_I, [_P, _L, _I, _L, _P, _P, _P, _L, _P, _P]),
     "fm_gram_assemble_i8": (_I, [_P, _I, _I, _L, _P, _P, _L, _P, _P]),
+    "fm_gram_assemble_i8_rowside": (_I, [_P, _I, _I, _L, _P, _P, _P, _I, _P, _P]),
     "fm_split_lo": (_I, [_P, _L, _I, _I, _P, _L, _P]),
     "fm_slice_rows": (_I, [_P, _L, _I, _L, _P, _P, _P, _L, _P]),
     "fm_splitk_reduce": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _L, _P]),
@@ -72,6 +73,7 @@ SIGNATURES = {
     "fm_sign_from_right": (_I, [_P, _L, _I, _I, _P, _P, _L, _I, _P]),
     "fm_solver_create": (_I, [C.POINTER(_P)]),
     "fm_solver_destroy": (_I, [_P]),
+    "fm_solver_check": (_I, [_P, _P]),
     "fm_syevd": (_I, [_P, _P, _I, _P, _I, _P]),
     "fm_syevd_batched": (_I, [_P, _P, _I, _I, _P, _P]),
     "fm_syevdx_top": (_I, [_P, _P, _I, _I, _P, _P]),

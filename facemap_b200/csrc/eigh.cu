@@ -3,7 +3,10 @@
 // sklearn randomized_svd -> scipy lu/qr/gesdd; matlab/utils/svdecon.m:24 `eig`).  Its time is
 // reported separately by the host and never claimed as a kernel of this library.
 #include <cusolverDn.h>
+#include <vector>
 #include "common.cuh"
+
+#define FM_SOLVER_INFO_SLOTS 4096
 
 struct fm_solver {
   cusolverDnHandle_t handle = nullptr;
@@ -12,7 +15,11 @@ struct fm_solver {
   size_t d_work_bytes = 0;
   void* h_work = nullptr;
   size_t h_work_bytes = 0;
+  // devInfo of every solve since the last fm_solver_check: a ring on the device, read back (one copy, one
+  // synchronisation) only when the caller asks — the solves themselves never block the host
   int* d_info = nullptr;
+  int info_used = 0;
+  int info_n[FM_SOLVER_INFO_SLOTS];     // matrix order of the solve that owns each slot (for the error text)
   float* d_f32 = nullptr;      // staging for the float32 solve
   size_t d_f32_elems = 0;
 };
@@ -54,7 +61,45 @@ static int ensure_workspace(fm_solver* s, size_t dbytes, size_t hbytes) {
   return FM_OK;
 }
 
+// `count` consecutive devInfo slots for one call; a full ring is drained (this does synchronise, once per
+// FM_SOLVER_INFO_SLOTS solves that nobody checked)
+static int read_infos(fm_solver* s, cudaStream_t st);
+static int take_info_slots(fm_solver* s, int count, int n, cudaStream_t st, int** out) {
+  FM_REQUIRE(count <= FM_SOLVER_INFO_SLOTS, "batch of %d eigensolves exceeds the %d devInfo slots", count, FM_SOLVER_INFO_SLOTS);
+  if (s->info_used + count > FM_SOLVER_INFO_SLOTS) {
+    int rc = read_infos(s, st);
+    if (rc != FM_OK) return rc;
+  }
+  *out = s->d_info + s->info_used;
+  for (int i = 0; i < count; ++i) s->info_n[s->info_used + i] = n;
+  s->info_used += count;
+  return FM_OK;
+}
+
+static int read_infos(fm_solver* s, cudaStream_t st) {
+  const int used = s->info_used;
+  s->info_used = 0;
+  if (used == 0) return FM_OK;
+  std::vector<int> h((size_t)used);
+  FM_CUDA_TRY(cudaMemcpyAsync(h.data(), s->d_info, sizeof(int) * (size_t)used, cudaMemcpyDeviceToHost, st));
+  FM_CUDA_TRY(cudaStreamSynchronize(st));
+  for (int i = 0; i < used; ++i)
+    if (h[(size_t)i] != 0) {
+      set_error("cuSOLVER eigensolve %d of %d since the last check: devInfo = %d (n = %d)", i, used, h[(size_t)i], s->info_n[i]);
+      return FM_ERR_SOLVER;
+    }
+  return FM_OK;
+}
+
 }  // namespace fm
+
+// Reads back the devInfo of every solve issued through `s` since the previous check (one copy + one stream
+// synchronisation) and fails on the first non-zero entry.  The solves themselves are asynchronous.
+extern "C" int fm_solver_check(fm_solver* s, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(s != nullptr, "fm_solver_check: null solver");
+  return read_infos(s, reinterpret_cast<cudaStream_t>(stream));
+}
 
 extern "C" int fm_solver_create(fm_solver** out) {
   using namespace fm;
@@ -73,7 +118,8 @@ extern "C" int fm_solver_create(fm_solver** out) {
     delete s;
     return FM_ERR_SOLVER;
   }
-  if (cudaMalloc(&s->d_info, sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc(&s->d_info, sizeof(int) * FM_SOLVER_INFO_SLOTS) != cudaSuccess ||
+      cudaMemset(s->d_info, 0, sizeof(int) * FM_SOLVER_INFO_SLOTS) != cudaSuccess) {
     set_error("fm_solver_create: cudaMalloc(devInfo) failed");
     cusolverDnDestroyParams(s->params);
     cusolverDnDestroy(s->handle);
@@ -127,20 +173,16 @@ extern "C" int fm_syevd(fm_solver* s, double* G, int n, double* lam, int use_fp3
                                             n, dt, A, n, dt, W, dt, &dbytes, &hbytes));
   int rc = ensure_workspace(s, dbytes, hbytes);
   if (rc != FM_OK) return rc;
+  int* d_info = nullptr;
+  rc = take_info_slots(s, 1, n, st, &d_info);
+  if (rc != FM_OK) return rc;
   FM_SOLVER_TRY(cusolverDnXsyevd(s->handle, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dt, A, n,
-                                 dt, W, dt, s->d_work, dbytes, s->h_work, hbytes, s->d_info));
+                                 dt, W, dt, s->d_work, dbytes, s->h_work, hbytes, d_info));
   if (use_fp32) {
     f32_to_f64_kernel<<<(unsigned)cdiv((int64_t)nn, 256), 256, 0, st>>>(s->d_f32, G, nn);
     FM_LAUNCH_CHECK();
     f32_to_f64_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(s->d_f32 + nn, lam, (size_t)n);
     FM_LAUNCH_CHECK();
-  }
-  int info = 0;
-  FM_CUDA_TRY(cudaMemcpyAsync(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
-  FM_CUDA_TRY(cudaStreamSynchronize(st));
-  if (info != 0) {
-    set_error("cusolverDnXsyevd: devInfo = %d (n = %d)", info, n);
-    return FM_ERR_SOLVER;
   }
   return FM_OK;
 }
@@ -156,21 +198,14 @@ extern "C" int fm_syevd_batched(fm_solver* s, double* G, int n, int batch, doubl
   FM_SOLVER_TRY(cusolverDnXsyevBatched_bufferSize(s->handle, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER,
                                                   n, CUDA_R_64F, G, n, CUDA_R_64F, lam, CUDA_R_64F, &dbytes, &hbytes,
                                                   batch));
-  int rc = ensure_workspace(s, dbytes + sizeof(int) * (size_t)batch, hbytes);
+  int rc = ensure_workspace(s, dbytes, hbytes);
   if (rc != FM_OK) return rc;
-  int* info = reinterpret_cast<int*>(static_cast<char*>(s->d_work) + dbytes);
+  int* info = nullptr;
+  rc = take_info_slots(s, batch, n, st, &info);
+  if (rc != FM_OK) return rc;
   FM_SOLVER_TRY(cusolverDnXsyevBatched(s->handle, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
                                        CUDA_R_64F, G, n, CUDA_R_64F, lam, CUDA_R_64F, s->d_work, dbytes, s->h_work,
                                        hbytes, info, batch));
-  int h_info[64];
-  const int ncheck = batch < 64 ? batch : 64;
-  FM_CUDA_TRY(cudaMemcpyAsync(h_info, info, sizeof(int) * ncheck, cudaMemcpyDeviceToHost, st));
-  FM_CUDA_TRY(cudaStreamSynchronize(st));
-  for (int i = 0; i < ncheck; ++i)
-    if (h_info[i] != 0) {
-      set_error("cusolverDnXsyevBatched: devInfo[%d] = %d (n = %d)", i, h_info[i], n);
-      return FM_ERR_SOLVER;
-    }
   return FM_OK;
 }
 
@@ -189,14 +224,14 @@ extern "C" int fm_syevdx_top(fm_solver* s, double* G, int n, int k, double* lam,
                                              CUDA_R_64F, lam, CUDA_R_64F, &dbytes, &hbytes));
   int rc = ensure_workspace(s, dbytes, hbytes);
   if (rc != FM_OK) return rc;
+  int* d_info = nullptr;
+  rc = take_info_slots(s, 1, n, st, &d_info);
+  if (rc != FM_OK) return rc;
   FM_SOLVER_TRY(cusolverDnXsyevdx(s->handle, s->params, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I,
                                   CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, G, n, &vl, &vu, n - k + 1, n, &meig, CUDA_R_64F,
-                                  lam, CUDA_R_64F, s->d_work, dbytes, s->h_work, hbytes, s->d_info));
-  int info = 0;
-  FM_CUDA_TRY(cudaMemcpyAsync(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
-  FM_CUDA_TRY(cudaStreamSynchronize(st));
-  if (info != 0 || meig != k) {
-    set_error("cusolverDnXsyevdx: devInfo = %d, found %lld of %d eigenpairs (n = %d)", info, (long long)meig, k, n);
+                                  lam, CUDA_R_64F, s->d_work, dbytes, s->h_work, hbytes, d_info));
+  if (meig != k) {       // an index range: the count is known to the host when the call returns
+    set_error("cusolverDnXsyevdx: found %lld of %d eigenpairs (n = %d)", (long long)meig, k, n);
     return FM_ERR_SOLVER;
   }
   return FM_OK;

@@ -449,9 +449,22 @@ __global__ void __launch_bounds__(256) slice_rows_i8_kernel(const float* __restr
 //   G[i,j] = 2^(e_i+e_j-14) [ P00 + (P01[i,j] + P01[j,i]) / 2^8 + (P11 + P02[i,j] + P02[j,i]) / 2^16
 //                             + (P12[i,j] + P12[j,i]) / 2^24 + P22 / 2^32 ] - ncols m_i m_j        (j >= i, mirrored)
 // Everything inside the bracket is an exact integer combination evaluated in float64.
+// ROWSIDE: the operand rows are the pixels of a wide matrix Y [p, c] and the centring is over its columns
+// (gram_assemble_rowside_kernel): the correction is  - q_i - q_j + mu.mu  instead of  - ncols m_i m_j.
+template <bool ROWSIDE>
 __global__ void gram_assemble_i8_kernel(const int32_t* __restrict__ P, int ksplit, int n, int64_t ldp,
                                         const int32_t* __restrict__ exps, const double* __restrict__ mean,
-                                        double ncols, double* __restrict__ G) {
+                                        double ncols, const double* __restrict__ mu, int nmu,
+                                        double* __restrict__ G) {
+  __shared__ double s_mumu;
+  if (ROWSIDE) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      double a = 0.0;
+      for (int t = 0; t < nmu; ++t) a += mu[t] * mu[t];
+      s_mumu = a;
+    }
+    __syncthreads();
+  }
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= n || j >= n || j < i) return;
@@ -471,7 +484,10 @@ __global__ void gram_assemble_i8_kernel(const int32_t* __restrict__ P, int kspli
   double v = (double)s00 + (double)s01 * (1.0 / 256.0) + ((double)s11 + (double)s02) * (1.0 / 65536.0) +
              (double)s12 * (1.0 / 16777216.0) + (double)s22 * (1.0 / 4294967296.0);
   v = ldexp(v, exps[i] + exps[j] - 14);
-  if (mean) v -= ncols * (mean[i] * mean[j]);
+  if (ROWSIDE)
+    v = v - (mean[i] + mean[j]) + s_mumu;          // `mean` carries q = Y mu here
+  else if (mean)
+    v -= ncols * (mean[i] * mean[j]);
   G[(size_t)i * n + j] = v;
   if (j != i) G[(size_t)j * n + i] = v;
 }
@@ -496,8 +512,20 @@ extern "C" int fm_gram_assemble_i8(const int32_t* P, int ksplit, int n, int64_t 
   using namespace fm;
   FM_REQUIRE(P && exps && G && ksplit >= 1 && n >= 1 && ldp >= n, "fm_gram_assemble_i8: bad args");
   dim3 block(32, 8), grid((unsigned)cdiv(n, 32), (unsigned)cdiv(n, 8));
-  gram_assemble_i8_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, ksplit, n, ldp, exps, mean,
-                                                                                      (double)ncols, G);
+  gram_assemble_i8_kernel<false><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      P, ksplit, n, ldp, exps, mean, (double)ncols, nullptr, 0, G);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+extern "C" int fm_gram_assemble_i8_rowside(const int32_t* P, int ksplit, int n, int64_t ldp, const int32_t* exps,
+                                           const double* q, const double* mu, int nmu, double* G, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(P && exps && q && mu && G && ksplit >= 1 && n >= 1 && nmu >= 1 && ldp >= n,
+             "fm_gram_assemble_i8_rowside: bad args");
+  dim3 block(32, 8), grid((unsigned)cdiv(n, 32), (unsigned)cdiv(n, 8));
+  gram_assemble_i8_kernel<true><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      P, ksplit, n, ldp, exps, q, 0.0, mu, nmu, G);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }

@@ -204,7 +204,7 @@ def gemm_i8_tn(A, B, C_out=None, *, ksplit=1, workspace=None, upper_only=False):
 
 
 def slice_rows_i8(X, out=None):
-    """EXPERIMENTAL (fm_slice_rows_i8): (Q0 int8, Q1 uint8, Q2 uint8, exps int32) digit planes of the rows of X, row
+    """fm_slice_rows_i8: (Q0 int8, Q1 uint8, Q2 uint8, exps int32) digit planes of the rows of X, row
     pitch a multiple of 16 bytes.  `out`: optional (Q0, Q1, Q2) [rows, cols] views sharing one pitch."""
     _need(X, torch.float32, "X", 2)
     rows, cols = X.shape
@@ -225,8 +225,10 @@ def slice_rows_i8(X, out=None):
     return Q0, Q1, Q2, exps
 
 
-def gram_assemble_i8(P, ksplit, n, exps, mean, ncols, out=None):
-    """EXPERIMENTAL (fm_gram_assemble_i8): P int32 [6, ksplit, n, ldp] plane products -> float64 centred Gram."""
+def gram_assemble_i8(P, ksplit, n, exps, mean, ncols, out=None, rowside=None):
+    """fm_gram_assemble_i8: P int32 [6, ksplit, n, ldp] plane products -> float64 centred Gram  X X^T - ncols m m^T.
+    rowside = (q, mu): the row-side form of a wide matrix instead,  Y Y^T - q 1^T - 1 q^T + mu.mu
+    (fm_gram_assemble_i8_rowside)."""
     _need(P, torch.int32, "P", 4)
     if P.shape[0] != 6 or P.shape[1] < ksplit or P.shape[2] != n or P.shape[3] < n or not P.is_contiguous():
         raise FacemapB200Error("gram_assemble_i8: P must be a contiguous int32 [6, ksplit, n, >=n] stack")
@@ -234,6 +236,15 @@ def gram_assemble_i8(P, ksplit, n, exps, mean, ncols, out=None):
     _need(mean, torch.float64, "mean")
     if out is None:
         out = torch.empty((n, n), dtype=torch.float64, device=P.device)
+    if rowside is not None:
+        q, mu = rowside
+        _need(q, torch.float64, "q", 1)
+        _need(mu, torch.float64, "mu", 1)
+        if q.numel() < n:
+            raise FacemapB200Error("gram_assemble_i8: q must hold one entry per row")
+        check(_lib.load().fm_gram_assemble_i8_rowside(ptr(P), int(ksplit), int(n), P.stride(2), ptr(exps), ptr(q), ptr(mu),
+                                                      mu.numel(), ptr(out), _stream()), "fm_gram_assemble_i8_rowside")
+        return out
     check(_lib.load().fm_gram_assemble_i8(ptr(P), int(ksplit), int(n), P.stride(2), ptr(exps), ptr(mean), int(ncols),
                                           ptr(out), _stream()), "fm_gram_assemble_i8")
     return out
@@ -374,7 +385,7 @@ class Solver:
 
     def syevd(self, G, use_fp32=False):
         """G: float64 [n,n] symmetric, overwritten by eigenvectors (row j <-> j-th smallest eigenvalue).
-        Returns lam (float64 [n], ascending).  Synchronises the stream."""
+        Returns lam (float64 [n], ascending).  Asynchronous; `check()` reads cuSOLVER's devInfo back."""
         _need(G, torch.float64, "G", 2)
         n = G.shape[0]
         if G.shape[1] != n or not G.is_contiguous():
@@ -402,6 +413,10 @@ class Solver:
         lam = torch.empty((b, n), dtype=torch.float64, device=G.device)
         check(_lib.load().fm_syevd_batched(self._h, ptr(G), n, b, ptr(lam), _stream()), "fm_syevd_batched")
         return lam
+
+    def check(self):
+        """devInfo of every solve since the last check (one D2H copy + stream synchronisation)."""
+        check(_lib.load().fm_solver_check(self._h, _stream()), "fm_solver_check")
 
     def close(self):
         if self._h:

@@ -115,11 +115,11 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     overlap_stage3: run stage 3's bin/diff pass on a side stream underneath the stage-2 eigensolves
             when the frames are HBM-resident (svd.Stage3.start_early).
     dist:   optional facemap_b200.parallel.Shard (frame-range sharding across ranks).
-    gram_mode: "tf32x3" (default), "sliced_merge", "sliced", "i8_merge" or "i8" — how the Gram matrices of the two
-            SVD levels are formed (svd.SvdWorkspace, svd.sliced_gram, svd.i8_gram); None reads the environment
-            variable FM_GRAM_MODE.
-    proj_mode: "tf32x3" (default) or "i8" (EXPERIMENTAL: stage 3 on byte planes and tcgen05 kind::i8, svd.Stage3);
-            None reads FM_PROJ_MODE."""
+    gram_mode: "i8" (default: exact integer products on tcgen05 kind::i8), "i8_merge", "tf32x3", "sliced_merge" or
+            "sliced" — how the Gram matrices of the two SVD levels are formed (svd.SvdWorkspace, svd.i8_gram,
+            svd.sliced_gram); None reads the environment variable FM_GRAM_MODE.
+    proj_mode: "i8" (default: stage 3 on byte planes and tcgen05 kind::i8, svd.Stage3) or "tf32x3" (float32 operands,
+            3xTF32 products); None reads FM_PROJ_MODE."""
     t_enter = time.perf_counter()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     _lib.require_device(dev.index or 0)
@@ -224,6 +224,8 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     if dist is not None and dist.world > 1 and not gather_outputs and s3 is not None:
         f0_out = s3.f0
     t_asm = time.perf_counter()
+    # the eigensolves ran asynchronously; their devInfo words are read once, here, where the host waits anyway
+    ws.solver.check()
     with timer("assemble.d2h"):
         avgframe_h = avgframe.cpu().numpy()
         avgmotion_h = avgmotion.cpu().numpy()

@@ -163,22 +163,29 @@ class SvdWorkspace:
         self.eig_fp32 = eig_fp32
         self.gemm_impl = gemm_impl
         # how the Gram matrices that feed the eigensolves are formed:
-        #   "tf32x3"        one 3xTF32 GEMM with float64-reduced K partials (centred_gram) — the measured default
-        #   "sliced_merge"  the second-level (merge) Gram from 8-bit row slices with an exact leading product
-        #   "sliced"        chunk Grams as well (sliced_gram; ~4x the Gram time, tail singular values to 1e-5)
-        self.gram_mode = _os.environ.get("FM_GRAM_MODE", "tf32x3") if gram_mode is None else gram_mode
-        #   "i8_merge" / "i8"  EXPERIMENTAL: s8/u8/u8 digit planes and exact integer products on tcgen05 kind::i8
-        #                   (i8_gram); same accuracy as exact Grams in the CPU model, fewer bytes than "tf32x3"
+        #   "i8"            (default) s8/u8/u8 digit planes and exact integer products on tcgen05 kind::i8 (i8_gram) at
+        #                   both SVD levels: all 500 singular values within 3e-6 of the exact float64 SVD
+        #   "i8_merge"      only the second-level (merge) Gram that way; chunk Grams as "tf32x3"
+        #   "tf32x3"        one 3xTF32 GEMM with float64-reduced K partials (centred_gram): tail singular values 5e-4 (motion)
+        #                   to 3e-2 (movie) off at component 500 (profiles/r01_accuracy.md) — kept for comparison
+        #   "sliced_merge"  the merge Gram from 8-bit float row slices with an exact leading product (sliced_gram)
+        #   "sliced"        chunk Grams as well (~4x the Gram time of "tf32x3")
+        self.gram_mode = _os.environ.get("FM_GRAM_MODE", "i8") if gram_mode is None else gram_mode
         if self.gram_mode not in ("tf32x3", "sliced_merge", "sliced", "i8_merge", "i8"):
             raise FacemapB200Error(f"unknown gram_mode {self.gram_mode!r}")
         # pass A of sliced_gram on the one-product kernel (fm_gemm_tn impl 10) instead of the 3xTF32 kernel with a
         # zero lo plane: a third of the MMAs, no zero plane to stage
         self.sliced_single = _os.environ.get("FM_SLICED_SINGLE", "0") == "1"
         # how stage 3 projects the frames onto the masks:
-        #   "tf32x3"  K1 writes float32 operands, one 3xTF32 GEMM per batch — the measured default
-        #   "i8"      EXPERIMENTAL: K1 writes the integer energies / block sums as byte planes, the masks become s8/u8/u8
-        #             digits and fm_project_i8 forms the products exactly on tcgen05 kind::i8 (Stage3)
-        self.proj_mode = _os.environ.get("FM_PROJ_MODE", "tf32x3") if proj_mode is None else proj_mode
+        #   "i8"      (default) K1 writes the integer energies / block sums as byte planes, the masks become s8/u8/u8
+        #             digits and fm_project_i8 forms the products exactly on tcgen05 kind::i8 (Stage3): 2x the 3xTF32
+        #             rate at sbin 4, 9x at sbin 1 on large views.  Two byte planes hold block sums up to sbin 16;
+        #             beyond that the default is "tf32x3" (an explicit "i8" is refused there, not silently replaced)
+        #   "tf32x3"  K1 writes float32 operands, one 3xTF32 GEMM per batch
+        self.proj_mode = _os.environ.get("FM_PROJ_MODE") if proj_mode is None else proj_mode
+        self.proj_mode_explicit = self.proj_mode is not None
+        if self.proj_mode is None:
+            self.proj_mode = "i8"
         if self.proj_mode not in ("tf32x3", "i8"):
             raise FacemapB200Error(f"unknown proj_mode {self.proj_mode!r}")
         self.proj_i8_impl = int(_os.environ.get("FM_PROJ_I8_IMPL", "0"))      # 1 = CTA pairs (fm_project_i8 impl)
@@ -322,15 +329,18 @@ def sliced_gram(ws: SvdWorkspace, X, timer, label, out=None):
 I8_KMAX = 32768        # K per int32 partial of fm_gemm_i8_tn (255^2 * 32768 < 2^31)
 
 
-def i8_gram(ws: SvdWorkspace, X, timer, label, out=None):
-    """EXPERIMENTAL — centred_gram on the integer tensor cores: the rows of X become s8 / u8 / u8 digit planes
+def i8_gram(ws: SvdWorkspace, X, timer, label, out=None, rowside_mu=None):
+    """centred_gram on the integer tensor cores: the rows of X become s8 / u8 / u8 digit planes
     (fm_slice_rows_i8: 23 bits below each row's bound, unbiased), the six plane products are formed by fm_gemm_i8_tn
     with exact int32 accumulation, fm_gram_assemble_i8 weighs and sums them in float64.  No rounding anywhere but the
-    2^-24 digit representation: scripts/model_accuracy.py (`i8`) puts all 500 singular values within 4e-6 of the
-    exact oracle's.  3 bytes per element are staged per product instead of the 8 (hi + lo planes) of the 3xTF32 Gram."""
+    2^-24 digit representation: all 500 singular values land within 3e-6 of the exact oracle's (measured on B200,
+    profiles/r02_accuracy.md).  3 bytes per element are staged per product instead of the 8 (hi + lo planes) of the
+    3xTF32 Gram.
+    rowside_mu: X is a wide matrix Y [p, c] centred over its COLUMNS (means `rowside_mu` [c]); returns (q, G) with
+    q = Y mu and G = Yc Yc^T (merge_components_rowside)."""
     n, p = X.shape
     with timer(label + ".colmean"):
-        mean = K.row_means(X)
+        mean = K.row_means(X) if rowside_mu is None else K.row_dot(X, rowside_mu)
     with timer(label + ".gram.split"):
         ldq = K.round_up(p, 16)
         raw = ws.raw("gram.i8", 3 * n * ldq, torch.uint8).view(3, n, ldq)
@@ -347,7 +357,8 @@ def i8_gram(ws: SvdWorkspace, X, timer, label, out=None):
             else:
                 K.gemm_i8_tn(A, B, P[d, 0], upper_only=upper)
     with timer(label + ".gram.assemble"):
-        G = K.gram_assemble_i8(P, ks, n, exps, mean, p, out=out)
+        G = K.gram_assemble_i8(P, ks, n, exps, mean, p, out=out,
+                               rowside=None if rowside_mu is None else (mean, rowside_mu))
     return mean, G
 
 
@@ -399,17 +410,21 @@ def merge_components_rowside(ws, Yt, k, timer, label="merge"):
     with timer(label + ".transpose"):
         Y = ws.matrix(label + ".Y", p, c)
         K.transpose(Yt, Y)
-        Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p, c)) if ws.gram_impl in (0, 9) else None
-    ksplit = _gram_ksplit(p, c)
-    part = ws.workspace(ksplit, p)
-    with timer(label + ".gram.mma"):
-        if ksplit > 1:
-            K.gemm_tn(Y, Y, ksplit=ksplit, workspace=part, upper_only=True, impl=ws.gram_impl, B_lo=Y_lo, A_lo=Y_lo)
-        else:
-            K.gemm_tn(Y, Y, part[0], upper_only=True, impl=ws.gram_impl, B_lo=Y_lo, A_lo=Y_lo)
-    with timer(label + ".gram.assemble"):
-        q = K.row_dot(Y, mu)
-        G = K.gram_assemble_rowside(part, ksplit, p, q, mu, True)
+    if gram_is_i8(ws, label):
+        _, G = i8_gram(ws, Y, timer, label, rowside_mu=mu)
+    else:
+        with timer(label + ".transpose"):
+            Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p, c)) if ws.gram_impl in (0, 9) else None
+        ksplit = _gram_ksplit(p, c)
+        part = ws.workspace(ksplit, p)
+        with timer(label + ".gram.mma"):
+            if ksplit > 1:
+                K.gemm_tn(Y, Y, ksplit=ksplit, workspace=part, upper_only=True, impl=ws.gram_impl, B_lo=Y_lo, A_lo=Y_lo)
+            else:
+                K.gemm_tn(Y, Y, part[0], upper_only=True, impl=ws.gram_impl, B_lo=Y_lo, A_lo=Y_lo)
+        with timer(label + ".gram.assemble"):
+            q = K.row_dot(Y, mu)
+            G = K.gram_assemble_rowside(part, ksplit, p, q, mu, True)
     with timer(label + ".syevd"):
         if ws.eig_fp32 or k == p:
             lam, nev = ws.solver.syevd(G, use_fp32=ws.eig_fp32), p
@@ -763,7 +778,9 @@ class Stage3:
         # a silent change of path
         self.i8 = ws.proj_mode == "i8" and bool(mods)
         if self.i8 and geo.sbin > 16:
-            raise FacemapB200Error("FM_PROJ_MODE=i8: two byte planes hold block sums up to sbin 16")
+            if getattr(ws, "proj_mode_explicit", True):
+                raise FacemapB200Error("proj_mode 'i8': two byte planes hold block sums up to sbin 16")
+            self.i8 = False                   # default mode: bins beyond 16 take the float32 operands
         self.ldq = K.round_up(geo.p, 16)
         self.rows_batch = projection_rows_per_batch(geo.p, kmax, elem_bytes=(1 if geo.sbin == 1 else 2) if self.i8 else 4)
         # fetch plan: GEMM batches of <= rows_batch rows, each filled by several fetches

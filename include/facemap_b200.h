@@ -177,7 +177,7 @@ int fm_gemm_i8_tn(const uint8_t* A, int64_t lda, int a_signed, const uint8_t* B,
                   int upper_only, void* stream);
 
 /*
- * EXPERIMENTAL companions of fm_gemm_i8_tn (svd.i8_gram; not yet run on a GPU):
+ * Companions of fm_gemm_i8_tn (svd.i8_gram, the default way the Gram matrices of both SVD levels are formed):
  * fm_slice_rows_i8: X[r,c] ~ 2^(exps[r] - 7) * (Q0 + Q1 / 2^8 + Q2 / 2^16), Q0 int8 (floor), Q1 uint8 (floor), Q2 uint8
  *   (nearest, carries propagated), 2^exps[r] bounding row r: 23 bits below the row bound, unbiased.  Plane row pitch
  *   ldq in bytes (a multiple of 16 for the GEMM); pad bytes zeroed.
@@ -189,9 +189,13 @@ int fm_slice_rows_i8(const float* X, int64_t ldx, int rows, int64_t ncols, int8_
                      int64_t ldq, int32_t* exps, void* stream);
 int fm_gram_assemble_i8(const int32_t* P, int ksplit, int n, int64_t ldp, const int32_t* exps, const double* mean,
                         int64_t ncols, double* G, void* stream);
+/* The same for the row-side Gram of a wide matrix Y [n, c] centred over its columns (fm_gram_assemble_rowside):
+ * G = Y Y^T - q 1^T - 1 q^T + (mu.mu) 1 1^T with q = Y mu (fm_row_dot), mu[nmu] the column means. */
+int fm_gram_assemble_i8_rowside(const int32_t* P, int ksplit, int n, int64_t ldp, const int32_t* exps,
+                                const double* q, const double* mu, int nmu, double* G, void* stream);
 
 /*
- * EXPERIMENTAL (not yet run on a GPU): the projection of process_ROIs (facemap/process.py:485, 495, 503, 510) on the
+ * The projection of process_ROIs (facemap/process.py:485, 495, 503, 510) on the
  * integer tensor cores.  V[t,c] (float32) = alpha * sum_p D[t,p] U[c,p] - bias[c] with the frame operand as integers
  * D = 256 * D_hi + D_lo (u8 planes [M, ldd]; D_hi may be NULL for operands below 256: sbin 1) — the motion energy
  * |S_t - S_(t-1)| or the block sum S_t that fm_bin_motion forms, alpha = 1 / sbin^2 — and the masks as the digit planes
@@ -260,11 +264,15 @@ int fm_sign_from_right(const float* T, int64_t ldt, int k, int ncols, const doub
  * Symmetric eigensolve (cuSOLVER syevd — the one library call on the path; timed separately,
  * not claimed as a kernel).  G is float64 n x n, overwritten with eigenvectors (row j =
  * eigenvector of the j-th smallest eigenvalue); lam[n] ascending.  `use_fp32` solves in float32
- * (G is converted in place to/from).  Synchronises the stream (reads devInfo).
+ * (G is converted in place to/from).  The solves are asynchronous like every other entry point:
+ * cuSOLVER's devInfo words are kept in a device ring owned by the solver and read back — one copy, one
+ * stream synchronisation — by fm_solver_check, which fails on the first non-zero entry since the
+ * previous check (the host calls it once per pass, when it collects the results anyway).
  */
 typedef struct fm_solver fm_solver;
 int fm_solver_create(fm_solver** out);
 int fm_solver_destroy(fm_solver* s);
+int fm_solver_check(fm_solver* s, void* stream);
 int fm_syevd(fm_solver* s, double* G, int n, double* lam, int use_fp32, void* stream);
 /* Only the k largest eigenpairs (cusolverDnXsyevdx): rows 0..k-1 of G and lam[0..k) in ascending order. */
 int fm_syevdx_top(fm_solver* s, double* G, int n, int k, double* lam, void* stream);

@@ -87,6 +87,35 @@ def resolved_count(S, gap_rel=1e-3, floor_rel=1e-3):
     return k
 
 
+def component_errors(U, U_ref, V, V_ref, S=None, S_ref=None):
+    """EVERY component of one target against the reference's: U / U_ref masks [p, k] (orthonormal columns, possibly
+    followed by all-zero ones), V / V_ref traces [frames, k].  Returns
+      S_rel[j]          |S_j - Sref_j| / Sref_j                                 (None without S)
+      prefix_sin[j]     sine of the largest principal angle between span(U[:, :j+1]) and span(U_ref[:, :j+1])
+      one_minus_cos[j]  1 - |<u_j, uref_j>|
+      trace_rel[j]      ||sg_j V_j - Vref_j|| / ||Vref_j||, sg_j the sign that aligns mask j
+      k                 number of (non-zero) components compared"""
+    U64, Ur64 = np.asarray(U, np.float64), np.asarray(U_ref, np.float64)
+    k = min(U64.shape[1], Ur64.shape[1])
+    nz = np.flatnonzero(np.linalg.norm(Ur64[:, :k], axis=0) > 0)
+    k = int(nz[-1]) + 1 if nz.size else 0
+    M = Ur64[:, :k].T @ U64[:, :k]
+    d = np.diag(M)
+    sg = np.where(d < 0, -1.0, 1.0)
+    prefix = np.zeros(k)
+    for j in range(k):
+        smin = np.linalg.svd(M[:j + 1, :j + 1], compute_uv=False)[-1]
+        prefix[j] = np.sqrt(max(0.0, 1.0 - min(1.0, smin) ** 2))
+    Va = np.asarray(V, np.float64)[:, :k] * sg[None, :]
+    Vr = np.asarray(V_ref, np.float64)[:, :k]
+    trace = np.linalg.norm(Va - Vr, axis=0) / (np.linalg.norm(Vr, axis=0) + 1e-300)
+    out = {"k": k, "prefix_sin": prefix, "one_minus_cos": 1.0 - np.abs(d), "trace_rel": trace, "S_rel": None}
+    if S is not None and S_ref is not None:
+        Sr = np.asarray(S_ref, np.float64)[:k]
+        out["S_rel"] = np.abs(np.asarray(S, np.float64)[:k] - Sr) / np.where(Sr > 0, Sr, 1.0)
+    return out
+
+
 def sign_align(A, B):
     """flip columns of A to match the sign of B's columns (largest-|.| entry rule may pick a
     different pixel when two entries are nearly tied)."""

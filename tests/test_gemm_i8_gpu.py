@@ -1,6 +1,6 @@
 """fm_gemm_i8_tn (tcgen05.mma kind::i8, int32 accumulation) against exact integer arithmetic.
 
-WRITTEN WITHOUT A GPU (round 1 had spent its GPU budget): opt-in with FM_EXPERIMENTAL=1 until it has run on a B200.
+First run on a B200 at the start of round 2 (19 passed, profiles/r02a_first_gpu_run.md); part of the regular `-m gpu` run.
 Exact equality everywhere — integer work; ragged shapes, both signednesses, split-K partials, upper-triangle skipping,
 a K range long enough to approach the int32 limit."""
 import os
@@ -9,8 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FM_EXPERIMENTAL") != "1", reason="opt-in until validated on a B200")]
+pytestmark = pytest.mark.gpu
 
 
 def _operand(rs, rows, K, signed, device, extreme=False):

@@ -7,8 +7,8 @@ reference in the build container (`python scripts/make_golden.py c1_s4 c2_20k_s4
     c3_4k_s4     configs[2] at 4 000 frames: two 640x480 cameras, motion + movie SVD, three motion ROIs
     c4_crop_s1   configs[3] on a 256-pixel-wide crop: 1024x256 at sbin 1 (262 144 pixels, float32 reference path)
 
-Same gates as tests/test_pipeline_gpu.py.  The fixtures were generated after the round's GPU budget was spent, so the
-comparison has not run on a B200 yet: opt-in with FM_EXPERIMENTAL=1 until it has."""
+Same gates as tests/test_pipeline_gpu.py; part of the regular `-m gpu` run (about four minutes, most of it the
+synthetic videos generated on the host)."""
 import os
 
 import numpy as np
@@ -18,8 +18,7 @@ import torch
 from tests.helpers import LARGE_CASES, case_rois, case_videos, frame_window
 from tests.test_pipeline_gpu import ANGLE_TOL, S_RTOL, TRACE_RTOL, leading_resolved, svd_metrics
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FM_EXPERIMENTAL") != "1", reason="opt-in until validated on a B200")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", list(LARGE_CASES))

@@ -1,6 +1,7 @@
 """fm_project_i8 and fm_bin_motion_planes on the GPU against their NumPy restatement (tests/i8_model.py).
 
-WRITTEN WITHOUT A GPU (round 1 had spent its GPU budget): opt-in with FM_EXPERIMENTAL=1 until it has run on a B200.
+First run on a B200 at the start of round 2 (17 passed for either kernel variant, profiles/r02a_first_gpu_run.md); part of the
+regular `-m gpu` run.
 Integer stages (planes, digits, class sums) are compared exactly; the projection itself bit for bit, because the model
 repeats the kernel's float64 scaling and its one rounding to float32; the whole path in FM_PROJ_MODE=i8 against the
 default path and the oracle within the north-star tolerance for projected traces (1e-3 relative; observed ~1e-6)."""
@@ -12,8 +13,7 @@ import torch
 
 from . import i8_model as M8
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FM_EXPERIMENTAL") != "1", reason="opt-in until validated on a B200")]
+pytestmark = pytest.mark.gpu
 
 
 # FM_TEST_I8_IMPLS=0 or =1 runs one kernel variant per process (a trapped kernel poisons the CUDA context for every test

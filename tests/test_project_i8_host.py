@@ -190,6 +190,10 @@ def test_stage3_i8_refuses_what_it_cannot_serve():
     src = ArraySource([np.zeros((5, 32, 32), np.uint8)])
     with pytest.raises(svd.FacemapB200Error):
         svd.Stage3(src, geo, None, None, ["mot"], True, ws, torch.device("cpu"), svd.StageTimer(enabled=False))
+    # the DEFAULT projection mode is "i8" too, but not asked for by name: bins beyond 16 take the float32 operands
+    ws.proj_mode_explicit = False
+    s3 = svd.Stage3(src, geo, None, None, ["mot"], True, ws, torch.device("cpu"), svd.StageTimer(enabled=False))
+    assert s3.i8 is False
 
 
 class FloatFakeKernels:

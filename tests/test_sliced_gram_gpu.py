@@ -13,8 +13,7 @@ import torch
 
 from oracle import facemap_oracle as orc
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FM_EXPERIMENTAL") != "1", reason="opt-in until validated on a B200")]
+pytestmark = pytest.mark.gpu
 
 
 def _graded(rs, n, p):

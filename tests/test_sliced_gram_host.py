@@ -128,7 +128,7 @@ class FakeI8Kernels(FakeKernels):
         self.calls.append(("i8", ksplit, upper_only, str(A.dtype), str(B.dtype)))
 
     @staticmethod
-    def gram_assemble_i8(P, ksplit, n, exps, mean, ncols, out=None):
+    def gram_assemble_i8(P, ksplit, n, exps, mean, ncols, out=None, rowside=None):
         S = P[:, :ksplit].numpy().astype(np.int64).sum(axis=1)[:, :, :n]     # [6, n, n]
         iu = np.triu_indices(n)
         poison = -(2 ** 31) * ksplit
@@ -139,7 +139,11 @@ class FakeI8Kernels(FakeKernels):
         G = np.triu(br * np.exp2(e[:, None] + e[None, :] - 14))
         G = G + np.triu(G, 1).T
         m = mean.numpy()
-        G = torch.from_numpy(G - ncols * np.outer(m, m))
+        if rowside is None:
+            G = torch.from_numpy(G - ncols * np.outer(m, m))
+        else:                                                   # row-side form: - q 1^T - 1 q^T + mu.mu
+            q, mu = rowside[0].numpy(), rowside[1].numpy()
+            G = torch.from_numpy(G - (q[:, None] + q[None, :]) + float(mu @ mu))
         if out is not None:
             out.copy_(G)
             return out
@@ -171,6 +175,31 @@ def test_i8_gram_matches_float64_gram(monkeypatch):
         assert [c[1] for c in fake.calls] == [ks_want] * 6
         assert [c[2] for c in fake.calls] == [True, True, True, False, False, False]
         assert [c[3:] for c in fake.calls][3] == ("torch.int8", "torch.uint8")
+
+
+def test_i8_gram_rowside_matches_float64(monkeypatch):
+    """the merge of a small ROI: Y [p, c] with fewer pixels than stacked components, centred over its columns"""
+    rs = np.random.RandomState(2)
+    p, c = 120, 700
+    Y = (rs.randn(p, 30) @ rs.randn(30, c) * np.logspace(1, -2, c)[None, :] + 0.2).astype(np.float32)
+    Y64 = Y.astype(np.float64)
+    mu = Y64.mean(axis=0)
+    Yc = Y64 - mu[None, :]
+    want = Yc @ Yc.T
+    fake = FakeI8Kernels()
+    fake.row_dot = staticmethod(lambda M, w: torch.from_numpy(M.numpy().astype(np.float64) @ w.numpy()))
+    monkeypatch.setattr(svd, "K", fake)
+    ws = _workspace()
+    ws.gram_mode = "i8"
+    X = ws.matrix("Y", p, c)
+    X.copy_(torch.from_numpy(Y))
+    q, G = svd.i8_gram(ws, X, ws.timer, "stage2.roi_merge", rowside_mu=torch.from_numpy(mu))
+    d = np.sqrt(np.diag(Y64 @ Y64.T))
+    assert np.allclose(q.numpy(), Y64 @ mu, rtol=1e-13)
+    # digits carry 2^-24 of each ROW's largest entry; with the columns graded over three decades a row's norm sits in
+    # a few of them, so the bound relative to the row norms is looser than for the chunk matrices above
+    assert (np.abs(G.numpy() - want) / np.outer(d, d)).max() < 5e-7
+    assert np.array_equal(G.numpy(), G.numpy().T)
 
 
 def _workspace():
