@@ -40,6 +40,10 @@ class FrameSource:
         """True if fetch() of any sub-range of [t0, t1) is a zero-copy view of HBM-resident frames."""
         return False
 
+    def begin_sweep(self):
+        """Called once before the sequential sweep over the whole frame range (stage 3); file sources use it to
+        make sure the sweep sees what a sequential decode delivers."""
+
     def prefetch(self, t0, t1, device):
         """Hint that [t0, t1) is the next range to be fetched (host sources start the H2D copy on a
         side stream so it overlaps the kernels of the current range)."""
@@ -285,11 +289,19 @@ class HostArraySource(FrameSource):
 
 
 class _DecodeCache:
-    """Decode-once cache of a file source: every frame of `home` is decoded exactly once, by `workers` threads
-    with their own capture handles (OpenCV releases the GIL while decoding), into pinned staging buffers and
-    copied into HBM-resident views on a private stream.  Pieces touched by the SVD sample ranges are decoded
-    first, the rest in frame order — the order in which stages 1-3 consume them.  Readers block (host side)
-    until the pieces they need are decoded, then wait (device side) on the copy event."""
+    """Decode-once cache of a file source: every frame of `home` is decoded by `workers` threads with their own
+    capture handles (OpenCV releases the GIL while decoding) into pinned staging buffers and copied into
+    HBM-resident views on a private stream.  Readers block (host side) until the pieces they need are decoded,
+    then wait (device side) on the copy event.
+
+    The work is dealt in RUNS — stretches of consecutive `piece`-frame pieces that one thread decodes sequentially
+    after ONE seek: first the runs the SVD sample ranges touch (the reference seeks to those as well,
+    utils.get_frames, facemap/utils.py:536-540), then the rest of `home` as one long span per thread, in frame
+    order.  The reference reads its stage-3 sweep sequentially, and a seek into an inter-frame codec can land a
+    frame off, so every seek is checked: the position the capture reports after it, and the frame at each run
+    start against the SAME frame decoded as the continuation of the run that ends there (one extra frame per run).
+    `verify()` waits for all decoders and says whether every seam agreed; a source whose seeks are not
+    frame-accurate sweeps through the sequential on-demand path instead (VideoFileSource.begin_sweep)."""
 
     def __init__(self, src, priority, home, device, piece=256, workers=8):
         import queue
@@ -301,30 +313,61 @@ class _DecodeCache:
         self.bufs = [torch.empty((n, h, w), dtype=torch.uint8, device=device) for h, w in zip(src.Ly, src.Lx)]
         self.npieces = -(-n // piece)
         nv = len(src.Ly)
-        order, seen = [], set()
-        for a, b in priority:
-            a, b = max(a, self.lo), min(b, self.hi)
-            if a >= b:
-                continue
-            for pc in range((a - self.lo) // piece, (b - 1 - self.lo) // piece + 1):
-                if pc not in seen:
-                    seen.add(pc)
-                    order.append(pc)
-        order += [pc for pc in range(self.npieces) if pc not in seen]
+        workers = max(1, workers)
+        self.runs = runs = self.plan_runs(priority, home, piece, nv, workers)
         self.ready = [[threading.Event() for _ in range(nv)] for _ in range(self.npieces)]
         self.copied = [[None] * nv for _ in range(self.npieces)]
         self.error = None
         self.stop = False
         self.stream = torch.cuda.Stream(device)
         self.jobs = queue.Queue()
-        for pc in order:
+        for (p0, p1) in runs:
             for v in range(nv):
-                self.jobs.put((pc, v))
+                self.jobs.put((p0, p1, v))
         self.decoded_frames = 0
+        self.seam_frames = 0
+        self.run_head = {}        # (view, frame) -> first frame decoded after the seek that starts a run
+        self.run_tail = {}        # (view, frame) -> that frame decoded as the continuation of the run ending there
+        self.seek_mismatch = False
         self._lock = threading.Lock()
-        self.threads = [threading.Thread(target=self._work, daemon=True) for _ in range(max(1, workers))]
+        self._verdict = None
+        self.threads = [threading.Thread(target=self._work, daemon=True) for _ in range(workers)]
         for t in self.threads:
             t.start()
+
+    @staticmethod
+    def plan_runs(priority, home, piece, nviews, workers):
+        """[(first piece, end piece)] in the order they are dealt: the runs the sample ranges touch, in access
+        order, then the rest of `home` cut into about `workers / nviews` long spans per view in frame order."""
+        lo, hi = home
+        npieces = -(-(hi - lo) // piece)
+        order, seen = [], set()
+        for a, b in priority:
+            a, b = max(a, lo), min(b, hi)
+            if a >= b:
+                continue
+            for pc in range((a - lo) // piece, (b - 1 - lo) // piece + 1):
+                if pc not in seen:
+                    seen.add(pc)
+                    order.append(pc)
+        runs = _DecodeCache._consecutive(order)
+        rest = [pc for pc in range(npieces) if pc not in seen]
+        span = max(1, -(-len(rest) * nviews // max(1, workers)))
+        for p0, p1 in _DecodeCache._consecutive(rest):
+            for q in range(p0, p1, span):
+                runs.append((q, min(p1, q + span)))
+        return runs
+
+    @staticmethod
+    def _consecutive(pieces):
+        """[p, p+1, ..., q-1, r, r+1, ...] -> [(p, q), (r, ...)] keeping the order of first appearance"""
+        out = []
+        for pc in pieces:
+            if out and out[-1][1] == pc:
+                out[-1] = (out[-1][0], pc + 1)
+            else:
+                out.append((pc, pc + 1))
+        return out
 
     def _work(self):
         import queue
@@ -336,25 +379,41 @@ class _DecodeCache:
             staging = {}
             while not self.stop:
                 try:
-                    pc, v = self.jobs.get_nowait()
+                    p0, p1, v = self.jobs.get_nowait()
                 except queue.Empty:
                     break
-                a = self.lo + pc * self.piece
-                b = min(self.hi, a + self.piece)
                 if v not in staging:
                     staging[v] = torch.empty((self.piece, self.src.Ly[v], self.src.Lx[v]), dtype=torch.uint8,
                                              pin_memory=True)
-                host = staging[v][:b - a]
-                self.src._read(v, a, b, out=host.numpy(), caps=caps)
-                with torch.cuda.stream(self.stream):
-                    self.bufs[v][a - self.lo:b - self.lo].copy_(host, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(self.stream)
-                self.copied[pc][v] = ev
-                self.ready[pc][v].set()
-                with self._lock:
-                    self.decoded_frames += b - a
-                ev.synchronize()                      # the staging buffer is free again
+                for pc in range(p0, p1):
+                    if self.stop:
+                        break
+                    a = self.lo + pc * self.piece
+                    b = min(self.hi, a + self.piece)
+                    host = staging[v][:b - a]
+                    seeks = []
+                    self.src._read(v, a, b, out=host.numpy(), caps=caps, seeks=seeks)
+                    if any(not ok for ok in seeks):
+                        self.seek_mismatch = True
+                    if pc == p0:
+                        with self._lock:
+                            self.run_head[(v, a)] = host[0].numpy().copy()
+                    with torch.cuda.stream(self.stream):
+                        self.bufs[v][a - self.lo:b - self.lo].copy_(host, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(self.stream)
+                    self.copied[pc][v] = ev
+                    self.ready[pc][v].set()
+                    with self._lock:
+                        self.decoded_frames += b - a
+                    ev.synchronize()                      # the staging buffer is free again
+                # the frame after the run, decoded as its continuation: what the next run's seek must reproduce
+                end = min(self.hi, self.lo + p1 * self.piece)
+                if end < self.hi and not self.stop:
+                    tail = self.src._read(v, end, end + 1, caps=caps)
+                    with self._lock:
+                        self.run_tail[(v, end)] = tail[0]
+                        self.seam_frames += 1
         except Exception as e:                        # surface in the reader instead of hanging it
             self.error = e
             for row in self.ready:
@@ -363,6 +422,23 @@ class _DecodeCache:
         finally:
             if caps is not None:
                 self.src._release(caps)
+
+    def verify(self):
+        """Wait for every decoder thread; True when each seek landed on the frame asked for: the capture reported
+        the requested position after every seek, and every run starts with the frame that the run before it
+        decodes there sequentially."""
+        if self._verdict is None:
+            for t in self.threads:
+                t.join()
+            if self.error is not None:
+                raise self.error
+            ok = not self.seek_mismatch
+            for key, head in self.run_head.items():
+                tail = self.run_tail.get(key)
+                if tail is not None and not np.array_equal(head, tail):
+                    ok = False
+            self._verdict = ok
+        return self._verdict
 
     def covers(self, a, b):
         return a >= self.lo and b <= self.hi
@@ -431,6 +507,7 @@ class VideoFileSource(FrameSource):
         self.cache_on_device = cache_on_device
         self.mem_fraction = mem_fraction
         self._cache = None
+        self.seek_inexact = False
 
     def _open(self):
         """a private set of capture handles [block][view] (a handle is not thread safe)"""
@@ -468,7 +545,9 @@ class VideoFileSource(FrameSource):
         self._cache = _DecodeCache(self, priority, (lo, hi), device, workers=self.decode_workers)
         self.h2d += nbytes
 
-    def _read(self, view, a, b, out=None, caps=None):
+    def _read(self, view, a, b, out=None, caps=None, seeks=None):
+        """frames [a, b) of one view (utils.get_frames, facemap/utils.py:522-553).  `seeks`: optional list that
+        receives, for every seek made, whether the capture then reported the requested position."""
         cv2 = self._cv2
         caps = self.caps if caps is None else caps
         if out is None:
@@ -482,6 +561,8 @@ class VideoFileSource(FrameSource):
             first = int(lo - self.cumframes[blk])
             if int(cap.get(cv2.CAP_PROP_POS_FRAMES)) != first:
                 cap.set(cv2.CAP_PROP_POS_FRAMES, first)
+                if seeks is not None:
+                    seeks.append(int(cap.get(cv2.CAP_PROP_POS_FRAMES)) == first)
             end = k + (hi - lo)
             while k < end:
                 ok, frame = cap.read()
@@ -497,6 +578,16 @@ class VideoFileSource(FrameSource):
                 out[k] = frame if frame.ndim == 2 else cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
                 k += 1
         return out
+
+    def begin_sweep(self):
+        """Called before the sequential sweep over all frames (stage 3, facemap/process.py:394-515): the reference
+        decodes that sweep without seeking, so the decode-once cache serves it only if every seek it made proved
+        frame-accurate (_DecodeCache.verify); otherwise the sweep decodes on demand, sequentially."""
+        if self._cache is not None and not self._cache.verify():
+            print("facemap_b200: seeks into this video are not frame-accurate; stage 3 decodes sequentially")
+            self.seek_inexact = True
+            self._cache.close()
+            self._cache = None
 
     def _decode_pinned(self, view, a, b):
         buf = torch.empty((b - a, self.Ly[view], self.Lx[view]), dtype=torch.uint8, pin_memory=True)

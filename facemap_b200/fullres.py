@@ -239,6 +239,7 @@ class FullRes:
 
     def sweep(self, source, fetch_frames=2368):
         """Stand-alone pass for runs without an SVD stage 3 (fullSVD off and no motion ROI)."""
+        source.begin_sweep()
         if self.f0 > 0:
             self.seed(source.fetch(self.f0 - 1, self.f0, self.device))
         for t in range(self.f0, self.f1, fetch_frames):

@@ -948,6 +948,7 @@ class Stage3:
             X = self.X_full
         else:
             X = self._operands("X3.", self.rows_batch)
+            self.source.begin_sweep()
             self._seed_halo()
         row0 = 0
         for fetches, filled in self.batches:

@@ -88,20 +88,30 @@ def resolved_count(S, gap_rel=1e-3, floor_rel=1e-3):
 
 
 def component_errors(U, U_ref, V, V_ref, S=None, S_ref=None):
-    """EVERY component of one target against the reference's: U / U_ref masks [p, k] (orthonormal columns, possibly
-    followed by all-zero ones), V / V_ref traces [frames, k].  Returns
+    """EVERY component of one target against the reference's: U / U_ref masks [p, k] (orthonormal columns up to
+    float32 rounding, possibly followed by all-zero ones), V / V_ref traces [frames, k].  Returns
       S_rel[j]          |S_j - Sref_j| / Sref_j                                 (None without S)
       prefix_sin[j]     sine of the largest principal angle between span(U[:, :j+1]) and span(U_ref[:, :j+1])
-      one_minus_cos[j]  1 - |<u_j, uref_j>|
+      one_minus_cos[j]  1 - |<u_j, uref_j>| / (|u_j| |uref_j|)
       trace_rel[j]      ||sg_j V_j - Vref_j|| / ||Vref_j||, sg_j the sign that aligns mask j
-      k                 number of (non-zero) components compared"""
+      k                 number of (non-zero) components compared
+    The prefixes are orthonormalised through the Cholesky factors of the two Gram matrices, whose leading blocks
+    are the factors of the leading blocks: one factorisation serves all k prefixes."""
     U64, Ur64 = np.asarray(U, np.float64), np.asarray(U_ref, np.float64)
     k = min(U64.shape[1], Ur64.shape[1])
     nz = np.flatnonzero(np.linalg.norm(Ur64[:, :k], axis=0) > 0)
     k = int(nz[-1]) + 1 if nz.size else 0
-    M = Ur64[:, :k].T @ U64[:, :k]
-    d = np.diag(M)
+    U64, Ur64 = U64[:, :k], Ur64[:, :k]
+    C = Ur64.T @ U64
+    nu, nr = np.linalg.norm(U64, axis=0), np.linalg.norm(Ur64, axis=0)
+    d = np.diag(C) / np.where(nu * nr > 0, nu * nr, 1.0)
     sg = np.where(d < 0, -1.0, 1.0)
+    import scipy.linalg
+
+    L = np.linalg.cholesky(U64.T @ U64)
+    Lr = np.linalg.cholesky(Ur64.T @ Ur64)
+    M = scipy.linalg.solve_triangular(Lr, C, lower=True)                       # Lr^-1 C
+    M = scipy.linalg.solve_triangular(L, M.T, lower=True).T                    # Lr^-1 C L^-T
     prefix = np.zeros(k)
     for j in range(k):
         smin = np.linalg.svd(M[:j + 1, :j + 1], compute_uv=False)[-1]
@@ -114,6 +124,27 @@ def component_errors(U, U_ref, V, V_ref, S=None, S_ref=None):
         Sr = np.asarray(S_ref, np.float64)[:k]
         out["S_rel"] = np.abs(np.asarray(S, np.float64)[:k] - Sr) / np.where(Sr > 0, Sr, 1.0)
     return out
+
+
+# What "gap-resolved" means (north_star: components / subspaces must match "after sign alignment"; a component whose
+# singular value is as good as tied with a neighbour's is not determined by the data): the chunk components U S the
+# reference itself stores are float32 (facemap/process.py:146-151, 229-259), a relative perturbation of 2^-24 ~ 6e-8
+# that moves a singular subspace by about  STORE_EPS * S_0 / gap.  A component (or a prefix of components) is held to
+# the tolerance wherever that floor is below a quarter of it.  Measured on B200 (profiles/r02_accuracy.md): the
+# trace error of every component stays below 3.3e-7 * S_0 / gap (motion) and 1.5e-6 * S_0 / gap (movie).
+STORE_EPS = 1e-7
+
+
+def gap_resolved(S_ref, tol):
+    """(component mask, prefix mask) over the singular values S_ref: component j resolved if both gaps to its
+    neighbours exceed 4 * STORE_EPS * S_0 / tol; prefix j (components 0..j) if the gap S_j - S_{j+1} does."""
+    S = np.asarray(S_ref, np.float64)
+    if S.size == 0 or S[0] <= 0:
+        return np.zeros(S.size, bool), np.zeros(S.size, bool)
+    need = 4.0 * STORE_EPS * S[0] / tol
+    down = np.r_[S[:-1] - S[1:], S[-1]]            # gap to the next one (the last keeps its own size: the cut-off)
+    up = np.r_[np.inf, S[:-1] - S[1:]]
+    return (np.minimum(up, down) >= need) & (S > 0), (down >= need) & (S > 0)
 
 
 def sign_align(A, B):

@@ -16,7 +16,7 @@ def _video(T, H, W, seed):
     return SynthVideo(H, W, T, seed=seed, nmodes=12).all_frames()
 
 
-def _compare(p, o, motSVD=True, movSVD=False, s_floor=1e-2):
+def _compare(p, o, motSVD=True, movSVD=False, s_floor=0.0):
     for key in ("avgframe", "avgmotion", "motion"):
         assert len(p[key]) == len(o[key]), key
         for a, b in zip(p[key], o[key]):
@@ -36,9 +36,11 @@ def _compare(p, o, motSVD=True, movSVD=False, s_floor=1e-2):
             assert err <= 1e-3 * np.abs(Vr[:, :k]).max(), (vk, err)
         S, Sr = np.asarray(p[sk], np.float64), np.asarray(o[sk], np.float64)
         if np.any(Sr):
-            # 1e-4 relative, with the float32 floor of the data path (a few eps of the top singular value)
+            # every singular value to 1e-4 relative; numerically zero ones (rank-deficient inputs: below the float32
+            # resolution of the operands, 2^-22 of the largest) are only held to that resolution
             big = Sr >= s_floor * Sr[0]
-            assert np.all(np.abs(S - Sr)[big] <= np.maximum(1e-4 * Sr[big], 4e-6 * Sr[0])), sk
+            assert np.all(np.abs(S - Sr)[big] <= np.maximum(1e-4 * Sr[big], 2.4e-7 * Sr[0])), \
+                (sk, float((np.abs(S - Sr)[big] / np.maximum(Sr[big], 1e-300)).max()))
 
 
 @pytest.mark.parametrize("N", [120, 499, 500, 501, 999, 1000, 1001, 1999, 2000, 2001, 3217])
@@ -70,8 +72,9 @@ def test_odd_geometry_and_bin_factors(cuda_device, H, W, sbin):
         for key in ("avgframe", "avgmotion", "motion"):
             assert np.array_equal(p[key][0], o[key][0]), key
         S, Sr = p["motSv"].astype(np.float64), o["motSv"].astype(np.float64)
-        big = Sr >= 1e-2 * Sr[0]
-        assert np.all(np.abs(S - Sr)[big] <= np.maximum(1e-4 * Sr[big], 4e-6 * Sr[0]))
+        # the float operand of a non-power-of-two bin is the reference's to <= 1 ulp, not bit for bit: singular values
+        # move by up to that relative to the LARGEST one
+        assert np.all(np.abs(S - Sr) <= np.maximum(1e-4 * Sr, 4e-6 * Sr[0]))
 
 
 def test_three_views_canvas(cuda_device):
@@ -112,14 +115,12 @@ def test_fullsvd_off_with_roi(cuda_device):
     assert p["motMask"][1].shape == o["motMask"][1].shape and p["motSVD"][1].shape == o["motSVD"][1].shape
     assert np.array_equal(p["motion"][1], o["motion"][1])
     S, Sr = p["motSv"].astype(np.float64), o["motSv"].astype(np.float64)
-    big = Sr >= 1e-2 * Sr[0]
-    assert S.shape == Sr.shape and (np.abs(S - Sr)[big] / Sr[big]).max() <= 1e-4
+    nz = Sr > 0
+    assert S.shape == Sr.shape and (np.abs(S - Sr)[nz] / Sr[nz]).max() <= 1e-4         # every singular value
     U, Ur = p["motMask"][1][:, :3].astype(np.float64), o["motMask"][1][:, :3].astype(np.float64)
     assert np.abs(np.abs((U * Ur).sum(axis=0)) - 1).max() < 1e-5
 
 
-@pytest.mark.skipif(__import__("os").environ.get("FM_EXPERIMENTAL") != "1",
-                    reason="written without a GPU (round 1 had spent its budget): opt-in until validated on a B200")
 @pytest.mark.parametrize("with_rois", [False, True])
 def test_movie_svd_without_motion_svd(cuda_device, with_rois):
     """motSVD off, movSVD on: the reference's merge loop runs over len(U_mot) (process.py:264), so the movie targets

@@ -15,8 +15,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import LARGE_CASES, case_rois, case_videos, frame_window
-from tests.test_pipeline_gpu import ANGLE_TOL, S_RTOL, TRACE_RTOL, leading_resolved, svd_metrics
+from tests.helpers import LARGE_CASES, case_rois, case_videos, frame_window, gap_resolved
+from tests.test_pipeline_gpu import ANGLE_TOL, S_RTOL, TRACE_RTOL, svd_metrics
 
 pytestmark = pytest.mark.gpu
 
@@ -60,19 +60,26 @@ def compare_with_fixture(proc, z, name):
             assert tuple(proc[mk][i].shape) == tuple(z[f"exact/{mk}_{i}_shape"]), (mk, i)
             S_ref = z[f"exact/{sk}"].astype(np.float64) if i == n_ref - 1 else None          # quirk Q3
             S = np.asarray(proc[sk]).astype(np.float64)
-            kres = min(keep, leading_resolved(S_ref) if S_ref is not None else 4)
-            kres = max(kres, min(2, keep))
-            met = svd_metrics(S_ref, z[f"exact/{mk}_{i}"], z[f"exact/{vk}_{i}"], S, proc[mk][i], proc[vk][i][w], kres)
-            print(name, mk, i, "kres", kres, "S_rel", None if met["S_rel"] is None else met["S_rel"].max(),
-                  "angle", max(met["angle"]), "trace", met["trace_rel"].max())
+            # every stored component whose subspace / direction the data determine (tests/helpers.gap_resolved);
+            # targets without their own spectrum in the file (quirk Q3) are held on a short prefix
+            met = svd_metrics(S_ref, z[f"exact/{mk}_{i}"], z[f"exact/{vk}_{i}"], S, proc[mk][i], proc[vk][i][w], keep)
+            if S_ref is not None:
+                comp, pre = gap_resolved(S_ref, ANGLE_TOL)
+                comp, pre = comp[:keep], pre[:keep]
+            else:
+                comp = pre = np.arange(keep) < 4
+            angle, trace = np.asarray(met["angle"])[pre].max(), met["trace_rel"][comp].max()
+            print(name, mk, i, "resolved prefixes", int(pre.sum()), "of", keep, "S_rel", None if met["S_rel"] is None else
+                  met["S_rel"].max(), "angle", angle, "trace", trace)
+            assert pre.sum() >= min(2, keep)
             if met["S_rel"] is not None:
                 assert met["S_rel"].max() <= S_RTOL, (mk, i)
-            assert max(met["angle"]) <= ANGLE_TOL and met["trace_rel"].max() <= TRACE_RTOL, (mk, i)
+            assert angle <= ANGLE_TOL and trace <= TRACE_RTOL, (mk, i)
         S_ref, S = z["exact/" + sk].astype(np.float64), np.asarray(proc[sk]).astype(np.float64)
-        big = S_ref >= 1e-2 * S_ref[0]
-        rel = np.abs(S - S_ref) / S_ref
-        print(name, sk, "S rel err: above 1e-2 of the first", rel[big].max(), "all", rel.max(), "count", int(big.sum()))
-        assert rel[big].max() <= S_RTOL, sk
+        nz = S_ref > 0
+        rel = np.abs(S - S_ref)[nz] / S_ref[nz]
+        print(name, sk, "S rel err over all", int(nz.sum()), "components:", rel.max())
+        assert rel.max() <= S_RTOL, sk                     # all 500 singular values within the north-star 1e-4
         # the stock reference on the components it resolves itself
         S1 = z["stock/" + sk].astype(np.float64)
         agree = np.abs(S1 - S_ref) / S_ref <= S_RTOL / 4

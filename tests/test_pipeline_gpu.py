@@ -14,7 +14,7 @@ import pytest
 import torch
 
 from oracle import facemap_oracle as orc
-from tests.helpers import CASES, KEEP, case_rois, case_videos, frame_window, sign_align, subspace_sin
+from tests.helpers import CASES, KEEP, case_rois, case_videos, frame_window, gap_resolved, sign_align, subspace_sin
 
 pytestmark = pytest.mark.gpu
 
@@ -117,22 +117,28 @@ def test_svd_outputs_match_exact_oracle_golden(cuda_device, golden_dir, name):
             S = np.asarray(proc[sk])
             if S_ref is not None:
                 assert S.shape == S_ref.shape
-            # resolved prefix from the mask's own spectrum when available, else a short prefix
-            kres = min(KEEP, leading_resolved(S_ref) if (S_ref is not None and np.any(S_ref)) else 6)
-            kres = max(kres, 3)
-            met = svd_metrics(S_ref, U_ref, V_ref, S, proc[mk][i], proc[vk][i][w], kres)
+            # every stored component (KEEP leading ones) whose subspace / direction the data determine
+            # (tests/helpers.gap_resolved); without the target's own spectrum (quirk Q3) a short prefix
+            kmax = min(KEEP, U_ref.shape[1])
+            met = svd_metrics(S_ref, U_ref, V_ref, S, proc[mk][i], proc[vk][i][w], kmax)
+            if S_ref is not None and np.any(S_ref):
+                comp, pre = gap_resolved(S_ref, ANGLE_TOL)
+                comp, pre = comp[:kmax], pre[:kmax]
+            else:
+                comp = pre = np.arange(kmax) < 6
+            assert pre.sum() >= min(3, kmax), (mk, i, "fewer than 3 resolved prefixes")
             if met["S_rel"] is not None:
                 assert met["S_rel"].max() <= S_RTOL, (mk, i, met["S_rel"])
-            assert max(met["angle"][:kres]) <= ANGLE_TOL, (mk, i, met["angle"])
-            assert met["trace_rel"].max() <= TRACE_RTOL, (mk, i, met["trace_rel"])
-    # all singular values, not only the leading ones
+            assert np.asarray(met["angle"])[pre].max() <= ANGLE_TOL, (mk, i, met["angle"])
+            assert met["trace_rel"][comp].max() <= TRACE_RTOL, (mk, i, met["trace_rel"])
+    # all singular values, not only the leading ones: every non-zero one within the north-star 1e-4
     for sk in ("motSv", "movSv"):
         S_ref, S = z["exact/" + sk].astype(np.float64), np.asarray(proc[sk]).astype(np.float64)
         if np.any(S_ref):
-            # below 1e-2 of the top singular value the float32 STORAGE of the chunk components (U S is a
-            # float32 array in the reference too) already perturbs a singular value by ~1e-4 relative
-            big = S_ref >= 1e-2 * S_ref[0]
-            assert (np.abs(S - S_ref)[big] / S_ref[big]).max() <= S_RTOL, sk
+            nz = S_ref > 0
+            rel = np.abs(S - S_ref)[nz] / S_ref[nz]
+            print(name, sk, "S rel err over all", int(nz.sum()), "components:", float(rel.max()))
+            assert rel.max() <= S_RTOL, (sk, float(rel.max()), int(np.argmax(rel)))
 
 
 @pytest.mark.parametrize("name", ["single_s2", "multi_roi_s4", "crop_s3"])
@@ -163,8 +169,8 @@ def test_svd_outputs_match_stock_reference_on_resolved_components(cuda_device, g
                 kres = k
             if i == n_ref - 1 and np.any(z["stock/" + sk]):
                 Ss, Se = z["stock/" + sk].astype(np.float64), z["exact/" + sk].astype(np.float64)
-                ks = 0     # resolved by the stock solver AND above the float32 floor of this implementation
-                while ks < len(Ss) and abs(Ss[ks] - Se[ks]) / Se[ks] <= S_RTOL and Se[ks] >= 1e-2 * Se[0]:
+                ks = 0     # resolved by the stock solver itself
+                while ks < len(Ss) and abs(Ss[ks] - Se[ks]) / Se[ks] <= S_RTOL:
                     ks += 1
                 S = np.asarray(proc[sk], np.float64)
                 assert ks >= 3 and (np.abs(S - Ss)[:ks] / Ss[:ks]).max() <= 2 * S_RTOL, (sk, ks)
@@ -191,8 +197,7 @@ def test_against_live_oracle_all_components(cuda_device):
     assert np.array_equal(p["motion"][0], o["motion"][0])
     S_ref, S = o["motSv"].astype(np.float64), p["motSv"].astype(np.float64)
     assert S.shape == S_ref.shape == (500,)
-    big = S_ref >= 3e-3 * S_ref[0]
-    assert (np.abs(S - S_ref)[big] / S_ref[big]).max() <= S_RTOL
+    assert (np.abs(S - S_ref) / S_ref).max() <= S_RTOL                 # all 500
     U, U_ref = p["motMask"][0], o["motMask"][0]
     assert U.shape == U_ref.shape
     gram = U.astype(np.float64).T @ U.astype(np.float64)

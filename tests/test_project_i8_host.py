@@ -143,6 +143,9 @@ class ArraySource:
     def resident(self, t0, t1):
         return False
 
+    def begin_sweep(self):
+        self.swept = True
+
 
 @pytest.mark.parametrize("sbin,mods", [(4, ["mot"]), (2, ["mot", "mov"]), (1, ["mot"])])
 def test_stage3_i8_orchestration(monkeypatch, sbin, mods):
