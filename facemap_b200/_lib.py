@@ -61,6 +61,7 @@ SIGNATURES = {
     "fm_bin_motion_planes": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, C.POINTER(Rois), _P, _P, _P, _P]),
     "fm_slice_rows_i8": (_I, [_P, _L, _I, _L, _P, _P, _P, _L, _P, _P]),
     "fm_gram_assemble_i8": (_I, [_P, _I, _I, _L, _P, _P, _L, _P, _P]),
+    "fm_gram_accumulate_i8": (_I, [_P, _I, _I, _L, _P, _P, _P]),
     "fm_gram_assemble_i8_rowside": (_I, [_P, _I, _I, _L, _P, _P, _P, _I, _P, _P]),
     "fm_split_lo": (_I, [_P, _L, _I, _I, _P, _L, _P]),
     "fm_slice_rows": (_I, [_P, _L, _I, _L, _P, _P, _P, _L, _P]),
@@ -74,6 +75,8 @@ SIGNATURES = {
     "fm_solver_create": (_I, [C.POINTER(_P)]),
     "fm_solver_destroy": (_I, [_P]),
     "fm_solver_check": (_I, [_P, _P]),
+    "fm_eigh_topk_scratch_bytes": (C.c_size_t, [_I, _I, _I]),
+    "fm_eigh_topk_batched": (_I, [_P, _I, _I, _I, _P, _P, _P, C.c_size_t, _P, _P]),
     "fm_syevd": (_I, [_P, _P, _I, _P, _I, _P]),
     "fm_syevd_batched": (_I, [_P, _P, _I, _I, _P, _P]),
     "fm_syevdx_top": (_I, [_P, _P, _I, _I, _P, _P]),

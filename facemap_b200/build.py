@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIBPATH = os.path.join(LIBDIR, "libfacemap_b200.so")
-SOURCES = ["api.cu", "bin_motion.cu", "svd_helpers.cu", "gemm_tf32x3.cu", "eigh.cu", "roi_procs.cu", "motion_ref.cu", "gemm_i8.cu", "project_i8.cu"]
+SOURCES = ["api.cu", "bin_motion.cu", "svd_helpers.cu", "gemm_tf32x3.cu", "eigh.cu", "eigh_cluster.cu", "roi_procs.cu", "motion_ref.cu", "gemm_i8.cu", "project_i8.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "numpy_sum.cuh"), os.path.join(CSRC, "pupil_math.cuh"),
            os.path.join(CSRC, "slice_math.cuh"), os.path.join(CSRC, "i8_mma.cuh"),
            os.path.join(os.path.dirname(PKG), "include", "facemap_b200.h")]

@@ -455,7 +455,7 @@ template <bool ROWSIDE>
 __global__ void gram_assemble_i8_kernel(const int32_t* __restrict__ P, int ksplit, int n, int64_t ldp,
                                         const int32_t* __restrict__ exps, const double* __restrict__ mean,
                                         double ncols, const double* __restrict__ mu, int nmu,
-                                        double* __restrict__ G) {
+                                        double* __restrict__ G, int accumulate) {
   __shared__ double s_mumu;
   if (ROWSIDE) {
     if (threadIdx.x == 0 && threadIdx.y == 0) {
@@ -488,6 +488,7 @@ __global__ void gram_assemble_i8_kernel(const int32_t* __restrict__ P, int kspli
     v = v - (mean[i] + mean[j]) + s_mumu;          // `mean` carries q = Y mu here
   else if (mean)
     v -= ncols * (mean[i] * mean[j]);
+  if (accumulate) v += G[(size_t)i * n + j];       // a further block of columns of the same operand
   G[(size_t)i * n + j] = v;
   if (j != i) G[(size_t)j * n + i] = v;
 }
@@ -513,7 +514,20 @@ extern "C" int fm_gram_assemble_i8(const int32_t* P, int ksplit, int n, int64_t 
   FM_REQUIRE(P && exps && G && ksplit >= 1 && n >= 1 && ldp >= n, "fm_gram_assemble_i8: bad args");
   dim3 block(32, 8), grid((unsigned)cdiv(n, 32), (unsigned)cdiv(n, 8));
   gram_assemble_i8_kernel<false><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      P, ksplit, n, ldp, exps, mean, (double)ncols, nullptr, 0, G);
+      P, ksplit, n, ldp, exps, mean, (double)ncols, nullptr, 0, G, 0);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+// G += the weighted plane products of a further block of columns (operands too wide to slice at once are processed
+// in column blocks, each with its own row exponents; the mean term went in with the first block)
+extern "C" int fm_gram_accumulate_i8(const int32_t* P, int ksplit, int n, int64_t ldp, const int32_t* exps, double* G,
+                                     void* stream) {
+  using namespace fm;
+  FM_REQUIRE(P && exps && G && ksplit >= 1 && n >= 1 && ldp >= n, "fm_gram_accumulate_i8: bad args");
+  dim3 block(32, 8), grid((unsigned)cdiv(n, 32), (unsigned)cdiv(n, 8));
+  gram_assemble_i8_kernel<false><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      P, ksplit, n, ldp, exps, nullptr, 0.0, nullptr, 0, G, 1);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }
@@ -525,7 +539,7 @@ extern "C" int fm_gram_assemble_i8_rowside(const int32_t* P, int ksplit, int n, 
              "fm_gram_assemble_i8_rowside: bad args");
   dim3 block(32, 8), grid((unsigned)cdiv(n, 32), (unsigned)cdiv(n, 8));
   gram_assemble_i8_kernel<true><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      P, ksplit, n, ldp, exps, q, 0.0, mu, nmu, G);
+      P, ksplit, n, ldp, exps, q, 0.0, mu, nmu, G, 0);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }

@@ -225,6 +225,19 @@ def slice_rows_i8(X, out=None):
     return Q0, Q1, Q2, exps
 
 
+def gram_accumulate_i8(P, ksplit, n, exps, G):
+    """fm_gram_accumulate_i8: G += the weighted plane products of a further block of columns."""
+    _need(P, torch.int32, "P", 4)
+    _need(G, torch.float64, "G", 2)
+    if P.shape[0] != 6 or P.shape[1] < ksplit or P.shape[2] != n or P.shape[3] < n or not P.is_contiguous():
+        raise FacemapB200Error("gram_accumulate_i8: P must be a contiguous int32 [6, ksplit, n, >=n] stack")
+    if tuple(G.shape) != (n, n) or not G.is_contiguous():
+        raise FacemapB200Error("gram_accumulate_i8: G must be a contiguous [n, n] float64 matrix")
+    check(_lib.load().fm_gram_accumulate_i8(ptr(P), int(ksplit), int(n), P.stride(2), ptr(exps), ptr(G), _stream()),
+          "fm_gram_accumulate_i8")
+    return G
+
+
 def gram_assemble_i8(P, ksplit, n, exps, mean, ncols, out=None, rowside=None):
     """fm_gram_assemble_i8: P int32 [6, ksplit, n, ldp] plane products -> float64 centred Gram  X X^T - ncols m m^T.
     rowside = (q, mu): the row-side form of a wide matrix instead,  Y Y^T - q 1^T - 1 q^T + mu.mu
@@ -376,8 +389,19 @@ def sign_from_right(T, mu, Ut):
                                          Ut.shape[1], _stream()), "fm_sign_from_right")
 
 
+EIGH_CLUSTER_NMAX = 1024       # largest matrix order fm_eigh_topk_batched takes (one reflector per shared-memory vector)
+
+
+def eigh_topk_scratch_bytes(n, batch, k):
+    return int(_lib.load().fm_eigh_topk_scratch_bytes(int(n), int(batch), int(k)))
+
+
+class EigCheckFailed(FacemapB200Error):
+    """the hand-written eigensolver's self-check flagged a batch (e.g. exactly repeated eigenvalues)"""
+
+
 class Solver:
-    """cuSOLVER handle + workspaces (fm_solver)."""
+    """cuSOLVER handle + workspaces (fm_solver), and the hand-written batched solver for chunk-sized matrices."""
 
     def __init__(self):
         self._h = C.c_void_p()
@@ -415,8 +439,36 @@ class Solver:
         return lam
 
     def check(self):
-        """devInfo of every solve since the last check (one D2H copy + stream synchronisation)."""
+        """devInfo of every cuSOLVER solve since the last check (one D2H copy + stream synchronisation), and the
+        self-check flags of the hand-written solver's batches (EigCheckFailed: the caller repeats the pass on
+        cuSOLVER)."""
         check(_lib.load().fm_solver_check(self._h, _stream()), "fm_solver_check")
+        pending, self._status = getattr(self, "_status", []), []
+        for st in pending:
+            flags = st.cpu()
+            if bool(flags.any()):
+                raise EigCheckFailed(f"hand-written eigensolver self-check flags {flags.tolist()}")
+
+    def eigh_topk_batched(self, G, k, scratch=None):
+        """fm_eigh_topk_batched: G float64 [batch, n, n] (destroyed), n <= 1024 -> (lam [batch, k], W [batch, k, n]),
+        ascending order of eigenvalue.  The self-check flags are read by check()."""
+        _need(G, torch.float64, "G", 3)
+        b, n, n2 = G.shape
+        if n != n2 or not G.is_contiguous():
+            raise FacemapB200Error("eigh_topk_batched: G must be contiguous [batch, n, n]")
+        lib = _lib.load()
+        need = int(lib.fm_eigh_topk_scratch_bytes(n, b, int(k)))
+        if scratch is None or scratch.numel() < need:
+            scratch = torch.empty(need, dtype=torch.uint8, device=G.device)
+        lam = torch.empty((b, int(k)), dtype=torch.float64, device=G.device)
+        W = torch.empty((b, int(k), n), dtype=torch.float64, device=G.device)
+        status = torch.empty(b, dtype=torch.int32, device=G.device)
+        check(lib.fm_eigh_topk_batched(ptr(G), n, b, int(k), ptr(lam), ptr(W), ptr(scratch), need, ptr(status), _stream()),
+              "fm_eigh_topk_batched")
+        if not hasattr(self, "_status"):
+            self._status = []
+        self._status.append(status)
+        return lam, W
 
     def close(self):
         if self._h:

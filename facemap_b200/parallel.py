@@ -40,6 +40,12 @@ class Shard:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
+    def any_rank(self, flag, device):
+        """True on every rank if `flag` is set on any (one tiny all-reduce): decisions every rank must take together"""
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(t.item())
+
     # ---- collectives on plain tensors (device agnostic: used by the gloo CPU tests too) ----
     def allreduce_segment_sums(self, local, nseg, p, device, dtype=torch.int64):
         """local: {segment index: (tsum_bin [p], tsum_adiff [p], T)} for the segments this rank computed -> the

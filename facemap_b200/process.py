@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib, fullres, svd
+from .kernels import EigCheckFailed
 from .frames import FrameSource, as_source
 from .utils import binned_inds, multivideo_reshape, roi_bin_ranges, video_placement
 
@@ -106,7 +107,7 @@ class _HostSink:
 
 def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD=True, device=None,
                    eig_fp32=False, gemm_impl=0, timing=None, dist=None, keep_on_device=False,
-                   overlap_stage3=True, gather_outputs=True, gram_mode=None, proj_mode=None):
+                   overlap_stage3=True, gather_outputs=True, gram_mode=None, proj_mode=None, eig_mode=None):
     """Run the three stages on a FrameSource and return the proc-dict entries this path owns.
 
     timing: optional dict that receives per-stage device times (ms) and wall times.
@@ -119,7 +120,13 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
             "sliced" — how the Gram matrices of the two SVD levels are formed (svd.SvdWorkspace, svd.i8_gram,
             svd.sliced_gram); None reads the environment variable FM_GRAM_MODE.
     proj_mode: "i8" (default: stage 3 on byte planes and tcgen05 kind::i8, svd.Stage3) or "tf32x3" (float32 operands,
-            3xTF32 products); None reads FM_PROJ_MODE."""
+            3xTF32 products); None reads FM_PROJ_MODE.
+    eig_mode: "cluster" (default: the hand-written batched eigensolver for the per-chunk Gram matrices,
+            csrc/eigh_cluster.cu) or "cusolver"; None reads FM_EIG.  If the hand-written solver's self-check flags a
+            matrix (exactly repeated eigenvalues), the pass is repeated with cuSOLVER — on every rank."""
+    call = dict(sbin=sbin, motSVD=motSVD, movSVD=movSVD, rois=rois, fullSVD=fullSVD, device=device, eig_fp32=eig_fp32,
+                gemm_impl=gemm_impl, timing=timing, dist=dist, keep_on_device=keep_on_device,
+                overlap_stage3=overlap_stage3, gather_outputs=gather_outputs, gram_mode=gram_mode, proj_mode=proj_mode)
     t_enter = time.perf_counter()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     _lib.require_device(dev.index or 0)
@@ -155,7 +162,7 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
 
     mark("start")
     ws = svd.SvdWorkspace(dev, eig_fp32=eig_fp32, gemm_impl=gemm_impl, timer=timer, gram_mode=gram_mode,
-                          proj_mode=proj_mode)
+                          proj_mode=proj_mode, eig_mode=eig_mode)
     source.plan_access(*svd.access_plan(source, dist), dev)
     mark("setup")
 
@@ -175,7 +182,9 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     fres = fullres.FullRes(rois, Ly, Lx, N, dev, frame_range=fr) if has_fullres else None
     if mods and (fullSVD or nroi > 0):
         s3 = svd.Stage3(source, geo, avgframe, avgmotion, mods, fullSVD, ws, dev, timer, frame_range=fr, fullres=fres)
-        if overlap_stage3:
+        # with cuSOLVER solving the chunks the SMs idle during all of stage 2; the hand-written chunk solver fills
+        # them (one cluster per matrix), so the bin pass then starts after the chunk phase, underneath the merge solve
+        if overlap_stage3 and ws.eig_mode != "cluster":
             s3.start_early()
     # ---- stage 2 ----
     masks = {}
@@ -185,8 +194,14 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
         else:
             Yt, ks, nsegs = dist.stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, dev, timer)
         mark("stage2.chunks")
+        if s3 is not None and overlap_stage3 and ws.eig_mode == "cluster":
+            s3.start_early()
+        if geo.p > svd.LEFT_BLOCK_PIXELS:
+            ws.release()               # large views: the chunk phase's buffers must not add to the merge's
         masks = svd.stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, nc=svd.stage2_plan(N)[2], mot_on=bool(motSVD))
         del Yt
+        if geo.p > svd.LEFT_BLOCK_PIXELS:
+            ws.release()
         mark("stage2.merge")
     nsegs_plan = svd.stage2_plan(N)[1]
     nc_plan = svd.stage2_plan(N)[2]
@@ -224,8 +239,20 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     if dist is not None and dist.world > 1 and not gather_outputs and s3 is not None:
         f0_out = s3.f0
     t_asm = time.perf_counter()
-    # the eigensolves ran asynchronously; their devInfo words are read once, here, where the host waits anyway
-    ws.solver.check()
+    # the eigensolves ran asynchronously; their devInfo words / self-check flags are read once, here, where the host
+    # waits anyway
+    eig_failed = False
+    try:
+        ws.solver.check()
+    except EigCheckFailed:
+        eig_failed = True
+    if dist is not None and dist.world > 1:
+        eig_failed = dist.any_rank(eig_failed, dev)
+    if eig_failed:
+        if ws.eig_mode != "cluster":
+            raise _lib.FacemapB200Error("eigensolver self-check failed")
+        timer.release()
+        return process_source(source, eig_mode="cusolver", **call)
     with timer("assemble.d2h"):
         avgframe_h = avgframe.cpu().numpy()
         avgmotion_h = avgmotion.cpu().numpy()

@@ -111,6 +111,7 @@ KCHAIN_GRAM = 320     # <= 3 in-kernel chains per float64-reduced partial
 # components come out of large cancelling sums, so they too keep float64-reduced partials (2 in-kernel chains each).
 # The projection of every frame (trace tolerance 1e-3) runs as one launch: 150 chains summed in registers.
 KCHAIN_LEFT = 256
+LEFT_BLOCK_PIXELS = 131072   # pixels per left-vector GEMM (a multiple of 32: block boundaries stay 128-byte aligned)
 KCHAIN_PROJ = 1200    # only when the projection runs the single-accumulator kernel (impl 9)
 
 
@@ -151,7 +152,7 @@ def get_solver(device):
 class SvdWorkspace:
     """Reusable device buffers for the Gram -> eigensolve -> left-vector sequence."""
 
-    def __init__(self, device, eig_fp32=False, gemm_impl=0, timer=None, gram_mode=None, proj_mode=None):
+    def __init__(self, device, eig_fp32=False, gemm_impl=0, timer=None, gram_mode=None, proj_mode=None, eig_mode=None):
         self.device = device
         self.timer = timer if timer is not None else StageTimer(enabled=False)
         self.solver = get_solver(device)
@@ -188,6 +189,12 @@ class SvdWorkspace:
             self.proj_mode = "i8"
         if self.proj_mode not in ("tf32x3", "i8"):
             raise FacemapB200Error(f"unknown proj_mode {self.proj_mode!r}")
+        # who solves the per-chunk eigenproblems (n = 999, a batch of them):
+        #   "cluster"   (default) the hand-written solver, one thread-block cluster per matrix (csrc/eigh_cluster.cu)
+        #   "cusolver"  cusolverDnXsyevBatched / syevd (host-driven: ~4.7 ms per matrix batched, 12 ms serial)
+        self.eig_mode = _os.environ.get("FM_EIG", "cluster") if eig_mode is None else eig_mode
+        if self.eig_mode not in ("cluster", "cusolver"):
+            raise FacemapB200Error(f"unknown eig_mode {self.eig_mode!r}")
         self.proj_i8_impl = int(_os.environ.get("FM_PROJ_I8_IMPL", "0"))      # 1 = CTA pairs (fm_project_i8 impl)
         self._ws = None
         self._bufs = {}
@@ -230,6 +237,13 @@ class SvdWorkspace:
             buf = torch.empty(max(int(numel), 1), dtype=dtype, device=self.device)
             self._bufs[tag] = buf
         return buf[:numel]
+
+    def release(self, keep=("X3",)):
+        """drop the reusable buffers of a finished phase (all but the tags starting with one of `keep`: stage 3's
+        operands may already be filling on the side stream) so that the next phase's do not add to them"""
+        for tag in [t for t in self._bufs if not t.startswith(tuple(keep))]:
+            del self._bufs[tag]
+        self._ws = None
 
     def matrix(self, tag, rows, cols):
         ld = max(32, K.round_up(cols, 32))
@@ -327,6 +341,7 @@ def sliced_gram(ws: SvdWorkspace, X, timer, label, out=None):
 
 
 I8_KMAX = 32768        # K per int32 partial of fm_gemm_i8_tn (255^2 * 32768 < 2^31)
+I8_BLOCK_COLS = 262144  # columns of a Gram operand sliced into digit planes at once (8 partials of I8_KMAX)
 
 
 def i8_gram(ws: SvdWorkspace, X, timer, label, out=None, rowside_mu=None):
@@ -341,24 +356,34 @@ def i8_gram(ws: SvdWorkspace, X, timer, label, out=None, rowside_mu=None):
     n, p = X.shape
     with timer(label + ".colmean"):
         mean = K.row_means(X) if rowside_mu is None else K.row_dot(X, rowside_mu)
-    with timer(label + ".gram.split"):
-        ldq = K.round_up(p, 16)
-        raw = ws.raw("gram.i8", 3 * n * ldq, torch.uint8).view(3, n, ldq)
-        Q0, Q1, Q2, exps = K.slice_rows_i8(X, out=(raw[0].view(torch.int8)[:, :p], raw[1][:, :p], raw[2][:, :p]))
-    # split K where the int32 accumulator demands it, and where the tile count alone cannot fill the machine
-    ks = max(1, math.ceil(math.ceil(p / 64) / (I8_KMAX // 64)), _fill_ksplit(math.ceil(n / 128) * math.ceil(n / 256), p))
+    # operands too wide to slice at once (sbin 1 on a large view: p = 1.3 M columns) go in column blocks, each with
+    # its own digit planes, row exponents and int32 partials; the float64 assembly accumulates them
+    blk = p if (p <= I8_BLOCK_COLS or rowside_mu is not None) else I8_BLOCK_COLS
     ldp = K.round_up(n, 4)
-    P = ws.raw("gram.i8.P", 6 * ks * n * ldp, torch.int32).view(6, ks, n, ldp)
-    with timer(label + ".gram.mma"):
-        for d, (A, B, upper) in enumerate(((Q0, Q0, True), (Q1, Q1, True), (Q2, Q2, True),
-                                           (Q0, Q1, False), (Q0, Q2, False), (Q1, Q2, False))):
-            if ks > 1:
-                K.gemm_i8_tn(A, B, ksplit=ks, workspace=P[d], upper_only=upper)
+    G = out
+    for c0 in range(0, p, blk):
+        c1 = min(p, c0 + blk)
+        w = c1 - c0
+        with timer(label + ".gram.split"):
+            ldq = K.round_up(w, 16)
+            raw = ws.raw("gram.i8", 3 * n * ldq, torch.uint8).view(3, n, ldq)
+            Q0, Q1, Q2, exps = K.slice_rows_i8(X[:, c0:c1], out=(raw[0].view(torch.int8)[:, :w], raw[1][:, :w], raw[2][:, :w]))
+        # split K where the int32 accumulator demands it, and where the tile count alone cannot fill the machine
+        ks = max(1, math.ceil(math.ceil(w / 64) / (I8_KMAX // 64)), _fill_ksplit(math.ceil(n / 128) * math.ceil(n / 256), w))
+        P = ws.raw("gram.i8.P", 6 * ks * n * ldp, torch.int32).view(6, ks, n, ldp)
+        with timer(label + ".gram.mma"):
+            for d, (A, B, upper) in enumerate(((Q0, Q0, True), (Q1, Q1, True), (Q2, Q2, True),
+                                               (Q0, Q1, False), (Q0, Q2, False), (Q1, Q2, False))):
+                if ks > 1:
+                    K.gemm_i8_tn(A, B, ksplit=ks, workspace=P[d], upper_only=upper)
+                else:
+                    K.gemm_i8_tn(A, B, P[d, 0], upper_only=upper)
+        with timer(label + ".gram.assemble"):
+            if c0 == 0:
+                G = K.gram_assemble_i8(P, ks, n, exps, mean, p, out=out,
+                                       rowside=None if rowside_mu is None else (mean, rowside_mu))
             else:
-                K.gemm_i8_tn(A, B, P[d, 0], upper_only=upper)
-    with timer(label + ".gram.assemble"):
-        G = K.gram_assemble_i8(P, ks, n, exps, mean, p, out=out,
-                               rowside=None if rowside_mu is None else (mean, rowside_mu))
+                K.gram_accumulate_i8(P, ks, n, exps, G)
     return mean, G
 
 
@@ -379,17 +404,22 @@ def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
     return Wt, sval, rbias, rscale
 
 
-def left_components(ws, X, evec, lam, mean, k, out_Yt, timer, label):
-    """(U S)^T = W^T X - (W^T m) 1^T for the top-k eigenvectors (rows of `evec`) -> out_Yt [k, p]."""
+def left_components(ws, X, evec, lam, mean, k, out_Yt, timer, label, nev=None):
+    """(U S)^T = W^T X - (W^T m) 1^T for the top-k eigenvectors (rows of `evec`, `nev` of them in ascending order:
+    all n after syevd, the top ones after the hand-written solver) -> out_Yt [k, p]."""
     n, p = X.shape
     with timer(label + ".topk"):
         Wt = ws.matrix(label + ".Wt", k, n)
-        _, rbias, _ = K.topk_components(evec, lam, k, mean, Wt, want_scale=False)
-    with timer(label + ".transpose"):
-        Xt = ws.matrix(label + ".Xt", p, n)
-        K.transpose(X, Xt)
-        Xt_lo = K.split_lo(Xt, out=ws.matrix(label + ".Xt_lo", p, n)) if ws.left_impl in (0, 9) else None
-    ws.gemm(Wt, Xt, out_Yt, rbias=rbias, label=label + ".left", B_lo=Xt_lo, chain=KCHAIN_LEFT, impl=ws.left_impl)
+        _, rbias, _ = K.topk_components(evec, lam, k, mean, Wt, want_scale=False, nev=nev)
+    # pixels in blocks: the transposed operand, its lo plane and the split-K partials stay bounded for any view size
+    for p0 in range(0, p, LEFT_BLOCK_PIXELS):
+        p1 = min(p, p0 + LEFT_BLOCK_PIXELS)
+        with timer(label + ".transpose"):
+            Xt = ws.matrix(label + ".Xt", p1 - p0, n)
+            K.transpose(X[:, p0:p1], Xt)
+            Xt_lo = K.split_lo(Xt, out=ws.matrix(label + ".Xt_lo", p1 - p0, n)) if ws.left_impl in (0, 9) else None
+        ws.gemm(Wt, Xt, out_Yt[:, p0:p1], rbias=rbias, label=label + ".left", B_lo=Xt_lo, chain=KCHAIN_LEFT,
+                impl=ws.left_impl)
 
 
 def chunk_components(ws, X, k, out_Yt, timer, label="chunk"):
@@ -451,13 +481,15 @@ def merge_components(ws, Yt, k, timer, label="merge"):
     if p < c:
         return merge_components_rowside(ws, Yt, k, timer, label)
     Wt, sval, rbias, rscale = gram_eig(ws, Yt, k, timer, True, label)
-    with timer(label + ".transpose"):
-        Y = ws.matrix(label + ".Y", p, c)
-        K.transpose(Yt, Y)
-        Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p, c)) if ws.left_impl in (0, 9) else None
     Ut = K.alloc_matrix(k, p, Yt.device)
-    ws.gemm(Wt, Y, Ut, rscale=rscale, rbias=rbias, label=label + ".left", B_lo=Y_lo, chain=KCHAIN_LEFT,
-            impl=ws.left_impl)
+    for p0 in range(0, p, LEFT_BLOCK_PIXELS):
+        p1 = min(p, p0 + LEFT_BLOCK_PIXELS)
+        with timer(label + ".transpose"):
+            Y = ws.matrix(label + ".Y", p1 - p0, c)
+            K.transpose(Yt[:, p0:p1], Y)
+            Y_lo = K.split_lo(Y, out=ws.matrix(label + ".Y_lo", p1 - p0, c)) if ws.left_impl in (0, 9) else None
+        ws.gemm(Wt, Y, Ut[:, p0:p1], rscale=rscale, rbias=rbias, label=label + ".left", B_lo=Y_lo, chain=KCHAIN_LEFT,
+                impl=ws.left_impl)
     with timer(label + ".transpose"):
         U = torch.empty((p, k), dtype=torch.float32, device=Yt.device)
         K.transpose(Ut, U)
@@ -663,16 +695,24 @@ def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, t
                         label = "stage2.roi"
                     mean, _ = centred_gram(ws, Xt, timer, label, out=G[len(jobs)])
                     jobs.append((slot, m, idx, Xt, mean, label))
-        with timer("stage2.chunk.syevd"):
-            # the batched solver carries ~50 ms of fixed cost on B200 (15 x 999^2: 68 ms, 2 x 999^2: 53 ms)
-            # against 12 ms per serial syevd: it pays off from 5 matrices on
-            if ws.eig_fp32 or len(jobs) < BATCHED_EIG_MIN:
-                lam = torch.stack([ws.solver.syevd(G[i], use_fp32=ws.eig_fp32) for i in range(len(jobs))])
-            else:
-                lam = ws.solver.syevd_batched(G)
+        evec, nev = G, None
+        if getattr(ws, "eig_mode", "cusolver") == "cluster" and not ws.eig_fp32 and 2 <= n <= K.EIGH_CLUSTER_NMAX:
+            # hand-written solver: only the eigenpairs the targets keep, no host round trips (csrc/eigh_cluster.cu)
+            nev = max(ks[idx] for (_, _, idx, _, _, _) in jobs)
+            with timer("stage2.chunk.eigh"):
+                lam, evec = ws.solver.eigh_topk_batched(G, nev, scratch=ws.raw("eigh.scratch", K.eigh_topk_scratch_bytes(
+                    n, G.shape[0], nev), torch.uint8))
+        else:
+            with timer("stage2.chunk.syevd"):
+                # the batched solver carries ~50 ms of fixed cost on B200 (15 x 999^2: 68 ms, 2 x 999^2: 53 ms)
+                # against 12 ms per serial syevd: it pays off from 5 matrices on
+                if ws.eig_fp32 or len(jobs) < BATCHED_EIG_MIN:
+                    lam = torch.stack([ws.solver.syevd(G[i], use_fp32=ws.eig_fp32) for i in range(len(jobs))])
+                else:
+                    lam = ws.solver.syevd_batched(G)
         for i, (slot, m, idx, Xt, mean, label) in enumerate(jobs):
             kk = ks[idx]
-            left_components(ws, Xt, G[i], lam[i], mean, kk, Yt[m][idx][slot * kk:(slot + 1) * kk], timer, label)
+            left_components(ws, Xt, evec[i], lam[i], mean, kk, Yt[m][idx][slot * kk:(slot + 1) * kk], timer, label, nev=nev)
     return Yt, ks, nsegs
 
 

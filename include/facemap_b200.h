@@ -189,6 +189,9 @@ int fm_slice_rows_i8(const float* X, int64_t ldx, int rows, int64_t ncols, int8_
                      int64_t ldq, int32_t* exps, void* stream);
 int fm_gram_assemble_i8(const int32_t* P, int ksplit, int n, int64_t ldp, const int32_t* exps, const double* mean,
                         int64_t ncols, double* G, void* stream);
+/* G += the weighted plane products of a further block of columns of the same operand (its own exps; no mean term). */
+int fm_gram_accumulate_i8(const int32_t* P, int ksplit, int n, int64_t ldp, const int32_t* exps, double* G,
+                          void* stream);
 /* The same for the row-side Gram of a wide matrix Y [n, c] centred over its columns (fm_gram_assemble_rowside):
  * G = Y Y^T - q 1^T - 1 q^T + (mu.mu) 1 1^T with q = Y mu (fm_row_dot), mu[nmu] the column means. */
 int fm_gram_assemble_i8_rowside(const int32_t* P, int ksplit, int n, int64_t ldp, const int32_t* exps,
@@ -278,6 +281,20 @@ int fm_syevd(fm_solver* s, double* G, int n, double* lam, int use_fp32, void* st
 int fm_syevdx_top(fm_solver* s, double* G, int n, int k, double* lam, void* stream);
 /* `batch` matrices stored back to back (cusolverDnXsyevBatched); lam is [batch, n]. */
 int fm_syevd_batched(fm_solver* s, double* G, int n, int batch, double* lam, void* stream);
+
+/*
+ * Hand-written eigensolver for batches of small Gram matrices (the per-chunk svdecon of facemap/process.py:229-259 in
+ * its Gram form, matlab/utils/svdecon.m:16-43): the k largest eigenpairs of `batch` symmetric n x n float64 matrices
+ * stored back to back, 2 <= n <= 1024, entirely on the device — Householder tridiagonalisation by one thread-block
+ * cluster per matrix, Sturm bisection, inverse iteration, back-transformation (csrc/eigh_cluster.cu).  G is destroyed.
+ * lam [batch, k] and W [batch, k, n] come back in ASCENDING order of eigenvalue (row k-1 = the largest): what
+ * fm_topk_components reads with nev = k.  status [batch] (int32) receives self-check flags (bit 0: neighbouring
+ * eigenvectors not orthogonal — eigenvalues too close for independent inverse iterations; bit 1: non-finite or
+ * non-unit vector); 0 = good.  `scratch` needs fm_eigh_topk_scratch_bytes(n, batch, k) bytes.  Asynchronous.
+ */
+size_t fm_eigh_topk_scratch_bytes(int n, int batch, int k);
+int fm_eigh_topk_batched(double* G, int n, int batch, int k, double* lam, double* W, void* scratch,
+                         size_t scratch_bytes, int* status, void* stream);
 
 /*
  * Top-k extraction with the reference's sign rule (sklearn/utils/extmath.py:924-982,

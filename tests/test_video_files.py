@@ -92,8 +92,9 @@ def test_run_on_video_files_matches_oracle(cuda_device, avi_files, tmp_path):
         U, Ur = d[mk][0].astype(np.float64), o[mk][0].astype(np.float64)
         assert U.shape == Ur.shape
         nrm, nrm_r = np.linalg.norm(U, axis=0), np.linalg.norm(Ur, axis=0)        # = singular values of the chunk
-        big = nrm_r > 0
-        assert (np.abs(nrm - nrm_r)[big] / nrm_r[big]).max() <= 1e-4, mk
+        # every component; the last one of a centred 192-pixel view is numerically zero, and a zero singular value
+        # comes out of a float64 Gram matrix as sqrt(n * 2^-53) ~ 1e-6 of the largest
+        assert np.all(np.abs(nrm - nrm_r) <= np.maximum(1e-4 * nrm_r, 2e-6 * nrm_r[0])), mk
         cos = np.abs((U[:, :4] * Ur[:, :4]).sum(axis=0)) / (nrm[:4] * nrm_r[:4])
         assert np.abs(cos - 1).max() < 1e-5, mk
 
@@ -183,7 +184,7 @@ class _CoarseSeekCapture:
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gop", [1, 8])
+@pytest.mark.parametrize("gop", [1, 7])      # 7: no piece boundary (multiples of 256) is a key frame
 def test_sweep_never_uses_inexact_seeks(cuda_device, gop):
     """a capture whose seeks land up to gop-1 frames early (and hide it): the decode-once cache notices at the run
     seams and stage 3's sweep is decoded sequentially instead; with exact seeks (gop 1) the cache serves the sweep"""
