@@ -61,11 +61,13 @@ def workload_config(world):
 # clocks sampling
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons of one GPU sampled DURING the timed region.  NVML from a thread
-    (pynvml; its calls release the GIL and cost microseconds) — a looping `nvidia-smi` subprocess stalls
-    the CUDA driver for 100-200 ms at a time on this platform, which showed up as outlier steps."""
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region.  NVML from a thread (pynvml; its
+    calls release the GIL) — a looping `nvidia-smi` subprocess stalls the CUDA driver for 100-200 ms at a time on this
+    platform.  Even the NVML calls contend with the driver lock that cuSOLVER's host-driven eigensolve takes for every
+    one of its ~10^4 launches (a query was seen to wait 149 ms, and the step it lands in runs 20-35 ms longer), so the
+    thread samples once a second, and the main thread adds one sample right behind the last step."""
 
-    def __init__(self, gpu_index, period_s=0.4):
+    def __init__(self, gpu_index, period_s=1.0):
         self.idx, self.period = gpu_index, period_s
         self.samples, self.stop_flag, self.thread, self.nvml = [], False, None, None
         self.call_ms = (0.0, 0.0)
@@ -83,22 +85,27 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
 
-    def _loop(self):
+    def sample(self):
         nv = self.nvml
-        while not self.stop_flag:
+        if nv is None:
+            return
+        try:
+            t0 = time.perf_counter()
+            sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+            t1 = time.perf_counter()
             try:
-                t0 = time.perf_counter()
-                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
-                t1 = time.perf_counter()
-                try:
-                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
-                except Exception:
-                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                t2 = time.perf_counter()
-                self.samples.append((t2, sm, rs))
-                self.call_ms = (max(self.call_ms[0], 1e3 * (t1 - t0)), max(self.call_ms[1], 1e3 * (t2 - t1)))
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
             except Exception:
-                pass
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            t2 = time.perf_counter()
+            self.samples.append((t2, sm, rs))
+            self.call_ms = (max(self.call_ms[0], 1e3 * (t1 - t0)), max(self.call_ms[1], 1e3 * (t2 - t1)))
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self.stop_flag:
+            self.sample()
             time.sleep(self.period)
 
     def stop(self, t0, t1):
@@ -523,6 +530,8 @@ def main():
         tm["host_ms"] = 1e3 * (time.perf_counter() - ts)
         timings.append(tm)
     ev1.record()
+    if rank == 0:
+        clocks.sample()                          # one sample for certain, right behind the last step
     barrier()
     w1 = time.perf_counter()
     gc.enable()

@@ -159,6 +159,61 @@ __global__ void __launch_bounds__(MR_THREADS) motion_ref_kernel(const MotionRefP
   }
 }
 
+// sbin == 1: the binned frame IS the frame (float32 of a byte), |difference| is an integer <= 255 and every partial sum
+// inside a leaf of numpy's pairwise tree (<= 128 elements: <= 32 640) is an integer below 2^24 — exact in float32 in
+// ANY order.  So the leaves are summed as integers straight from the bytes (8-byte loads, SAD) and only the fold of
+// the leaf sums, where the float32 roundings of the reference happen, follows the plan.  One block walks a run of
+// consecutive rows; a half-warp owns a leaf; scratch = the leaf sums only.
+__global__ void __launch_bounds__(MR_THREADS) motion_ref_u8_kernel(const MotionRefParams<float> p) {
+  float* leaf_sum = p.scratch + (size_t)blockIdx.x * p.nleaves;
+  const size_t hw = (size_t)p.H * p.W;
+  const int per_block = (p.rows + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * per_block;
+  const int r_end = min(p.rows, r_begin + per_block);
+  const int group = threadIdx.x >> 4, j = threadIdx.x & 15;
+  for (int row = r_begin; row < r_end; ++row) {
+    const int f = row + p.frame_off;
+    const uint8_t* cur = p.frames + (size_t)f * hw;
+    const uint8_t* prv = f > 0 ? p.frames + (size_t)(f - 1) * hw : p.prev_frame;
+    const bool al = ((reinterpret_cast<uintptr_t>(cur) | reinterpret_cast<uintptr_t>(prv) |
+                      reinterpret_cast<uintptr_t>(p.ormask)) & 7) == 0;
+    for (int l0 = 0; l0 < p.nleaves; l0 += MR_THREADS / 16) {      // uniform trip count: the shuffles stay convergent
+      const int l = l0 + group;
+      const int len = l < p.nleaves ? p.leaf_len[l] : 0;
+      const int lo = l < p.nleaves ? p.leaf_lo[l] : 0;
+      unsigned sum = 0;
+      for (int w0 = 8 * j; w0 < len; w0 += 128) {                  // one pass: leaves hold at most 128 elements
+        const int nb = min(8, len - w0);
+        if (nb == 8 && al && ((lo + w0) & 7) == 0) {
+          uint2 c = __ldg(reinterpret_cast<const uint2*>(cur + lo + w0));
+          uint2 q = __ldg(reinterpret_cast<const uint2*>(prv + lo + w0));
+          if (p.ormask) {
+            const uint2 m = __ldg(reinterpret_cast<const uint2*>(p.ormask + lo + w0));
+            c.x |= m.x; c.y |= m.y; q.x |= m.x; q.y |= m.y;
+          }
+          sum = __vsadu4(c.x, q.x) + __vsadu4(c.y, q.y) + sum;
+        } else {
+          for (int b = 0; b < nb; ++b) {
+            int x = cur[lo + w0 + b], y = prv[lo + w0 + b];
+            if (p.ormask) { x |= p.ormask[lo + w0 + b]; y |= p.ormask[lo + w0 + b]; }
+            sum += (unsigned)abs(x - y);
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, 16);
+      if (j == 0 && l < p.nleaves) leaf_sum[l] = (float)sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float vstack[32];
+      p.out[row] = (double)fadd_rn(0.0f, pairwise_fold_plan<float>(p.nleaves, leaf_sum, p.leaf_comb, vstack));
+    }
+    __syncthreads();
+  }
+}
+
 // Stage-1 segment means in the reference's arithmetic (process.py:77-87) for a non-power-of-two sbin: per binned
 // pixel the float64 binned values of the segment's frames are added in frame order and divided by T
 // (`imbin.mean(axis=0)` reduces the leading axis sequentially), likewise the T-1 absolute differences.
@@ -205,7 +260,8 @@ extern "C" int fm_pairwise_plan(int n, int cap, int32_t* lo, int32_t* len, uint8
 extern "C" int fm_motion_ref_scratch_bytes(int H, int W, int sbin, int nleaves, int blocks, size_t* bytes) {
   using namespace fm;
   FM_REQUIRE(H >= 1 && W >= 1 && sbin >= 1 && nleaves >= 1 && blocks >= 1 && bytes, "fm_motion_ref_scratch_bytes: bad args");
-  *bytes = (size_t)blocks * (2 * (size_t)(H / sbin) * (W / sbin) + nleaves) * (sbin == 1 ? 4 : 8);
+  // sbin 1 keeps only the leaf sums (motion_ref_u8_kernel); other bins also two rows of binned values
+  *bytes = sbin == 1 ? (size_t)blocks * nleaves * 4 : (size_t)blocks * (2 * (size_t)(H / sbin) * (W / sbin) + nleaves) * 8;
   return FM_OK;
 }
 
@@ -225,7 +281,7 @@ extern "C" int fm_motion_ref(const uint8_t* frames, int T, int H, int W, int sbi
   if (sbin == 1) {
     MotionRefParams<float> p{frames, prev_frame, ormask, T, H, W, sbin, Lyb, Lxb, rows, prev_frame ? 0 : 1,
                              leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<float*>(scratch), out};
-    motion_ref_kernel<float, false><<<grid, MR_THREADS, 0, st>>>(p);
+    motion_ref_u8_kernel<<<grid, MR_THREADS, 0, st>>>(p);
   } else {
     MotionRefParams<double> p{frames, prev_frame, ormask, T, H, W, sbin, Lyb, Lxb, rows, prev_frame ? 0 : 1,
                               leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<double*>(scratch), out};

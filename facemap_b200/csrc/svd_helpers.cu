@@ -232,8 +232,10 @@ extern "C" int fm_gather_roi(const float* X, int64_t ldx, int rows, int64_t col0
                              int x0, int x1, float* out, int64_t ldout, void* stream) {
   using namespace fm;
   const int ny = y1 - y0, nx = x1 - x0;
-  FM_REQUIRE(X && out && rows >= 0 && ny >= 1 && nx >= 1 && x1 <= Lxb && ldout >= (int64_t)ny * nx,
-             "fm_gather_roi: bad args");
+  FM_REQUIRE(X && out && rows >= 0 && ny >= 1 && nx >= 1 && y0 >= 0 && x0 >= 0 && col0 >= 0 && x1 <= Lxb &&
+                 col0 + (int64_t)y1 * Lxb <= ldx && ldout >= (int64_t)ny * nx,
+             "fm_gather_roi: rectangle rows [%d, %d) x columns [%d, %d) does not fit a view of %d columns at column %lld of "
+             "a %lld-wide operand", y0, y1, x0, x1, Lxb, (long long)col0, (long long)ldx);
   if (rows == 0) return FM_OK;
   FM_REQUIRE(rows <= 65535, "fm_gather_roi: too many rows per call (%d)", rows);
   dim3 grid((unsigned)cdiv((int64_t)ny * nx, 256), (unsigned)rows);
@@ -247,8 +249,10 @@ extern "C" int fm_gather_roi_u8(const uint8_t* X, int64_t ldx, int rows, int64_t
                                 int x0, int x1, uint8_t* out, int64_t ldout, void* stream) {
   using namespace fm;
   const int ny = y1 - y0, nx = x1 - x0;
-  FM_REQUIRE(X && out && rows >= 0 && ny >= 1 && nx >= 1 && x1 <= Lxb && ldout >= (int64_t)ny * nx,
-             "fm_gather_roi_u8: bad args");
+  FM_REQUIRE(X && out && rows >= 0 && ny >= 1 && nx >= 1 && y0 >= 0 && x0 >= 0 && col0 >= 0 && x1 <= Lxb &&
+                 col0 + (int64_t)y1 * Lxb <= ldx && ldout >= (int64_t)ny * nx,
+             "fm_gather_roi_u8: rectangle rows [%d, %d) x columns [%d, %d) does not fit a view of %d columns at column %lld "
+             "of a %lld-wide operand", y0, y1, x0, x1, Lxb, (long long)col0, (long long)ldx);
   if (rows == 0) return FM_OK;
   FM_REQUIRE(rows <= 65535, "fm_gather_roi_u8: too many rows per call (%d)", rows);
   dim3 grid((unsigned)cdiv((int64_t)ny * nx, 256), (unsigned)rows);

@@ -510,7 +510,17 @@ class Geometry:
                 yb, xb = r["yrange_bin"], r["xrange_bin"]
                 if yb.size == 0 or xb.size == 0:
                     raise FacemapB200Error("motion ROI is empty after binning")
-                self.mot_rois.append((int(r["ivid"]), int(yb[0]), int(yb[-1]) + 1, int(xb[0]), int(xb[-1]) + 1))
+                v, y0, y1, x0, x1 = int(r["ivid"]), int(yb[0]), int(yb[-1]) + 1, int(xb[0]), int(xb[-1]) + 1
+                # the reference would fail (or silently wrap) on a rectangle outside its view; here it would read
+                # device memory out of bounds — refuse it by name.  (The reproduced x-stop rule, floor(x) / sbin, can
+                # reach Lxb + 1 for a ROI touching the right border of a view whose width is no multiple of sbin.)
+                if not 0 <= v < len(self.Ly):
+                    raise FacemapB200Error(f"motion ROI {len(self.mot_rois)}: ivid {v} outside the {len(self.Ly)} views")
+                if not (0 <= y0 < y1 <= int(self.Lyb[v]) and 0 <= x0 < x1 <= int(self.Lxb[v])):
+                    raise FacemapB200Error(
+                        f"motion ROI {len(self.mot_rois)} on view {v}: binned rows [{y0}, {y1}) x columns [{x0}, {x1}) "
+                        f"outside the {int(self.Lyb[v])} x {int(self.Lxb[v])} binned view")
+                self.mot_rois.append((v, y0, y1, x0, x1))
         self.roi_npix = [(y1 - y0) * (x1 - x0) for (_, y0, y1, x0, x1) in self.mot_rois]
         self.rois_on_view = [[j for j, r in enumerate(self.mot_rois) if r[0] == v] for v in range(len(Ly))]
 
@@ -773,7 +783,7 @@ def motion_ref_blocks(npix, nleaves, sbin):
     """Persistent blocks of fm_motion_ref for one view: as many as fill the machine, fewer when the per-block
     scratch (two rows of binned values + the leaf sums, fm_motion_ref_scratch_bytes) would pass the budget —
     a 1280x1024 view at sbin 1 needs 10.5 MB per block."""
-    per_block = (2 * int(npix) + int(nleaves)) * (4 if sbin == 1 else 8)
+    per_block = int(nleaves) * 4 if sbin == 1 else (2 * int(npix) + int(nleaves)) * 8
     return int(max(8, min(MOTION_REF_BLOCKS, MOTION_REF_SCRATCH_MAX // per_block)))
 
 

@@ -174,8 +174,9 @@ def test_motion_ref_block_count_respects_scratch_budget():
     from facemap_b200 import svd
 
     assert svd.motion_ref_blocks(34080, 400, 3) == svd.MOTION_REF_BLOCKS                  # 640x480 at sbin 3: 548 KB per block
-    big = svd.motion_ref_blocks(1280 * 1024, 13000, 1)                                    # C4 at sbin 1: 10.5 MB per block
-    assert 8 <= big < svd.MOTION_REF_BLOCKS and big * (2 * 1280 * 1024 + 13000) * 4 <= svd.MOTION_REF_SCRATCH_MAX
+    assert svd.motion_ref_blocks(1280 * 1024, 13000, 1) == svd.MOTION_REF_BLOCKS          # sbin 1 keeps leaf sums only: 52 KB
+    big = svd.motion_ref_blocks(1280 * 1024 // 9, 1500, 3)                                # a 1280x1024 view at sbin 3: 2.3 MB per block
+    assert 8 <= big < svd.MOTION_REF_BLOCKS and big * (2 * (1280 * 1024 // 9) + 1500) * 8 <= svd.MOTION_REF_SCRATCH_MAX
     assert svd.motion_ref_blocks(10 ** 9, 10 ** 7, 7) == 8                                # never below 8 blocks
 
 
@@ -250,3 +251,19 @@ def test_merge_loop_follows_the_references_len_u_mot_quirk(monkeypatch):
     merged_calls.clear()
     svd.stage2_merge({"mot": [full, r0], "mov": [full, r0]}, None, 2, None, ["mot", "mov"], True, ws, t, nc=250, mot_on=True)
     assert len(merged_calls) == 4
+
+
+def test_geometry_refuses_rois_outside_their_view():
+    """a rectangle outside its binned view would make fm_gather_roi read out of bounds: refused by name"""
+    import pytest
+
+    from facemap_b200 import svd
+
+    def roi(ivid, yb, xb):
+        return {"rind": 1, "ivid": ivid, "yrange_bin": np.asarray(yb), "xrange_bin": np.asarray(xb)}
+
+    svd.Geometry([48], [64], 4, [roi(0, range(2, 12), range(3, 16))])                # touches the border: fine
+    for bad in (roi(1, range(2, 5), range(3, 6)), roi(0, range(2, 13), range(3, 6)), roi(0, range(2, 5), range(3, 17)),
+                roi(0, range(-1, 5), range(3, 6))):
+        with pytest.raises(svd.FacemapB200Error, match="motion ROI 0"):
+            svd.Geometry([48], [64], 4, [bad])

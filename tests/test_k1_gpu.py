@@ -199,7 +199,8 @@ def test_k1_painted_equals_k1_on_painted_frames(cuda_device, T, H, W, sbin, with
 
 
 @pytest.mark.parametrize("T,H,W,sbin", [(9, 61, 67, 3), (7, 144, 192, 12), (12, 140, 196, 7), (6, 50, 70, 5),
-                                        (5, 300, 310, 1), (4, 24, 32, 1), (5, 96, 128, 4), (3, 400, 600, 1)])
+                                        (5, 300, 310, 1), (4, 24, 32, 1), (5, 96, 128, 4), (3, 400, 600, 1),
+                                        (4, 251, 263, 1), (3, 5, 7, 1)])
 def test_motion_ref_matches_numpy_bitwise(cuda_device, T, H, W, sbin):
     """fm_motion_ref == the reference's `np.abs(np.diff(spatial_bin(im))).sum(-1)` (process.py:34-43, 455-460),
     bit for bit, with and without a carried previous frame and a paint mask"""
@@ -207,7 +208,7 @@ def test_motion_ref_matches_numpy_bitwise(cuda_device, T, H, W, sbin):
 
     dev = cuda_device
     frames = _video(T + 1, H, W, seed=11 * T + sbin)
-    if H * W > 200000:        # white noise: float32 sums beyond 2^24, where the summation order shows
+    if H * W > 60000:         # white noise: float32 sums beyond 2^24, where the summation order shows
         frames = np.random.RandomState(9).randint(0, 256, size=(T + 1, H, W)).astype(np.uint8)
     m = np.where(np.random.RandomState(3).rand(H, W) < 0.2, 255, 0).astype(np.uint8)
     Lyb, Lxb = H // sbin, W // sbin
@@ -239,7 +240,7 @@ def test_motion_ref_full_resolution_view_with_budgeted_blocks(cuda_device):
     frames = np.random.RandomState(5).randint(0, 256, size=(T + 1, H, W)).astype(np.uint8)
     plan = K.pairwise_plan(H * W, dev)
     blocks = svd.motion_ref_blocks(H * W, plan[0].numel(), 1)
-    assert 8 <= blocks < svd.MOTION_REF_BLOCKS
+    assert 8 <= blocks <= svd.MOTION_REF_BLOCKS
     scratch = K.motion_ref_scratch(H, W, 1, plan[0].numel(), blocks, dev)
     assert scratch.numel() <= svd.MOTION_REF_SCRATCH_MAX
     ref = np.abs(np.diff(orc.bin_frames(frames, 1, H, W), axis=0)).sum(axis=-1)
