@@ -35,7 +35,6 @@ import json
 import os
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -61,15 +60,15 @@ def workload_config(world):
 # clocks sampling
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons of one GPU sampled DURING the timed region.  NVML from a thread (pynvml; its
-    calls release the GIL) — a looping `nvidia-smi` subprocess stalls the CUDA driver for 100-200 ms at a time on this
-    platform.  Even the NVML calls contend with the driver lock that cuSOLVER's host-driven eigensolve takes for every
-    one of its ~10^4 launches (a query was seen to wait 149 ms, and the step it lands in runs 20-35 ms longer), so the
-    thread samples once a second, and the main thread adds one sample right behind the last step."""
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region, through NVML (pynvml), from the main
+    thread at step boundaries (every other step, ~1 ms per sample, inside the timed region).  A sampling THREAD is not
+    an option on this path: every NVML query contends for the driver lock that cuSOLVER's host-driven eigensolve
+    takes for each of its ~10^4 launches — queries were seen to wait 46-149 ms and the step they landed in ran 30-60 ms
+    longer (profiles/r02_summary.md); a looping `nvidia-smi` subprocess is worse still (100-200 ms driver stalls)."""
 
-    def __init__(self, gpu_index, period_s=1.0):
-        self.idx, self.period = gpu_index, period_s
-        self.samples, self.stop_flag, self.thread, self.nvml = [], False, None, None
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.samples, self.nvml = [], None
         self.call_ms = (0.0, 0.0)
 
     def start(self):
@@ -81,9 +80,6 @@ class ClockSampler:
             self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nvml = None
-            return
-        self.thread = threading.Thread(target=self._loop, daemon=True)
-        self.thread.start()
 
     def sample(self):
         nv = self.nvml
@@ -103,16 +99,9 @@ class ClockSampler:
         except Exception:
             pass
 
-    def _loop(self):
-        while not self.stop_flag:
-            self.sample()
-            time.sleep(self.period)
-
     def stop(self, t0, t1):
-        self.stop_flag = True
         if self.nvml is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
-        self.thread.join(1.0)
         nv = self.nvml
         names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
@@ -126,7 +115,8 @@ class ClockSampler:
                     if rs & bit:
                         reasons.add(k)
         return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.smax),
-                "reasons": sorted(reasons), "samples": len(sm), "how": f"NVML every {self.period} s, rank-0 GPU",
+                "reasons": sorted(reasons), "samples": len(sm),
+                "how": "NVML from the main thread after every other timed step, rank-0 GPU",
                 "nvml_call_ms_max": {"clock": round(self.call_ms[0], 2), "reasons": round(self.call_ms[1], 2)}}
 
 
@@ -509,9 +499,9 @@ def main():
 
     nwarm = max(args.warmup, 5)      # allocator pools, cuSOLVER workspaces and NCCL channels settle in ~4 passes
     clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                           # NVML handle of rank 0's GPU, opened outside the timed region
     for i in range(nwarm):
-        if i == nwarm - 1 and rank == 0:
-            clocks.start()                       # one sampler (rank 0's GPU), spawned outside the timed region
         one_step(dev_src, timing={})             # same code path as the timed steps (CUDA-event timers on)
     barrier()
     timings = []
@@ -523,15 +513,15 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     ev0.record()
-    for _ in range(args.steps):
+    for step in range(args.steps):
         tm = {}
         ts = time.perf_counter()
         one_step(dev_src, timing=tm)
         tm["host_ms"] = 1e3 * (time.perf_counter() - ts)
         timings.append(tm)
+        if rank == 0 and (step % 2 == 0 or step == args.steps - 1):
+            clocks.sample()                      # inside the timed region, between two steps
     ev1.record()
-    if rank == 0:
-        clocks.sample()                          # one sample for certain, right behind the last step
     barrier()
     w1 = time.perf_counter()
     gc.enable()
@@ -824,8 +814,15 @@ def main():
                                       for tm in timings],
             "kernels_only_frames_per_s": total_frames / ((ms_step - solver_ms) / 1e3) if ms_step > solver_ms else None,
         }
+        if world > 1:
+            time.sleep(1.0)                      # the other ranks are gone by now (they leave right after the barrier)
         sys.stdout.flush()
         print("\n" + json.dumps(line), flush=True)
+    # NCCL (with NCCL_DEBUG=INFO, which the driver may set) logs from its library destructors at process exit, after
+    # anything Python can print: leave without running them so that the JSON line stays the last line of stdout
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -177,7 +177,7 @@ def gemm_tn(A, B, C_out=None, *, rscale=None, rbias=None, ksplit=1, workspace=No
 
 
 def gemm_i8_tn(A, B, C_out=None, *, ksplit=1, workspace=None, upper_only=False):
-    """EXPERIMENTAL (fm_gemm_i8_tn): int32 C[M,N] = A[M,K] @ B[N,K]^T for uint8 / int8 operands, exact.
+    """fm_gemm_i8_tn: int32 C[M,N] = A[M,K] @ B[N,K]^T for uint8 / int8 operands, exact.
     With ksplit > 1 the int32 partials go to `workspace` [ksplit, M, ldw]."""
     for t, name in ((A, "A"), (B, "B")):
         if t.dtype not in (torch.uint8, torch.int8) or t.dim() != 2 or t.stride(1) != 1 or not t.is_cuda:
@@ -265,7 +265,7 @@ def gram_assemble_i8(P, ksplit, n, exps, mean, ncols, out=None, rowside=None):
 
 def bin_motion_planes(frames, sbin, *, prev_sum=None, q_mot=None, q_mov=None, col0=0, energy=None, rois=None,
                       roi_energy=None, last_sum=None, ormask=None):
-    """EXPERIMENTAL (fm_bin_motion_planes): K1 writing its integer results as byte planes.  q_mot / q_mov: (hi, lo)
+    """fm_bin_motion_planes: K1 writing its integer results as byte planes.  q_mot / q_mov: (hi, lo)
     pairs of uint8 [rows, >= col0 + npix] matrices sharing one row pitch (hi may be None when sbin == 1); they receive
     |S_t - S_(t-1)| and S_t as 256 * hi + lo — the frame operands of `project_i8`."""
     _need(frames, torch.uint8, "frames", 3)
@@ -312,7 +312,7 @@ def bin_motion_planes(frames, sbin, *, prev_sum=None, q_mot=None, q_mov=None, co
 
 
 def project_i8(D, Q, exps, alpha, bias, V, impl=0):
-    """EXPERIMENTAL (fm_project_i8): V[t, c] = alpha * sum_p D[t, p] U[c, p] - bias[c] on tcgen05 kind::i8, exactly.
+    """fm_project_i8: V[t, c] = alpha * sum_p D[t, p] U[c, p] - bias[c] on tcgen05 kind::i8, exactly.
     D: (hi, lo) uint8 [M, K] planes of one pitch (hi None for operands < 256); Q: the (Q0 int8, Q1, Q2 uint8) [N, K]
     digit planes and `exps` of `slice_rows_i8(U)`; bias: float64 [N] or None; V: float32 [M, >= N] row-major;
     impl: 0 = one CTA per tile, 1 = CTA pairs (cta_group::2)."""
@@ -511,7 +511,7 @@ def transpose(src, dst):
 
 
 def gather_roi_u8(X, rows, col0, Lxb, rect, out):
-    """EXPERIMENTAL (fm_gather_roi_u8): ROI columns of one uint8 plane."""
+    """fm_gather_roi_u8: ROI columns of one uint8 plane."""
     _need(X, torch.uint8, "X", 2)
     _need(out, torch.uint8, "out", 2)
     y0, y1, x0, x1 = rect

@@ -6,8 +6,9 @@ admits:
   stage 1  the 10 mean segments are dealt round-robin; their INTEGER sums are all-reduced (exact,
            order independent) and the float32 accumulation is replayed in segment order on every
            rank, so avgframe/avgmotion are bit-identical to the single-GPU result;
-  stage 2  the <= 15 SVD chunks are dealt round-robin; one all-gather collects the per-chunk
-           component blocks (U S)^T; the merge eigensolve is replicated (deterministic);
+  stage 2  the <= 15 SVD chunks are dealt in consecutive runs; every rank writes its component blocks (U S)^T at
+           their FINAL rows of the stacked buffer and one in-place all-gather fills in the others' (no staging
+           copies); the merge eigensolve is replicated (deterministic);
   stage 3  contiguous frame ranges aligned to the reference's 500-frame grid, one-frame halo, no
            communication; the projections / energies are all-gathered at the end.
 """
@@ -22,6 +23,13 @@ from . import svd
 def assign_round_robin(n_items, world):
     """item i -> rank i % world."""
     return [list(range(r, n_items, world)) for r in range(world)]
+
+
+def assign_contiguous(n_items, world):
+    """consecutive items per rank, ceil(n / world) each (the last ranks may hold fewer or none): rank r's items sit at
+    positions [r * per, (r + 1) * per) of the gathered order, so an all-gather can run in place."""
+    per = -(-n_items // world) if n_items else 0
+    return [list(range(r * per, min(n_items, (r + 1) * per))) for r in range(world)]
 
 
 def frame_ranges(N, world, align=500):
@@ -100,22 +108,48 @@ class Shard:
             sums = self.allreduce_segment_sums(local, nseg, geo.p, device, dtype=dt)
         return svd.stage1_finish(sums, nseg, geo, device)
 
+    def chunk_buffers(self, nsegs, ks, sizes, mods, fullSVD, device):
+        """Per (modality, target) the stacked component buffer [world * per * k, ld] every rank allocates alike, and
+        this rank's window on it: rows [rank * per * k, ...) are where its chunks' blocks belong."""
+        per = -(-nsegs // self.world)
+        bases, mine = {}, {}
+        for m in mods:
+            bases[m], mine[m] = [], []
+            for idx, (k, p) in enumerate(zip(ks, sizes)):
+                if idx == 0 and not fullSVD:
+                    bases[m].append(None)
+                    mine[m].append(None)
+                    continue
+                ld = max(32, svd.K.round_up(p, 32))
+                base = torch.empty((self.world * per * k, ld), dtype=torch.float32, device=device)
+                bases[m].append(base)
+                mine[m].append(base[self.rank * per * k:(self.rank + 1) * per * k, :p])
+        return bases, mine, per
+
+    def gather_in_place(self, base, rows_per_rank):
+        """all-gather of a buffer whose rows [r * rows_per_rank, (r + 1) * rows_per_rank) rank r has filled"""
+        seg = base[self.rank * rows_per_rank:(self.rank + 1) * rows_per_rank]
+        dist.all_gather_into_tensor(base, seg, group=self.group)
+        return base
+
     def stage2_chunks(self, source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer):
-        nsegs = svd.stage2_plan(source.nframes)[1]
-        mine = assign_round_robin(nsegs, self.world)[self.rank]
-        Yt, ks, _ = svd.stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer, chunks=mine)
+        nt0, nsegs, nc, _ = svd.stage2_plan(source.nframes)
+        mine = assign_contiguous(nsegs, self.world)[self.rank]
+        sizes = [geo.p] + geo.roi_npix
+        ks = [min(nc, s) for s in sizes]
+        bases, windows, per = self.chunk_buffers(nsegs, ks, sizes, mods, fullSVD, device)
+        # every rank's blocks land at their final rows; the gather then needs no padding, reordering or copy
+        svd.stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer, chunks=mine, Yt_out=windows)
         full = {}
         with timer("stage2.allgather"):
             for m in mods:
                 full[m] = []
-                for idx, blk in enumerate(Yt[m]):
-                    if blk is None:
+                for idx, base in enumerate(bases[m]):
+                    if base is None:
                         full[m].append(None)
                         continue
-                    g = self.gather_chunk_blocks(blk, ks[idx], nsegs)
-                    out = svd.K.alloc_matrix(g.shape[0], g.shape[1], device)
-                    out.copy_(g)
-                    full[m].append(out)
+                    self.gather_in_place(base, per * ks[idx])
+                    full[m].append(base[:nsegs * ks[idx], :sizes[idx]])
         return full, ks, nsegs
 
     def gather_stage3(self, V, E, E_roi, N, mods, timer):

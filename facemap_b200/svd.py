@@ -528,14 +528,14 @@ class Geometry:
 def access_plan(source, dist=None):
     """(priority ranges, home range) of one pass for this rank: the stage-1 segments and stage-2
     chunks it will read, in order, and the frame range it sweeps in stage 3 (with its halo)."""
-    from .parallel import assign_round_robin, frame_ranges
+    from .parallel import assign_contiguous, assign_round_robin, frame_ranges
 
     N = source.nframes
     rank, world = (0, 1) if dist is None else (dist.rank, dist.world)
     nt1, tf1 = stage1_plan(N, source.block_frames)
     nt2, nsegs, _, tf2 = stage2_plan(N)
     pri = [(int(tf1[i]), int(tf1[i]) + nt1) for i in assign_round_robin(len(tf1), world)[rank]]
-    pri += [(int(tf2[i]), int(tf2[i]) + nt2) for i in assign_round_robin(nsegs, world)[rank]]
+    pri += [(int(tf2[i]), int(tf2[i]) + nt2) for i in assign_contiguous(nsegs, world)[rank]]
     f0, f1 = frame_ranges(N, world)[rank]
     return pri, (max(0, f0 - 1), f1)
 
@@ -658,7 +658,7 @@ def _bin_chunk(frames, geo, avgframe, avgmotion, mods, X, prev=None, last=None, 
 
 
 def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, timer, chunks=None,
-                  x_budget_bytes=24 << 30):
+                  x_budget_bytes=24 << 30, Yt_out=None):
     """Per-chunk components.  Returns Yt[m][idx] = [n_chunks * k, p_idx] stacked blocks (idx 0 = full
     frame, 1+j = motion ROI j) for the chunk indices in `chunks` (default all).
 
@@ -671,8 +671,10 @@ def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, t
     todo = list(range(nsegs)) if chunks is None else list(chunks)
     sizes = [geo.p] + geo.roi_npix
     ks = [min(nc, s) for s in sizes]
-    Yt = {m: [K.alloc_matrix(len(todo) * ks[i], sizes[i], device) if (i > 0 or fullSVD) else None
-              for i in range(1 + nroi)] for m in mods}
+    # Yt_out: the caller's buffers for the blocks (multi-GPU: windows on the gathered buffer, parallel.Shard)
+    Yt = Yt_out if Yt_out is not None else {
+        m: [K.alloc_matrix(len(todo) * ks[i], sizes[i], device) if (i > 0 or fullSVD) else None
+            for i in range(1 + nroi)] for m in mods}
     n = nt0 - 1
     if n < 1 or not todo:
         return Yt, ks, nsegs

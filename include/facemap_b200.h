@@ -96,7 +96,7 @@ int fm_bin_motion_painted(const uint8_t* frames, int T, int H, int W, int sbin,
                           const uint8_t* ormask, void* stream);
 
 /*
- * EXPERIMENTAL (not yet run on a GPU): K1 writing its integer results instead of the float32 operands — the motion
+ * K1 writing its integer results instead of the float32 operands (the stage-3 default) — the motion
  * energy |S_t - S_(t-1)| (q_mot_*) and / or the block sum S_t (q_mov_*) of every binned pixel (facemap/process.py:34-43,
  * 455-461 before the division and the subtraction of the average) as two uint8 planes, value = 256 * hi + lo, rows and
  * columns like x_mot / x_mov of fm_bin_motion, row pitch ldq bytes.  These are the frame operands of fm_project_i8.
@@ -165,7 +165,7 @@ int fm_gemm_tn(const float* A, int64_t lda, const float* A_lo, int64_t lda_lo, c
                int ksplit, float* workspace, int64_t ldw, int upper_only, int impl, void* stream);
 
 /*
- * EXPERIMENTAL (compiles for sm_100a, not yet run on a GPU; nothing in the product path calls it):
+ * The digit-plane product of the Gram matrices (svd.i8_gram, the default):
  * C[M,N] (int32) = A[M,K] . B[N,K]^T with 8-bit operands, K-contiguous, on tcgen05.mma kind::i8 with exact int32
  * accumulation.  a_signed / b_signed: 0 = uint8, 1 = int8.  Row pitches in bytes, multiples of 16; 16-byte aligned
  * bases.  ksplit > 1 writes raw int32 partials to workspace[ksplit, M, ldw] (sum them in int64); at most 32 768 K
@@ -320,7 +320,7 @@ int fm_transpose(const float* in, int64_t ldin, int rows, int cols, float* out, 
  * X[r, col0 + y*Lxb + x] for the binned rectangle. */
 int fm_gather_roi(const float* X, int64_t ldx, int rows, int64_t col0, int Lxb,
                   int y0, int y1, int x0, int x1, float* out, int64_t ldout, void* stream);
-/* EXPERIMENTAL (not yet run on a GPU): the same gather on one byte plane of fm_bin_motion_planes (pitches in bytes). */
+/* The same gather on one byte plane of fm_bin_motion_planes (pitches in bytes). */
 int fm_gather_roi_u8(const uint8_t* X, int64_t ldx, int rows, int64_t col0, int Lxb,
                      int y0, int y1, int x0, int x1, uint8_t* out, int64_t ldout, void* stream);
 

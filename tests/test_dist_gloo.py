@@ -18,6 +18,10 @@ def test_assignments_cover_everything_once():
         for n in (1, 2, 10, 15):
             got = sorted(i for r in parallel.assign_round_robin(n, world) for i in r)
             assert got == list(range(n))
+            runs = parallel.assign_contiguous(n, world)
+            assert [i for r in runs for i in r] == list(range(n)) and len(runs) == world
+            per = -(-n // world)
+            assert all(r == list(range(q * per, min(n, (q + 1) * per))) for q, r in enumerate(runs))
         for N in (1, 499, 500, 501, 2300, 100000, 800000):
             rg = parallel.frame_ranges(N, world)
             assert rg[0][0] == 0 and rg[-1][1] == N and len(rg) == world
@@ -56,6 +60,18 @@ def _worker(rank, world, port, out):
         loc = torch.from_numpy(np.concatenate([blocks[c * k:(c + 1) * k] for c in mine], axis=0)) if mine \
             else torch.zeros((0, cols))
         ok2 = np.array_equal(sh.gather_chunk_blocks(loc, k, nsegs).numpy(), blocks)
+        # the product's form: consecutive chunks per rank, written at their final rows, gathered in place
+        ks, sizes = [k, 2], [cols, 5]
+        bases, windows, per = sh.chunk_buffers(nsegs, ks, sizes, ["mot"], True, torch.device("cpu"))
+        blocks_roi = rng.rand(nsegs * 2, 5).astype(np.float32)
+        mine_c = parallel.assign_contiguous(nsegs, world)[rank]
+        for slot, c in enumerate(mine_c):
+            windows["mot"][0][slot * k:(slot + 1) * k] = torch.from_numpy(blocks[c * k:(c + 1) * k])
+            windows["mot"][1][slot * 2:(slot + 1) * 2] = torch.from_numpy(blocks_roi[c * 2:(c + 1) * 2])
+        g0 = sh.gather_in_place(bases["mot"][0], per * k)[:nsegs * k, :cols]
+        g1 = sh.gather_in_place(bases["mot"][1], per * 2)[:nsegs * 2, :5]
+        ok2 = ok2 and np.array_equal(g0.numpy(), blocks) and np.array_equal(g1.numpy(), blocks_roi) \
+            and g0.stride(0) % 32 == 0
         # stage-3 row gather
         N = 2300
         rows = rng.rand(N, 5).astype(np.float32)
