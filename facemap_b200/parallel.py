@@ -54,6 +54,20 @@ class Shard:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return bool(t.item())
 
+    def broadcast_merge(self, Ut, s, src):
+        """masks (U^T [k, p]: a view of a row-padded buffer, kernels.alloc_matrix) and singular values of one merged
+        target from the rank that solved it; the padded storage travels as it is"""
+        whole = Ut if Ut.is_contiguous() else Ut._base
+        if whole is not None and whole.is_contiguous() and whole.data_ptr() == Ut.data_ptr():
+            dist.broadcast(whole, src=src, group=self.group)
+        else:                                                  # some other kind of view: through a packed copy
+            tmp = Ut.contiguous()
+            dist.broadcast(tmp, src=src, group=self.group)
+            if self.rank != src:
+                Ut.copy_(tmp)
+        dist.broadcast(s, src=src, group=self.group)
+        return Ut, s
+
     # ---- collectives on plain tensors (device agnostic: used by the gloo CPU tests too) ----
     def allreduce_segment_sums(self, local, nseg, p, device, dtype=torch.int64):
         """local: {segment index: (tsum_bin [p], tsum_adiff [p], T)} for the segments this rank computed -> the

@@ -256,7 +256,8 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
             s3.start_early()
         if geo.p > svd.LEFT_BLOCK_PIXELS:
             ws.release()               # large views: the chunk phase's buffers must not add to the merge's
-        masks = svd.stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, nc=svd.stage2_plan(N)[2], mot_on=bool(motSVD))
+        masks = svd.stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, nc=svd.stage2_plan(N)[2], mot_on=bool(motSVD),
+                                 shard=dist if (dist is not None and dist.world > 1) else None)
         del Yt
         if geo.p > svd.LEFT_BLOCK_PIXELS:
             ws.release()

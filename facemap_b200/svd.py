@@ -728,9 +728,53 @@ def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, t
     return Yt, ks, nsegs
 
 
-def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS, nc=None, mot_on=True):
+def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS, nc=None, mot_on=True, shard=None):
     """Second-level SVD (process.py:264-295).  Returns per modality lists Ut, U, and Sv (the
-    singular values of the LAST target processed, quirk Q3)."""
+    singular values of the LAST target processed, quirk Q3).
+    shard (parallel.Shard, several ranks): every rank holds all stacked chunk components after the all-gather, and
+    the merges of different targets (modalities x full frame / ROIs) are independent, so they are dealt across the
+    ranks instead of replicated — heaviest first — and every result is broadcast by its owner (deterministic: the
+    same bits as the replicated solve).  With ONE target (motion SVD of the full frame only) there is nothing to deal
+    and every rank solves it."""
+    # which targets get merged, and who solves them
+    todo = []
+    for m in mods:
+        for idx, Y in enumerate(Yt[m]):
+            if Y is not None and nsegs > 1 and idx < (1 if mot_on else 0) + (len(Yt[m]) - 1):
+                todo.append((m, idx))
+    owner = {}
+    world = 1 if shard is None else shard.world
+    if world > 1 and len(todo) > 1:
+        load = [0.0] * world
+        for t in sorted(todo, key=lambda t: -float(min(Yt[t[0]][t[1]].shape)) ** 3):     # eigensolve cost ~ n^3
+            r = min(range(world), key=lambda q: load[q])
+            owner[t] = r
+            load[r] += float(min(Yt[t[0]][t[1]].shape)) ** 3
+    # the solves this rank owns come first (cuSOLVER blocks the host, and a broadcast waiting in the stream would block
+    # the solves queued behind it), the broadcasts of all dealt targets follow in target order
+    solved = {}
+    for (m, idx) in todo:
+        src = owner.get((m, idx))
+        if src is None or src == shard.rank:
+            Y = Yt[m][idx]
+            solved[(m, idx)] = merge_components(ws, Y, min(ncomps, Y.shape[1] - 1), timer,
+                                                "stage2.merge" if idx == 0 else "stage2.roi_merge")
+    for (m, idx) in todo:
+        src = owner.get((m, idx))
+        if src is None:
+            continue
+        Y = Yt[m][idx]
+        k, p_idx = min(ncomps, Y.shape[1] - 1), Y.shape[1]
+        if src == shard.rank:
+            Ut, U, sv_t = solved[(m, idx)]
+        else:
+            Ut, U, sv_t = K.alloc_matrix(k, p_idx, ws.device), None, torch.empty(k, dtype=torch.float32, device=ws.device)
+        with timer("stage2.merge.bcast"):
+            Ut, sv_t = shard.broadcast_merge(Ut, sv_t, src)
+        if U is None:
+            U = torch.empty((p_idx, k), dtype=torch.float32, device=ws.device)
+            K.transpose(Ut, U)
+        solved[(m, idx)] = (Ut, U, sv_t)
     out = {}
     for m in mods:
         Uts, Us = [], []
@@ -744,11 +788,8 @@ def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS, nc
             # quirk Q8: the reference's merge loop runs over range(len(U_mot)) and indexes both lists with it
             # (process.py:264-295); with the motion SVD off, U_mot holds only the ROI placeholders, so the movie targets
             # from that position on (all of them without ROIs, the last ROI otherwise) keep their stacked chunk blocks
-            merged = idx < (1 if mot_on else 0) + (len(Yt[m]) - 1)
-            if nsegs > 1 and merged:
-                k = min(ncomps, p_idx - 1)
-                Ut, U, s = merge_components(ws, Y, k, timer, "stage2.merge" if idx == 0 else "stage2.roi_merge")
-                sv = s
+            if (m, idx) in solved:
+                Ut, U, sv = solved[(m, idx)]
             else:                               # quirk Q6 / Q8: not merged -> the chunks' U S as they are, Sv stays zero
                 Ut = Y
                 # the reference's full-frame buffer is nsegs * nc wide and only cut to its filled columns inside

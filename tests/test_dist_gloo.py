@@ -93,7 +93,19 @@ def _worker(rank, world, port, out):
         ok5 = (np.array_equal(sh.gather_rows(torch.from_numpy(pup[a:b]), ranges).numpy(), pup, equal_nan=True)
                and np.array_equal(sh.gather_rows(torch.from_numpy(run[a:b]), ranges).numpy(), run)
                and np.array_equal(sh.gather_rows(torch.from_numpy(eref[a:b]), ranges).numpy(), eref))
-        out[rank] = (ok1, ok2, ok3, ok4, ok5)
+        # masks of a merged target from the rank that solved it: a row-padded view (kernels.alloc_matrix layout)
+        k_, p_ = 5, 37
+        buf = torch.zeros((k_, 64))
+        Ut = buf[:, :p_]
+        sv = torch.zeros(k_)
+        want_U, want_s = rng.rand(k_, p_).astype(np.float32), rng.rand(k_).astype(np.float32)
+        src = world - 1
+        if rank == src:
+            Ut.copy_(torch.from_numpy(want_U))
+            sv.copy_(torch.from_numpy(want_s))
+        Ut2, sv2 = sh.broadcast_merge(Ut, sv, src)
+        ok6 = np.array_equal(Ut2.numpy(), want_U) and np.array_equal(sv2.numpy(), want_s) and Ut2.data_ptr() == buf.data_ptr()
+        out[rank] = (ok1, ok2, ok3, ok4, ok5, ok6)
     finally:
         dist.destroy_process_group()
 
