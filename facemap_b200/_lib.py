@@ -53,11 +53,14 @@ SIGNATURES = {
     "fm_pairwise_plan": (_I, [_I, _I, _P, _P, _P]),
     "fm_motion_ref_scratch_bytes": (_I, [_I, _I, _I, _I, _I, C.POINTER(C.c_size_t)]),
     "fm_motion_ref": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P]),
+    "fm_motion_ref_planes": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _L, _L, _P, _P]),
     "fm_mean_ref": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "fm_mean_update": (_I, [_P, _P, _L, _I, _I, _I, _P]),
     "fm_gemm_tn": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _I, _P, _L, _I, _I, _P]),
     "fm_gemm_i8_tn": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _L, _I, _P, _L, _I, _P]),
     "fm_project_i8": (_I, [_P, _P, _L, _P, _P, _P, _L, _P, _I, _I, _I, C.c_double, _P, _P, _L, _I, _P]),
+    "fm_project_i8_blocked": (_I, [_P, _P, _L, _P, _P, _P, _L, _L, _P, _I, _I, _I, C.c_double, _P, _P, _L, _I, _P]),
+    "fm_retile_u8": (_I, [_P, _L, _I, _L, _P, _L, _L, _P]),
     "fm_bin_motion_planes": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, C.POINTER(Rois), _P, _P, _P, _P]),
     "fm_slice_rows_i8": (_I, [_P, _L, _I, _L, _P, _P, _P, _L, _P, _P]),
     "fm_gram_assemble_i8": (_I, [_P, _I, _I, _L, _P, _P, _L, _P, _P]),

@@ -52,6 +52,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 3-D form: (byte inside a K block, row, K block) — the K-blocked operand layout [K / kb][rows][kb], of which the plain
+// row-major matrix is the one-block case
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -177,6 +185,33 @@ static int make_map_u8(CUtensorMap* map, const uint8_t* base, int64_t ld, int ro
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(u8) failed with CUresult %d (base %p ld %lld rows %d K %d)", (int)r, base,
               (long long)ld, rows, K);
+    return FM_ERR_CUDA;
+  }
+  return FM_OK;
+}
+
+// K-blocked operand: element (row, k) at base + (k / kb) * block_stride + row * kb + k % kb.  kb == 0 describes the
+// plain row-major matrix of pitch `ld` (one block as wide as K).  Rows past `rows` and bytes past a block's end read
+// as zeros (TMA out-of-bounds fill); bytes between K and the end of the last block must BE zeros in one operand.
+static int make_map_u8_3d(CUtensorMap* map, const uint8_t* base, int64_t ld, int64_t kb, int64_t block_stride, int rows,
+                          int K, int box_rows) {
+  auto enc = encoder();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable (driver too old?)");
+    return FM_ERR_CUDA;
+  }
+  const bool blocked = kb > 0;
+  const int64_t nblk = blocked ? (K + kb - 1) / kb : 1;
+  cuuint64_t gdim[3] = {(cuuint64_t)(blocked ? kb : K), (cuuint64_t)rows, (cuuint64_t)nblk};
+  cuuint64_t gstride[2] = {(cuuint64_t)(blocked ? kb : ld), (cuuint64_t)(blocked ? block_stride : (int64_t)rows * ld)};
+  cuuint32_t box[3] = {(cuuint32_t)BKB, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(u8, 3-D) failed with CUresult %d (base %p ld %lld kb %lld block stride %lld rows %d K %d)",
+              (int)r, base, (long long)ld, (long long)kb, (long long)block_stride, rows, K);
     return FM_ERR_CUDA;
   }
   return FM_OK;

@@ -29,6 +29,11 @@ struct MotionRefParams {
   int nleaves;
   F* scratch;                  // [grid, 2 * npix + nleaves]: |differences|, previous binned frame, leaf sums
   double* out;                 // [rows]
+  // sbin == 1 only (motion_ref_u8_kernel<true>): the |difference| bytes as the stage-3 operand plane and the exact
+  // integer energy — what K1 would produce in a pass of its own
+  uint8_t* plane;              // [rows, ldq], written at columns [col0, col0 + H * W)
+  int64_t ldq, col0;
+  unsigned long long* energy;  // [rows], += sum of |differences|
 };
 
 // the reference's binned value of one pixel block (process.py:34-43)
@@ -164,7 +169,9 @@ __global__ void __launch_bounds__(MR_THREADS) motion_ref_kernel(const MotionRefP
 // ANY order.  So the leaves are summed as integers straight from the bytes (8-byte loads, SAD) and only the fold of
 // the leaf sums, where the float32 roundings of the reference happen, follows the plan.  One block walks a run of
 // consecutive rows; a half-warp owns a leaf; scratch = the leaf sums only.
+template <bool PLANE>
 __global__ void __launch_bounds__(MR_THREADS) motion_ref_u8_kernel(const MotionRefParams<float> p) {
+  __shared__ unsigned long long s_energy;
   float* leaf_sum = p.scratch + (size_t)blockIdx.x * p.nleaves;
   const size_t hw = (size_t)p.H * p.W;
   const int per_block = (p.rows + gridDim.x - 1) / gridDim.x;
@@ -177,33 +184,69 @@ __global__ void __launch_bounds__(MR_THREADS) motion_ref_u8_kernel(const MotionR
     const uint8_t* prv = f > 0 ? p.frames + (size_t)(f - 1) * hw : p.prev_frame;
     const bool al = ((reinterpret_cast<uintptr_t>(cur) | reinterpret_cast<uintptr_t>(prv) |
                       reinterpret_cast<uintptr_t>(p.ormask)) & 7) == 0;
-    for (int l0 = 0; l0 < p.nleaves; l0 += MR_THREADS / 16) {      // uniform trip count: the shuffles stay convergent
-      const int l = l0 + group;
-      const int len = l < p.nleaves ? p.leaf_len[l] : 0;
-      const int lo = l < p.nleaves ? p.leaf_lo[l] : 0;
-      unsigned sum = 0;
-      for (int w0 = 8 * j; w0 < len; w0 += 128) {                  // one pass: leaves hold at most 128 elements
-        const int nb = min(8, len - w0);
-        if (nb == 8 && al && ((lo + w0) & 7) == 0) {
-          uint2 c = __ldg(reinterpret_cast<const uint2*>(cur + lo + w0));
-          uint2 q = __ldg(reinterpret_cast<const uint2*>(prv + lo + w0));
-          if (p.ormask) {
-            const uint2 m = __ldg(reinterpret_cast<const uint2*>(p.ormask + lo + w0));
-            c.x |= m.x; c.y |= m.y; q.x |= m.x; q.y |= m.y;
-          }
-          sum = __vsadu4(c.x, q.x) + __vsadu4(c.y, q.y) + sum;
-        } else {
-          for (int b = 0; b < nb; ++b) {
-            int x = cur[lo + w0 + b], y = prv[lo + w0 + b];
-            if (p.ormask) { x |= p.ormask[lo + w0 + b]; y |= p.ormask[lo + w0 + b]; }
-            sum += (unsigned)abs(x - y);
+    uint8_t* prow = PLANE ? p.plane + (size_t)row * p.ldq + p.col0 : nullptr;
+    const bool pal = PLANE && ((reinterpret_cast<uintptr_t>(prow) & 7) == 0);
+    unsigned long long esum = 0;
+    if (PLANE && threadIdx.x == 0) s_energy = 0;
+    constexpr int GROUPS = MR_THREADS / 16, UNR = 4;                // four leaves per half-warp in flight
+    for (int l0 = 0; l0 < p.nleaves; l0 += GROUPS * UNR) {         // uniform trip count: the shuffles stay convergent
+      unsigned sum[UNR];
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int l = l0 + q * GROUPS + group;
+        const int len = l < p.nleaves ? p.leaf_len[l] : 0;
+        const int lo = l < p.nleaves ? p.leaf_lo[l] : 0;
+        sum[q] = 0;
+        for (int w0 = 8 * j; w0 < len; w0 += 128) {                // one pass: leaves hold at most 128 elements
+          const int nb = min(8, len - w0);
+          if (nb == 8 && al && ((lo + w0) & 7) == 0) {
+            uint2 c = __ldg(reinterpret_cast<const uint2*>(cur + lo + w0));
+            uint2 qv = __ldg(reinterpret_cast<const uint2*>(prv + lo + w0));
+            if (p.ormask) {
+              const uint2 m = __ldg(reinterpret_cast<const uint2*>(p.ormask + lo + w0));
+              c.x |= m.x; c.y |= m.y; qv.x |= m.x; qv.y |= m.y;
+            }
+            sum[q] = __vsadu4(c.x, qv.x) + __vsadu4(c.y, qv.y) + sum[q];
+            if (PLANE) {
+              const uint2 dv = make_uint2(__vabsdiffu4(c.x, qv.x), __vabsdiffu4(c.y, qv.y));
+              if (pal) {
+                *reinterpret_cast<uint2*>(prow + lo + w0) = dv;
+              } else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                  prow[lo + w0 + b] = (uint8_t)(dv.x >> (8 * b));
+                  prow[lo + w0 + 4 + b] = (uint8_t)(dv.y >> (8 * b));
+                }
+              }
+            }
+          } else {
+            for (int b = 0; b < nb; ++b) {
+              int x = cur[lo + w0 + b], y = prv[lo + w0 + b];
+              if (p.ormask) { x |= p.ormask[lo + w0 + b]; y |= p.ormask[lo + w0 + b]; }
+              sum[q] += (unsigned)abs(x - y);
+              if (PLANE) prow[lo + w0 + b] = (uint8_t)abs(x - y);
+            }
           }
         }
       }
       __syncwarp();
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, 16);
-      if (j == 0 && l < p.nleaves) leaf_sum[l] = (float)sum;
+      for (int q = 0; q < UNR; ++q) {
+        unsigned v = sum[q];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, 16);
+        const int l = l0 + q * GROUPS + group;
+        if (j == 0 && l < p.nleaves) {
+          leaf_sum[l] = (float)v;
+          esum += v;
+        }
+      }
+    }
+    if (PLANE && p.energy) {                                       // exact integer energy of the row (K1's)
+      __syncthreads();
+      if (esum) atomicAdd(&s_energy, esum);
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(p.energy + row, s_energy);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -280,17 +323,42 @@ extern "C" int fm_motion_ref(const uint8_t* frames, int T, int H, int W, int sbi
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (sbin == 1) {
     MotionRefParams<float> p{frames, prev_frame, ormask, T, H, W, sbin, Lyb, Lxb, rows, prev_frame ? 0 : 1,
-                             leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<float*>(scratch), out};
-    motion_ref_u8_kernel<<<grid, MR_THREADS, 0, st>>>(p);
+                             leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<float*>(scratch), out,
+                             nullptr, 0, 0, nullptr};
+    motion_ref_u8_kernel<false><<<grid, MR_THREADS, 0, st>>>(p);
   } else {
     MotionRefParams<double> p{frames, prev_frame, ormask, T, H, W, sbin, Lyb, Lxb, rows, prev_frame ? 0 : 1,
-                              leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<double*>(scratch), out};
+                              leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<double*>(scratch), out,
+                              nullptr, 0, 0, nullptr};
     const bool aligned = sbin >= 3 && W % 4 == 0 &&
                          ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(prev_frame) |
                            reinterpret_cast<uintptr_t>(ormask)) % 4 == 0);
     if (aligned) motion_ref_kernel<double, true><<<grid, MR_THREADS, 0, st>>>(p);
     else motion_ref_kernel<double, false><<<grid, MR_THREADS, 0, st>>>(p);
   }
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}
+
+
+// sbin == 1, one pass for everything stage 3 needs of a view: the reference-arithmetic motion sums (as fm_motion_ref), the
+// |difference| bytes as the projection's operand plane (what fm_bin_motion_planes writes at sbin 1) and the exact integer
+// energy.  Replaces K1 + fm_motion_ref (two passes over the frames) on large full-resolution views (BASELINE configs[3]).
+extern "C" int fm_motion_ref_planes(const uint8_t* frames, int T, int H, int W, const uint8_t* prev_frame,
+                                    const uint8_t* ormask, const int32_t* leaf_lo, const int32_t* leaf_len,
+                                    const uint8_t* leaf_comb, int nleaves, void* scratch, int blocks, double* out,
+                                    uint8_t* plane, int64_t ldq, int64_t col0, uint64_t* energy, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(frames && leaf_lo && leaf_len && leaf_comb && scratch && out && plane && T >= 1 && H >= 1 && W >= 1 &&
+                 nleaves >= 1 && blocks >= 1 && col0 >= 0 && ldq >= col0 + (int64_t)H * W,
+             "fm_motion_ref_planes: bad args");
+  const int rows = prev_frame ? T : T - 1;
+  if (rows == 0) return FM_OK;
+  const int grid = rows < blocks ? rows : blocks;
+  MotionRefParams<float> p{frames, prev_frame, ormask, T, H, W, 1, H, W, rows, prev_frame ? 0 : 1,
+                           leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<float*>(scratch), out,
+                           plane, ldq, col0, reinterpret_cast<unsigned long long*>(energy)};
+  motion_ref_u8_kernel<true><<<grid, MR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   FM_LAUNCH_CHECK();
   return FM_OK;
 }

@@ -55,6 +55,7 @@ struct Params {
   const double* bias;
   double alpha;
   uint32_t idesc_s8, idesc_u8;           // B operand signed (digit 0) / unsigned (digits 1, 2)
+  int kb_shift;                          // log2 of the K-block width of the operand layout (31: plain row-major matrices)
 };
 
 #define FM_I8_TMEM_LD_X8(taddr, r)                                                                       \
@@ -169,11 +170,12 @@ project_i8_kernel(const __grid_constant__ CUtensorMap tmD0, const __grid_constan
         const uint32_t stage = smem_base + s * C::STAGE_BYTES;
         const uint32_t qbase = stage + ND * BM * BKB;
         mbar_expect_tx(full_bar(s), (uint32_t)C::STAGE_BYTES);
-        tma_load_2d(stage, &tmD0, full_bar(s), i * BKB, m0);
-        if constexpr (ND == 2) tma_load_2d(stage + BM * BKB, &tmD1, full_bar(s), i * BKB, m0);
-        tma_load_2d(qbase, &tmQ0, full_bar(s), i * BKB, n0);
-        tma_load_2d(qbase + BN * BKB, &tmQ1, full_bar(s), i * BKB, n0);
-        tma_load_2d(qbase + 2 * BN * BKB, &tmQ2, full_bar(s), i * BKB, n0);
+        const int kblk = (i * BKB) >> p.kb_shift, kin = (i * BKB) - (kblk << p.kb_shift);
+        tma_load_3d(stage, &tmD0, full_bar(s), kin, m0, kblk);
+        if constexpr (ND == 2) tma_load_3d(stage + BM * BKB, &tmD1, full_bar(s), kin, m0, kblk);
+        tma_load_3d(qbase, &tmQ0, full_bar(s), kin, n0, kblk);
+        tma_load_3d(qbase + BN * BKB, &tmQ1, full_bar(s), kin, n0, kblk);
+        tma_load_3d(qbase + 2 * BN * BKB, &tmQ2, full_bar(s), kin, n0, kblk);
       }
     }
   } else if (warp == 1) {
@@ -322,11 +324,12 @@ project_i8_pair_kernel(const __grid_constant__ CUtensorMap tmD0, const __grid_co
         const uint32_t qbase = stage + ND * BM * BKB;
         const int nq = n0 + (int)rank * QROWS;
         mbar_expect_tx(full_bar(s), (uint32_t)C::STAGE_BYTES);
-        tma_load_2d(stage, &tmD0, full_bar(s), i * BKB, m0);
-        if constexpr (ND == 2) tma_load_2d(stage + BM * BKB, &tmD1, full_bar(s), i * BKB, m0);
-        tma_load_2d(qbase, &tmQ0, full_bar(s), i * BKB, nq);
-        tma_load_2d(qbase + QROWS * BKB, &tmQ1, full_bar(s), i * BKB, nq);
-        tma_load_2d(qbase + 2 * QROWS * BKB, &tmQ2, full_bar(s), i * BKB, nq);
+        const int kblk = (i * BKB) >> p.kb_shift, kin = (i * BKB) - (kblk << p.kb_shift);
+        tma_load_3d(stage, &tmD0, full_bar(s), kin, m0, kblk);
+        if constexpr (ND == 2) tma_load_3d(stage + BM * BKB, &tmD1, full_bar(s), kin, m0, kblk);
+        tma_load_3d(qbase, &tmQ0, full_bar(s), kin, nq, kblk);
+        tma_load_3d(qbase + QROWS * BKB, &tmQ1, full_bar(s), kin, nq, kblk);
+        tma_load_3d(qbase + 2 * QROWS * BKB, &tmQ2, full_bar(s), kin, nq, kblk);
       }
     }
   } else if (warp == 1) {
@@ -399,20 +402,25 @@ project_i8_pair_kernel(const __grid_constant__ CUtensorMap tmD0, const __grid_co
   }
 }
 
+// kb == 0: plain row-major operands of pitch ldd / ldq; kb > 0 (a power of two): K-blocked operands, ldd / ldq are
+// then the block strides
 template <int ND>
 static int launch(const uint8_t* D_hi, const uint8_t* D_lo, int64_t ldd, const int8_t* Q0, const uint8_t* Q1,
-                  const uint8_t* Q2, int64_t ldq, Params p, int impl, cudaStream_t st) {
+                  const uint8_t* Q2, int64_t ldq, Params p, int impl, cudaStream_t st, int64_t kb = 0) {
   const bool pair = impl == 1;
   CUtensorMap td0, td1, tq0, tq1, tq2;
   int rc;
   // plane 0 is the most significant one; a pair CTA stages half of every digit tile
   const int qrows = pair ? BN / 2 : BN;
-  if ((rc = make_map_u8(&td0, ND == 2 ? D_hi : D_lo, ldd, p.M, p.K, BM)) != FM_OK) return rc;
+  p.kb_shift = 31;
+  if (kb > 0)
+    for (p.kb_shift = 0; ((int64_t)1 << p.kb_shift) < kb; ++p.kb_shift) {}
+  if ((rc = make_map_u8_3d(&td0, ND == 2 ? D_hi : D_lo, ldd, kb, ldd, p.M, p.K, BM)) != FM_OK) return rc;
   td1 = td0;
-  if (ND == 2 && (rc = make_map_u8(&td1, D_lo, ldd, p.M, p.K, BM)) != FM_OK) return rc;
-  if ((rc = make_map_u8(&tq0, reinterpret_cast<const uint8_t*>(Q0), ldq, p.N, p.K, qrows)) != FM_OK) return rc;
-  if ((rc = make_map_u8(&tq1, Q1, ldq, p.N, p.K, qrows)) != FM_OK) return rc;
-  if ((rc = make_map_u8(&tq2, Q2, ldq, p.N, p.K, qrows)) != FM_OK) return rc;
+  if (ND == 2 && (rc = make_map_u8_3d(&td1, D_lo, ldd, kb, ldd, p.M, p.K, BM)) != FM_OK) return rc;
+  if ((rc = make_map_u8_3d(&tq0, reinterpret_cast<const uint8_t*>(Q0), ldq, kb, ldq, p.N, p.K, qrows)) != FM_OK) return rc;
+  if ((rc = make_map_u8_3d(&tq1, Q1, ldq, kb, ldq, p.N, p.K, qrows)) != FM_OK) return rc;
+  if ((rc = make_map_u8_3d(&tq2, Q2, ldq, kb, ldq, p.N, p.K, qrows)) != FM_OK) return rc;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess, attr_err_pair = cudaSuccess;
   std::call_once(once, [] {
@@ -459,8 +467,38 @@ extern "C" int fm_project_i8(const uint8_t* D_hi, const uint8_t* D_lo, int64_t l
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp layout): c_format S32 = 2 at bit 4, a/b format (0 = u8,
   // 1 = s8) at bits 7 / 10, K-major operands, N >> 3 at bit 17, M >> 4 at bit 24
   const uint32_t idesc_u8 = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-  Params p{M, N, K, V, ldv, exps, bias, alpha, idesc_u8 | (1u << 10), idesc_u8};
+  Params p{M, N, K, V, ldv, exps, bias, alpha, idesc_u8 | (1u << 10), idesc_u8, 31};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return D_hi ? launch<2>(D_hi, D_lo, ldd, Q0, Q1, Q2, ldq, p, impl, st)
               : launch<1>(nullptr, D_lo, ldd, Q0, Q1, Q2, ldq, p, impl, st);
+}
+
+// The same projection on K-BLOCKED operands: element (row, k) of a plane lives at base + (k / kb) * block_stride +
+// row * kb + k % kb (fm_retile_u8 makes that layout).  With the plain layout a 128-row operand tile of a wide view
+// (row pitch 1.3 MB at 1280x1024, sbin 1) touches one 2 MB page per row and the projection runs at a third of its rate
+// (profiles/r02_summary.md: 803 -> 278 TFLOP/s from the pitch alone); blocked, a tile is 128 * kb contiguous bytes.
+// kb: a power of two >= 64; block strides multiples of 16, >= rows * kb; bytes between K and the end of the last block
+// must be zero in the digit planes.
+extern "C" int fm_project_i8_blocked(const uint8_t* D_hi, const uint8_t* D_lo, int64_t d_block_stride, const int8_t* Q0,
+                                     const uint8_t* Q1, const uint8_t* Q2, int64_t q_block_stride, int64_t kb,
+                                     const int32_t* exps, int M, int N, int K, double alpha, const double* bias, float* V,
+                                     int64_t ldv, int impl, void* stream) {
+  using namespace fm;
+  using namespace fm::pi8;
+  FM_REQUIRE(D_lo && Q0 && Q1 && Q2 && exps && V && M >= 1 && N >= 1 && K >= 1 && ldv >= N,
+             "fm_project_i8_blocked: bad args M=%d N=%d K=%d", M, N, K);
+  FM_REQUIRE(kb >= BKB && (kb & (kb - 1)) == 0 && d_block_stride >= (int64_t)M * kb && q_block_stride >= (int64_t)N * kb &&
+                 d_block_stride % 16 == 0 && q_block_stride % 16 == 0 &&
+                 ((reinterpret_cast<uintptr_t>(D_hi) | reinterpret_cast<uintptr_t>(D_lo) | reinterpret_cast<uintptr_t>(Q0) |
+                   reinterpret_cast<uintptr_t>(Q1) | reinterpret_cast<uintptr_t>(Q2)) & 15) == 0,
+             "fm_project_i8_blocked: kb must be a power of two >= %d, block strides >= rows * kb and multiples of 16, bases "
+             "16-byte aligned (kb=%lld strides %lld %lld)", BKB, (long long)kb, (long long)d_block_stride, (long long)q_block_stride);
+  FM_REQUIRE(cdiv(M, BM) <= 65535, "fm_project_i8_blocked: more than 65535 frame tiles; project in batches");
+  FM_REQUIRE(impl == 0 || impl == 1, "fm_project_i8_blocked: unknown impl %d", impl);
+  FM_REQUIRE(K <= (1 << 22), "fm_project_i8_blocked: K = %d exceeds 2^22", K);
+  const uint32_t idesc_u8 = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  Params p{M, N, K, V, ldv, exps, bias, alpha, idesc_u8 | (1u << 10), idesc_u8, 31};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return D_hi ? launch<2>(D_hi, D_lo, d_block_stride, Q0, Q1, Q2, q_block_stride, p, impl, st, kb)
+              : launch<1>(nullptr, D_lo, d_block_stride, Q0, Q1, Q2, q_block_stride, p, impl, st, kb);
 }

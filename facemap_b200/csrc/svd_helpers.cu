@@ -666,3 +666,42 @@ extern "C" int fm_sign_from_right(const float* T, int64_t ldt, int k, int ncols,
   FM_LAUNCH_CHECK();
   return FM_OK;
 }
+
+
+// ---- K-blocked copy of a byte plane (operand layout of fm_project_i8_blocked) ------------------------------------------
+namespace fm {
+// dst[(c / kb) * block_stride + r * kb + c % kb] = src[r * ld + c] for c < cols, 0 for cols <= c < nblk * kb.
+// One thread moves 16 bytes (kb, ld, cols offsets: multiples of 16 where the fast path applies).
+__global__ void __launch_bounds__(256) retile_u8_kernel(const uint8_t* __restrict__ src, int64_t ld, int rows, int64_t cols,
+                                                        uint8_t* __restrict__ dst, int64_t kb, int64_t block_stride,
+                                                        int64_t cols_pad, int vec_ok) {
+  const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  const int r = blockIdx.y;
+  if (c0 >= cols_pad) return;
+  const int64_t blk = c0 / kb, kin = c0 - blk * kb;
+  uint8_t* out = dst + blk * block_stride + (int64_t)r * kb + kin;
+  if (c0 + 16 <= cols && vec_ok) {
+    *reinterpret_cast<uint4*>(out) = *reinterpret_cast<const uint4*>(src + (int64_t)r * ld + c0);
+    return;
+  }
+  for (int b = 0; b < 16; ++b) out[b] = (c0 + b < cols) ? src[(int64_t)r * ld + c0 + b] : (uint8_t)0;
+}
+}  // namespace fm
+
+extern "C" int fm_retile_u8(const uint8_t* src, int64_t ld, int rows, int64_t cols, uint8_t* dst, int64_t kb,
+                            int64_t block_stride, void* stream) {
+  using namespace fm;
+  FM_REQUIRE(src && dst && rows >= 0 && cols >= 1 && ld >= cols && kb >= 16 && kb % 16 == 0 && block_stride >= (int64_t)rows * kb,
+             "fm_retile_u8: bad args (rows %d cols %lld ld %lld kb %lld block stride %lld)", rows, (long long)cols,
+             (long long)ld, (long long)kb, (long long)block_stride);
+  if (rows == 0) return FM_OK;
+  FM_REQUIRE(rows <= 65535, "fm_retile_u8: too many rows per call (%d)", rows);
+  const int64_t cols_pad = cdiv(cols, kb) * kb;
+  const int vec_ok = (ld % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % 16 == 0) &&
+                     (block_stride % 16 == 0);
+  dim3 grid((unsigned)cdiv(cols_pad / 16, 256), (unsigned)rows);
+  retile_u8_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, ld, rows, cols, dst, kb, block_stride,
+                                                                           cols_pad, vec_ok);
+  FM_LAUNCH_CHECK();
+  return FM_OK;
+}

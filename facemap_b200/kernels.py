@@ -337,6 +337,52 @@ def project_i8(D, Q, exps, alpha, bias, V, impl=0):
     return V
 
 
+def retile_u8(src, kb, out=None):
+    """fm_retile_u8: a byte plane [rows, cols] (row-major, any pitch) -> its K-blocked copy, a contiguous
+    [ceil(cols / kb), rows, kb] tensor (int8 in, int8 out), zero-filled behind `cols`."""
+    if src.dtype not in (torch.uint8, torch.int8) or src.dim() != 2 or src.stride(1) != 1 or not src.is_cuda:
+        raise FacemapB200Error("retile_u8: expected a row-major CUDA uint8 / int8 matrix")
+    rows, cols = src.shape
+    nblk = -(-cols // int(kb))
+    if out is None:
+        out = torch.empty((nblk, max(rows, 1), int(kb)), dtype=src.dtype, device=src.device)[:, :rows]
+    if out.dtype != src.dtype or tuple(out.shape) != (nblk, rows, int(kb)) or out.stride(2) != 1 or out.stride(1) != int(kb):
+        raise FacemapB200Error("retile_u8: out must be a [nblk, rows, kb] tensor with packed rows")
+    for r0 in range(0, rows, 32768):
+        r1 = min(rows, r0 + 32768)
+        check(_lib.load().fm_retile_u8(ptr(src[r0:r1]), src.stride(0), r1 - r0, cols, ptr(out[:, r0:r1]), int(kb),
+                                       out.stride(0), _stream()), "fm_retile_u8")
+    return out
+
+
+def project_i8_blocked(D, Q, exps, alpha, bias, V, K_total, impl=0):
+    """fm_project_i8_blocked: project_i8 on K-blocked planes (retile_u8): D = (hi or None, lo) [nblk, M, kb],
+    Q = (Q0 int8, Q1, Q2 uint8) [nblk, N, kb]; K_total = the number of valid columns."""
+    hi, lo = D
+    Q0, Q1, Q2 = Q
+    nblk, M, kb = lo.shape
+    N = Q0.shape[1]
+    for t, dt, rows, name in ((lo, torch.uint8, M, "D_lo"), (hi, torch.uint8, M, "D_hi"), (Q0, torch.int8, N, "Q0"),
+                              (Q1, torch.uint8, N, "Q1"), (Q2, torch.uint8, N, "Q2")):
+        if t is None:
+            continue
+        if t.dtype != dt or not t.is_cuda or tuple(t.shape) != (nblk, rows, kb) or t.stride(2) != 1 or t.stride(1) != kb:
+            raise FacemapB200Error(f"project_i8_blocked: {name} must be a {dt} [nblk, rows, kb] tensor with packed rows")
+    if hi is not None and hi.stride(0) != lo.stride(0) or Q1.stride(0) != Q0.stride(0) or Q2.stride(0) != Q0.stride(0):
+        raise FacemapB200Error("project_i8_blocked: the planes of an operand must share one block stride")
+    if not (nblk - 1) * kb < int(K_total) <= nblk * kb:
+        raise FacemapB200Error("project_i8_blocked: K_total does not match the number of blocks")
+    _need(exps, torch.int32, "exps", 1)
+    _need(bias, torch.float64, "bias", 1)
+    _need(V, torch.float32, "V", 2)
+    if exps.numel() < N or (bias is not None and bias.numel() < N) or V.shape[0] < M or V.shape[1] < N or V.stride(1) != 1:
+        raise FacemapB200Error("project_i8_blocked: exps / bias need N entries and V must be row-major [>= M, >= N]")
+    check(_lib.load().fm_project_i8_blocked(ptr(hi), ptr(lo), lo.stride(0), ptr(Q0), ptr(Q1), ptr(Q2), Q0.stride(0), int(kb),
+                                            ptr(exps), M, N, int(K_total), float(alpha), ptr(bias), ptr(V), V.stride(0),
+                                            int(impl), _stream()), "fm_project_i8_blocked")
+    return V
+
+
 def splitk_reduce(workspace, ksplit, C_out, *, rscale=None, rbias=None):
     """C[m,n] = rscale[m] * sum_s workspace[s,m,n] + rbias[m], summed in float64."""
     _need(workspace, torch.float32, "workspace", 3)
@@ -652,6 +698,31 @@ def motion_ref(frames, sbin, plan, scratch, blocks, out, prev_frame=None, ormask
     check(_lib.load().fm_motion_ref(ptr(frames), T, H, W, int(sbin), ptr(prev_frame), ptr(ormask), ptr(lo), ptr(ln),
                                     ptr(comb), int(lo.numel()), ptr(scratch), int(blocks), ptr(out), _stream()),
           "fm_motion_ref")
+    return rows
+
+
+def motion_ref_planes(frames, plan, scratch, blocks, out, plane, col0=0, energy=None, prev_frame=None, ormask=None):
+    """fm_motion_ref_planes (sbin 1): one pass over the frames of a view for the reference-arithmetic motion sums
+    (`out`, float64 [rows]), the |difference| bytes (`plane`: uint8 [rows, >= col0 + H * W] row-major) and the integer
+    energy (`energy`: int64 [rows], +=)."""
+    T, H, W = _frames3(frames)
+    lo, ln, comb = plan
+    _need(out, torch.float64, "out", 1)
+    _need(plane, torch.uint8, "plane", 2)
+    _need(energy, torch.int64, "energy", 1)
+    rows = T if prev_frame is not None else T - 1
+    if out.numel() < rows or not out.is_contiguous() or (energy is not None and (energy.numel() < rows or not energy.is_contiguous())):
+        raise FacemapB200Error("motion_ref_planes: out / energy too small")
+    if plane.shape[0] < rows or plane.stride(1) != 1 or plane.shape[1] < col0 + H * W:
+        raise FacemapB200Error("motion_ref_planes: plane must be row-major [>= rows, >= col0 + H * W]")
+    for t, name in ((prev_frame, "prev_frame"), (ormask, "ormask")):
+        if t is not None:
+            _need(t, torch.uint8, name, 2)
+            if tuple(t.shape) != (H, W) or not t.is_contiguous():
+                raise FacemapB200Error(f"{name}: expected a contiguous [{H}, {W}] uint8 tensor")
+    check(_lib.load().fm_motion_ref_planes(ptr(frames), T, H, W, ptr(prev_frame), ptr(ormask), ptr(lo), ptr(ln), ptr(comb),
+                                           int(lo.numel()), ptr(scratch), int(blocks), ptr(out), ptr(plane), plane.stride(0),
+                                           int(col0), ptr(energy), _stream()), "fm_motion_ref_planes")
     return rows
 
 

@@ -627,12 +627,14 @@ def stage2_plan(N, ncomps=NCOMPS):
 
 
 def _bin_chunk(frames, geo, avgframe, avgmotion, mods, X, prev=None, last=None, energy=None, roi_energy=None,
-               ormask=None, planes=False):
+               ormask=None, planes=False, skip=()):
     """K1 over every view of one fetched chunk into the modality matrices X[m] ([rows, p]).
     ormask: per-view paint masks (fullres.FullRes.ormask) OR-ed into the frames on load, or None.
     planes: X[m] are (hi, lo) uint8 plane pairs that receive the integer results (fm_bin_motion_planes)."""
     rows = None
     for v, fr in enumerate(frames):
+        if v in skip:               # served by another kernel (Stage3: fm_motion_ref_planes)
+            continue
         c0, n = geo.col0[v], geo.npix_v[v]
         rects = [geo.mot_rois[j][1:] for j in geo.rois_on_view[v]]
         if planes and mods:
@@ -818,6 +820,8 @@ def projection_rows_per_batch(p, k, budget_bytes=6 << 30, elem_bytes=4):
     return int(min(rows, cap))
 
 
+PROJ_KB = 4096                       # K-block width of the blocked projection operands (fm_retile_u8)
+PROJ_BLOCKED_MIN_PITCH = 262144      # plane row pitch (bytes) from which the projection reads K-blocked copies
 MOTION_REF_BLOCKS = 148 * 4
 MOTION_REF_SCRATCH_MAX = 1 << 30        # bytes of per-block scratch of fm_motion_ref per view
 
@@ -875,6 +879,8 @@ class Stage3:
                 raise FacemapB200Error("proj_mode 'i8': two byte planes hold block sums up to sbin 16")
             self.i8 = False                   # default mode: bins beyond 16 take the float32 operands
         self.ldq = K.round_up(geo.p, 16)
+        # row pitches beyond this put every row of an operand tile on its own 2 MB page: project from K-blocked copies
+        self.blocked = self.i8 and self.ldq > PROJ_BLOCKED_MIN_PITCH
         self.rows_batch = projection_rows_per_batch(geo.p, kmax, elem_bytes=(1 if geo.sbin == 1 else 2) if self.i8 else 4)
         # fetch plan: GEMM batches of <= rows_batch rows, each filled by several fetches
         self.have0 = self.f0 > 0                         # a shard starting mid-video carries a 1-frame halo
@@ -908,6 +914,10 @@ class Stage3:
             self.ref_scratch = {v: K.motion_ref_scratch(geo.Ly[v], geo.Lx[v], geo.sbin, self.ref_plan[v][0].numel(),
                                                         self.ref_blocks[v], device) for v in self.ref_views}
             self.ref_last = {v: None for v in self.ref_views}
+        # full-resolution views (sbin 1) that need the reference-arithmetic sums anyway: ONE pass writes those, the
+        # operand plane and the integer energy (fm_motion_ref_planes) instead of K1 plus fm_motion_ref
+        self.fused_views = [v for v in self.ref_views
+                            if self.i8 and geo.sbin == 1 and list(mods) == ["mot"] and not geo.rois_on_view[v]]
 
     def _operands(self, tag, rows):
         """per-modality stage-3 operands for `rows` difference rows: float32 [rows, p], or (hi, lo) byte planes"""
@@ -969,13 +979,19 @@ class Stage3:
                            prev=self.carry[self.flip] if have else None, last=self.carry[1 - self.flip],
                            energy=energy if rows > 0 else None,
                            roi_energy=roi_e if (self.nroi and rows > 0) else None,
-                           ormask=None if self.fullres is None else self.fullres.ormask, planes=self.i8)
+                           ormask=None if self.fullres is None else self.fullres.ormask, planes=self.i8,
+                           skip=self.fused_views)
                 if self.nroi and rows > 0:
                     for v in range(self.nv):
                         for q, j in enumerate(geo.rois_on_view[v]):
                             self.E_roi[j, o:o + rows] = roi_e[v][q, :rows]
                 for v in self.ref_views:
-                    if rows > 0:
+                    if rows > 0 and v in self.fused_views:
+                        K.motion_ref_planes(frames[v], self.ref_plan[v], self.ref_scratch[v], self.ref_blocks[v],
+                                            self.Eref[v, o:o + rows], Xv["mot"][1], col0=geo.col0[v], energy=energy[v],
+                                            prev_frame=self.ref_last[v] if have else None,
+                                            ormask=None if self.fullres is None else self.fullres.ormask[v])
+                    elif rows > 0:
                         K.motion_ref(frames[v], geo.sbin, self.ref_plan[v], self.ref_scratch[v], self.ref_blocks[v],
                                      self.Eref[v, o:o + rows], prev_frame=self.ref_last[v] if have else None,
                                      ormask=None if self.fullres is None else self.fullres.ormask[v])
@@ -1044,6 +1060,7 @@ class Stage3:
             self.source.begin_sweep()
             self._seed_halo()
         row0 = 0
+        Ut_qb = {}                      # K-blocked copies of the mask digits (wide views)
         for fetches, filled in self.batches:
             if self.X_full is None:
                 self._bin_fetches(fetches, X, 0)
@@ -1058,7 +1075,23 @@ class Stage3:
                 if self.i8:
                     alpha = 1.0 / (geo.sbin * geo.sbin)
                     hi, lo = self._rows_of(X, base, base + filled)[m]
-                    if self.fullSVD and Uts[0] is not None:
+                    if self.fullSVD and Uts[0] is not None and self.blocked:
+                        # wide view: both operands in the K-blocked layout (a 128-row tile = 128 * PROJ_KB contiguous
+                        # bytes instead of one 2 MB page per row; fm_project_i8_blocked)
+                        with timer("stage3.project.retile"):
+                            nblk = -(-geo.p // PROJ_KB)
+                            if m not in Ut_qb:
+                                Ut_qb[m] = tuple(K.retile_u8(q, PROJ_KB) for q in Ut_q[m][0][:3])
+                            Db = []
+                            for tag, pl in (("hi", hi), ("lo", lo)):
+                                Db.append(None if pl is None else K.retile_u8(pl, PROJ_KB, out=ws.raw(
+                                    "X3blk." + tag, nblk * filled * PROJ_KB, torch.uint8).view(nblk, filled, PROJ_KB)))
+                        with timer("stage3.project.mma"):
+                            K.project_i8_blocked(tuple(Db), Ut_qb[m], Ut_q[m][0][3], alpha, Ut_bias[m][0],
+                                                 V[m][0][o:o + filled], geo.p, impl=ws.proj_i8_impl)
+                        if sink is not None:
+                            sink.copy(V[m][0][o:o + filled], V_host[m][0][o:o + filled])
+                    elif self.fullSVD and Uts[0] is not None:
                         with timer("stage3.project.mma"):
                             K.project_i8((hi, lo), Ut_q[m][0][:3], Ut_q[m][0][3], alpha, Ut_bias[m][0], V[m][0][o:o + filled],
                                          impl=ws.proj_i8_impl)

@@ -122,6 +122,13 @@ int fm_motion_ref_scratch_bytes(int H, int W, int sbin, int nleaves, int blocks,
 int fm_motion_ref(const uint8_t* frames, int T, int H, int W, int sbin, const uint8_t* prev_frame,
                   const uint8_t* ormask, const int32_t* leaf_lo, const int32_t* leaf_len,
                   const uint8_t* leaf_comb, int nleaves, void* scratch, int blocks, double* out, void* stream);
+/* sbin == 1, everything stage 3 needs of a view in ONE pass over its frames: `out` as fm_motion_ref, the |difference|
+ * bytes as the projection's operand plane (plane [rows, ldq] at columns col0 ..: what fm_bin_motion_planes writes at sbin 1)
+ * and the exact integer energy (energy [rows] +=, may be NULL).  facemap/process.py:448-461 on full-resolution views. */
+int fm_motion_ref_planes(const uint8_t* frames, int T, int H, int W, const uint8_t* prev_frame, const uint8_t* ormask,
+                         const int32_t* leaf_lo, const int32_t* leaf_len, const uint8_t* leaf_comb, int nleaves,
+                         void* scratch, int blocks, double* out, uint8_t* plane, int64_t ldq, int64_t col0,
+                         uint64_t* energy, void* stream);
 
 /*
  * Stage-1 segment means in the reference's float64 arithmetic for a non-power-of-two sbin (process.py:77-87):
@@ -320,6 +327,21 @@ int fm_transpose(const float* in, int64_t ldin, int rows, int cols, float* out, 
  * X[r, col0 + y*Lxb + x] for the binned rectangle. */
 int fm_gather_roi(const float* X, int64_t ldx, int rows, int64_t col0, int Lxb,
                   int y0, int y1, int x0, int x1, float* out, int64_t ldout, void* stream);
+/*
+ * K-blocked operands for wide views.  fm_retile_u8 copies a byte plane [rows, ld] into the layout
+ * dst[(c / kb) * block_stride + r * kb + c % kb] (zero-filled up to the end of the last block); fm_project_i8_blocked is
+ * fm_project_i8 on planes in that layout (block strides instead of row pitches; kb a power of two >= 64).  With row pitches
+ * beyond ~256 KB (1280x1024 at sbin 1: 1.3 MB) every row of an operand tile lies on its own 2 MB page and the projection
+ * drops to a third of its rate; blocked, a 128-row tile is 128 * kb contiguous bytes (facemap/process.py:485, 503 at
+ * BASELINE configs[3]).
+ */
+int fm_retile_u8(const uint8_t* src, int64_t ld, int rows, int64_t cols, uint8_t* dst, int64_t kb, int64_t block_stride,
+                 void* stream);
+int fm_project_i8_blocked(const uint8_t* D_hi, const uint8_t* D_lo, int64_t d_block_stride, const int8_t* Q0,
+                          const uint8_t* Q1, const uint8_t* Q2, int64_t q_block_stride, int64_t kb, const int32_t* exps,
+                          int M, int N, int K, double alpha, const double* bias, float* V, int64_t ldv, int impl,
+                          void* stream);
+
 /* The same gather on one byte plane of fm_bin_motion_planes (pitches in bytes). */
 int fm_gather_roi_u8(const uint8_t* X, int64_t ldx, int rows, int64_t col0, int Lxb,
                      int y0, int y1, int x0, int x1, uint8_t* out, int64_t ldout, void* stream);

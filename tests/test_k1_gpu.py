@@ -230,6 +230,48 @@ def test_motion_ref_matches_numpy_bitwise(cuda_device, T, H, W, sbin):
         assert rows == T and np.array_equal(out2.cpu().numpy(), ref.astype(np.float64))
 
 
+@pytest.mark.parametrize("T,H,W,col0,masked", [(6, 300, 310, 0, False), (5, 251, 263, 24, True), (4, 1024, 1280, 0, False),
+                                               (3, 40, 56, 7, True)])
+def test_motion_ref_planes_is_k1_plus_motion_ref(cuda_device, T, H, W, col0, masked):
+    """fm_motion_ref_planes (sbin 1: one pass for the reference-arithmetic sums, the operand plane and the integer
+    energy) against the two kernels it replaces in stage 3, fm_bin_motion_planes and fm_motion_ref, bit for bit — with
+    and without a carried previous frame, a paint mask, an unaligned column offset"""
+    from facemap_b200 import kernels as K
+
+    dev = cuda_device
+    frames = np.random.RandomState(T * H).randint(0, 256, size=(T + 1, H, W)).astype(np.uint8)
+    mask = torch.from_numpy(np.where(np.random.RandomState(3).rand(H, W) < 0.2, 255, 0).astype(np.uint8)).to(dev) if masked else None
+    npix = H * W
+    ldq = K.round_up(col0 + npix, 16)
+    plan = K.pairwise_plan(npix, dev)
+    blocks = 5
+    scratch = K.motion_ref_scratch(H, W, 1, plan[0].numel(), blocks, dev)
+    fr = torch.from_numpy(frames).to(dev)
+    for carried in (False, True):
+        src = fr[1:] if carried else fr
+        prev = fr[0].contiguous() if carried else None
+        rows = T
+        prev_sum = None
+        if carried:
+            prev_sum = torch.zeros(npix, dtype=torch.int32, device=dev)
+            K.bin_motion(fr[:1].contiguous(), 1, last_sum=prev_sum, ormask=mask)
+        # the two-kernel route
+        want_plane = torch.full((rows, ldq), 7, dtype=torch.uint8, device=dev)
+        want_e = torch.zeros(rows, dtype=torch.int64, device=dev)
+        K.bin_motion_planes(src.contiguous(), 1, prev_sum=prev_sum, q_mot=(None, want_plane[:, :col0 + npix]), col0=col0,
+                            energy=want_e, ormask=mask)
+        want_ref = torch.zeros(rows, dtype=torch.float64, device=dev)
+        K.motion_ref(src.contiguous(), 1, plan, scratch, blocks, want_ref, prev_frame=prev, ormask=mask)
+        # the fused kernel
+        got_plane = torch.full((rows, ldq), 7, dtype=torch.uint8, device=dev)
+        got_e = torch.zeros(rows, dtype=torch.int64, device=dev)
+        got_ref = torch.zeros(rows, dtype=torch.float64, device=dev)
+        assert K.motion_ref_planes(src.contiguous(), plan, scratch, blocks, got_ref, got_plane[:, :col0 + npix], col0=col0,
+                                   energy=got_e, prev_frame=prev, ormask=mask) == rows
+        torch.cuda.synchronize()
+        assert torch.equal(got_plane, want_plane) and torch.equal(got_e, want_e) and torch.equal(got_ref, want_ref)
+
+
 def test_motion_ref_full_resolution_view_with_budgeted_blocks(cuda_device):
     """a 1280x1024 view at sbin 1 (BASELINE configs[3]) with the block count svd.motion_ref_blocks picks under its
     1 GiB scratch budget: still the reference's float32 sums, bit for bit"""

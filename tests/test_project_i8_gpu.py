@@ -69,6 +69,59 @@ def test_project_i8_bit_exact_against_model(cuda_device, M, N, K, sbin, impl):
     assert torch.isnan(V2[:, 0]).all()
 
 
+@pytest.mark.parametrize("M,N,K,sbin,kb", [(300, 500, 10000, 4, 4096), (130, 70, 4096, 1, 4096), (260, 250, 16384 + 640, 2, 1024),
+                                           (77, 130, 1000, 1, 64)])
+@pytest.mark.parametrize("impl", IMPLS)
+def test_blocked_projection_equals_plain(cuda_device, M, N, K, sbin, kb, impl):
+    """fm_retile_u8 + fm_project_i8_blocked (K-blocked operands for wide views) give the bits of fm_project_i8 on the
+    plain planes, whatever garbage the plain planes carry in their pitch padding (the blocked copy zero-fills its tail)"""
+    from facemap_b200 import kernels as K_
+
+    rs = np.random.RandomState(M + K + kb)
+    D = rs.randint(0, 255 * sbin * sbin + 1, size=(M, K))
+    hi, lo = M8.planes_of(D)
+    pitch = -(-K // 16) * 16 + 32
+    planes = torch.randint(0, 256, (2, M, pitch), dtype=torch.uint8, device=cuda_device)      # garbage in the padding
+    planes[0, :, :K] = torch.from_numpy(hi).to(cuda_device)
+    planes[1, :, :K] = torch.from_numpy(lo).to(cuda_device)
+    Dg = (None if sbin == 1 else planes[0, :, :K], planes[1, :, :K])
+    Ug = K_.alloc_matrix(N, K, cuda_device)
+    Ug.copy_(torch.from_numpy(_masks(rs, N, K)))
+    Q0, Q1, Q2, exps = K_.slice_rows_i8(Ug)
+    bias = K_.row_dot(Ug, torch.rand(K, device=cuda_device, dtype=torch.float64))
+    V = torch.full((M, -(-N // 4) * 4), float("nan"), dtype=torch.float32, device=cuda_device)
+    Vb = torch.full_like(V, float("nan"))
+    K_.project_i8(Dg, (Q0, Q1, Q2), exps, 1.0 / sbin ** 2, bias, V, impl=impl)
+    Db = tuple(None if pl is None else K_.retile_u8(pl, kb) for pl in Dg)
+    Qb = tuple(K_.retile_u8(q, kb) for q in (Q0, Q1, Q2))
+    nblk = -(-K // kb)
+    assert Db[1].shape == (nblk, M, kb) and Qb[0].dtype == torch.int8
+    # the blocked copy holds the plane and zeros behind it
+    flat = Db[1].permute(1, 0, 2).reshape(M, nblk * kb)
+    assert torch.equal(flat[:, :K], planes[1, :, :K]) and not flat[:, K:].any()
+    K_.project_i8_blocked(Db, Qb, exps, 1.0 / sbin ** 2, bias, Vb, K, impl=impl)
+    torch.cuda.synchronize()
+    assert torch.equal(V[:, :N], Vb[:, :N]) and not torch.isnan(Vb[:, :N]).any()
+
+
+def test_pipeline_with_blocked_projection(cuda_device, monkeypatch):
+    """Stage3 takes the blocked route for wide views (plane pitch > PROJ_BLOCKED_MIN_PITCH); forced on a small video, the
+    whole path gives the same bits as the plain route"""
+    from facemap_b200 import process, svd
+    from facemap_b200.frames import DeviceArraySource
+    from facemap_b200.synth import SynthVideo
+
+    v = SynthVideo(48, 64, 2300, seed=13).all_frames()
+    src = DeviceArraySource([torch.from_numpy(v).to(cuda_device)])
+    want = process.process_source(src, sbin=1, motSVD=True, movSVD=True)
+    monkeypatch.setattr(svd, "PROJ_BLOCKED_MIN_PITCH", 1024)
+    monkeypatch.setattr(svd, "PROJ_KB", 512)
+    got = process.process_source(src, sbin=1, motSVD=True, movSVD=True)
+    for key in ("motSVD", "movSVD", "motMask", "movMask", "motion"):
+        for a, b in zip(got[key], want[key]):
+            assert np.array_equal(a, b), key
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 def test_project_i8_extreme_digits_fill_the_int32_chain(cuda_device, impl):
     from facemap_b200 import kernels as K_
