@@ -53,7 +53,7 @@ SIGNATURES = {
     "fm_pairwise_plan": (_I, [_I, _I, _P, _P, _P]),
     "fm_motion_ref_scratch_bytes": (_I, [_I, _I, _I, _I, _I, C.POINTER(C.c_size_t)]),
     "fm_motion_ref": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P]),
-    "fm_motion_ref_planes": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _L, _L, _P, _P]),
+    "fm_motion_ref_planes": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _I, _P, _P, _L, _L, _P, _P]),
     "fm_mean_ref": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "fm_mean_update": (_I, [_P, _P, _L, _I, _I, _I, _P]),
     "fm_gemm_tn": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _I, _P, _L, _I, _I, _P]),

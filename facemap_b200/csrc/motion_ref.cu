@@ -34,6 +34,11 @@ struct MotionRefParams {
   uint8_t* plane;              // [rows, ldq], written at columns [col0, col0 + H * W)
   int64_t ldq, col0;
   unsigned long long* energy;  // [rows], += sum of |differences|
+  // fold plan over the exact subtrees (groups of leaves whose float32 sum cannot round), or ngroups == 0
+  const int* grp_first;
+  const int* grp_n;
+  const unsigned char* grp_comb;
+  int ngroups;
 };
 
 // the reference's binned value of one pixel block (process.py:34-43)
@@ -172,6 +177,7 @@ __global__ void __launch_bounds__(MR_THREADS) motion_ref_kernel(const MotionRefP
 template <bool PLANE>
 __global__ void __launch_bounds__(MR_THREADS) motion_ref_u8_kernel(const MotionRefParams<float> p) {
   __shared__ unsigned long long s_energy;
+  __shared__ float s_group[256];
   float* leaf_sum = p.scratch + (size_t)blockIdx.x * p.nleaves;
   const size_t hw = (size_t)p.H * p.W;
   const int per_block = (p.rows + gridDim.x - 1) / gridDim.x;
@@ -249,9 +255,23 @@ __global__ void __launch_bounds__(MR_THREADS) motion_ref_u8_kernel(const MotionR
       if (threadIdx.x == 0) atomicAdd(p.energy + row, s_energy);
     }
     __syncthreads();
+    if (p.ngroups > 0) {
+      // the exact subtrees: integer sums of their leaves by whole warps, in any order
+      for (int g = threadIdx.x >> 5; g < p.ngroups; g += MR_THREADS / 32) {
+        const float* a = leaf_sum + p.grp_first[g];
+        unsigned v = 0;
+        for (int i = threadIdx.x & 31; i < p.grp_n[g]; i += 32) v += __float2uint_rn(a[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) s_group[g] = (float)v;              // < 2^24: exact
+      }
+      __syncthreads();
+    }
     if (threadIdx.x == 0) {
       float vstack[32];
-      p.out[row] = (double)fadd_rn(0.0f, pairwise_fold_plan<float>(p.nleaves, leaf_sum, p.leaf_comb, vstack));
+      const float r = p.ngroups > 0 ? pairwise_fold_plan<float>(p.ngroups, s_group, p.grp_comb, vstack)
+                                    : pairwise_fold_plan<float>(p.nleaves, leaf_sum, p.leaf_comb, vstack);
+      p.out[row] = (double)fadd_rn(0.0f, r);
     }
     __syncthreads();
   }
@@ -324,12 +344,12 @@ extern "C" int fm_motion_ref(const uint8_t* frames, int T, int H, int W, int sbi
   if (sbin == 1) {
     MotionRefParams<float> p{frames, prev_frame, ormask, T, H, W, sbin, Lyb, Lxb, rows, prev_frame ? 0 : 1,
                              leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<float*>(scratch), out,
-                             nullptr, 0, 0, nullptr};
+                             nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 0};
     motion_ref_u8_kernel<false><<<grid, MR_THREADS, 0, st>>>(p);
   } else {
     MotionRefParams<double> p{frames, prev_frame, ormask, T, H, W, sbin, Lyb, Lxb, rows, prev_frame ? 0 : 1,
                               leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<double*>(scratch), out,
-                              nullptr, 0, 0, nullptr};
+                              nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 0};
     const bool aligned = sbin >= 3 && W % 4 == 0 &&
                          ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(prev_frame) |
                            reinterpret_cast<uintptr_t>(ormask)) % 4 == 0);
@@ -346,7 +366,8 @@ extern "C" int fm_motion_ref(const uint8_t* frames, int T, int H, int W, int sbi
 // energy.  Replaces K1 + fm_motion_ref (two passes over the frames) on large full-resolution views (BASELINE configs[3]).
 extern "C" int fm_motion_ref_planes(const uint8_t* frames, int T, int H, int W, const uint8_t* prev_frame,
                                     const uint8_t* ormask, const int32_t* leaf_lo, const int32_t* leaf_len,
-                                    const uint8_t* leaf_comb, int nleaves, void* scratch, int blocks, double* out,
+                                    const uint8_t* leaf_comb, int nleaves, const int32_t* grp_first, const int32_t* grp_n,
+                                    const uint8_t* grp_comb, int ngroups, void* scratch, int blocks, double* out,
                                     uint8_t* plane, int64_t ldq, int64_t col0, uint64_t* energy, void* stream) {
   using namespace fm;
   FM_REQUIRE(frames && leaf_lo && leaf_len && leaf_comb && scratch && out && plane && T >= 1 && H >= 1 && W >= 1 &&
@@ -357,7 +378,13 @@ extern "C" int fm_motion_ref_planes(const uint8_t* frames, int T, int H, int W, 
   const int grid = rows < blocks ? rows : blocks;
   MotionRefParams<float> p{frames, prev_frame, ormask, T, H, W, 1, H, W, rows, prev_frame ? 0 : 1,
                            leaf_lo, leaf_len, leaf_comb, nleaves, reinterpret_cast<float*>(scratch), out,
-                           plane, ldq, col0, reinterpret_cast<unsigned long long*>(energy)};
+                           plane, ldq, col0, reinterpret_cast<unsigned long long*>(energy), nullptr, nullptr, nullptr, 0};
+  if (ngroups > 0 && ngroups <= 256 && grp_first && grp_n && grp_comb) {
+    p.grp_first = grp_first;
+    p.grp_n = grp_n;
+    p.grp_comb = grp_comb;
+    p.ngroups = ngroups;
+  }
   motion_ref_u8_kernel<true><<<grid, MR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   FM_LAUNCH_CHECK();
   return FM_OK;

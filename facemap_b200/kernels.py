@@ -662,8 +662,45 @@ def pupil(frames, rect, mask, dark_offset, sigma, scratch, blocks, out, reflecto
 # ---------------------------------------------------------------------------------------------
 # motion energy in the reference's floating-point arithmetic (fm_motion_ref)
 # ---------------------------------------------------------------------------------------------
-def pairwise_plan(n, device):
-    """(lo int32, len int32, comb uint8) device tensors: the leaves of NumPy's pairwise sum over n elements."""
+EXACT_BYTE_SUM_PIXELS = 65793      # 255 * 65 793 < 2^24: a float32 sum of that many byte values never rounds
+
+
+def exact_groups(ln, comb, limit=EXACT_BYTE_SUM_PIXELS):
+    """For sums of BYTE-valued elements (sbin 1): the maximal subtrees of NumPy's pairwise tree that hold at most
+    `limit` elements.  Every partial sum inside them is an integer below 2^24, i.e. exact in float32 in any order, so
+    a subtree's value is the integer sum of its leaves; only the merges above them round.  Returns (first leaf, number
+    of leaves, comb) per group, left to right: the fold plan over the groups (comb = merges right after a group)."""
+    import numpy as np
+
+    ln, comb = np.asarray(ln, np.int64), np.asarray(comb, np.int64)
+    stack, found, ends = [], [], {}
+    for l in range(len(ln)):
+        stack.append([l, 1, int(ln[l])])
+        for _ in range(int(comb[l])):
+            b = stack.pop()
+            a = stack.pop()
+            if a[2] + b[2] > limit:                       # a rounding merge: its exact children are maximal
+                for node in (a, b):
+                    if node[2] <= limit:
+                        found.append((node[0], node[1]))
+                e = b[0] + b[1] - 1
+                ends[e] = ends.get(e, 0) + 1
+                stack.append([a[0], a[1] + b[1], limit + 1])          # never exact again
+            else:
+                stack.append([a[0], a[1] + b[1], a[2] + b[2]])
+    if not found:                                         # the whole tree is exact
+        found = [(0, len(ln))]
+    found.sort()
+    first = np.array([f for f, _ in found], np.int32)
+    count = np.array([c for _, c in found], np.int32)
+    gcomb = np.array([ends.get(int(f + c - 1), 0) for f, c in found], np.uint8)
+    assert int(count.sum()) == len(ln) and (first[1:] == first[:-1] + count[:-1]).all()
+    return first, count, gcomb
+
+
+def pairwise_plan(n, device, groups=False):
+    """(lo int32, len int32, comb uint8) device tensors: the leaves of NumPy's pairwise sum over n elements.
+    groups=True appends the exact-subtree fold plan of byte-valued sums (exact_groups): three more tensors."""
     import numpy as np
 
     cap = max(1, n // 64 + 2)
@@ -672,7 +709,10 @@ def pairwise_plan(n, device):
                                              C.c_void_p(comb.ctypes.data)))
     if count < 1 or count > cap:
         raise FacemapB200Error(f"fm_pairwise_plan({n}) failed ({count})")
-    return tuple(torch.from_numpy(a[:count].copy()).to(device) for a in (lo, ln, comb))
+    arrays = [lo[:count].copy(), ln[:count].copy(), comb[:count].copy()]
+    if groups:
+        arrays += list(exact_groups(arrays[1], arrays[2]))
+    return tuple(torch.from_numpy(a).to(device) for a in arrays)
 
 
 def motion_ref_scratch(H, W, sbin, nleaves, blocks, device):
@@ -685,7 +725,7 @@ def motion_ref_scratch(H, W, sbin, nleaves, blocks, device):
 def motion_ref(frames, sbin, plan, scratch, blocks, out, prev_frame=None, ormask=None):
     """out[r] (float64) = the reference's `imbin_mot.sum(-1)` of one view, bit for bit (rows as bin_motion)."""
     T, H, W = _frames3(frames)
-    lo, ln, comb = plan
+    lo, ln, comb = plan[:3]
     _need(out, torch.float64, "out", 1)
     rows = T if prev_frame is not None else T - 1
     if out.numel() < rows or not out.is_contiguous():
@@ -706,7 +746,8 @@ def motion_ref_planes(frames, plan, scratch, blocks, out, plane, col0=0, energy=
     (`out`, float64 [rows]), the |difference| bytes (`plane`: uint8 [rows, >= col0 + H * W] row-major) and the integer
     energy (`energy`: int64 [rows], +=)."""
     T, H, W = _frames3(frames)
-    lo, ln, comb = plan
+    lo, ln, comb = plan[:3]
+    gf, gn, gc = plan[3:6] if len(plan) >= 6 else (None, None, None)
     _need(out, torch.float64, "out", 1)
     _need(plane, torch.uint8, "plane", 2)
     _need(energy, torch.int64, "energy", 1)
@@ -721,7 +762,8 @@ def motion_ref_planes(frames, plan, scratch, blocks, out, plane, col0=0, energy=
             if tuple(t.shape) != (H, W) or not t.is_contiguous():
                 raise FacemapB200Error(f"{name}: expected a contiguous [{H}, {W}] uint8 tensor")
     check(_lib.load().fm_motion_ref_planes(ptr(frames), T, H, W, ptr(prev_frame), ptr(ormask), ptr(lo), ptr(ln), ptr(comb),
-                                           int(lo.numel()), ptr(scratch), int(blocks), ptr(out), ptr(plane), plane.stride(0),
+                                           int(lo.numel()), ptr(gf), ptr(gn), ptr(gc), 0 if gf is None else int(gf.numel()),
+                                           ptr(scratch), int(blocks), ptr(out), ptr(plane), plane.stride(0),
                                            int(col0), ptr(energy), _stream()), "fm_motion_ref_planes")
     return rows
 

@@ -908,7 +908,7 @@ class Stage3:
             self.ref_views = [v for v in range(self.nv) if motion_needs_reference(geo.sbin, geo.npix_v[v])]
         if self.ref_views:
             self.Eref = torch.zeros((self.nv, self.n_out), dtype=torch.float64, device=device)
-            self.ref_plan = {v: K.pairwise_plan(geo.npix_v[v], device) for v in self.ref_views}
+            self.ref_plan = {v: K.pairwise_plan(geo.npix_v[v], device, groups=geo.sbin == 1) for v in self.ref_views}
             self.ref_blocks = {v: motion_ref_blocks(geo.npix_v[v], self.ref_plan[v][0].numel(), geo.sbin)
                                for v in self.ref_views}
             self.ref_scratch = {v: K.motion_ref_scratch(geo.Ly[v], geo.Lx[v], geo.sbin, self.ref_plan[v][0].numel(),

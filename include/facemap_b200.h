@@ -124,9 +124,13 @@ int fm_motion_ref(const uint8_t* frames, int T, int H, int W, int sbin, const ui
                   const uint8_t* leaf_comb, int nleaves, void* scratch, int blocks, double* out, void* stream);
 /* sbin == 1, everything stage 3 needs of a view in ONE pass over its frames: `out` as fm_motion_ref, the |difference|
  * bytes as the projection's operand plane (plane [rows, ldq] at columns col0 ..: what fm_bin_motion_planes writes at sbin 1)
- * and the exact integer energy (energy [rows] +=, may be NULL).  facemap/process.py:448-461 on full-resolution views. */
+ * and the exact integer energy (energy [rows] +=, may be NULL).  grp_* (ngroups <= 256, or 0): the maximal subtrees of the
+ * pairwise tree holding at most 65 793 byte values — their float32 sums never round, so they are summed as integers by
+ * whole warps and only the merges above them are folded in order (kernels.exact_groups); without them one thread folds
+ * all leaves.  facemap/process.py:448-461 on full-resolution views. */
 int fm_motion_ref_planes(const uint8_t* frames, int T, int H, int W, const uint8_t* prev_frame, const uint8_t* ormask,
                          const int32_t* leaf_lo, const int32_t* leaf_len, const uint8_t* leaf_comb, int nleaves,
+                         const int32_t* grp_first, const int32_t* grp_n, const uint8_t* grp_comb, int ngroups,
                          void* scratch, int blocks, double* out, uint8_t* plane, int64_t ldq, int64_t col0,
                          uint64_t* energy, void* stream);
 

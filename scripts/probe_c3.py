@@ -57,6 +57,17 @@ if which in ("all", "motion"):
     out["motion_ref_1280x1024_512frames"] = {"ms": ms, "us_per_frame": 1e3 * ms / T, "blocks": blocks,
                                              "GBps_frames": (T * H * W) / (ms * 1e-3) / 1e9}
     print("motion_ref sbin 1:", out["motion_ref_1280x1024_512frames"], flush=True)
+    gplan = K.pairwise_plan(H * W, dev, groups=True)
+    ldq = K.round_up(H * W, 16)
+    pl2 = torch.empty((T, ldq), dtype=torch.uint8, device=dev)
+    e2 = torch.zeros(T, dtype=torch.int64, device=dev)
+    res2 = torch.zeros(T, dtype=torch.float64, device=dev)
+    for label, pp in (("leaf-by-leaf fold", plan), ("exact-group fold", gplan)):
+        ms2 = timed(lambda: K.motion_ref_planes(frames, pp, scratch, blocks, res2, pl2[:, :H * W], energy=e2))
+        out["motion_ref_planes_" + label.replace(" ", "_")] = {"ms": ms2, "us_per_frame": 1e3 * ms2 / T,
+                                                               "GBps_frames_read_once_plus_plane": (2 * T * H * W) / (ms2 * 1e-3) / 1e9}
+        print(f"fm_motion_ref_planes ({label}): {ms2:.2f} ms, {1e3 * ms2 / T:.2f} us per frame; equal to fm_motion_ref:",
+              bool(torch.equal(res2[:T - 1], res[:T - 1])), flush=True)
     fr = frames[:5].cpu().numpy().astype(np.float32).reshape(5, -1)
     ref = np.abs(np.diff(fr, axis=0)).sum(axis=-1)
     got = res[:4].cpu().numpy()

@@ -299,3 +299,40 @@ def test_save_npy_writes_what_np_save_writes(tmp_path):
 
     assert same(x, y)
     assert abs(os.path.getsize(a) - os.path.getsize(b)) < 4096
+
+
+def test_exact_groups_fold_equals_numpy_float32_sum():
+    """kernels.exact_groups: for byte-valued data the maximal subtrees of NumPy's pairwise tree with <= 65 793 elements
+    never round in float32, so summing them as integers and folding only the merges above them reproduces
+    `a.astype(float32).sum()` bit for bit (what fm_motion_ref_planes does on the device)"""
+    import ctypes as C
+
+    from facemap_b200 import _lib
+    from facemap_b200 import kernels as K
+
+    def plan(n):
+        cap = max(1, n // 64 + 2)
+        lo, ln, comb = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.uint8)
+        c = int(_lib.load().fm_pairwise_plan(int(n), cap, C.c_void_p(lo.ctypes.data), C.c_void_p(ln.ctypes.data),
+                                             C.c_void_p(comb.ctypes.data)))
+        return lo[:c], ln[:c], comb[:c]
+
+    rs = np.random.RandomState(0)
+    for n in (35, 4096, 65793, 65794, 66013, 93000, 198039, 1024 * 1280, 1000003):
+        lo, ln, comb = plan(n)
+        gf, gn, gc = K.exact_groups(ln, comb)
+        assert max(int(ln[f:f + c].sum()) for f, c in zip(gf, gn)) <= K.EXACT_BYTE_SUM_PIXELS
+        assert (len(gf) == 1) == (n <= K.EXACT_BYTE_SUM_PIXELS)
+        for lo_v, hi_v in ((200, 256), (0, 256), (255, 256)):
+            a = rs.randint(lo_v, hi_v, size=n).astype(np.uint8)
+            want = a.astype(np.float32).sum(dtype=np.float32)
+            csum = np.concatenate(([0], np.cumsum(a.astype(np.int64))))
+            leaf = csum[lo + ln] - csum[lo]
+            lsum = np.concatenate(([0], np.cumsum(leaf)))
+            stack = []
+            for f, c, cmb in zip(gf, gn, gc):
+                v = np.float32(lsum[f + c] - lsum[f])
+                for _ in range(int(cmb)):
+                    v = np.float32(stack.pop() + v)
+                stack.append(v)
+            assert len(stack) == 1 and stack[0] == want, (n, lo_v)

@@ -244,6 +244,8 @@ def test_motion_ref_planes_is_k1_plus_motion_ref(cuda_device, T, H, W, col0, mas
     npix = H * W
     ldq = K.round_up(col0 + npix, 16)
     plan = K.pairwise_plan(npix, dev)
+    gplan = K.pairwise_plan(npix, dev, groups=True)          # + the exact-subtree fold plan (kernels.exact_groups)
+    assert len(gplan) == 6 and int(gplan[4].sum()) == plan[0].numel()
     blocks = 5
     scratch = K.motion_ref_scratch(H, W, 1, plan[0].numel(), blocks, dev)
     fr = torch.from_numpy(frames).to(dev)
@@ -270,6 +272,15 @@ def test_motion_ref_planes_is_k1_plus_motion_ref(cuda_device, T, H, W, col0, mas
                                    energy=got_e, prev_frame=prev, ormask=mask) == rows
         torch.cuda.synchronize()
         assert torch.equal(got_plane, want_plane) and torch.equal(got_e, want_e) and torch.equal(got_ref, want_ref)
+        # the same with the leaves folded by exact groups instead of one by one
+        got_ref2 = torch.zeros(rows, dtype=torch.float64, device=dev)
+        got_plane.fill_(9)
+        got_e.zero_()
+        K.motion_ref_planes(src.contiguous(), gplan, scratch, blocks, got_ref2, got_plane[:, :col0 + npix], col0=col0,
+                            energy=got_e, prev_frame=prev, ormask=mask)
+        torch.cuda.synchronize()
+        assert torch.equal(got_ref2, want_ref) and torch.equal(got_e, want_e)
+        assert torch.equal(got_plane[:, col0:col0 + npix], want_plane[:, col0:col0 + npix])
 
 
 def test_motion_ref_full_resolution_view_with_budgeted_blocks(cuda_device):
