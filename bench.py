@@ -412,7 +412,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--c2-frames", type=int, default=20_000, help="frames per GPU of the configs[2] side measurement")
-    ap.add_argument("--c3-frames", type=int, default=16_000, help="frames per GPU of the configs[3] side measurement")
+    ap.add_argument("--c3-frames", type=int, default=50_000, help="frames per GPU of the configs[3] side measurement")
     ap.add_argument("--with-rois", action="store_true",
                     help="side measurement (not the headline workload): add a pupil, a blink and a running ROI")
     args = ap.parse_args()

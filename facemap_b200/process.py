@@ -267,13 +267,25 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
 
     # ---- stage 3 ----
     sink = None if keep_on_device else _HostSink(dev)
-    pending_masks = {}
+    pending_masks, pending_canvas = {}, {}
     V, E, E_roi, Eref = {}, None, None, None
     if mods and masks:
         single = dist is None or dist.world == 1 or not gather_outputs
         if sink is not None:
             # masks and singular values leave while stage 3 runs; projections leave batch by batch
             pending_masks = {m: ([sink.to_host(u) for u in masks[m][1]], sink.to_host(masks[m][2])) for m in masks}
+            if fullSVD and len(Ly) > 1:
+                # several views: the tiled (LYbin, LXbin, ncomp) canvas of utils.multivideo_reshape (utils.py:622-630) is
+                # laid out on the device — one strided copy per view — and leaves as one contiguous transfer, instead
+                # of a host-side scatter of the 77 MB mask matrix after the GPU is done
+                for m in masks:
+                    U_dev = masks[m][1][0]
+                    canvas = torch.zeros((int(LYbin), int(LXbin), U_dev.shape[1]), dtype=torch.float32, device=dev)
+                    for v in range(len(Ly)):
+                        c0, n = geo.col0[v], geo.npix_v[v]
+                        canvas[int(sybin[v]):int(sybin[v]) + int(Lybin[v]), int(sxbin[v]):int(sxbin[v]) + int(Lxbin[v])] = \
+                            U_dev[c0:c0 + n].view(int(Lybin[v]), int(Lxbin[v]), -1)
+                    pending_canvas[m] = sink.to_host(canvas)
         V, E, E_roi = s3.project(masks, sink=sink if single else None)
         Eref = s3.Eref
         if not single:
@@ -372,6 +384,8 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                 if fullSVD and len(Ly) == 1:
                     # one view: the canvas IS the mask matrix seen as (Lyb, Lxb, ncomp) — no copy
                     U_resh[m][0] = U_out[m][0].reshape(int(Lybin[0]), int(Lxbin[0]), -1)
+                elif fullSVD and m in pending_canvas:
+                    U_resh[m][0] = unwrap(pending_canvas[m])
                 elif fullSVD:
                     U_resh[m][0] = multivideo_reshape(U_out[m][0], LYbin, LXbin, sybin, sxbin, Lybin, Lxbin, iinds)
                 for j, (_, y0, y1, x0, x1) in enumerate(geo.mot_rois):

@@ -95,6 +95,12 @@ def test_three_views_canvas(cuda_device):
     # the canvas of the first mask is the scatter of its rows
     k0 = np.abs(p["motMask_reshape"][0][..., 0]).sum()
     assert np.isclose(k0, np.abs(p["motMask"][0][:, 0]).sum(), rtol=1e-6)
+    # laid out on the device, it is exactly what utils.multivideo_reshape (utils.py:622-630) makes of the mask matrix
+    from facemap_b200.utils import binned_inds, multivideo_reshape
+
+    _, _, iinds = binned_inds([32, 40, 24], [48, 40, 64], 2)
+    want = multivideo_reshape(p["motMask"][0], p["LYbin"], p["LXbin"], p["sybin"], p["sxbin"], p["Lybin"], p["Lxbin"], iinds)
+    assert np.array_equal(p["motMask_reshape"][0], want)
 
 
 def test_fullsvd_off_with_roi(cuda_device):
