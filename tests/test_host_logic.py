@@ -336,3 +336,50 @@ def test_exact_groups_fold_equals_numpy_float32_sum():
                     v = np.float32(stack.pop() + v)
                 stack.append(v)
             assert len(stack) == 1 and stack[0] == want, (n, lo_v)
+
+
+def test_pinned_pool_reuses_a_buffer_only_after_its_last_user_is_gone():
+    """process._PinnedPool with a plain allocator: whatever still refers to a handed-out buffer — the tensor, a slice
+    of it, a NumPy array made from it, a view of that array — keeps it out of the pool."""
+    import gc
+
+    import torch
+
+    from facemap_b200.process import _PinnedPool
+
+    sizes = []
+    pool = _PinnedPool(allocate=lambda n: (sizes.append(n), torch.empty(n, dtype=torch.uint8))[1])
+    a = pool.take((1000, 500))
+    arr, ptr_a = a.numpy(), a.data_ptr()
+    a[3:5] = 7.0
+    assert arr[3, 0] == 7.0 and arr.flags.writeable
+    del a
+    gc.collect()
+    b = pool.take((1000, 500))
+    assert b.data_ptr() != ptr_a                          # the array is still held
+    view = arr[10:20]
+    del arr
+    gc.collect()
+    c = pool.take((1000, 500))
+    assert c.data_ptr() != ptr_a                          # ... and so is a view of it
+    piece, ptr_c = c[5:9], c.data_ptr()
+    del c
+    gc.collect()
+    assert pool.take((1000, 500)).data_ptr() != ptr_c     # a tensor slice holds its buffer too
+    del view
+    gc.collect()
+    d = pool.take((999, 500))                             # a slightly smaller request shares the 2 MB size class
+    assert d.data_ptr() == ptr_a
+    assert sizes == [2 << 20] * 4 and pool.stats["reused"] == 1
+    assert tuple(pool.take((0, 1)).shape) == (0, 1) and len(sizes) == 4          # empty results take no buffer
+    small = pool.take((3,), torch.int32)
+    assert small.dtype == torch.int32 and sizes[-1] == 4096
+    del piece
+    gc.collect()
+    assert pool.take((1000, 500)).data_ptr() == ptr_c
+    # free buffers beyond keep_bytes are dropped instead of kept
+    tiny = _PinnedPool(allocate=lambda n: torch.empty(n, dtype=torch.uint8), keep_bytes=4096)
+    x, y = tiny.take((1024,)), tiny.take((1024,))
+    del x, y
+    gc.collect()
+    assert tiny.free_bytes == 4096

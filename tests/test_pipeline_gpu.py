@@ -228,6 +228,33 @@ def test_host_source_equals_device_source(cuda_device):
     assert np.array_equal(a["motSv"], b["motSv"])
 
 
+def test_result_buffers_are_pinned_and_reused_across_calls(cuda_device):
+    """The page-locked result buffers come from a pool that persists across calls (process._PinnedPool): a call whose
+    predecessor's results were dropped locks no new memory, a call whose predecessor's results are still held never
+    writes into them, and what is handed out really is page-locked (asynchronous device-to-host copies)."""
+    import gc
+
+    from facemap_b200 import process
+
+    assert process._HostSink.alloc((1 << 20,)).is_pinned()
+    a, _ = _run_cuda("short_s2", cuda_device, "device")
+    keep = {k: [np.array(x, copy=True) for x in a[k]] for k in ("motMask", "motSVD")}
+    b, _ = _run_cuda("short_s2", cuda_device, "device")            # `a` is alive: nothing of it may be reused
+    for k in keep:
+        for x, y, z in zip(a[k], keep[k], b[k]):
+            assert np.array_equal(x, y) and np.array_equal(x, z), k
+            assert not np.shares_memory(x, z), k
+    del a, b
+    gc.collect()
+    before = dict(process._POOL.stats)
+    c, _ = _run_cuda("short_s2", cuda_device, "device")
+    assert process._POOL.stats["allocated"] == before["allocated"], (before, process._POOL.stats)
+    assert process._POOL.stats["reused"] > before["reused"]
+    for k in keep:
+        for x, y in zip(c[k], keep[k]):
+            assert np.array_equal(x, y), k
+
+
 def test_streaming_host_source_equals_cached(cuda_device):
     """Videos that do not fit HBM stream through pinned buffers chunk by chunk (prefetch on a copy stream);
     forcing that path must give bit-identical outputs to the upload-once cache."""
