@@ -1,4 +1,4 @@
-"""Multi-rank host logic on CPU (gloo, world_size 2 and 3): work assignment, the integer (and, for
+"""Multi-rank host logic on CPU (gloo, world_size 2, 3 and 4): work assignment, the integer (and, for
 non-power-of-two bins, float64) all-reduce of stage 1, the chunk-block all-gather of stage 2 and the row gather of
 stage 3 and of the ROI-processor outputs."""
 import os
@@ -110,7 +110,7 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_shard_collectives_gloo(world):
     port = _free_port()
     ctx = mp.get_context("spawn")
