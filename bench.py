@@ -116,7 +116,7 @@ class ClockSampler:
                         reasons.add(k)
         return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.smax),
                 "reasons": sorted(reasons), "samples": len(sm),
-                "how": "NVML from the main thread after every other timed step, rank-0 GPU",
+                "how": "NVML from the main thread between timed steps (after 1/4, 1/2, 3/4 of them), rank-0 GPU",
                 "nvml_call_ms_max": {"clock": round(self.call_ms[0], 2), "reasons": round(self.call_ms[1], 2)}}
 
 
@@ -514,13 +514,17 @@ def main():
     w0 = time.perf_counter()
     torch.cuda.cudart().cudaProfilerStart()      # no-op outside a profiler; `ncu --profile-from-start off` lists the timed region only
     ev0.record()
+    # NVML is read three times inside the timed region (after a quarter, half, three quarters of the steps): a query
+    # normally takes 2 ms, but now and then the driver answers after 25 - 100 ms and the step that follows runs
+    # 20 - 50 ms long (r02_logs/bench_r2t.json), so the sampling is kept sparse
+    sample_after = {max(0, args.steps // 4 - 1), max(0, args.steps // 2 - 1), max(0, (3 * args.steps) // 4 - 1)}
     for step in range(args.steps):
         tm = {}
         ts = time.perf_counter()
         one_step(dev_src, timing=tm)
         tm["host_ms"] = 1e3 * (time.perf_counter() - ts)
         timings.append(tm)
-        if rank == 0 and (step % 2 == 0 or step == args.steps - 1):
+        if rank == 0 and step in sample_after:
             clocks.sample()                      # inside the timed region, between two steps
     ev1.record()
     barrier()
@@ -689,6 +693,7 @@ def main():
                    "steps": len(run_s), "api": "facemap_b200.process.run(HostArraySource([pinned uint8 frames]), savepath=tmp): "
                                                "H2D of every frame, D2H of every output, _proc.npy written, all inside the timed region",
                    "wall_s_each_step": [round(x, 4) for x in run_s], "proc_file_bytes": int(out_bytes), "savepath": savedir,
+                   "last_run_split_s": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in process.LAST_RUN.items()},
                    "pin_host_frames_s_outside_timed_region": round(pin_s, 3),
                    "process_source_only": {"frames_per_s": FRAMES_PER_GPU / min(ps_s), "wall_s": [round(x, 4) for x in ps_s],
                                            "note": "same pass without assembling the reference's dict layout into a file"},

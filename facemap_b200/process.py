@@ -37,7 +37,10 @@ def save_npy(path, obj, threads=8, piece=32 << 20):
     """`np.save(path, obj)` for an object (the proc dict: facemap/process.py:612) — the same .npy container (version 1.0
     header, object array, pickled payload; `np.load(path, allow_pickle=True).item()` gives the dict back) — written
     faster: pickle protocol 5 hands the big arrays over as buffers instead of copying them into the stream, and the
-    pieces go to the file in parallel with positioned writes (277 MB of a 100k-frame video: 0.23 s -> ~0.07 s)."""
+    pieces go to the file in parallel with positioned writes (277 MB of a 100k-frame video: 0.23 s -> ~0.07 s).
+    (Creating the file's page-cache pages ahead of time, with zeros written during the GPU pass, was tried and
+    dropped: 4x faster on a quiet file system, slower on the B200 boxes' ext4-on-virtio, where the overwrite waits for
+    the writeback of the zero pages — profiles/r02_logs/bench_r2u.json.)"""
     import io
     import pickle
     from concurrent.futures import ThreadPoolExecutor
@@ -80,14 +83,15 @@ def save_npy(path, obj, threads=8, piece=32 << 20):
     return path
 
 
+def _proc_file_name(names, savepath):
+    folder, name = os.path.split(names[0][0])
+    return (folder if savepath is None else savepath), os.path.splitext(name)[0]
+
+
 def save(proc, savepath=None):
     """Write the proc dict next to the first video (or into `savepath`) as `<name>_proc.npy`, plus
     a flattened `.mat` when proc["save_mat"] (reference process.py:605-635)."""
-    first = proc["filenames"][0][0]
-    folder, name = os.path.split(first)
-    stem = os.path.splitext(name)[0]
-    if savepath is not None:
-        folder = savepath
+    folder, stem = _proc_file_name(proc["filenames"], savepath)
     savename = os.path.join(folder, f"{stem}_proc.npy")
     save_npy(savename, proc)
     if proc["save_mat"]:
@@ -536,6 +540,9 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     return proc
 
 
+LAST_RUN = {}       # wall-clock split of the last run() call (diagnostic: bench.py reports it)
+
+
 def run(filenames, sbin=1, motSVD=True, movSVD=False, GUIobject=None, parent=None, proc=None, savepath=None):
     """Process video files: SVD of the motion and/or raw movie, projections of every frame, motion
     energy.  Arguments, precedence and return value as facemap.process.run (process.py:638-708):
@@ -547,6 +554,7 @@ def run(filenames, sbin=1, motSVD=True, movSVD=False, GUIobject=None, parent=Non
     savepath  : output folder (default: folder of the first video)
     Returns the path of the written `_proc.npy`."""
     start = time.time()
+    start_pc = time.perf_counter()
     rois = None
     sy, sx = 0, 0
     if parent is not None:
@@ -569,10 +577,13 @@ def run(filenames, sbin=1, motSVD=True, movSVD=False, GUIobject=None, parent=Non
     source = as_source(filenames)
     names = filenames if not isinstance(filenames, FrameSource) and isinstance(filenames[0], (list, tuple)) \
         else [["array_input.avi"]]
+    t_pass = time.perf_counter()
     try:
         out = process_source(source, sbin=sbin, motSVD=motSVD, movSVD=movSVD, rois=rois, fullSVD=fullSVD)
     finally:
+        t_close = time.perf_counter()
         source.close()
+    t_save = time.perf_counter()
     if parent is not None:
         parent.update_status_bar("Computed projection")
     if GUIobject is not None:
@@ -591,6 +602,9 @@ def run(filenames, sbin=1, motSVD=True, movSVD=False, GUIobject=None, parent=Non
         "pupil": out["pupil"], "running": out["running"], "blink": out["blink"], "rois": rois, "sy": sy, "sx": sx,
     }
     savename = save(full, savepath)
+    LAST_RUN.clear()
+    LAST_RUN.update({"setup_s": t_pass - start_pc, "pass_s": t_close - t_pass, "close_s": t_save - t_close,
+                     "save_s": time.perf_counter() - t_save})
     if parent is not None:
         parent.update_status_bar("Output saved in " + str(savepath))
     if GUIobject is not None:

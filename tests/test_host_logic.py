@@ -383,3 +383,4 @@ def test_pinned_pool_reuses_a_buffer_only_after_its_last_user_is_gone():
     del x, y
     gc.collect()
     assert tiny.free_bytes == 4096
+
