@@ -752,6 +752,8 @@ def main():
                     "yrange": np.arange(y0, y1), "xrange": np.arange(x0, x1), "saturation": 0}
 
         def side(name, views, frames, sbin, mov, rois_fn, what):
+            if frames <= 0:
+                return
             try:
                 n_tot = world * frames
                 syn = [SynthVideo(h, w, n_tot, seed=s) for (h, w, s) in views]
@@ -768,6 +770,16 @@ def main():
                                 "cusolver_ms_per_step_rank0": round(sum(v for k, v in dm.items() if k.endswith(".syevd")), 2),
                                 "stage_ms_rank0": {k: round(v, 2) for k, v in sorted(dm.items()) if v > 1.0},
                                 "peak_mem_gb_rank0": round(torch.cuda.max_memory_allocated(device) / 1e9, 1)}
+                if world > 1:       # every rank's own view of its last pass: the slowest one sets the step
+                    mine = {"wall_ms": round(1e3 * tms.get("wall_s", 0.0), 1),
+                            "syevd_ms": round(sum(v for k, v in dm.items() if k.endswith(".syevd")), 1),
+                            "chunk_eigh_ms": round(dm.get("stage2.chunk.eigh", 0.0), 1),
+                            "bcast_wait_ms": round(dm.get("stage2.merge.bcast", 0.0), 1),
+                            "stage3_bin_ms": round(dm.get("stage3.bin", 0.0), 1),
+                            "host_marks_ms": tms.get("host_marks_ms", {})}
+                    every = [None] * world
+                    dist.all_gather_object(every, mine)
+                    extras[name]["per_rank"] = every
                 pp = sum((h // sbin) * (w // sbin) for (h, w, _) in views)
                 f_a, f_b = (0, n_tot) if shard is None else frame_ranges(n_tot, world)[rank]
                 if dm.get("stage3.project.mma"):

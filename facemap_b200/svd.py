@@ -730,6 +730,21 @@ def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, t
     return Yt, ks, nsegs
 
 
+def deal_merges(sizes, world):
+    """Which rank solves which merge: sizes = {target: order n of its eigenproblem} -> {target: rank}, heaviest first
+    onto the least loaded rank.  The cost of a solve is taken as PROPORTIONAL TO n: cuSOLVER's syevd(x) spends about
+    19 us per matrix column whatever the size (999 columns 12 ms, 3 750 columns 71 ms: profiles/r02_eig.md), not n^3.
+    One target or one rank: nothing to deal ({})."""
+    if world <= 1 or len(sizes) <= 1:
+        return {}
+    owner, load = {}, [0.0] * world
+    for t in sorted(sizes, key=lambda t: -float(sizes[t])):          # sorted() is stable: ties keep the target order
+        r = min(range(world), key=lambda q: load[q])
+        owner[t] = r
+        load[r] += float(sizes[t])
+    return owner
+
+
 def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS, nc=None, mot_on=True, shard=None):
     """Second-level SVD (process.py:264-295).  Returns per modality lists Ut, U, and Sv (the
     singular values of the LAST target processed, quirk Q3).
@@ -744,14 +759,8 @@ def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS, nc
         for idx, Y in enumerate(Yt[m]):
             if Y is not None and nsegs > 1 and idx < (1 if mot_on else 0) + (len(Yt[m]) - 1):
                 todo.append((m, idx))
-    owner = {}
     world = 1 if shard is None else shard.world
-    if world > 1 and len(todo) > 1:
-        load = [0.0] * world
-        for t in sorted(todo, key=lambda t: -float(min(Yt[t[0]][t[1]].shape)) ** 3):     # eigensolve cost ~ n^3
-            r = min(range(world), key=lambda q: load[q])
-            owner[t] = r
-            load[r] += float(min(Yt[t[0]][t[1]].shape)) ** 3
+    owner = deal_merges({t: min(Yt[t[0]][t[1]].shape) for t in todo}, world)
     # the solves this rank owns come first (cuSOLVER blocks the host, and a broadcast waiting in the stream would block
     # the solves queued behind it), the broadcasts of all dealt targets follow in target order
     solved = {}

@@ -384,3 +384,18 @@ def test_pinned_pool_reuses_a_buffer_only_after_its_last_user_is_gone():
     gc.collect()
     assert tiny.free_bytes == 4096
 
+
+def test_merges_are_dealt_by_a_cost_linear_in_the_problem_order():
+    """svd.deal_merges: configs[2]'s eight merge problems (2 modalities x (full frame 3750 + ROIs 2400, 1888, 2500)).
+    cuSOLVER's eigensolve costs ~19 us per column, so the full-frame problems must not each fill a rank on their own."""
+    from facemap_b200.svd import deal_merges
+
+    sizes = {(m, i): n for m in ("mot", "mov") for i, n in enumerate((3750, 2400, 1888, 2500))}
+    assert deal_merges(sizes, 1) == {} and deal_merges({("mot", 0): 3750}, 8) == {}
+    for world, worst in ((2, 10538), (4, 5638), (8, 3750)):
+        own = deal_merges(sizes, world)
+        assert set(own) == set(sizes) and set(own.values()) <= set(range(world))
+        load = [sum(n for t, n in sizes.items() if own[t] == r) for r in range(world)]
+        assert max(load) == worst, (world, load)
+    # deterministic: every rank computes the same table
+    assert deal_merges(sizes, 4) == deal_merges(dict(sizes), 4)
