@@ -41,9 +41,22 @@ def save_npy(path, obj, threads=8, piece=32 << 20):
     (Creating the file's page-cache pages ahead of time, with zeros written during the GPU pass, was tried and
     dropped: 4x faster on a quiet file system, slower on the B200 boxes' ext4-on-virtio, where the overwrite waits for
     the writeback of the zero pages — profiles/r02_logs/bench_r2u.json.)"""
+    segs = _npy_segments(obj)
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+    try:
+        os.ftruncate(fd, segs[-1][0] + segs[-1][1].nbytes)
+        _write_segments(fd, [(off, mv) for off, mv, _ in segs], threads, piece)
+    finally:
+        os.close(fd)
+    return path
+
+
+def _npy_segments(obj):
+    """The bytes of `np.save(path, obj)` for an object, as a list of (file offset, memoryview, address): header and
+    pickle stream in the order they go to the file; the big arrays are views of the arrays' own memory (address =
+    where that memory starts; None for the pickler's own byte strings)."""
     import io
     import pickle
-    from concurrent.futures import ThreadPoolExecutor
 
     from numpy.lib import format as npy_format
 
@@ -54,33 +67,194 @@ def save_npy(path, obj, threads=8, piece=32 << 20):
     sink = _Segments()
     sink.write(head.getvalue())
     pickle.Pickler(sink, protocol=5).dump(arr)
-    jobs, off = [], 0
+    out, off = [], 0
     for seg in sink.segs:
         mv = memoryview(seg).cast("B")
-        for a in range(0, max(mv.nbytes, 1), piece):
-            if mv.nbytes:
-                jobs.append((off + a, mv[a:a + piece]))
+        if mv.nbytes == 0:
+            continue
+        addr = None if isinstance(seg, bytes) else int(np.frombuffer(mv, np.uint8).__array_interface__["data"][0])
+        out.append((off, mv, addr))
         off += mv.nbytes
-    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
-    try:
-        os.ftruncate(fd, off)
+    return out
 
-        def put(job):
-            pos, mv = job
-            while mv.nbytes:
-                n = os.pwrite(fd, mv, pos)
-                pos, mv = pos + n, mv[n:]
 
-        small = [j for j in jobs if j[1].nbytes < (1 << 20)]
-        big = [j for j in jobs if j[1].nbytes >= (1 << 20)]
-        for j in small:
-            put(j)
-        if big:
-            with ThreadPoolExecutor(max_workers=max(1, min(threads, len(big)))) as pool:
-                list(pool.map(put, big))
-    finally:
-        os.close(fd)
-    return path
+def _write_segments(fd, jobs, threads=8, piece=32 << 20):
+    """positioned writes of [(offset, memoryview)]: small ones in order, big ones cut into pieces on a thread pool"""
+    from concurrent.futures import ThreadPoolExecutor
+
+    cut = []
+    for off, mv in jobs:
+        for a in range(0, mv.nbytes, piece):
+            cut.append((off + a, mv[a:a + piece]))
+
+    def put(job):
+        pos, mv = job
+        while mv.nbytes:
+            n = os.pwrite(fd, mv, pos)
+            pos, mv = pos + n, mv[n:]
+
+    small = [j for j in cut if j[1].nbytes < (1 << 20)]
+    big = [j for j in cut if j[1].nbytes >= (1 << 20)]
+    for j in small:
+        put(j)
+    if big:
+        with ThreadPoolExecutor(max_workers=max(1, min(threads, len(big)))) as pool:
+            list(pool.map(put, big))
+
+
+class _EarlyFile:
+    """Writes the big arrays of the proc file while the GPU pass is still running.
+
+    A 100k-frame proc file is 277 MB, of which 200 MB are the projections; written after the pass it costs 0.13 - 0.19 s
+    of a 0.57 s call, while during the pass the host has nothing to do.  The projections land in page-locked host
+    buffers batch by batch (`_HostSink.copy`), the masks right after the merge; process_source announces those buffers
+    before stage 3 starts, inside a dict that has the layout of its return value (`begin`), and the file layout follows
+    from pickling that dict: every big array sits at an offset that depends on shapes only.  A writer thread then waits
+    for each copy's event and writes the rows to their place in `<name>.partial`.  When the pass is over the final dict
+    is pickled again: if its layout (every segment's length, the buffer behind every array written early) is the
+    announced one, only
+    what was not written early — or was changed on the host since (`dirty`) — is written, and the file takes its name;
+    if anything differs, or anything failed, the caller writes the file the plain way.  What is in the file is always
+    the final pickle of the final dict."""
+
+    BIG = 1 << 16           # the pickler hands over buffers from 64 KB on; smaller arrays are copied into its stream
+
+    def __init__(self, path, build_full):
+        import queue
+
+        self.final_path, self.path, self.build_full = path, path + ".partial", build_full
+        self.q, self.thread, self.fd = queue.Queue(), None, None
+        self.sig, self.where, self.bases = None, {}, []
+        self.waiting, self.done, self.redo, self.used = [], [], [], set()
+        self.failed = False
+
+    @staticmethod
+    def _signature(segs):
+        return [mv.nbytes for _, mv, _ in segs]
+
+    def begin(self, out_like):
+        """out_like: a dict with the layout of process_source's return value whose big arrays ARE the buffers the
+        results will land in"""
+        import threading
+
+        if self.sig is not None:                # a repeated pass (eigensolver fallback): leave it to the plain writer
+            self.failed = True
+            return
+        try:
+            segs = _npy_segments(self.build_full(out_like))
+            self.sig = self._signature(segs)
+            for off, mv, addr in segs:
+                if addr is not None and mv.nbytes >= self.BIG:
+                    self.where.setdefault(addr, []).append((off, mv.nbytes))     # a mask and its canvas view: two places
+            self.bases = sorted(self.where)
+            self.fd = os.open(self.path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+            os.ftruncate(self.fd, segs[-1][0] + segs[-1][1].nbytes)
+        except Exception:       # noqa: BLE001 — an optimisation: the plain writer takes over
+            self.failed = True
+            return
+        self.thread = threading.Thread(target=self._work, daemon=True)
+        self.thread.start()
+        for job in self.waiting:
+            self.q.put(job)
+        self.waiting = []
+
+    def landed(self, host_tensor, event):
+        """a device-to-host copy into `host_tensor` (contiguous) was enqueued; `event` fires when it is done"""
+        job = (host_tensor, event)
+        if self.thread is None:
+            self.waiting.append(job)
+        else:
+            self.q.put(job)
+
+    def dirty(self, host_array):
+        """rows changed on the host after they landed: written again at the end"""
+        self.redo.append(host_array)
+
+    def _place(self, addr, nbytes):
+        import bisect
+
+        i = bisect.bisect_right(self.bases, addr) - 1
+        if i < 0:
+            return []
+        base = self.bases[i]
+        return [(off + addr - base, off, base) for off, n in self.where[base] if addr + nbytes <= base + n]
+
+    def _work(self):
+        while True:
+            job = self.q.get()
+            if job is None:
+                return
+            try:
+                t, event = job
+                spots = self._place(t.data_ptr(), t.numel() * t.element_size())
+                if not spots:
+                    continue
+                event.synchronize()
+                mv = memoryview(t.numpy()).cast("B")
+                for pos, seg_off, base in spots:
+                    m = mv
+                    p0 = pos
+                    while m.nbytes:
+                        n = os.pwrite(self.fd, m, p0)
+                        p0, m = p0 + n, m[n:]
+                    self.done.append((pos, pos + mv.nbytes))
+                    self.used.add((seg_off, base))
+            except Exception:   # noqa: BLE001
+                self.failed = True
+
+    def _stop(self):
+        if self.thread is not None:
+            self.q.put(None)
+            self.thread.join()
+            self.thread = None
+
+    def abandon(self):
+        self._stop()
+        if self.fd is not None:
+            os.close(self.fd)
+            self.fd = None
+            try:
+                os.remove(self.path)
+            except OSError:
+                pass
+
+    def finish(self, full):
+        """True: the file is complete under its final name.  False: nothing usable was written (plain writer's turn)."""
+        self._stop()
+        if self.failed or self.sig is None or self.fd is None:
+            self.abandon()
+            return False
+        try:
+            segs = _npy_segments(full)
+            at = {off: addr for off, _, addr in segs}
+            if self._signature(segs) != self.sig or any(at.get(off) != base for off, base in self.used):
+                self.abandon()          # not the announced layout, or an early-written array is not the saved one
+                return False
+            covered = sorted(self.done)
+            jobs = []
+            for off, mv, addr in segs:
+                a = off
+                for lo, hi in covered:                       # what the writer thread did not cover
+                    if hi <= a or lo >= off + mv.nbytes:
+                        continue
+                    if lo > a:
+                        jobs.append((a, mv[a - off:lo - off]))
+                    a = max(a, hi)
+                if a < off + mv.nbytes:
+                    jobs.append((a, mv[a - off:]))
+            for arr in self.redo:
+                mv = memoryview(np.ascontiguousarray(arr)).cast("B")
+                addr = int(arr.__array_interface__["data"][0])
+                for pos, _, _ in self._place(addr, mv.nbytes):
+                    jobs.append((pos, mv))
+            _write_segments(self.fd, jobs)
+            os.close(self.fd)
+            self.fd = None
+            os.replace(self.path, self.final_path)
+            return True
+        except Exception:       # noqa: BLE001
+            self.abandon()
+            return False
 
 
 def _proc_file_name(names, savepath):
@@ -88,12 +262,14 @@ def _proc_file_name(names, savepath):
     return (folder if savepath is None else savepath), os.path.splitext(name)[0]
 
 
-def save(proc, savepath=None):
+def save(proc, savepath=None, npy_written=False):
     """Write the proc dict next to the first video (or into `savepath`) as `<name>_proc.npy`, plus
-    a flattened `.mat` when proc["save_mat"] (reference process.py:605-635)."""
+    a flattened `.mat` when proc["save_mat"] (reference process.py:605-635).  npy_written: the .npy file is
+    already there (run: written while the pass ran)."""
     folder, stem = _proc_file_name(proc["filenames"], savepath)
     savename = os.path.join(folder, f"{stem}_proc.npy")
-    save_npy(savename, proc)
+    if not npy_written:
+        save_npy(savename, proc)
     if proc["save_mat"]:
         from scipy import io
 
@@ -216,8 +392,9 @@ class _HostSink:
     the GPU while later batches are still being computed, and land in pinned memory (fast DMA) taken from a pool
     that persists across calls (_PinnedPool)."""
 
-    def __init__(self, device):
+    def __init__(self, device, listener=None):
         self.stream = torch.cuda.Stream(device)
+        self.listener = listener            # _EarlyFile: told about every copy, with an event that fires when it is done
 
     @staticmethod
     def alloc(shape, dtype=torch.float32):
@@ -229,6 +406,10 @@ class _HostSink:
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
             host_tensor.copy_(dev_tensor, non_blocking=True)
+            if self.listener is not None and host_tensor.is_contiguous():
+                done = torch.cuda.Event()
+                done.record(self.stream)
+                self.listener.landed(host_tensor, done)
         dev_tensor.record_stream(self.stream)
 
     def to_host(self, dev_tensor):
@@ -242,7 +423,8 @@ class _HostSink:
 
 def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD=True, device=None,
                    eig_fp32=False, gemm_impl=0, timing=None, dist=None, keep_on_device=False,
-                   overlap_stage3=True, gather_outputs=True, gram_mode=None, proj_mode=None, eig_mode=None):
+                   overlap_stage3=True, gather_outputs=True, gram_mode=None, proj_mode=None, eig_mode=None,
+                   stream_out=None):
     """Run the three stages on a FrameSource and return the proc-dict entries this path owns.
 
     timing: optional dict that receives per-stage device times (ms) and wall times.
@@ -258,10 +440,13 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
             3xTF32 products); None reads FM_PROJ_MODE.
     eig_mode: "cluster" (default: the hand-written batched eigensolver for the per-chunk Gram matrices,
             csrc/eigh_cluster.cu) or "cusolver"; None reads FM_EIG.  If the hand-written solver's self-check flags a
-            matrix (exactly repeated eigenvalues), the pass is repeated with cuSOLVER — on every rank."""
+            matrix (exactly repeated eigenvalues), the pass is repeated with cuSOLVER — on every rank.
+    stream_out: optional _EarlyFile (run): told before stage 3 which host buffers the big results will land in, and
+            of every device-to-host copy, so that the proc file is written while the pass runs."""
     call = dict(sbin=sbin, motSVD=motSVD, movSVD=movSVD, rois=rois, fullSVD=fullSVD, device=device, eig_fp32=eig_fp32,
                 gemm_impl=gemm_impl, timing=timing, dist=dist, keep_on_device=keep_on_device,
-                overlap_stage3=overlap_stage3, gather_outputs=gather_outputs, gram_mode=gram_mode, proj_mode=proj_mode)
+                overlap_stage3=overlap_stage3, gather_outputs=gather_outputs, gram_mode=gram_mode, proj_mode=proj_mode,
+                stream_out=stream_out)
     t_enter = time.perf_counter()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     _lib.require_device(dev.index or 0)
@@ -343,8 +528,9 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
     nc_plan = svd.stage2_plan(N)[2]
 
     # ---- stage 3 ----
-    sink = None if keep_on_device else _HostSink(dev)
+    sink = None if keep_on_device else _HostSink(dev, listener=stream_out)
     pending_masks, pending_canvas = {}, {}
+    V_early = None
     V, E, E_roi, Eref = {}, None, None, None
     if mods and masks:
         single = dist is None or dist.world == 1 or not gather_outputs
@@ -363,7 +549,33 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                         canvas[int(sybin[v]):int(sybin[v]) + int(Lybin[v]), int(sxbin[v]):int(sxbin[v]) + int(Lxbin[v])] = \
                             U_dev[c0:c0 + n].view(int(Lybin[v]), int(Lxbin[v]), -1)
                     pending_canvas[m] = sink.to_host(canvas)
-        V, E, E_roi = s3.project(masks, sink=sink if single else None)
+        if stream_out is not None and sink is not None and single and fullSVD and nroi == 0 and fres is None \
+                and (dist is None or dist.world == 1):
+            # the simple layout (no ROIs of any kind, one rank): announce where the results will land, in a dict shaped
+            # like the one returned below (_EarlyFile.begin; a wrong guess only costs the early writing)
+            V_early = {m: [None if Ut is None else sink.alloc((s3.n_out, Ut.shape[0])) for Ut in masks[m][0]]
+                       for m in mods}
+            like = {"Ly": Ly, "Lx": Lx, "sbin": sbin, "fullSVD": fullSVD, "Lybin": Lybin, "Lxbin": Lxbin, "sybin": sybin,
+                    "sxbin": sxbin, "LYbin": LYbin, "LXbin": LXbin, "rois": rois, "pupil": [], "blink": [], "running": [],
+                    "avgframe": [np.empty(len(ir), np.float32) for ir in iinds],
+                    "avgmotion": [np.empty(len(ir), np.float32) for ir in iinds],
+                    "motion": [np.empty(N, np.float32)]}                 # one trace per target: the full frame only
+            flat = np.empty((sum(len(ir) for ir in iinds), 1), np.float32)
+            for key in ("avgframe_reshape", "avgmotion_reshape"):
+                like[key] = np.squeeze(multivideo_reshape(flat, LYbin, LXbin, sybin, sxbin, Lybin, Lxbin, iinds))
+            for m in ("mot", "mov"):
+                if m in mods:
+                    Us, sv = pending_masks[m]
+                    like[m + "Mask"] = [u.numpy() for u in Us]
+                    like[m + "Sv"] = sv.numpy()
+                    like[m + "Mask_reshape"] = [pending_canvas[m].numpy() if m in pending_canvas else
+                                                Us[0].numpy().reshape(int(Lybin[0]), int(Lxbin[0]), -1)]
+                    like[m + "SVD"] = [v.numpy() for v in V_early[m]]
+                else:
+                    like[m + "Mask"], like[m + "Mask_reshape"], like[m + "SVD"] = [], [], []
+                    like[m + "Sv"] = np.zeros(500, np.float32)
+            stream_out.begin(like)
+        V, E, E_roi = s3.project(masks, sink=sink if single else None, V_host=V_early)
         Eref = s3.Eref
         if not single:
             V, E, E_roi = dist.gather_stage3(V, E, E_roi, N, mods, timer)
@@ -484,6 +696,8 @@ def process_source(source, sbin=1, motSVD=True, movSVD=False, rois=None, fullSVD
                     v = v.numpy()
                 if N > 1 and f0_out == 0 and v.shape[0] > 1:
                     v[0] = v[1]                         # quirk Q2: first projected row duplicated
+                    if stream_out is not None:
+                        stream_out.dirty(v[0:1])
                 V_out[m].append(v)
         if fullSVD:
             refs = None if Eref_h is None else [Eref_h[v] if v in s3.ref_views else None for v in range(len(Ly))]
@@ -577,9 +791,38 @@ def run(filenames, sbin=1, motSVD=True, movSVD=False, GUIobject=None, parent=Non
     source = as_source(filenames)
     names = filenames if not isinstance(filenames, FrameSource) and isinstance(filenames[0], (list, tuple)) \
         else [["array_input.avi"]]
+
+    def build_full(out):
+        return {
+            "filenames": names, "save_path": savepath, "Ly": out["Ly"], "Lx": out["Lx"], "sbin": sbin,
+            "fullSVD": fullSVD, "save_mat": save_mat,
+            "Lybin": out["Lybin"], "Lxbin": out["Lxbin"], "sybin": out["sybin"], "sxbin": out["sxbin"],
+            "LYbin": out["LYbin"], "LXbin": out["LXbin"],
+            "avgframe": out["avgframe"], "avgmotion": out["avgmotion"],
+            "avgframe_reshape": out["avgframe_reshape"], "avgmotion_reshape": out["avgmotion_reshape"],
+            "motion": out["motion"], "motSv": out["motSv"], "movSv": out["movSv"],
+            "motMask": out["motMask"], "movMask": out["movMask"],
+            "motMask_reshape": out["motMask_reshape"], "movMask_reshape": out["movMask_reshape"],
+            "motSVD": out["motSVD"], "movSVD": out["movSVD"],
+            "pupil": out["pupil"], "running": out["running"], "blink": out["blink"], "rois": rois, "sy": sy, "sx": sx,
+        }
+
+    # the big arrays go to the file while the pass runs (_EarlyFile); anything it cannot do is written afterwards
+    early = None
+    try:
+        folder, stem = _proc_file_name(names, savepath)
+        if os.path.isdir(folder or "."):
+            early = _EarlyFile(os.path.join(folder, f"{stem}_proc.npy"), build_full)
+    except Exception:           # noqa: BLE001
+        early = None
     t_pass = time.perf_counter()
     try:
-        out = process_source(source, sbin=sbin, motSVD=motSVD, movSVD=movSVD, rois=rois, fullSVD=fullSVD)
+        out = process_source(source, sbin=sbin, motSVD=motSVD, movSVD=movSVD, rois=rois, fullSVD=fullSVD,
+                             stream_out=early)
+    except BaseException:
+        if early is not None:
+            early.abandon()
+        raise
     finally:
         t_close = time.perf_counter()
         source.close()
@@ -588,23 +831,13 @@ def run(filenames, sbin=1, motSVD=True, movSVD=False, GUIobject=None, parent=Non
         parent.update_status_bar("Computed projection")
     if GUIobject is not None:
         GUIobject.QApplication.processEvents()
-    full = {
-        "filenames": names, "save_path": savepath, "Ly": out["Ly"], "Lx": out["Lx"], "sbin": sbin,
-        "fullSVD": fullSVD, "save_mat": save_mat,
-        "Lybin": out["Lybin"], "Lxbin": out["Lxbin"], "sybin": out["sybin"], "sxbin": out["sxbin"],
-        "LYbin": out["LYbin"], "LXbin": out["LXbin"],
-        "avgframe": out["avgframe"], "avgmotion": out["avgmotion"],
-        "avgframe_reshape": out["avgframe_reshape"], "avgmotion_reshape": out["avgmotion_reshape"],
-        "motion": out["motion"], "motSv": out["motSv"], "movSv": out["movSv"],
-        "motMask": out["motMask"], "movMask": out["movMask"],
-        "motMask_reshape": out["motMask_reshape"], "movMask_reshape": out["movMask_reshape"],
-        "motSVD": out["motSVD"], "movSVD": out["movSVD"],
-        "pupil": out["pupil"], "running": out["running"], "blink": out["blink"], "rois": rois, "sy": sy, "sx": sx,
-    }
-    savename = save(full, savepath)
+    full = build_full(out)
+    written_early = early is not None and early.finish(full)
+    savename = save(full, savepath, npy_written=written_early)
     LAST_RUN.clear()
     LAST_RUN.update({"setup_s": t_pass - start_pc, "pass_s": t_close - t_pass, "close_s": t_save - t_close,
-                     "save_s": time.perf_counter() - t_save})
+                     "save_s": time.perf_counter() - t_save, "written_early": bool(written_early),
+                     "early_bytes": 0 if early is None else sum(b - a for a, b in early.done)})
     if parent is not None:
         parent.update_status_bar("Output saved in " + str(savepath))
     if GUIobject is not None:

@@ -1032,16 +1032,17 @@ class Stage3:
         return True
 
     # ---- project phase ---------------------------------------------------------------------------
-    def project(self, masks, sink=None):
+    def project(self, masks, sink=None, V_host=None):
         """sink: optional host sink (process._HostSink); the projections are then copied to pinned host
         arrays batch by batch on its stream and returned as CPU tensors."""
         geo, mods, ws, timer, device = self.geo, self.mods, self.ws, self.timer, self.device
-        V, V_host = {}, {}
+        V, V_host = {}, dict(V_host or {})
         for m in mods:
             V[m] = [None if Ut is None else torch.zeros((self.n_out, Ut.shape[0]), dtype=torch.float32, device=device)
                     for Ut in masks[m][0]]
             if sink is not None:
-                V_host[m] = [None if v is None else sink.alloc(v.shape) for v in V[m]]
+                if m not in V_host:
+                    V_host[m] = [None if v is None else sink.alloc(v.shape) for v in V[m]]
                 for h in V_host[m]:
                     if h is not None and self.first_row_frame > self.f0:
                         h[:self.first_row_frame - self.f0].zero_()      # frame 0 has no difference row

@@ -399,3 +399,72 @@ def test_merges_are_dealt_by_a_cost_linear_in_the_problem_order():
         assert max(load) == worst, (world, load)
     # deterministic: every rank computes the same table
     assert deal_merges(sizes, 4) == deal_merges(dict(sizes), 4)
+
+
+class _FiredEvent:
+    def synchronize(self):
+        pass
+
+
+def test_early_file_is_the_final_pickle_or_nothing(tmp_path):
+    """process._EarlyFile on CPU tensors: rows written while 'the pass runs' land where the final pickle puts them
+    (mask and its canvas view: twice), rows changed on the host afterwards are written again, and a final dict whose
+    layout is not the announced one leaves no file behind."""
+    import torch
+
+    from facemap_b200.process import _EarlyFile, save_npy
+
+    rng = np.random.default_rng(5)
+    N, p, k = 6000, 1200, 500
+
+    def build_full(out):
+        return {"filenames": [["a.avi"]], "sbin": 2, "motion": out["motion"], "motSv": out["motSv"],
+                "motMask": out["motMask"], "motMask_reshape": out["motMask_reshape"], "motSVD": out["motSVD"], "rois": None}
+
+    def scenario(path, final_motion_len=N, second_begin=False, copy_v=False):
+        V = torch.zeros((N, k), dtype=torch.float32)
+        U = torch.zeros((p, k), dtype=torch.float32)
+        S = torch.zeros(k, dtype=torch.float32)
+        early = _EarlyFile(path, build_full)
+        U.copy_(torch.from_numpy(rng.standard_normal((p, k)).astype(np.float32)))
+        early.landed(U, _FiredEvent())                       # the masks land before the layout is announced
+        like = {"motion": [np.empty(N, np.float32)], "motSv": S.numpy(), "motMask": [U.numpy()],
+                "motMask_reshape": [U.numpy().reshape(30, 40, k)], "motSVD": [V.numpy()]}
+        early.begin(like)
+        if second_begin:
+            early.begin(like)
+        for a in range(0, N, 1000):
+            V[a:a + 1000] = torch.from_numpy(rng.standard_normal((1000, k)).astype(np.float32))
+            if a != 3000:                                    # one batch is never announced: written at the end
+                early.landed(V[a:a + 1000], _FiredEvent())
+        S.copy_(torch.arange(k, dtype=torch.float32))
+        v = V.numpy()
+        v[0] = v[1]
+        early.dirty(v[0:1])
+        out = {"motion": [rng.standard_normal(final_motion_len).astype(np.float32)], "motSv": S.numpy(),
+               "motMask": [U.numpy()], "motMask_reshape": [U.numpy().reshape(30, 40, k)],
+               "motSVD": [v.copy() if copy_v else v]}
+        full = build_full(out)
+        return early, full
+
+    path = str(tmp_path / "a_proc.npy")
+    early, full = scenario(path)
+    assert early.finish(full) is True
+    assert sum(b - a for a, b in early.done) == 4 * (5 * 1000 * k + 2 * p * k)       # five batches, the mask twice
+    plain = str(tmp_path / "plain.npy")
+    save_npy(plain, full)
+    assert open(path, "rb").read() == open(plain, "rb").read()
+    assert sorted(os.listdir(tmp_path)) == ["a_proc.npy", "plain.npy"]
+    back = np.load(path, allow_pickle=True).item()
+    assert np.array_equal(back["motSVD"][0], full["motSVD"][0]) and np.array_equal(back["motSVD"][0][0], back["motSVD"][0][1])
+    assert np.array_equal(back["motMask_reshape"][0], full["motMask"][0].reshape(30, 40, k))
+    # not the announced layout, or not the announced buffers -> nothing is left, the caller writes the file the plain way
+    for kw in ({"final_motion_len": N + 1}, {"second_begin": True}, {"copy_v": True}):
+        path2 = str(tmp_path / "b_proc.npy")
+        early, full = scenario(path2, **kw)
+        assert early.finish(full) is False
+        assert sorted(os.listdir(tmp_path)) == ["a_proc.npy", "plain.npy"]
+    # a pass that raises
+    early, _ = scenario(str(tmp_path / "c_proc.npy"))
+    early.abandon()
+    assert sorted(os.listdir(tmp_path)) == ["a_proc.npy", "plain.npy"]

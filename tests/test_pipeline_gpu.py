@@ -296,6 +296,48 @@ def test_run_with_proc_settings_and_mat_output(cuda_device, tmp_path):
     assert mat["motSVD_0"].shape == d["motSVD"][0].shape
 
 
+@pytest.mark.parametrize("case,mot,mov", [("single_s2", True, False), ("short_s2", True, True), ("multi_roi_s4", False, True),
+                                          ("crop_s3", True, False), ("tiny_onechunk_s2", True, True)])
+def test_run_writes_the_file_while_the_pass_runs(cuda_device, tmp_path, case, mot, mov):
+    """run() streams the big arrays into the file during the pass (process._EarlyFile).  Whatever went to disk early,
+    the file must hold exactly what process_source returns for the same input — every key, bit for bit.  (One and
+    two views, motion / movie / both, a non-power-of-two bin factor, the single-chunk regime; no ROIs.)"""
+    from facemap_b200 import process
+
+    vids = [torch.from_numpy(v) for v in case_videos(case)]
+    sbin = CASES[case][2]
+    name = process.run(vids, sbin=sbin, motSVD=mot, movSVD=mov, savepath=str(tmp_path))
+    split = dict(process.LAST_RUN)
+    assert split["written_early"] is True and split["early_bytes"] > 0, split
+    assert sorted(os.listdir(tmp_path)) == ["array_input_proc.npy"]
+    d = np.load(name, allow_pickle=True).item()
+    want = process.process_source(vids, sbin=sbin, motSVD=mot, movSVD=mov)
+    for key, val in want.items():
+        if isinstance(val, list):
+            assert len(d[key]) == len(val), key
+            for a, b in zip(d[key], val):
+                assert np.asarray(a).dtype == np.asarray(b).dtype and np.array_equal(a, b), key
+        elif isinstance(val, np.ndarray):
+            assert d[key].dtype == val.dtype and np.array_equal(d[key], val), key
+    # and it is the file the plain writer produces for the same dict
+    plain = str(tmp_path / "plain.npy")
+    process.save_npy(plain, d)
+    assert os.path.getsize(plain) == os.path.getsize(name)
+
+
+def test_run_with_motion_rois_falls_back_to_the_plain_writer(cuda_device, tmp_path):
+    from facemap_b200 import process
+    from tests.helpers import motion_roi
+
+    vids = [torch.from_numpy(v) for v in case_videos("short_s2")]
+    settings = {"sbin": 2, "fullSVD": True, "save_mat": False, "rois": [motion_roi(0, 4, 30, 6, 40)], "sy": 0, "sx": 0,
+                "savepath": str(tmp_path)}
+    name = process.run(vids, proc=settings)
+    assert process.LAST_RUN["written_early"] is False
+    assert sorted(os.listdir(tmp_path)) == ["array_input_proc.npy"]
+    assert len(np.load(name, allow_pickle=True).item()["motSVD"]) == 2
+
+
 def test_run_writes_reference_proc_file(cuda_device, tmp_path):
     """process.run: same signature / file naming / keys as facemap.process.run (process.py:605-647, 859-892)."""
     from facemap_b200 import process

@@ -47,7 +47,10 @@ def test_defaults_and_key_order(stub, tmp_path):
     files = [[str(tmp_path / "a.avi")]]
     name = process.run(files, sbin=3, motSVD=True, movSVD=True)
     assert name == str(tmp_path / "a_proc.npy") and stub["source"].closed
+    early = stub["kw"].pop("stream_out")              # the writer that streams the file during the pass; never begun here
+    assert isinstance(early, process._EarlyFile) and early.final_path == name
     assert stub["kw"] == {"sbin": 3, "motSVD": True, "movSVD": True, "rois": None, "fullSVD": True}
+    assert process.LAST_RUN["written_early"] is False and sorted(os.listdir(tmp_path)) == ["a_proc.npy"]
     proc = np.load(name, allow_pickle=True).item()
     assert list(proc.keys()) == REF_KEYS
     assert proc["fullSVD"] is True and proc["save_mat"] is False and proc["rois"] is None
