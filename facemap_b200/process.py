@@ -118,6 +118,7 @@ class _EarlyFile:
     the final pickle of the final dict."""
 
     BIG = 1 << 16           # the pickler hands over buffers from 64 KB on; smaller arrays are copied into its stream
+    WRITERS, PIECE = 4, 8 << 20
 
     def __init__(self, path, build_full):
         import queue
@@ -126,7 +127,7 @@ class _EarlyFile:
         self.q, self.thread, self.fd = queue.Queue(), None, None
         self.sig, self.where, self.bases = None, {}, []
         self.waiting, self.done, self.redo, self.used = [], [], [], set()
-        self.failed = False
+        self.failed, self.split = False, {}
 
     @staticmethod
     def _signature(segs):
@@ -152,19 +153,28 @@ class _EarlyFile:
         except Exception:       # noqa: BLE001 — an optimisation: the plain writer takes over
             self.failed = True
             return
-        self.thread = threading.Thread(target=self._work, daemon=True)
-        self.thread.start()
-        for job in self.waiting:
-            self.q.put(job)
-        self.waiting = []
+        # several writers: one thread writes fresh pages at ~1 GB/s and fell 40 - 57 ms behind a 100k-frame pass
+        # (profiles/r02_logs/bench_r2y2.json); positioned writes to different places of a file proceed in parallel
+        self.thread = [threading.Thread(target=self._work, daemon=True) for _ in range(self.WRITERS)]
+        for t in self.thread:
+            t.start()
+        waiting, self.waiting = self.waiting, []
+        for t, event in waiting:
+            self.landed(t, event)
 
     def landed(self, host_tensor, event):
         """a device-to-host copy into `host_tensor` (contiguous) was enqueued; `event` fires when it is done"""
-        job = (host_tensor, event)
         if self.thread is None:
-            self.waiting.append(job)
+            self.waiting.append((host_tensor, event))
+            return
+        rows = host_tensor.shape[0] if host_tensor.dim() > 1 else 0
+        per = host_tensor[0].numel() * host_tensor.element_size() if rows else 0
+        step = max(1, self.PIECE // per) if per else 0
+        if rows and rows > step:                 # big arrays in pieces, so that the writers share them
+            for a in range(0, rows, step):
+                self.q.put((host_tensor[a:a + step], event))
         else:
-            self.q.put(job)
+            self.q.put((host_tensor, event))
 
     def dirty(self, host_array):
         """rows changed on the host after they landed: written again at the end"""
@@ -204,8 +214,10 @@ class _EarlyFile:
 
     def _stop(self):
         if self.thread is not None:
-            self.q.put(None)
-            self.thread.join()
+            for _ in self.thread:
+                self.q.put(None)
+            for t in self.thread:
+                t.join()
             self.thread = None
 
     def abandon(self):
@@ -220,12 +232,16 @@ class _EarlyFile:
 
     def finish(self, full):
         """True: the file is complete under its final name.  False: nothing usable was written (plain writer's turn)."""
+        t0 = time.perf_counter()
         self._stop()
+        self.split = {"join_s": time.perf_counter() - t0}
         if self.failed or self.sig is None or self.fd is None:
             self.abandon()
             return False
         try:
+            t1 = time.perf_counter()
             segs = _npy_segments(full)
+            self.split["pickle_s"] = time.perf_counter() - t1
             at = {off: addr for off, _, addr in segs}
             if self._signature(segs) != self.sig or any(at.get(off) != base for off, base in self.used):
                 self.abandon()          # not the announced layout, or an early-written array is not the saved one
@@ -247,10 +263,15 @@ class _EarlyFile:
                 addr = int(arr.__array_interface__["data"][0])
                 for pos, _, _ in self._place(addr, mv.nbytes):
                     jobs.append((pos, mv))
+            t2 = time.perf_counter()
             _write_segments(self.fd, jobs)
+            self.split["late_bytes"] = sum(mv.nbytes for _, mv in jobs)
+            self.split["write_s"] = time.perf_counter() - t2
+            t3 = time.perf_counter()
             os.close(self.fd)
             self.fd = None
             os.replace(self.path, self.final_path)
+            self.split["close_rename_s"] = time.perf_counter() - t3
             return True
         except Exception:       # noqa: BLE001
             self.abandon()
@@ -811,7 +832,7 @@ def run(filenames, sbin=1, motSVD=True, movSVD=False, GUIobject=None, parent=Non
     early = None
     try:
         folder, stem = _proc_file_name(names, savepath)
-        if os.path.isdir(folder or "."):
+        if os.path.isdir(folder or ".") and os.environ.get("FM_EARLY_FILE", "1") != "0":
             early = _EarlyFile(os.path.join(folder, f"{stem}_proc.npy"), build_full)
     except Exception:           # noqa: BLE001
         early = None
@@ -837,7 +858,8 @@ def run(filenames, sbin=1, motSVD=True, movSVD=False, GUIobject=None, parent=Non
     LAST_RUN.clear()
     LAST_RUN.update({"setup_s": t_pass - start_pc, "pass_s": t_close - t_pass, "close_s": t_save - t_close,
                      "save_s": time.perf_counter() - t_save, "written_early": bool(written_early),
-                     "early_bytes": 0 if early is None else sum(b - a for a, b in early.done)})
+                     "early_bytes": 0 if early is None else sum(b - a for a, b in early.done),
+                     "early_finish": {} if early is None else dict(early.split)})
     if parent is not None:
         parent.update_status_bar("Output saved in " + str(savepath))
     if GUIobject is not None:
