@@ -1024,8 +1024,14 @@ class Stage3:
         with torch.cuda.stream(side):
             self._seed_halo()
             row0 = 0
+            # one event per batch: project() starts on a batch as soon as it is binned, so that with frames still
+            # arriving from the host the projections, and their copies back to the host, spread over the upload
+            self.early_events = []
             for fetches, filled in self.batches:
                 row0 += self._bin_fetches(fetches, self.X_full, row0)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                self.early_events.append(ev)
             self.early_done = torch.cuda.Event()
             self.early_done.record(side)
         self._side = side
@@ -1063,7 +1069,6 @@ class Stage3:
             else:
                 Ut_lo = {m: [None if Ut is None else K.split_lo(Ut) for Ut in masks[m][0]] for m in mods}
         if self.X_full is not None:
-            torch.cuda.current_stream().wait_event(self.early_done)
             X = self.X_full
         else:
             X = self._operands("X3.", self.rows_batch)
@@ -1071,11 +1076,12 @@ class Stage3:
             self._seed_halo()
         row0 = 0
         Ut_qb = {}                      # K-blocked copies of the mask digits (wide views)
-        for fetches, filled in self.batches:
+        for ib, (fetches, filled) in enumerate(self.batches):
             if self.X_full is None:
                 self._bin_fetches(fetches, X, 0)
                 base = 0
             else:
+                torch.cuda.current_stream().wait_event(self.early_events[ib])
                 base = row0
             if filled == 0:
                 continue
@@ -1141,6 +1147,8 @@ class Stage3:
                         if sink is not None:
                             sink.copy(V[m][1 + j][o + r0:o + r1], V_host[m][1 + j][o + r0:o + r1])
             row0 += filled
+        if self.X_full is not None:
+            torch.cuda.current_stream().wait_event(self.early_done)     # the energies of the whole pass
         if sink is not None:
             return V_host, self.E, self.E_roi
         return V, self.E, self.E_roi
