@@ -778,3 +778,27 @@ def mean_ref(frames, sbin, mean_bin, mean_adiff):
             raise FacemapB200Error(f"{name}: needs {npix} contiguous float64 elements")
     check(_lib.load().fm_mean_ref(ptr(frames), T, H, W, int(sbin), ptr(mean_bin), ptr(mean_adiff), _stream()),
           "fm_mean_ref")
+
+
+_STREAMS = {}
+
+
+def shared_stream(device, name):
+    """One stream per (device, purpose) for the life of the process.  Creating a stream — like cudaMemGetInfo — goes
+    through the kernel-mode driver, and such calls wait whenever something else holds it (an NVML poller on the box:
+    single queries were seen to take 50 - 100 ms, profiles/r02_logs/bench_r2z2.json); kernel launches do not.  The
+    per-pass side streams (stage 3's early bin pass, the host sink, the frame upload) are therefore made once."""
+    key = (torch.device(device).index or 0, name)
+    if key not in _STREAMS:
+        _STREAMS[key] = torch.cuda.Stream(device)
+    return _STREAMS[key]
+
+
+def free_memory(device, need):
+    """Free device memory for a decision about `need` bytes — from the allocator's own books (no driver call) when
+    the request is under a quarter of what they show, from cudaMemGetInfo otherwise."""
+    total = torch.cuda.get_device_properties(device).total_memory
+    est = total - torch.cuda.memory_reserved(device)
+    if need <= est // 4:
+        return est
+    return torch.cuda.mem_get_info(device)[0]

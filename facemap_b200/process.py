@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib, fullres, svd
+from . import kernels as K
 from .kernels import EigCheckFailed
 from .frames import FrameSource, as_source
 from .utils import binned_inds, multivideo_reshape, roi_bin_ranges, video_placement
@@ -414,7 +415,7 @@ class _HostSink:
     that persists across calls (_PinnedPool)."""
 
     def __init__(self, device, listener=None):
-        self.stream = torch.cuda.Stream(device)
+        self.stream = K.shared_stream(device, "host_sink")
         self.listener = listener            # _EarlyFile: told about every copy, with an event that fires when it is done
 
     @staticmethod

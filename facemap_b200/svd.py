@@ -1014,12 +1014,11 @@ class Stage3:
         if self.rows_total == 0 or not self.mods or not self.source.resident(self.f0, self.f1):
             return False
         need = len(self.mods) * self.rows_total * (2 * self.ldq if self.i8 else max(32, K.round_up(self.geo.p, 32)) * 4)
-        free, _ = torch.cuda.mem_get_info(self.device)
-        if need > budget_bytes or need > 0.5 * free:
+        if need > budget_bytes or need > 0.5 * K.free_memory(self.device, need):
             return False
         self.X_full = self._operands("X3full.", self.rows_total)
         main = torch.cuda.current_stream()
-        side = torch.cuda.Stream(self.device)
+        side = K.shared_stream(self.device, "stage3.early")
         side.wait_stream(main)
         with torch.cuda.stream(side):
             self._seed_halo()
