@@ -195,6 +195,11 @@ class SvdWorkspace:
         self.eig_mode = _os.environ.get("FM_EIG", "cluster") if eig_mode is None else eig_mode
         if self.eig_mode not in ("cluster", "cusolver"):
             raise FacemapB200Error(f"unknown eig_mode {self.eig_mode!r}")
+        # merge-level eigensolve: "subspace" (block subspace iteration + Rayleigh-Ritz for large problems,
+        # subspace_topk) or "cusolver" (syevdx always); a pass repeated on cuSOLVER (eig_mode "cusolver") uses syevdx
+        self.merge_eig = _os.environ.get("FM_MERGE_EIG", MERGE_EIG_DEFAULT) if self.eig_mode == "cluster" else "cusolver"
+        if self.merge_eig not in ("subspace", "cusolver"):
+            raise FacemapB200Error(f"unknown FM_MERGE_EIG {self.merge_eig!r}")
         self.proj_i8_impl = int(_os.environ.get("FM_PROJ_I8_IMPL", "0"))      # 1 = CTA pairs (fm_project_i8 impl)
         self._ws = None
         self._bufs = {}
@@ -393,15 +398,110 @@ def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
     terms for the left-vector GEMM."""
     n, p = X.shape
     mean, G = centred_gram(ws, X, timer, label)
+    evec = G
     with timer(label + ".syevd"):
-        if ws.eig_fp32 or k == n:
+        top = None
+        if getattr(ws, "merge_eig", "cusolver") == "subspace" and not ws.eig_fp32 and subspace_eligible(n, k):
+            top = subspace_topk(G[:n, :n], k, rr=lambda Hm, kk: _rr_cluster(ws, Hm, kk))
+        if top is not None:
+            lam, evec, nev = top[0], top[1], k
+        elif ws.eig_fp32 or k == n:
             lam, nev = ws.solver.syevd(G, use_fp32=ws.eig_fp32), n
         else:
             lam, nev = ws.solver.syevdx_top(G, k), k      # only the k largest eigenpairs (rows 0..k-1 of G)
     with timer(label + ".topk"):
         Wt = ws.matrix(label + ".Wt", k, n)
-        sval, rbias, rscale = K.topk_components(G, lam, k, mean, Wt, want_scale=want_scale, nev=nev)
+        sval, rbias, rscale = K.topk_components(evec, lam, k, mean, Wt, want_scale=want_scale, nev=nev)
     return Wt, sval, rbias, rscale
+
+
+MERGE_EIG_DEFAULT = "cusolver"
+SUBSPACE_MIN_N = 3000          # the merge of >= 12 chunks (3 000 ... 3 750 stacked components); smaller ones stay direct
+SUBSPACE_EXTRA = 250           # guard vectors next to the k wanted ones
+SUBSPACE_MULTS = 8             # multiplications by G before the first Rayleigh-Ritz step
+SUBSPACE_MORE = 4              # ... and per further round when the residuals are not there yet
+SUBSPACE_ROUNDS = 3
+_SUBSPACE_START = {}
+
+
+def subspace_eligible(n, k):
+    return n >= SUBSPACE_MIN_N and 64 <= k and 4 * (k + SUBSPACE_EXTRA) <= n
+
+
+def _rr_cluster(ws, Hm, k):
+    """top-k eigenpairs of the projected matrix on the hand-written solver: (lam [k], Z [k, b]) ascending; its
+    self-check flags are read by ws.solver.check() like those of the chunk problems"""
+    lam, Wt = ws.solver.eigh_topk_batched(Hm[None].contiguous(), k)
+    return lam[0], Wt[0]
+
+
+def _rr_lapack(Hm, k):
+    th, Z = torch.linalg.eigh(Hm)
+    return th[-k:], Z[:, -k:].T.contiguous()
+
+
+def subspace_topk(G, k, rr=_rr_lapack, mults=None, seed=0):
+    """The k largest eigenpairs of the symmetric positive semi-definite G [n, n] (float64) by block subspace
+    iteration with Rayleigh-Ritz: Q <- orth(G Q) for a block of k + 250 vectors (float64 GEMMs, Cholesky-QR after
+    every multiplication: the spectrum spans 1e6 and more), then the eigenpairs of Q^T G Q.  Measured on the merge
+    problem of the benchmark (n = 3 750, k = 500, B200): 8 multiplications bring every singular value within 1e-8
+    and every gap-resolved vector within 1e-7 of LAPACK's, in 25 ms against 69 - 74 ms for cusolverDnXsyevdx
+    (profiles/r02_eig.md, scripts/probe_merge_subspace.py).
+
+    Accepted only if the a-posteriori estimates are well inside the path's gates, with up to two more rounds of
+    multiplications; otherwise, or if a Cholesky factor breaks down, None: the caller solves directly.  With the
+    residuals r_j = G w_j - theta_j w_j: (a) eigenvalues — the residuals point out of the block, where G's spectrum
+    lies below `edge` (the mean of the block's unwanted Ritz values, an upper bound of it), so theta_j is off by about
+    |r_j|^2 / (theta_j - edge); required: 1e-5 theta_j (singular value to 5e-6; the gate is 1e-4).  (b) vectors — a
+    component whose singular value stands 4e-4 S_0 clear of both neighbours (what the tests call resolved) turns by
+    at most |r_j| / gap_j; required: 2.5e-4 (the gate is 1e-3).
+    Returns (lam [k] ascending, W [k, n] rows = eigenvectors, ascending) — what fm_topk_components reads with nev = k.
+    Deterministic: the start block is a fixed pseudo-random matrix."""
+    n = G.shape[0]
+    b = k + SUBSPACE_EXTRA
+    key = (str(G.device), n, b, seed)
+    if key not in _SUBSPACE_START:
+        g = torch.Generator(device="cpu")
+        g.manual_seed(1234 + seed)
+        _SUBSPACE_START[key] = torch.randn((n, b), dtype=torch.float64, generator=g).to(G.device)
+    infos = []
+
+    def orth(Z):
+        L, info = torch.linalg.cholesky_ex(Z.T @ Z, check_errors=False)
+        infos.append(info)
+        return torch.linalg.solve_triangular(L, Z.T, upper=False).T.contiguous()
+
+    Q = orth(_SUBSPACE_START[key])
+    todo = SUBSPACE_MULTS if mults is None else int(mults)
+    for _ in range(SUBSPACE_ROUNDS):
+        for _ in range(todo):
+            Q = orth(G @ Q)
+        GQ = G @ Q
+        Hm = Q.T @ GQ
+        Hm = ((Hm + Hm.T) / 2).contiguous()
+        trace = torch.trace(Hm)                                     # before rr: a solver may destroy its input
+        th, Zt = rr(Hm, k)                                          # ascending; rows of Zt are the vectors
+        W = Zt @ Q.T                                                # [k, n]
+        R = Zt @ GQ.T - th[:, None] * W
+        rn = torch.linalg.vector_norm(R, dim=1)
+        tiny = 1e-300
+        thc = th.clamp_min(0)
+        edge = ((trace - th.sum()) / (b - k)).clamp_min(0)
+        est = rn * rn / (thc - edge).clamp_min(tiny)
+        bad_a = (est > 1e-5 * thc).any()
+        S = torch.sqrt(thc)
+        lo_nb = torch.cat([torch.sqrt(edge).reshape(1), S[:-1]])               # the neighbour below (ascending order)
+        gap_dn, gap_up = S - lo_nb, torch.cat([S[1:] - S[:-1], S[-1:]])
+        resolved = torch.minimum(gap_dn, gap_up) >= 4e-4 * S[-1]
+        gap_lam = torch.minimum(thc - torch.cat([edge.reshape(1), thc[:-1]]),
+                                torch.cat([thc[1:] - thc[:-1], thc[-1:]])).clamp_min(tiny)
+        bad_b = (resolved & (rn > 2.5e-4 * gap_lam)).any()
+        bad = bad_a | bad_b | torch.stack([i.reshape(()) != 0 for i in infos]).any() | ~torch.isfinite(rn).all()
+        infos.clear()
+        if not bool(bad):                                           # the one host synchronisation of the solve
+            return th, W.contiguous()
+        todo = SUBSPACE_MORE
+    return None
 
 
 def left_components(ws, X, evec, lam, mean, k, out_Yt, timer, label, nev=None):

@@ -468,3 +468,40 @@ def test_early_file_is_the_final_pickle_or_nothing(tmp_path):
     early, _ = scenario(str(tmp_path / "c_proc.npy"))
     early.abandon()
     assert sorted(os.listdir(tmp_path)) == ["a_proc.npy", "plain.npy"]
+
+
+def test_subspace_topk_matches_lapack_or_declines():
+    """svd.subspace_topk (torch, runs on the CPU here): on a decaying spectrum the top-k eigenpairs agree with LAPACK
+    far inside the path's gates and come back in the layout fm_topk_components reads (ascending rows); on a flat
+    spectrum, where the block cannot converge in the allowed rounds, it declines (None: the caller solves directly)."""
+    import torch
+
+    from facemap_b200 import svd
+
+    rng = np.random.default_rng(11)
+    n, k = 1200, 200
+    Qr, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = (np.arange(1, n + 1, dtype=np.float64) ** -1.6) * (1 + 0.2 * rng.random(n))        # S ~ k^-0.8: a video's tail
+    lam = np.sort(lam)[::-1]
+    G = torch.from_numpy((Qr * lam) @ Qr.T)
+    G = (G + G.T) / 2
+    calls = []
+
+    def rr(Hm, kk):
+        calls.append(Hm.shape[0])
+        return svd._rr_lapack(Hm, kk)
+
+    th, W = svd.subspace_topk(G, k, rr=rr)
+    assert calls == [k + svd.SUBSPACE_EXTRA]                         # accepted at the first Rayleigh-Ritz step
+    assert th.shape == (k,) and W.shape == (k, n) and W.is_contiguous() and bool((th[1:] >= th[:-1]).all())
+    assert np.max(np.abs(th.numpy()[::-1] - lam[:k]) / lam[:k]) < 1e-6
+    lead = np.abs(np.sum(W.numpy()[::-1][:20].T * Qr[:, :20], axis=0))       # well-separated leading vectors
+    assert np.sqrt(np.max(1 - np.minimum(lead, 1.0) ** 2)) < 1e-5
+    assert float((W @ W.T - torch.eye(k, dtype=torch.float64)).abs().max()) < 1e-10
+    th2, W2 = svd.subspace_topk(G, k, rr=rr)                         # deterministic
+    assert torch.equal(th, th2) and torch.equal(W, W2)
+    # flat tail: lambda_{b+1} / lambda_k = 0.98 -> no convergence in 8 + 4 + 4 multiplications
+    lam_flat = np.r_[np.linspace(1.0, 0.5, 50), np.linspace(0.2, 0.19, n - 50)]
+    Gf = torch.from_numpy((Qr * lam_flat) @ Qr.T)
+    assert svd.subspace_topk((Gf + Gf.T) / 2, k) is None
+    assert svd.subspace_eligible(3750, 500) and not svd.subspace_eligible(2500, 500) and not svd.subspace_eligible(3750, 999)
