@@ -415,7 +415,7 @@ def gram_eig(ws: SvdWorkspace, X, k, timer, want_scale, label):
     return Wt, sval, rbias, rscale
 
 
-MERGE_EIG_DEFAULT = "cusolver"
+MERGE_EIG_DEFAULT = "subspace"
 SUBSPACE_MIN_N = 3000          # the merge of >= 12 chunks (3 000 ... 3 750 stacked components); smaller ones stay direct
 SUBSPACE_EXTRA = 250           # guard vectors next to the k wanted ones
 SUBSPACE_MULTS = 8             # multiplications by G before the first Rayleigh-Ritz step
