@@ -830,9 +830,21 @@ def stage2_chunks(source, geo, avgframe, avgmotion, mods, fullSVD, ws, device, t
     return Yt, ks, nsegs
 
 
+def merge_cost(shape, ncomps, merge_eig):
+    """Cost of one merge in units of cuSOLVER columns (~19 us each): the order of its eigenproblem — the smaller side
+    of Yt [c, p] — unless the problem goes to the subspace solver (gram_eig: p >= c and subspace_eligible), which takes
+    what cuSOLVER takes for ~1 500 columns (29 ms)."""
+    c, p = shape
+    n = min(c, p)
+    k = min(ncomps, p - 1)
+    if merge_eig == "subspace" and p >= c and subspace_eligible(c, k):
+        return 1500
+    return n
+
+
 def deal_merges(sizes, world):
-    """Which rank solves which merge: sizes = {target: order n of its eigenproblem} -> {target: rank}, heaviest first
-    onto the least loaded rank.  The cost of a solve is taken as PROPORTIONAL TO n: cuSOLVER's syevd(x) spends about
+    """Which rank solves which merge: sizes = {target: cost (merge_cost)} -> {target: rank}, heaviest first
+    onto the least loaded rank.  The cost of a direct solve is PROPORTIONAL TO n: cuSOLVER's syevd(x) spends about
     19 us per matrix column whatever the size (999 columns 12 ms, 3 750 columns 71 ms: profiles/r02_eig.md), not n^3.
     One target or one rank: nothing to deal ({})."""
     if world <= 1 or len(sizes) <= 1:
@@ -860,7 +872,8 @@ def stage2_merge(Yt, ks, nsegs, geo, mods, fullSVD, ws, timer, ncomps=NCOMPS, nc
             if Y is not None and nsegs > 1 and idx < (1 if mot_on else 0) + (len(Yt[m]) - 1):
                 todo.append((m, idx))
     world = 1 if shard is None else shard.world
-    owner = deal_merges({t: min(Yt[t[0]][t[1]].shape) for t in todo}, world)
+    owner = deal_merges({t: merge_cost(tuple(Yt[t[0]][t[1]].shape), ncomps, getattr(ws, "merge_eig", "cusolver"))
+                         for t in todo}, world)
     # the solves this rank owns come first (cuSOLVER blocks the host, and a broadcast waiting in the stream would block
     # the solves queued behind it), the broadcasts of all dealt targets follow in target order
     solved = {}

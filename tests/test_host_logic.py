@@ -505,3 +505,12 @@ def test_subspace_topk_matches_lapack_or_declines():
     Gf = torch.from_numpy((Qr * lam_flat) @ Qr.T)
     assert svd.subspace_topk((Gf + Gf.T) / 2, k) is None
     assert svd.subspace_eligible(3750, 500) and not svd.subspace_eligible(2500, 500) and not svd.subspace_eligible(3750, 999)
+
+
+def test_merge_cost_knows_which_solver_a_merge_gets():
+    from facemap_b200.svd import merge_cost
+
+    assert merge_cost((3750, 38400), 500, "cusolver") == 3750          # direct solve: the order of the problem
+    assert merge_cost((3750, 38400), 500, "subspace") == 1500          # subspace iteration: 29 ms ~ 1 500 cuSOLVER columns
+    assert merge_cost((3750, 2400), 500, "subspace") == 2400           # wide ROI merge: row-side problem, always direct
+    assert merge_cost((1000, 38400), 500, "subspace") == 1000          # too small for the subspace solver
