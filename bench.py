@@ -824,7 +824,9 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32",
             "dtype_detail": "u8 frames, integer block sums / energies; Gram matrices and projections as exact s8/u8 digit-plane "
                             "products on tcgen05 kind::i8 (int32 accumulation, float64 assembly); left singular vectors as 3xTF32 "
-                            "products with f64-reduced partials; f64 eigensolve (cuSOLVER)",
+                            "products with f64-reduced partials; f64 eigensolves (chunks: hand-written cluster solver; merge: block subspace "
+                            "iteration on f64 library GEMMs + Cholesky-QR, projected problem on the cluster solver, cuSOLVER syevdx as "
+                            "the fallback)",
             "data": "synthetic",
             "config": {**workload_config(world),
                        **({"rois": "pupil 100x140 + blink 100x140 + running 120x400 (side measurement)"} if args.with_rois else {})},
